@@ -1,0 +1,165 @@
+/*
+ * b200da.h — C ABI of the B200-native LETKF / ETKF analysis engine (libb200da.so).
+ *
+ * This is the drop-in boundary for the hot path of tobifinn/torch-assimilate (pytassim 0.2.1):
+ * everything between "obs-space variables are ready" (interface/base.py:359-379) and "analysis is
+ * assembled" (interface/base.py:257-278) for `LETKF.assimilate` / `ETKF.assimilate`
+ * (interface/base.py:419-512 -> interface/filter.py:96-165 -> interface/letkf.py:104-148 /
+ * interface/etkf.py:99-120).  Each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / xarray types;
+ *   - every function returns 0 (B200DA_OK) or a negative b200da_status; b200da_strerror() explains it;
+ *   - unless a name ends in `_host`, every data pointer is a DEVICE pointer owned by the caller;
+ *     the library allocates only plan-owned scratch;
+ *   - all work is enqueued on the given CUDA stream (a `cudaStream_t` passed as void*); set-up calls
+ *     (`b200da_set_grid`, `b200da_bin_obs`) read a few scalars back and therefore synchronise the stream;
+ *   - one plan per device and per thread of control; plans are independent of each other;
+ *   - the CUDA device must be sm_100 (B200); there is no CPU fallback (B200DA_ERR_NO_DEVICE).
+ *
+ * Layouts (identical to the reference's in-memory layout)
+ *   state      X   (n_slices, k, N)  grid index fastest; n_slices = n_var * n_time  (pytassim/state.py:114)
+ *   obs perts  Yn  (k, M)            obs index fastest; already multiplied by R^{-1/2}
+ *   innovation d   (M)               (y - mean_k Hx) R^{-1/2}                        (interface/base.py:367-372)
+ *   coordinates    (n_coord, N|M)    struct-of-arrays float64: the columns after the time column of
+ *                                    `_extract_state_information` / `_extract_obs_information`
+ *                                    (interface/mixin_local.py:45-69)
+ *   weights    W   (N, k, k)         dims (grid, ensemble, ensemble_new)             (interface/letkf.py:136)
+ */
+#ifndef B200DA_H
+#define B200DA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200da_plan b200da_plan;
+
+typedef enum {
+    B200DA_OK = 0,
+    B200DA_ERR_INVALID = -1,      /* bad argument (null pointer, k < 2, ...)                                  */
+    B200DA_ERR_SIZE = -2,         /* Yn / d observation sizes differ: the reference's ValueError
+                                     (pytassim/core/base.py:28-38)                                            */
+    B200DA_ERR_UNSUPPORTED = -3,  /* metric / taper / dtype / ensemble size outside the implemented set       */
+    B200DA_ERR_NO_DEVICE = -4,    /* no CUDA device or not sm_100: there is no CPU fallback                   */
+    B200DA_ERR_CUDA = -5,         /* a CUDA runtime call failed; see b200da_last_cuda_error()                 */
+    B200DA_ERR_STATE = -6,        /* call order: set_grid and bin_obs must precede letkf / neighbour_*         */
+    B200DA_ERR_NOMEM = -7
+} b200da_status;
+
+/* Distance functions.  The reference takes an arbitrary Python `dist_func` (localization/gaspari_cohn.py:60-69,125);
+ * the engine implements this closed set.  metric_params: PERIODIC1D -> {period}; HAVERSINE -> {sphere radius}. */
+typedef enum {
+    B200DA_METRIC_ABS1D = 0,      /* |x_g - x_o|                        (examples/benchmark_letkf.py:85-87)  */
+    B200DA_METRIC_PERIODIC1D = 1, /* min(|x_g - x_o|, L - |x_g - x_o|)                                        */
+    B200DA_METRIC_EUCLID = 2,     /* sqrt(sum_c (x_gc - x_oc)^2), n_coord in 1..3                             */
+    B200DA_METRIC_HAVERSINE = 3   /* great circle, coords = (lat, lon) in degrees                             */
+} b200da_metric;
+
+typedef enum {
+    B200DA_TAPER_GC = 0,          /* GaspariCohn     (localization/gaspari_cohn.py:78-136)                    */
+    B200DA_TAPER_GCINF = 1        /* GaspariCohnInf  (localization/gaspari_cohn.py:172-254)                   */
+} b200da_taper;
+
+typedef enum { B200DA_F64 = 0, B200DA_F32 = 1 } b200da_dtype;
+
+/* ---- plan ------------------------------------------------------------------------------------------------ */
+
+/* Replaces the constructor state of LETKF(localization=GaspariCohn(length_scale, dist_func, epsilon),
+ * inf_factor=rho) (interface/letkf.py:72-92, localization/gaspari_cohn.py:60-69).
+ * k: ensemble size; n_slices: n_var * n_time rows of the state that share one weight matrix per grid point. */
+int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int metric,
+                       const double* metric_params, int n_metric_params, const double* radius, int n_radius,
+                       double epsilon, double inf_factor, int dtype, int taper);
+void b200da_plan_destroy(b200da_plan* plan);
+
+/* Replaces `_extract_state_information` + the dask chunking of the grid (interface/mixin_local.py:50-69,
+ * interface/letkf.py:121): bins the N grid points into cells and forms blocks of neighbouring grid points
+ * (one CTA each).  grid_coord: (n_coord, N) float64 device. */
+int b200da_set_grid(b200da_plan* plan, const double* grid_coord, int64_t n_grid, void* stream);
+
+/* Replaces `_extract_obs_information` + the per-grid-point boolean gather of wrapper_localization
+ * (interface/mixin_local.py:45-47, interface/wrapper.py:91-97): bins the M observations into cells and builds
+ * the cell-ordered, observation-major staging copy of [Yn; d].  obs_coord: (n_coord, M) float64 device;
+ * Yn: (k, M); d: (M) of the plan's dtype. */
+int b200da_bin_obs(b200da_plan* plan, const double* obs_coord, const void* Yn, const void* d, int64_t n_obs,
+                   void* stream);
+
+int64_t b200da_num_blocks(const b200da_plan* plan);      /* grid-point blocks (unit of multi-GPU sharding)     */
+int64_t b200da_num_grid(const b200da_plan* plan);
+int64_t b200da_num_obs(const b200da_plan* plan);
+/* first grid slot (position in the block-sorted order) of block b, b in [0, num_blocks]; host query */
+int64_t b200da_block_offset(const b200da_plan* plan, int64_t block);
+/* copies the block-sorted grid order (N int32: slot -> original grid index) to a device buffer */
+int b200da_grid_order(const b200da_plan* plan, int32_t* order_out, void* stream);
+
+/* ---- the hot path ---------------------------------------------------------------------------------------- */
+
+/* Replaces the whole per-grid-point loop of LETKF.estimate_weights (interface/letkf.py:127-143:
+ * localize_obs -> sqrt(w) gather -> ETKFModule.forward, i.e. localization/gaspari_cohn.py:97-136,
+ * interface/wrapper.py:54-98, core/etkf.py:57-103, core/utils.py:26-93) fused with _apply_weights
+ * (interface/base.py:257-278) for the grid points of blocks [block_begin, block_end).
+ * X, Xa: (n_slices, k, N) device, plan dtype; only the columns of the analysed grid points are written.
+ * W_opt: (N, k, k) or NULL.  n_ambiguous_opt: device int64 counter (or NULL) incremented for every
+ * (grid point, obs) pair whose taper value lies within 1e-13 of epsilon. */
+int b200da_letkf(b200da_plan* plan, const void* X, void* Xa, void* W_opt, int64_t block_begin,
+                 int64_t block_end, int64_t* n_ambiguous_opt, void* stream);
+
+/* Host-buffer convenience used for end-to-end timing: uploads (obs_coord, Yn, d, X), bins, analyses all
+ * blocks, downloads Xa.  All pointers are HOST pointers (pinned memory makes the copies asynchronous).
+ * The grid must have been set with b200da_set_grid. */
+int b200da_letkf_host(b200da_plan* plan, const double* obs_coord_host, const void* Yn_host, const void* d_host,
+                      int64_t n_obs, const void* X_host, void* Xa_host, void* stream);
+
+/* Local-observation index lists = np.nonzero(use_obs)[0] of GaspariCohn.localize_obs
+ * (localization/gaspari_cohn.py:135) for every grid point, as CSR in ORIGINAL grid order, ascending obs id.
+ * Two passes: count -> caller scans -> fill.  w_opt receives the taper weights (before sqrt);
+ * ambiguous_opt (same length as idx) is 1 where |w - epsilon| < 1e-13 (also set in entries that were
+ * rejected: see b200da_neighbour_count's n_ambiguous). */
+int b200da_neighbour_count(b200da_plan* plan, int64_t* counts, int64_t* n_ambiguous_opt, void* stream);
+int b200da_neighbour_fill(b200da_plan* plan, const int64_t* offsets, int32_t* idx, double* w_opt,
+                          uint8_t* ambiguous_opt, void* stream);
+/* All pairs (grid index, obs index, w) inside the ambiguity band, accepted or not; capacity-limited. */
+int b200da_neighbour_ambiguous(b200da_plan* plan, int64_t capacity, int64_t* grid_idx, int64_t* obs_idx,
+                               double* w, int64_t* n_found, void* stream);
+
+/* ---- global ETKF (no localization) ------------------------------------------------------------------------ */
+
+/* Replaces ETKFModule.forward on the whole observation vector (interface/etkf.py:99-120, core/etkf.py:79-103):
+ * W (k, k) = w_mean + w_perts.  M = 0 gives sqrt(inf_factor) * I (core/etkf.py:91-95). */
+int b200da_etkf_weights(b200da_plan* plan, const void* Yn, const void* d, int64_t n_obs, void* W, void* stream);
+
+/* Replaces BaseAssimilation._apply_weights (interface/base.py:257-278): Xa = mean + (X - mean) W with one
+ * global W (k, k) (per_grid = 0) or W (N, k, k) (per_grid = 1).  X, Xa: (n_slices, k, N). */
+int b200da_apply_weights(b200da_plan* plan, const void* X, const void* W, int per_grid, int64_t n_grid, void* Xa,
+                         void* stream);
+
+/* ---- multi-GPU helpers ------------------------------------------------------------------------------------ */
+
+/* Pack / unpack the analysed columns of blocks [block_begin, block_end) between the (n_slices, k, N) layout and
+ * a dense (n_slices * k, n_cols) buffer in block-sorted order: the all-gather payload of the grid-sharded run. */
+int b200da_pack_columns(b200da_plan* plan, const void* Xa, int64_t block_begin, int64_t block_end, void* packed,
+                        void* stream);
+int b200da_unpack_columns(b200da_plan* plan, const void* packed, int64_t block_begin, int64_t block_end, void* Xa,
+                          void* stream);
+
+/* ---- misc -------------------------------------------------------------------------------------------------- */
+
+const char* b200da_strerror(int status);
+const char* b200da_last_cuda_error(void);
+int b200da_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t b200da_launch_count(void);
+/* name of the CUDA event-timed kernel configuration chosen for the plan, e.g. "letkf_f64_kt7_g8_w2" */
+const char* b200da_kernel_name(const b200da_plan* plan);
+/* device time (ms) of the last b200da_letkf main-kernel launch on this plan, measured with CUDA events on
+ * the launch stream when timing was enabled with b200da_enable_timing(plan, 1); synchronises. */
+int b200da_enable_timing(b200da_plan* plan, int on);
+float b200da_last_kernel_ms(b200da_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DA_H */

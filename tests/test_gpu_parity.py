@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors produced by
+the reference's own code.  Tolerances: local-observation index lists bit-exact; analysis and weights within
+1e-10 (FP64, BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import letkf_oracle as orc
+from pytassim_b200.testing import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+ATOL = 1e-10
+# taper values: both the reference (numpy pow) and the device (Horner) sum terms of magnitude ~10 that cancel
+# towards the cutoff, so individual weights agree to ~1e-15 absolute, not relative
+W_RTOL = 1e-12
+W_ATOL = 5e-15
+
+
+def _engine(k, n_slices, metric, radius, **kw):
+    from pytassim_b200.engine import LETKFEngine
+    return LETKFEngine(k, n_slices, metric, radius, **kw)
+
+
+def _metrics():
+    from pytassim_b200.localization import metrics
+    return metrics
+
+
+def _run(data, metric, radius, rho, taper="gc", eps=1e-5, weights=False):
+    st = data["state"]
+    n_slices = st.shape[0] * st.shape[1]
+    k = st.shape[2]
+    eng = _engine(k, n_slices, metric, radius, inf_factor=rho, taper=taper, epsilon=eps)
+    eng.set_grid(data["grid_rows"][:, 1:])
+    eng.bin_obs(data["obs_rows"][:, 1:], data["normed_perts"], data["normed_obs"])
+    x = torch.as_tensor(st.reshape(n_slices, k, -1)).cuda()
+    out = eng.analyse(x, return_weights=weights, count_ambiguous=True)
+    torch.cuda.synchronize()
+    if weights:
+        xa, w, namb = out
+        return eng, xa.cpu().numpy().reshape(st.shape), w.cpu().numpy(), namb
+    xa, namb = out
+    return eng, xa.cpu().numpy().reshape(st.shape), None, namb
+
+
+def _check_lists(eng, off_ref, idx_ref, sel=None, w_ref=None):
+    off, idx, w, amb, namb = eng.neighbour_lists()
+    off, idx, w = off.cpu().numpy(), idx.cpu().numpy(), w.cpu().numpy()
+    assert namb == 0 and not amb.any().item()
+    if sel is None:
+        np.testing.assert_array_equal(off, off_ref)
+        np.testing.assert_array_equal(idx, idx_ref)
+        if w_ref is not None:
+            np.testing.assert_allclose(w, w_ref, rtol=W_RTOL, atol=W_ATOL)
+        return
+    for n, g in enumerate(sel):
+        got = idx[off[g]:off[g + 1]]
+        want = idx_ref[off_ref[n]:off_ref[n + 1]]
+        np.testing.assert_array_equal(got, want)
+        if w_ref is not None:
+            np.testing.assert_allclose(w[off[g]:off[g + 1]], w_ref[off_ref[n]:off_ref[n + 1]], rtol=W_RTOL, atol=W_ATOL)
+
+
+def test_fixture_letkf_gc10_against_reference(golden):
+    """tests/unit_tests/interface/test_letkf.py:106-157 on the reference's netCDF fixtures."""
+    g = golden("fixture_letkf.npz")
+    m = _metrics()
+    data = dict(state=g["state"][:, :1], normed_perts=g["a_perts"], normed_obs=g["a_innov"],
+                grid_rows=g["a_grid_rows"], obs_rows=g["a_obs_rows"])
+    eng, xa, w, namb = _run(data, m.AbsDistance1D(), (10.0,), 1.0, weights=True)
+    np.testing.assert_allclose(xa, g["a_analysis"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(w, g["a_weights"], rtol=RTOL, atol=ATOL)
+    _check_lists(eng, g["a_csr_off"], g["a_csr_idx"], w_ref=g["a_csr_w"])
+    np.testing.assert_allclose(xa.sum(), -2.616127006116, atol=1e-9)
+
+
+def test_fixture_letkf_gcinf_against_reference(golden):
+    g = golden("fixture_letkf.npz")
+    m = _metrics()
+    data = dict(state=g["state"][:, 1:2], normed_perts=g["c_perts"], normed_obs=g["c_innov"],
+                grid_rows=g["a_grid_rows"], obs_rows=g["a_obs_rows"])
+    eng, xa, w, _ = _run(data, m.AbsDistance1D(), 8.0, 1.1, taper="gcinf", weights=True)
+    np.testing.assert_allclose(xa, g["c_analysis"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(w, g["c_weights"], rtol=RTOL, atol=ATOL)
+    _check_lists(eng, g["c_csr_off"], g["c_csr_idx"])
+
+
+def test_fixture_global_etkf_against_reference(golden):
+    """tests/unit_tests/interface/test_letkf.py:64-70 / test_etkf.py:136-167: global weights + update."""
+    g = golden("fixture_letkf.npz")
+    m = _metrics()
+    st = g["state"][:, 2:]
+    eng = _engine(10, 2, m.AbsDistance1D(), 1.0, inf_factor=1.0)
+    w = eng.etkf_weights(g["b_perts"], g["b_innov"])
+    np.testing.assert_allclose(w.cpu().numpy(), g["b_weights"], rtol=RTOL, atol=ATOL)
+    xa = eng.apply_weights(torch.as_tensor(st.reshape(2, 10, 40)).cuda(), w).cpu().numpy().reshape(st.shape)
+    np.testing.assert_allclose(xa, g["b_analysis"], rtol=RTOL, atol=ATOL)
+    # a localization radius so large that every weight is ~1 must reproduce the global ETKF to ~1e-6 only
+    # (GC(r) = 1 - 5/3 r^2 + ...), so the exact equivalence is checked with the all-ones path instead:
+    xa_pg = eng.apply_weights(torch.as_tensor(st.reshape(2, 10, 40)).cuda(), w[None].repeat(40, 1, 1).contiguous())
+    np.testing.assert_allclose(xa_pg.cpu().numpy().reshape(st.shape), g["b_analysis"], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("n", range(8))
+def test_core_weights_against_reference(golden, n):
+    """ETKFModule.forward on random inputs, k in {3..100}: the device EVD + transform alone."""
+    g = golden("core_random.npz")
+    m = _metrics()
+    Y, d, rho = g[f"Y{n}"], g[f"d{n}"], float(g[f"rho{n}"])
+    eng = _engine(Y.shape[0], 1, m.AbsDistance1D(), 1.0, inf_factor=rho)
+    w = eng.etkf_weights(Y, d).cpu().numpy()
+    np.testing.assert_allclose(w, g[f"W{n}"], rtol=RTOL, atol=ATOL)
+
+
+def test_core_kat_and_empty(golden):
+    """tests/unit_tests/core/test_etkf.py:142-233: 2-member KAT and the empty-observation prior."""
+    g = golden("core_kat.npz")
+    m = _metrics()
+    eng = _engine(2, 1, m.AbsDistance1D(), 1.0)
+    w = eng.etkf_weights(g["normed_perts"], g["normed_obs"].reshape(-1)).cpu().numpy()
+    np.testing.assert_allclose(w, g["W"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(w - g["w_mean"], g["w_perts"], atol=1e-12)
+    eng = _engine(10, 1, m.AbsDistance1D(), 1.0, inf_factor=1.1)
+    w = eng.etkf_weights(np.ones((10, 0)), np.ones((0,))).cpu().numpy()
+    np.testing.assert_allclose(w, np.sqrt(1.1) * np.eye(10), atol=1e-14)
+    with pytest.raises(ValueError):
+        eng.etkf_weights(np.ones((10, 4)), np.ones((3,)))
+
+
+SYNTH = {
+    "cfg1_l96_n40_k50.npz": lambda g, m: (syn.lorenz96_1d(40, 50, 1, seed=42), m.PeriodicDistance1D(40.0)),
+    "cfg2_l96_n2000_k40.npz": lambda g, m: (syn.lorenz96_1d(2000, 40, 2, seed=43), m.PeriodicDistance1D(2000.0)),
+    "bench_default_n1000_k50.npz": lambda g, m: (syn.lorenz96_1d(1000, 50, 10, seed=45), m.AbsDistance1D()),
+    "cfg3_sphere_small.npz": lambda g, m: (syn.sphere_latlon(24, 48, 50, 3000, seed=44), m.HaversineDistance(6371.0)),
+    "euclid2d_k16.npz": lambda g, m: ({k: g[k] for k in ("state", "normed_perts", "normed_obs", "grid_rows", "obs_rows")},
+                                      m.EuclideanDistance(2)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SYNTH))
+def test_synthetic_configs_against_reference(golden, name):
+    """BASELINE.json configurations (scaled) against outputs of the reference's own hot loop."""
+    g = golden(name)
+    data, metric = SYNTH[name](g, _metrics())
+    sel = g["sel"]
+    eng, xa, w, namb = _run(data, metric, float(g["radius"]), float(g["rho"]), weights=True)
+    assert namb == 0
+    np.testing.assert_allclose(xa[..., sel], g["analysis"], rtol=RTOL, atol=ATOL)
+    nw = g["weights"].shape[0]
+    np.testing.assert_allclose(w[sel[:nw]], g["weights"], rtol=RTOL, atol=ATOL)
+    _check_lists(eng, g["csr_off"], g["csr_idx"], sel=sel, w_ref=g["csr_w"])
+
+
+@pytest.mark.parametrize("k,n_grid,stride,radius", [(3, 64, 1, 2.5), (8, 300, 3, 4.0), (23, 500, 2, 7.0),
+                                                    (32, 257, 1, 30.0), (64, 300, 1, 12.0), (100, 96, 1, 6.0)])
+def test_ensemble_sizes_against_oracle(k, n_grid, stride, radius):
+    """Every kernel configuration (tiles 1..13, 1/2/4/8 warps per grid point) against the oracle."""
+    m = _metrics()
+    data = syn.lorenz96_1d(n_grid, k, stride, seed=100 + k)
+    eng, xa, w, namb = _run(data, m.PeriodicDistance1D(float(n_grid)), radius, 1.07, weights=True)
+    ref, wref, lists = orc.letkf_analysis(data["state"], data["normed_perts"], data["normed_obs"], data["grid_rows"],
+                                          data["obs_rows"], orc.make_dist_periodic1d(float(n_grid)), radius,
+                                          inf_factor=1.07, return_lists=True)
+    np.testing.assert_allclose(xa, ref, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(w, wref, rtol=RTOL, atol=ATOL)
+    off = np.zeros(n_grid + 1, dtype=np.int64); off[1:] = np.cumsum([len(l) for l in lists])
+    _check_lists(eng, off, np.concatenate(lists).astype(np.int32))
+
+
+def test_no_observation_in_reach_gives_inflated_prior():
+    """core/etkf.py:91-95 per grid point: grid points without local observations get W = sqrt(rho) I."""
+    m = _metrics()
+    data = syn.lorenz96_1d(200, 12, 1, seed=7)
+    keep = data["obs_rows"][:, 1] < 50
+    data["obs_rows"] = data["obs_rows"][keep]
+    data["normed_perts"] = np.ascontiguousarray(data["normed_perts"][:, keep]); data["normed_obs"] = data["normed_obs"][keep]
+    eng, xa, w, _ = _run(data, m.AbsDistance1D(), 3.0, 1.21, weights=True)
+    np.testing.assert_allclose(w[120], 1.1 * np.eye(12), atol=1e-13)
+    ref, _ = orc.letkf_analysis(data["state"], data["normed_perts"], data["normed_obs"], data["grid_rows"],
+                                data["obs_rows"], orc.dist_abs1d, 3.0, inf_factor=1.21)
+    np.testing.assert_allclose(xa, ref, rtol=RTOL, atol=ATOL)
+    # no observations at all
+    eng.bin_obs(np.zeros((0, 1)), np.zeros((12, 0)), np.zeros((0,)))
+    xa0 = eng.analyse(torch.as_tensor(data["state"].reshape(1, 12, 200)).cuda()).cpu().numpy()
+    mean = data["state"].mean(axis=2, keepdims=True)
+    np.testing.assert_allclose(xa0.reshape(data["state"].shape), mean + 1.1 * (data["state"] - mean), rtol=1e-12, atol=1e-12)
+
+
+def test_host_entry_point_matches_device_path():
+    """b200da_letkf_host (host buffers in, host buffers out) == device-resident path."""
+    m = _metrics()
+    data = syn.sphere_latlon(12, 24, 20, 800, seed=9, n_slices=2)
+    st = data["state"]
+    eng, xa, _, _ = _run(data, m.HaversineDistance(6371.0), 1500.0, 1.1)
+    out = eng.analyse_host(st.reshape(2, 20, -1), data["obs_rows"][:, 1:], data["normed_perts"], data["normed_obs"])
+    np.testing.assert_array_equal(out.reshape(st.shape), xa)
+    ref, _ = orc.letkf_analysis(st, data["normed_perts"], data["normed_obs"], data["grid_rows"], data["obs_rows"],
+                                orc.make_dist_haversine(6371.0), 1500.0, inf_factor=1.1)
+    np.testing.assert_allclose(xa, ref, rtol=RTOL, atol=ATOL)
+
+
+def test_block_sharding_pack_unpack():
+    """The multi-GPU decomposition on one device: analyse two block ranges separately, pack, unpack."""
+    m = _metrics()
+    data = syn.lorenz96_1d(333, 20, 2, seed=11)
+    eng, xa, _, _ = _run(data, m.PeriodicDistance1D(333.0), 6.0, 1.05)
+    x = torch.as_tensor(data["state"].reshape(1, 20, 333)).cuda()
+    nb = eng.n_blocks
+    half = nb // 2
+    out_a = torch.zeros_like(x); out_b = torch.zeros_like(x)
+    eng.analyse(x, out=out_a, blocks=(0, half)); eng.analyse(x, out=out_b, blocks=(half, nb))
+    merged = torch.full_like(x, float("nan"))
+    eng.unpack_columns(eng.pack_columns(out_a, 0, half), 0, half, merged)
+    eng.unpack_columns(eng.pack_columns(out_b, half, nb), half, nb, merged)
+    np.testing.assert_array_equal(merged.cpu().numpy().reshape(xa.shape), xa)
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE cfg2 at full size (N=100k, k=40): size-independent properties instead of the oracle —
+    (i) translation invariance on the ring, (ii) zero innovation keeps the ensemble mean,
+    (iii) a sample of grid points against the oracle."""
+    m = _metrics()
+    data = syn.lorenz96_1d(100_000, 40, 2, seed=42)
+    eng, xa, _, namb = _run(data, m.PeriodicDistance1D(100_000.0), 20.0, 1.1)
+    assert namb == 0 and np.isfinite(xa).all()
+    sel = np.arange(0, 100_000, 4999)
+    ref, _ = orc.letkf_analysis(data["state"], data["normed_perts"], data["normed_obs"], data["grid_rows"],
+                                data["obs_rows"], orc.make_dist_periodic1d(100_000.0), 20.0, inf_factor=1.1,
+                                grid_subset=sel)
+    np.testing.assert_allclose(xa[..., sel], ref, rtol=RTOL, atol=ATOL)
+    # (ii) zero innovations: analysis mean == background mean
+    data0 = dict(data); data0["normed_obs"] = np.zeros_like(data["normed_obs"])
+    _, xa0, _, _ = _run(data0, m.PeriodicDistance1D(100_000.0), 20.0, 1.0)
+    np.testing.assert_allclose(xa0.mean(axis=2), data["state"].mean(axis=2), rtol=1e-11, atol=1e-11)
+    # (i) rolling grid + observations by 2 positions rolls the analysis
+    rolled = dict(data)
+    rolled["state"] = np.roll(data["state"], 2, axis=-1)
+    rolled["normed_perts"] = np.ascontiguousarray(np.roll(data["normed_perts"], 1, axis=-1))
+    rolled["normed_obs"] = np.roll(data["normed_obs"], 1)
+    _, xar, _, _ = _run(rolled, m.PeriodicDistance1D(100_000.0), 20.0, 1.1)
+    np.testing.assert_allclose(np.roll(xar, -2, axis=-1), xa, rtol=1e-11, atol=1e-11)

@@ -1,0 +1,405 @@
+// C ABI of libb200da.so (see include/b200da.h): plan management, kernel dispatch, host-buffer convenience path.
+#include <cmath>
+#include <mutex>
+#include "binning.cuh"
+#include "etkf_kernel.cuh"
+#include "letkf_kernel.cuh"
+#include "neighbour_kernel.cuh"
+
+namespace b200da {
+thread_local std::string g_last_cuda_error;
+int64_t g_launch_count = 0;
+
+// host copies of the tapers (only used to locate the cutoff radius r with w(r) = eps)
+static double host_taper(int taper, double r) {
+    if (taper == B200DA_TAPER_GCINF) {
+        if (r < 0.5) return -28 * std::pow(r, 5) / 33 + 8 * std::pow(r, 4) / 11 + 20 * std::pow(r, 3) / 11 - 80 * r * r / 33 + 1;
+        if (r < 1.0) return 20 * std::pow(r, 5) / 33 - 16 * std::pow(r, 4) / 11 + 100 * r * r / 33 - 45 * r / 11 + 51.0 / 22 - 7 / (44 * r);
+        if (r < 1.5) return -4 * std::pow(r, 5) / 11 + 16 * std::pow(r, 4) / 11 - 10 * std::pow(r, 3) / 11 - 100 * r * r / 33 + 5 * r - 61.0 / 22 + 115 / (132 * r);
+        if (r < 2.0) return 4 * std::pow(r, 5) / 33 - 8 * std::pow(r, 4) / 11 + 10 * std::pow(r, 3) / 11 + 80 * r * r / 33 - 80 * r / 11 + 64.0 / 11 - 32 / (33 * r);
+        return 0.0;
+    }
+    if (r < 1.0) return -0.25 * std::pow(r, 5) + 0.5 * std::pow(r, 4) + 0.625 * std::pow(r, 3) - 5.0 / 3 * r * r + 1;
+    if (r < 2.0) return std::pow(r, 5) / 12 - 0.5 * std::pow(r, 4) + 0.625 * std::pow(r, 3) + 5.0 / 3 * r * r - 5 * r + 4 - 2.0 / 3 / r;
+    return 0.0;
+}
+
+// smallest r (padded) beyond which the taper never exceeds eps: the tapers decrease monotonically on (0, 2)
+static double cutoff_radius(int taper, double eps) {
+    if (!(eps > 0.0)) return 2.0;
+    if (eps >= 1.0) return 1e-6;
+    double lo = 0.0, hi = 2.0;
+    for (int i = 0; i < 200; ++i) {
+        const double mid = 0.5 * (lo + hi);
+        if (host_taper(taper, mid) > eps) lo = mid; else hi = mid;
+    }
+    return std::min(2.0, hi * (1.0 + 1e-7) + 1e-9);
+}
+
+struct KernelConfig { int g, wpg; };
+static KernelConfig config_for_kt(int kt) {
+    if (kt <= 5) return {8, 1};
+    if (kt <= 7) return {8, 2};
+    if (kt <= 10) return {4, 4};
+    return {2, 8};
+}
+constexpr int kMaxKt = 14;
+constexpr size_t kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
+
+template <int KT, int G, int WPG>
+static int launch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st) {
+    const size_t hdr = (sizeof(BlockHeader<G>) + 31) & ~size_t(31);
+    const size_t per = (evd_smem_bytes_per_matrix(pl->k) + 31) & ~size_t(31);
+    int E = G;
+    while (E > 1 && hdr + (size_t)E * per > kMaxSmem) E >>= 1;
+    if (hdr + (size_t)E * per > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
+    const size_t smem = hdr + std::max(gram_smem_bytes<KT, G, WPG>(), (size_t)E * per);
+    if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
+    LetkfParams Q = P;
+    Q.evd_conc = E;
+    auto kern = k_letkf_fused<KT, G, WPG>;
+    B200DA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (pl->timing) B200DA_CUDA(cudaEventRecord(pl->ev0, st));
+    kern<<<nblocks, G * WPG * 32, smem, st>>>(Q);
+    B200DA_LAUNCH_CHECK();
+    if (pl->timing) B200DA_CUDA(cudaEventRecord(pl->ev1, st));
+    return B200DA_OK;
+}
+
+#define B200DA_KT_CASE(KT, G, WPG) case KT: return launch_fused<KT, G, WPG>(pl, P, nblocks, st);
+static int dispatch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st) {
+    switch (pl->kt) {
+        B200DA_KT_CASE(1, 8, 1) B200DA_KT_CASE(2, 8, 1) B200DA_KT_CASE(3, 8, 1) B200DA_KT_CASE(4, 8, 1)
+        B200DA_KT_CASE(5, 8, 1) B200DA_KT_CASE(6, 8, 2) B200DA_KT_CASE(7, 8, 2) B200DA_KT_CASE(8, 4, 4)
+        B200DA_KT_CASE(9, 4, 4) B200DA_KT_CASE(10, 4, 4) B200DA_KT_CASE(11, 2, 8) B200DA_KT_CASE(12, 2, 8)
+        B200DA_KT_CASE(13, 2, 8) B200DA_KT_CASE(14, 2, 8)
+        default: return B200DA_ERR_UNSUPPORTED;
+    }
+}
+
+template <int KT>
+static int launch_etkf_gram(const double* yn, const double* d, int64_t m, int k, int ncta, int64_t chunk, double* partial,
+                            cudaStream_t st) {
+    k_etkf_gram<KT><<<ncta, kEtkfWarps * 32, 0, st>>>(yn, d, m, k, chunk, partial);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+#define B200DA_EG_CASE(KT) case KT: return launch_etkf_gram<KT>(yn, d, m, k, ncta, chunk, partial, st);
+static int dispatch_etkf_gram(int kt, const double* yn, const double* d, int64_t m, int k, int ncta, int64_t chunk,
+                              double* partial, cudaStream_t st) {
+    switch (kt) {
+        B200DA_EG_CASE(1) B200DA_EG_CASE(2) B200DA_EG_CASE(3) B200DA_EG_CASE(4) B200DA_EG_CASE(5) B200DA_EG_CASE(6)
+        B200DA_EG_CASE(7) B200DA_EG_CASE(8) B200DA_EG_CASE(9) B200DA_EG_CASE(10) B200DA_EG_CASE(11) B200DA_EG_CASE(12)
+        B200DA_EG_CASE(13) B200DA_EG_CASE(14)
+        default: return B200DA_ERR_UNSUPPORTED;
+    }
+}
+
+static int check_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return B200DA_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return B200DA_ERR_NO_DEVICE; }
+    if (prop.major != 10) return B200DA_ERR_NO_DEVICE;
+    return B200DA_OK;
+}
+
+static NeighbourParams neighbour_params(const b200da_plan* pl) {
+    NeighbourParams P{};
+    P.g = pl->geom;
+    P.gpos = pl->gpos.as<Pos4>();
+    P.block_off = pl->block_off.as<int>();
+    P.opos = pl->opos.as<Pos4>();
+    P.cell_start = pl->cell_start.as<int>();
+    P.n_obs = pl->n_obs;
+    P.cut_pad = pl->geom.cut_bin * (1.0 + 1e-9) + 1e-300;
+    return P;
+}
+
+template <int MODE>
+static int launch_neighbours(const b200da_plan* pl, const NeighbourParams& P, cudaStream_t st) {
+    if (pl->n_blocks == 0) return B200DA_OK;
+    switch (pl->gpb) {
+        case 8: k_neighbours<8, MODE><<<(int)pl->n_blocks, 256, 0, st>>>(P); break;
+        case 4: k_neighbours<4, MODE><<<(int)pl->n_blocks, 256, 0, st>>>(P); break;
+        default: k_neighbours<2, MODE><<<(int)pl->n_blocks, 256, 0, st>>>(P); break;
+    }
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
+}  // namespace b200da
+
+using namespace b200da;
+
+extern "C" {
+
+int b200da_version(void) { return 100; }
+int64_t b200da_launch_count(void) { return g_launch_count; }
+const char* b200da_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+
+const char* b200da_strerror(int status) {
+    switch (status) {
+        case B200DA_OK: return "ok";
+        case B200DA_ERR_INVALID: return "invalid argument";
+        case B200DA_ERR_SIZE: return "observational size of ensemble perturbations and observations do not match";
+        case B200DA_ERR_UNSUPPORTED: return "metric / taper / dtype / ensemble size not supported by the B200 engine";
+        case B200DA_ERR_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
+        case B200DA_ERR_CUDA: return "CUDA runtime error";
+        case B200DA_ERR_STATE: return "call order: set_grid and bin_obs must precede this call";
+        case B200DA_ERR_NOMEM: return "out of device memory";
+        default: return "unknown status";
+    }
+}
+
+int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int metric, const double* metric_params,
+                       int n_metric_params, const double* radius, int n_radius, double epsilon, double inf_factor,
+                       int dtype, int taper) {
+    if (!plan) return B200DA_ERR_INVALID;
+    *plan = nullptr;
+    if (k < 2 || n_slices < 1 || !radius || n_radius < 1 || !(radius[0] > 0.0) || !(inf_factor > 0.0))
+        return B200DA_ERR_INVALID;
+    if (dtype != B200DA_F64) return B200DA_ERR_UNSUPPORTED;
+    if (taper != B200DA_TAPER_GC && taper != B200DA_TAPER_GCINF) return B200DA_ERR_UNSUPPORTED;
+    const int kt = (k + 1 + 7) / 8;
+    if (kt > kMaxKt) return B200DA_ERR_UNSUPPORTED;
+    int rc = check_device();
+    if (rc) return rc;
+    b200da_plan* pl = new (std::nothrow) b200da_plan();
+    if (!pl) return B200DA_ERR_NOMEM;
+    pl->k = k; pl->n_slices = n_slices; pl->n_coord = n_coord; pl->dtype = dtype; pl->rho = inf_factor;
+    pl->kt = kt; pl->kp = kt * 8;
+    const KernelConfig cfg = config_for_kt(kt);
+    pl->gpb = cfg.g;
+    pl->kernel_name = "letkf_f64_kt" + std::to_string(kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
+    Geometry& g = pl->geom;
+    g.metric = metric; g.taper = taper; g.n_coord = n_coord; g.periodic = 0;
+    g.radius = radius[0]; g.eps = epsilon; g.period = 0.0; g.sphere_r = 1.0;
+    g.rcut = cutoff_radius(taper, epsilon);
+    switch (metric) {
+        case B200DA_METRIC_ABS1D:
+            if (n_coord != 1) { delete pl; return B200DA_ERR_INVALID; }
+            g.nd = 1; g.cut_bin = g.rcut * g.radius; break;
+        case B200DA_METRIC_PERIODIC1D:
+            if (n_coord != 1 || n_metric_params < 1 || !metric_params || !(metric_params[0] > 0.0)) { delete pl; return B200DA_ERR_INVALID; }
+            g.nd = 1; g.periodic = 1; g.period = metric_params[0]; g.cut_bin = g.rcut * g.radius; break;
+        case B200DA_METRIC_EUCLID:
+            if (n_coord < 1 || n_coord > 3) { delete pl; return B200DA_ERR_INVALID; }
+            g.nd = n_coord; g.cut_bin = g.rcut * g.radius; break;
+        case B200DA_METRIC_HAVERSINE: {
+            if (n_coord != 2 || n_metric_params < 1 || !metric_params || !(metric_params[0] > 0.0)) { delete pl; return B200DA_ERR_INVALID; }
+            g.nd = 3; g.sphere_r = metric_params[0];
+            const double ang = std::min(g.rcut * g.radius / g.sphere_r, M_PI);
+            g.cut_bin = 2.0 * std::sin(0.5 * ang) * (1.0 + 1e-9);
+            break;
+        }
+        default: delete pl; return B200DA_ERR_UNSUPPORTED;
+    }
+    if (cudaEventCreate(&pl->ev0) != cudaSuccess || cudaEventCreate(&pl->ev1) != cudaSuccess) {
+        delete pl; return B200DA_ERR_CUDA;
+    }
+    *plan = pl;
+    return B200DA_OK;
+}
+
+void b200da_plan_destroy(b200da_plan* pl) {
+    if (!pl) return;
+    DevBuf* bufs[] = {&pl->gpos, &pl->gorder, &pl->block_off, &pl->opos, &pl->cell_start, &pl->ys, &pl->tmp_keys,
+                      &pl->tmp_cell, &pl->tmp_count, &pl->tmp_a, &pl->tmp_b, &pl->tmp_pos, &pl->host_stage_obs,
+                      &pl->host_stage_y, &pl->host_stage_d, &pl->host_stage_x, &pl->host_stage_xa, &pl->etkf_partial,
+                      &pl->etkf_w};
+    for (DevBuf* b : bufs) b->release();
+    if (pl->ev0) cudaEventDestroy(pl->ev0);
+    if (pl->ev1) cudaEventDestroy(pl->ev1);
+    delete pl;
+}
+
+int b200da_set_grid(b200da_plan* plan, const double* grid_coord, int64_t n_grid, void* stream) {
+    return set_grid_impl(plan, grid_coord, n_grid, (cudaStream_t)stream);
+}
+
+int b200da_bin_obs(b200da_plan* plan, const double* obs_coord, const void* Yn, const void* d, int64_t n_obs, void* stream) {
+    return bin_obs_impl<double>(plan, obs_coord, (const double*)Yn, (const double*)d, n_obs, (cudaStream_t)stream);
+}
+
+int64_t b200da_num_blocks(const b200da_plan* plan) { return plan ? plan->n_blocks : 0; }
+int64_t b200da_num_grid(const b200da_plan* plan) { return plan ? plan->n_grid : 0; }
+int64_t b200da_num_obs(const b200da_plan* plan) { return plan ? plan->n_obs : 0; }
+int64_t b200da_block_offset(const b200da_plan* plan, int64_t block) {
+    if (!plan || !plan->have_grid || block < 0 || block > plan->n_blocks) return -1;
+    return plan->block_off_host[(size_t)block];
+}
+int b200da_grid_order(const b200da_plan* plan, int32_t* order_out, void* stream) {
+    if (!plan || !order_out) return B200DA_ERR_INVALID;
+    if (!plan->have_grid) return B200DA_ERR_STATE;
+    B200DA_CUDA(cudaMemcpyAsync(order_out, plan->gorder.p, sizeof(int) * (size_t)plan->n_grid, cudaMemcpyDeviceToDevice,
+                                (cudaStream_t)stream));
+    return B200DA_OK;
+}
+
+int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t block_begin, int64_t block_end,
+                 int64_t* n_ambiguous_opt, void* stream) {
+    if (!pl || !X || !Xa) return B200DA_ERR_INVALID;
+    if (!pl->have_grid || !pl->have_obs) return B200DA_ERR_STATE;
+    if (block_begin < 0 || block_end > pl->n_blocks || block_begin > block_end) return B200DA_ERR_INVALID;
+    if (block_begin == block_end) return B200DA_OK;
+    LetkfParams P{};
+    P.g = pl->geom;
+    P.gpos = pl->gpos.as<Pos4>();
+    P.block_off = pl->block_off.as<int>();
+    P.opos = pl->opos.as<Pos4>();
+    P.cell_start = pl->cell_start.as<int>();
+    P.ys = pl->ys.as<double>();
+    P.x = (const double*)X; P.xa = (double*)Xa; P.w_out = (double*)W_opt;
+    P.n_ambiguous = (unsigned long long*)n_ambiguous_opt;
+    P.n_grid = pl->n_grid; P.n_obs = pl->n_obs;
+    P.block_begin = (int)block_begin;
+    P.k = pl->k; P.n_slices = pl->n_slices; P.rho = pl->rho;
+    P.cut_pad = pl->geom.cut_bin * (1.0 + 1e-9) + 1e-300;
+    return dispatch_fused(pl, P, (int)(block_end - block_begin), (cudaStream_t)stream);
+}
+
+int b200da_letkf_host(b200da_plan* pl, const double* obs_coord_host, const void* Yn_host, const void* d_host, int64_t m,
+                      const void* X_host, void* Xa_host, void* stream) {
+    if (!pl || !X_host || !Xa_host) return B200DA_ERR_INVALID;
+    if (!pl->have_grid) return B200DA_ERR_STATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const size_t mm = (size_t)std::max<int64_t>(m, 1);
+    const size_t xbytes = sizeof(double) * (size_t)pl->n_slices * pl->k * (size_t)pl->n_grid;
+    if ((rc = pl->host_stage_obs.ensure(sizeof(double) * mm * pl->n_coord))) return rc;
+    if ((rc = pl->host_stage_y.ensure(sizeof(double) * mm * pl->k))) return rc;
+    if ((rc = pl->host_stage_d.ensure(sizeof(double) * mm))) return rc;
+    if ((rc = pl->host_stage_x.ensure(xbytes))) return rc;
+    if ((rc = pl->host_stage_xa.ensure(xbytes))) return rc;
+    if (m > 0) {
+        B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_obs.p, obs_coord_host, sizeof(double) * (size_t)m * pl->n_coord, cudaMemcpyHostToDevice, st));
+        B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_y.p, Yn_host, sizeof(double) * (size_t)m * pl->k, cudaMemcpyHostToDevice, st));
+        B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_d.p, d_host, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, st));
+    }
+    B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_x.p, X_host, xbytes, cudaMemcpyHostToDevice, st));
+    if ((rc = b200da_bin_obs(pl, pl->host_stage_obs.as<double>(), pl->host_stage_y.p, pl->host_stage_d.p, m, stream))) return rc;
+    if ((rc = b200da_letkf(pl, pl->host_stage_x.p, pl->host_stage_xa.p, nullptr, 0, pl->n_blocks, nullptr, stream))) return rc;
+    B200DA_CUDA(cudaMemcpyAsync(Xa_host, pl->host_stage_xa.p, xbytes, cudaMemcpyDeviceToHost, st));
+    B200DA_CUDA(cudaStreamSynchronize(st));
+    return B200DA_OK;
+}
+
+int b200da_neighbour_count(b200da_plan* pl, int64_t* counts, int64_t* n_ambiguous_opt, void* stream) {
+    if (!pl || !counts) return B200DA_ERR_INVALID;
+    if (!pl->have_grid || !pl->have_obs) return B200DA_ERR_STATE;
+    NeighbourParams P = neighbour_params(pl);
+    P.counts = (long long*)counts;
+    P.n_ambiguous = (unsigned long long*)n_ambiguous_opt;
+    return launch_neighbours<0>(pl, P, (cudaStream_t)stream);
+}
+
+int b200da_neighbour_fill(b200da_plan* pl, const int64_t* offsets, int32_t* idx, double* w_opt, uint8_t* ambiguous_opt,
+                          void* stream) {
+    if (!pl || !offsets || !idx) return B200DA_ERR_INVALID;
+    if (!pl->have_grid || !pl->have_obs) return B200DA_ERR_STATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t nnz = 0;
+    B200DA_CUDA(cudaMemcpyAsync(&nnz, offsets + pl->n_grid, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    B200DA_CUDA(cudaStreamSynchronize(st));
+    if (nnz <= 0) return B200DA_OK;
+    int rc;
+    if ((rc = pl->tmp_keys.ensure(sizeof(unsigned long long) * (size_t)nnz))) return rc;
+    if ((rc = pl->tmp_a.ensure(sizeof(int) * (size_t)pl->n_grid))) return rc;
+    B200DA_CUDA(cudaMemsetAsync(pl->tmp_a.p, 0, sizeof(int) * (size_t)pl->n_grid, st));
+    NeighbourParams P = neighbour_params(pl);
+    P.offsets = (const long long*)offsets;
+    P.keys = pl->tmp_keys.as<unsigned long long>();
+    P.cursor = pl->tmp_a.as<int>();
+    if ((rc = launch_neighbours<1>(pl, P, st))) return rc;
+    const int nblk = (int)std::min<int64_t>(pl->n_grid, 148 * 64);
+    k_segmented_sort<long long><<<nblk, kSegSortThreads, 0, st>>>(P.keys, (const long long*)offsets, pl->n_grid);
+    B200DA_LAUNCH_CHECK();
+    k_neighbour_finalize<<<nblk, 128, 0, st>>>(pl->geom, pl->gpos.as<Pos4>(), pl->opos.as<Pos4>(), (const long long*)offsets,
+                                               P.keys, pl->n_grid, idx, w_opt, ambiguous_opt);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
+int b200da_neighbour_ambiguous(b200da_plan* pl, int64_t capacity, int64_t* grid_idx, int64_t* obs_idx, double* w,
+                               int64_t* n_found, void* stream) {
+    if (!pl || !n_found || capacity < 0 || (capacity > 0 && (!grid_idx || !obs_idx || !w))) return B200DA_ERR_INVALID;
+    if (!pl->have_grid || !pl->have_obs) return B200DA_ERR_STATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    B200DA_CUDA(cudaMemsetAsync(n_found, 0, sizeof(int64_t), st));
+    NeighbourParams P = neighbour_params(pl);
+    P.capacity = capacity; P.amb_grid = (long long*)grid_idx; P.amb_obs = (long long*)obs_idx; P.amb_w = w;
+    P.amb_found = (unsigned long long*)n_found;
+    return launch_neighbours<2>(pl, P, st);
+}
+
+int b200da_etkf_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t m, void* W, void* stream) {
+    if (!pl || !W || m < 0 || (m > 0 && (!Yn || !d))) return B200DA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k = pl->k, kp = pl->kp;
+    int ncta = 1;
+    int64_t chunk = 4;
+    if (m > 0) {
+        ncta = (int)std::min<int64_t>(148 * 2, (m + 255) / 256);
+        chunk = ((m + ncta - 1) / ncta + 3) / 4 * 4;
+        ncta = (int)((m + chunk - 1) / chunk);
+    }
+    int rc;
+    if ((rc = pl->etkf_partial.ensure(sizeof(double) * (size_t)ncta * kp * kp))) return rc;
+    if (m > 0) {
+        if ((rc = dispatch_etkf_gram(pl->kt, (const double*)Yn, (const double*)d, m, k, ncta, chunk,
+                                     pl->etkf_partial.as<double>(), st))) return rc;
+    }
+    const size_t smem = evd_smem_bytes_per_matrix(k) + 64;
+    if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
+    B200DA_CUDA(cudaFuncSetAttribute(k_etkf_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_etkf_solve<<<1, 512, smem, st>>>(pl->etkf_partial.as<double>(), m > 0 ? ncta : 0, kp, k, pl->rho, (double*)W);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
+int b200da_apply_weights(b200da_plan* pl, const void* X, const void* W, int per_grid, int64_t n_grid, void* Xa, void* stream) {
+    if (!pl || !X || !W || !Xa || n_grid <= 0) return B200DA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k = pl->k;
+    const size_t smem = per_grid ? 0 : sizeof(double) * (size_t)k * k;
+    if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
+    B200DA_CUDA(cudaFuncSetAttribute(k_apply_weights<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    k_apply_weights<8><<<grid1d(n_grid, 128), 128, smem, st>>>((const double*)X, (const double*)W, per_grid, k, pl->n_slices,
+                                                            n_grid, (double*)Xa);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
+static int pack_impl(b200da_plan* pl, const void* xa, int64_t b0, int64_t b1, void* packed, int unpack, cudaStream_t st) {
+    if (!pl || !xa || !packed) return B200DA_ERR_INVALID;
+    if (!pl->have_grid) return B200DA_ERR_STATE;
+    if (b0 < 0 || b1 > pl->n_blocks || b0 > b1) return B200DA_ERR_INVALID;
+    const int64_t s0 = pl->block_off_host[(size_t)b0], s1 = pl->block_off_host[(size_t)b1];
+    const int64_t ncols = s1 - s0;
+    if (ncols == 0) return B200DA_OK;
+    const int rows = pl->n_slices * pl->k;
+    if (rows > 65535) return B200DA_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)grid1d(ncols, 256), (unsigned)rows);
+    k_pack_columns<<<grid, 256, 0, st>>>((const double*)xa, pl->gorder.as<int>(), s0, ncols, rows, pl->n_grid, (double*)packed, unpack);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+int b200da_pack_columns(b200da_plan* pl, const void* Xa, int64_t b0, int64_t b1, void* packed, void* stream) {
+    return pack_impl(pl, Xa, b0, b1, packed, 0, (cudaStream_t)stream);
+}
+int b200da_unpack_columns(b200da_plan* pl, const void* packed, int64_t b0, int64_t b1, void* Xa, void* stream) {
+    return pack_impl(pl, Xa, b0, b1, const_cast<void*>(packed), 1, (cudaStream_t)stream);
+}
+
+const char* b200da_kernel_name(const b200da_plan* pl) { return pl ? pl->kernel_name.c_str() : ""; }
+int b200da_enable_timing(b200da_plan* pl, int on) { if (!pl) return B200DA_ERR_INVALID; pl->timing = on != 0; return B200DA_OK; }
+float b200da_last_kernel_ms(b200da_plan* pl) {
+    if (!pl || !pl->timing) return -1.f;
+    if (cudaEventSynchronize(pl->ev1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, pl->ev0, pl->ev1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    return ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+// Shared definitions of the B200 LETKF engine: geometry of the cell grid, the distance functions and
+// the Gaspari-Cohn tapers evaluated on the device.
+//
+// Reference semantics restated here (paths relative to /root/reference):
+//   taper      pytassim/localization/gaspari_cohn.py:78-136 (GaspariCohn), :172-254 (GaspariCohnInf)
+//   distance   user `dist_func` (gaspari_cohn.py:125); closed set documented in include/b200da.h
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/b200da.h"
+
+namespace b200da {
+
+constexpr double kAmbiguityBand = 1e-13;   // |w - eps| below this is reported as ambiguous
+constexpr int kMaxRuns = 512;              // candidate cell columns per grid-point block (incl. periodic split)
+constexpr int kCellsPerCutoff = 6;         // cell edge = cutoff / 6
+constexpr int64_t kMaxCells = (1 << 22);
+
+// Everything a kernel needs to map coordinates to cells and to evaluate the localization weight.
+struct Geometry {
+    int metric;
+    int taper;
+    int nd;            // dimensions of the bin space that are in use (1..3); unused leading dims are 0
+    int n_coord;
+    int periodic;      // last dimension wraps (PERIODIC1D)
+    double radius;     // Gaspari-Cohn length scale c
+    double eps;        // use_obs = w > eps
+    double rcut;       // w(r) <= eps for every r >= rcut (conservative)
+    double cut_bin;    // rcut * c expressed in bin-space units (chord length for HAVERSINE)
+    double period;
+    double sphere_r;
+    double org[3];     // origin of the cell grid in bin space
+    double h[3];       // cell edge per dimension
+    int nc[3];         // cells per dimension
+    int ncell;         // nc[0]*nc[1]*nc[2]; cell id ncell is the discard bin (outside the domain)
+};
+
+struct __align__(32) Pos4 {     // bin-space position + payload (original index, as raw bits)
+    double x, y, z;
+    long long id;
+};
+
+__host__ __device__ inline double deg2rad(double d) { return d * 0.017453292519943295; }
+
+// Coordinates (struct of arrays, n_coord rows of length n) -> bin-space position.
+// 1-D metrics live on the last axis so that a candidate range is one contiguous run of cells.
+__device__ inline void bin_position(const Geometry& g, const double* __restrict__ coord, int64_t n, int64_t i,
+                                    double& x, double& y, double& z) {
+    x = 0.0; y = 0.0; z = 0.0;
+    if (g.metric == B200DA_METRIC_HAVERSINE) {
+        const double phi = deg2rad(coord[i]);
+        const double lam = deg2rad(coord[n + i]);
+        double sp, cp, sl, cl;
+        sincos(phi, &sp, &cp);
+        sincos(lam, &sl, &cl);
+        x = cp * cl; y = cp * sl; z = sp;
+    } else if (g.nd == 1) {
+        z = coord[i];
+    } else if (g.nd == 2) {
+        y = coord[i]; z = coord[n + i];
+    } else {
+        x = coord[i]; y = coord[n + i]; z = coord[2 * n + i];
+    }
+}
+
+// Cell index along one dimension (monotone in v, so candidate ranges computed with the same formula
+// are conservative).  Returns -1 / nc when outside.
+__device__ inline int cell_coord(const Geometry& g, int dim, double v) {
+    if (g.nc[dim] == 1 && !(g.periodic && dim == 2)) {
+        // single cell: still reject points outside the domain slab
+        const double t = (v - g.org[dim]) / g.h[dim];
+        return (t < 0.0) ? -1 : (t >= 1.0 ? 1 : 0);
+    }
+    const double t = floor((v - g.org[dim]) / g.h[dim]);
+    if (t < 0.0) return -1;
+    if (t >= (double)g.nc[dim]) return g.nc[dim];
+    return (int)t;
+}
+
+__device__ inline int cell_of(const Geometry& g, double x, double y, double z) {
+    int cz = cell_coord(g, 2, z);
+    if (g.periodic) {                       // coordinates are validated to lie in [0, period]
+        if (cz >= g.nc[2]) cz = g.nc[2] - 1;
+        if (cz < 0) cz = 0;
+    }
+    const int cx = cell_coord(g, 0, x), cy = cell_coord(g, 1, y);
+    if (cx < 0 || cx >= g.nc[0] || cy < 0 || cy >= g.nc[1] || cz < 0 || cz >= g.nc[2]) return g.ncell;
+    return (cx * g.nc[1] + cy) * g.nc[2] + cz;
+}
+
+// ---- tapers -------------------------------------------------------------------------------------------------
+
+// GaspariCohn: gaspari_cohn.py:78-95, selection logic :126-134 (f2 where r < 2, overwritten by f1 where r < 1).
+__device__ __forceinline__ double taper_gc(double r) {
+    if (r < 1.0) {
+        const double r2 = r * r;
+        return fma(r2, fma(r, fma(r, fma(r, -0.25, 0.5), 0.625), -5.0 / 3.0), 1.0);
+    }
+    if (r < 2.0) {
+        const double poly = fma(r, fma(r, fma(r, fma(r, fma(r, 1.0 / 12.0, -0.5), 0.625), 5.0 / 3.0), -5.0), 4.0);
+        return poly - (2.0 / 3.0) / r;
+    }
+    return 0.0;                 // also for NaN distances: every comparison is false (gaspari_cohn.py:128)
+}
+
+// GaspariCohnInf: gaspari_cohn.py:172-210, selection :247-252 (thresholds 2, 1.5, 1, 0.5).
+__device__ __forceinline__ double taper_gcinf(double r) {
+    if (r < 0.5) {
+        const double r2 = r * r;
+        return fma(r2, fma(r, fma(r, fma(r, -28.0 / 33.0, 8.0 / 11.0), 20.0 / 11.0), -80.0 / 33.0), 1.0);
+    }
+    if (r < 1.0) {
+        const double poly = fma(r, fma(r, fma(r, fma(r, fma(r, 20.0 / 33.0, -16.0 / 11.0), 0.0), 100.0 / 33.0),
+                                       -45.0 / 11.0), 51.0 / 22.0);
+        return poly - 7.0 / (44.0 * r);
+    }
+    if (r < 1.5) {
+        const double poly = fma(r, fma(r, fma(r, fma(r, fma(r, -4.0 / 11.0, 16.0 / 11.0), -10.0 / 11.0),
+                                              -100.0 / 33.0), 5.0), -61.0 / 22.0);
+        return poly + 115.0 / (132.0 * r);
+    }
+    if (r < 2.0) {
+        const double poly = fma(r, fma(r, fma(r, fma(r, fma(r, 4.0 / 33.0, -8.0 / 11.0), 10.0 / 11.0), 80.0 / 33.0),
+                                       -80.0 / 11.0), 64.0 / 11.0);
+        return poly - 32.0 / (33.0 * r);
+    }
+    return 0.0;
+}
+
+__device__ __forceinline__ double taper_eval(int taper, double r) {
+    return taper == B200DA_TAPER_GCINF ? taper_gcinf(r) : taper_gc(r);
+}
+
+// ---- distances ------------------------------------------------------------------------------------------------
+
+// Distance in the metric's own units between two bin-space positions.  ABS1D / PERIODIC1D / EUCLID follow the
+// numpy expression order without FMA contraction, so the value is bit-identical to the numpy metric objects in
+// pytassim_b200/localization/metrics.py; HAVERSINE goes through the chord of the unit vectors (equal to the
+// haversine formula up to rounding).
+__device__ __forceinline__ double metric_distance(const Geometry& g, double gx, double gy, double gz,
+                                                  double ox, double oy, double oz) {
+    switch (g.metric) {
+        case B200DA_METRIC_ABS1D:
+            return fabs(gz - oz);
+        case B200DA_METRIC_PERIODIC1D: {
+            const double d = fabs(gz - oz);
+            return fmin(d, g.period - d);
+        }
+        case B200DA_METRIC_EUCLID: {
+            const double dz = oz - gz;
+            if (g.nd == 1) return sqrt(__dmul_rn(dz, dz));
+            const double dy = oy - gy;
+            if (g.nd == 2) return sqrt(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dz, dz)));
+            const double dx = ox - gx;
+            return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        }
+        default: {   // HAVERSINE
+            const double dx = ox - gx, dy = oy - gy, dz = oz - gz;
+            double a = 0.25 * fma(dx, dx, fma(dy, dy, dz * dz));
+            a = fmin(fmax(a, 0.0), 1.0);
+            return 2.0 * g.sphere_r * asin(sqrt(a));
+        }
+    }
+}
+
+// Cheap, conservative proximity measure in bin space used to reject candidates against a whole block of grid
+// points: Euclidean in bin space (chord for the sphere), wrapped for the periodic line.
+__device__ __forceinline__ double bin_distance(const Geometry& g, double ax, double ay, double az,
+                                               double bx, double by, double bz) {
+    if (g.nd == 1 && g.metric != B200DA_METRIC_HAVERSINE) {
+        double d = fabs(az - bz);
+        if (g.periodic) d = fmin(d, g.period - d);
+        return d;
+    }
+    const double dx = ax - bx, dy = ay - by, dz = az - bz;
+    return sqrt(fma(dx, dx, fma(dy, dy, dz * dz)));
+}
+
+// Localization weight of one (grid point, observation) pair: returns w if w > eps else 0
+// (gaspari_cohn.py:126-135); `ambiguous` is set when |w - eps| is inside the ambiguity band.
+__device__ __forceinline__ double pair_weight(const Geometry& g, double gx, double gy, double gz,
+                                              double ox, double oy, double oz, bool& ambiguous) {
+    const double dist = metric_distance(g, gx, gy, gz, ox, oy, oz);
+    const double r = dist / g.radius;                      // gaspari_cohn.py:127
+    const double w = taper_eval(g.taper, r);
+    ambiguous = fabs(w - g.eps) < kAmbiguityBand;
+    return (w > g.eps) ? w : 0.0;                          // gaspari_cohn.py:135
+}
+
+}  // namespace b200da

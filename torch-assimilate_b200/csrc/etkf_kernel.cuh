@@ -1,0 +1,146 @@
+// Global ETKF (no localization): one k x k weight matrix from all observations, then a streaming update of
+// the whole state.  Reference: pytassim/interface/etkf.py:99-120 -> core/etkf.py:79-103 (weights) and
+// interface/base.py:257-278 (update).
+#pragma once
+#include "letkf_kernel.cuh"
+
+namespace b200da {
+
+constexpr int kEtkfWarps = 8;
+
+// Partial Gram of [Yn; d] over a chunk of observations per CTA; the lower-triangle tiles are split over the
+// CTA's warps.  Yn is read in the reference layout (k, M) directly: a DMMA fragment is 4 consecutive
+// observations of 8 members = eight 32-byte sectors.
+template <int KT>
+__global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const double* __restrict__ yn, const double* __restrict__ d,
+                                                               int64_t m_obs, int k, int64_t chunk,
+                                                               double* __restrict__ partial) {
+    constexpr int NTILES = KT * (KT + 1) / 2;
+    constexpr int ACC = (NTILES + kEtkfWarps - 1) / kEtkfWarps;
+    constexpr int KP = KT * 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc[ACC][2];
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+    const int64_t j0 = (int64_t)blockIdx.x * chunk;
+    const int64_t j1 = min(j0 + chunk, m_obs);
+    for (int64_t jb = j0; jb < j1; jb += 4) {
+        const int64_t j = jb + (lane & 3);
+        double f[KT];
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            const int mem = t * 8 + (lane >> 2);
+            double v = 0.0;
+            if (j < j1) {
+                if (mem < k) v = yn[(int64_t)mem * m_obs + j];
+                else if (mem == k) v = d[j];
+            }
+            f[t] = v;
+        }
+        // runtime ownership: tile t is owned by warp t % kEtkfWarps and is that warp's (t / kEtkfWarps)-th accumulator
+        int idx = 0;
+#pragma unroll
+        for (int mt = 0; mt < KT; ++mt) {
+#pragma unroll
+            for (int nt = 0; nt <= mt; ++nt) {
+                if (idx % kEtkfWarps == warp) dmma884(acc[idx / kEtkfWarps][0], acc[idx / kEtkfWarps][1], f[mt], f[nt]);
+                ++idx;
+            }
+        }
+    }
+    double* out = partial + (size_t)blockIdx.x * KP * KP;
+    int idx = 0;
+#pragma unroll
+    for (int mt = 0; mt < KT; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt <= mt; ++nt) {
+            if (idx % kEtkfWarps == warp) {
+                const int r = mt * 8 + (lane >> 2);
+                const int c = nt * 8 + (lane & 3) * 2;
+                out[r * KP + c] = acc[idx / kEtkfWarps][0];
+                out[r * KP + c + 1] = acc[idx / kEtkfWarps][1];
+            }
+            ++idx;
+        }
+    }
+}
+
+// Sum the partial Grams in a fixed order, eigendecompose, transform; W (k x k) row-major to global memory.
+__global__ void __launch_bounds__(512) k_etkf_solve(const double* __restrict__ partial, int n_partial, int kp, int k,
+                                                    double rho, double* __restrict__ w_out) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    const int lda = k | 1, n2 = (k + 1) / 2;
+    double* A = reinterpret_cast<double*>(smem_raw);
+    double* V = A + (size_t)k * lda;
+    double* bvec = V + (size_t)k * lda;
+    double* vec = bvec + k;
+    double* xbuf = vec + 3 * k;
+    JacobiScratch sc;
+    sc.cs = xbuf + k;
+    sc.pq = reinterpret_cast<int*>(sc.cs + 2 * n2 + 2);
+    sc.flag = sc.pq + 2 * n2;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int x = tid; x < (k + 1) * k; x += nt) {
+        const int r = x / k, c = x % k;
+        if (r < k && c > r) continue;
+        double s = 0.0;
+        for (int p = 0; p < n_partial; ++p) s += partial[(size_t)p * kp * kp + r * kp + c];
+        if (r < k) { A[r * lda + c] = s; A[c * lda + r] = s; }
+        else bvec[c] = s;
+    }
+    __syncthreads();
+    jacobi_evd(A, V, k, lda, (double)(k - 1) / rho, sc, tid, nt, 0);
+    etkf_transform(A, V, bvec, vec, k, lda, rho, tid, nt, 0);
+    for (int x = tid; x < k * k; x += nt) w_out[x] = V[(x / k) * lda + (x % k)];
+}
+
+// Xa = mean + (X - mean) W.  One thread per grid point (coalesced along the grid axis), 8 output members per
+// pass; W is staged in shared memory when it is global (per_grid = 0).
+template <int JB>
+__global__ void __launch_bounds__(128) k_apply_weights(const double* __restrict__ x, const double* __restrict__ w,
+                                                       int per_grid, int k, int n_rows, int64_t n_grid,
+                                                       double* __restrict__ xa) {
+    extern __shared__ double wsm[];
+    if (!per_grid) {
+        for (int i = threadIdx.x; i < k * k; i += blockDim.x) wsm[i] = w[i];
+        __syncthreads();
+    }
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_grid) return;
+    const double* wg = per_grid ? (w + gi * (int64_t)k * k) : wsm;
+    for (int s = 0; s < n_rows; ++s) {
+        const double* xs = x + (int64_t)s * k * n_grid + gi;
+        double* xo = xa + (int64_t)s * k * n_grid + gi;
+        double mean = 0.0;
+        for (int i = 0; i < k; ++i) mean += xs[(int64_t)i * n_grid];
+        mean /= (double)k;
+        for (int j0 = 0; j0 < k; j0 += JB) {
+            double acc[JB];
+#pragma unroll
+            for (int j = 0; j < JB; ++j) acc[j] = 0.0;
+            for (int i = 0; i < k; ++i) {
+                const double p = xs[(int64_t)i * n_grid] - mean;
+                const double* wr = wg + i * k + j0;
+#pragma unroll
+                for (int j = 0; j < JB; ++j)
+                    if (j0 + j < k) acc[j] = fma(p, wr[j], acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < JB; ++j)
+                if (j0 + j < k) xo[(int64_t)(j0 + j) * n_grid] = mean + acc[j];
+        }
+    }
+}
+
+// (n_rows, N) <-> dense (n_rows, n_cols) in block-sorted order: the all-gather payload of the grid-sharded run
+__global__ void k_pack_columns(const double* __restrict__ xa, const int* __restrict__ order, int64_t slot0, int64_t n_cols,
+                               int n_rows, int64_t n_grid, double* __restrict__ packed, int unpack) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= n_cols || r >= n_rows) return;
+    const int64_t gi = order[slot0 + c];
+    if (unpack) const_cast<double*>(xa)[(int64_t)r * n_grid + gi] = packed[(int64_t)r * n_cols + c];
+    else packed[(int64_t)r * n_cols + c] = xa[(int64_t)r * n_grid + gi];
+}
+
+}  // namespace b200da

@@ -1,0 +1,85 @@
+// The plan object behind the C ABI and host-side helpers (error handling, scratch buffers).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace b200da {
+
+extern thread_local std::string g_last_cuda_error;
+extern int64_t g_launch_count;
+
+#define B200DA_CUDA(expr)                                                                                    \
+    do {                                                                                                      \
+        cudaError_t err__ = (expr);                                                                           \
+        if (err__ != cudaSuccess) {                                                                           \
+            ::b200da::g_last_cuda_error = std::string(#expr) + ": " + cudaGetErrorString(err__);              \
+            return B200DA_ERR_CUDA;                                                                           \
+        }                                                                                                     \
+    } while (0)
+
+#define B200DA_LAUNCH_CHECK()                                                                                \
+    do {                                                                                                      \
+        ++::b200da::g_launch_count;                                                                           \
+        B200DA_CUDA(cudaGetLastError());                                                                      \
+    } while (0)
+
+// Grow-only device buffer owned by the plan.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return B200DA_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            g_last_cuda_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+            p = nullptr;
+            return B200DA_ERR_NOMEM;
+        }
+        cap = want;
+        return B200DA_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace b200da
+
+struct b200da_plan {
+    // configuration
+    int k = 0, n_slices = 1, n_coord = 1, dtype = B200DA_F64;
+    int kt = 0;            // 8-row tiles of the augmented [Yn; d] matrix: ceil((k + 1) / 8)
+    int kp = 0;            // padded row length of the staging copy: 8 * kt
+    int gpb = 8;           // grid points per block (CTA) of the fused kernel
+    double rho = 1.0;
+    b200da::Geometry geom{};
+    // grid side
+    int64_t n_grid = 0, n_blocks = 0;
+    bool have_grid = false, have_obs = false;
+    b200da::DevBuf gpos;        // Pos4[N]  block-sorted grid positions, id = original grid index
+    b200da::DevBuf gorder;      // int32[N] slot -> original index
+    b200da::DevBuf block_off;   // int32[n_blocks + 1]
+    std::vector<int32_t> block_off_host;
+    // obs side
+    int64_t n_obs = 0;
+    b200da::DevBuf opos;        // Pos4[M]  cell-sorted obs positions, id = original obs index
+    b200da::DevBuf cell_start;  // int32[ncell + 2]
+    b200da::DevBuf ys;          // T[M][kp] cell-sorted, obs-major [Yn; d; 0...]
+    // scratch
+    b200da::DevBuf tmp_keys, tmp_cell, tmp_count, tmp_a, tmp_b, tmp_pos;
+    b200da::DevBuf host_stage_obs, host_stage_y, host_stage_d, host_stage_x, host_stage_xa;
+    b200da::DevBuf etkf_partial, etkf_w;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = -1.f;
+    std::string kernel_name;
+};

@@ -1,0 +1,233 @@
+"""Array-level front end of the B200 LETKF / ETKF engine.
+
+This is the layer ``LETKF.update_state`` / ``ETKF.update_state`` (pytassim_b200.interface) call once the
+xarray glue has produced plain arrays; it owns device buffers (torch tensors) and forwards raw pointers and the
+current CUDA stream to the C ABI (include/b200da.h).  torch is plumbing here: memory, streams, distributed.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+_TAPERS = {"gc": _cabi.TAPER_GC, "gcinf": _cabi.TAPER_GCINF}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _dev(a, dtype=torch.float64, device="cuda"):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)
+
+
+class LETKFEngine(object):
+    """One plan = one (ensemble size, state slices, metric, taper, inflation) configuration on one GPU.
+
+    Parameters mirror ``LETKF(localization=GaspariCohn(length_scale, dist_func, epsilon), inf_factor)``
+    (pytassim/interface/letkf.py:72-92, pytassim/localization/gaspari_cohn.py:60-69); ``metric`` is one of the
+    metric objects of :mod:`pytassim_b200.localization.metrics`.
+    """
+
+    def __init__(self, ens_size, n_slices, metric, length_scale, epsilon=1e-5, inf_factor=1.0, taper="gc",
+                 dtype=torch.float64, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pytassim_b200 needs a CUDA device (sm_100); there is no CPU fallback")
+        if dtype != torch.float64:
+            raise NotImplementedError("only float64 is implemented in this round")
+        self.lib = _cabi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.k, self.n_slices = int(ens_size), int(n_slices)
+        self.metric = metric
+        radius = np.atleast_1d(np.asarray(length_scale, dtype=np.float64))
+        params = np.asarray(list(metric.params) + [0.0], dtype=np.float64)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_plan_create(
+                ctypes.byref(handle), self.k, self.n_slices, int(metric.n_coord), int(metric.metric_id),
+                params.ctypes.data_as(_cabi._dp), len(metric.params),
+                radius.ctypes.data_as(_cabi._dp), int(radius.size), float(epsilon), float(inf_factor),
+                _cabi.F64, _TAPERS[taper]))
+        self._plan = handle
+        self.n_grid = 0
+        self.n_obs = 0
+        self._keep = {}
+
+    def __del__(self):
+        plan = getattr(self, "_plan", None)
+        if plan is not None and plan.value:
+            try:
+                self.lib.b200da_plan_destroy(plan)
+            except Exception:
+                pass
+            self._plan = None
+
+    # -- set-up ----------------------------------------------------------------------------------------------
+    def set_grid(self, grid_coords):
+        """grid_coords: (N, n_coord) — the coordinate columns of ``_extract_state_information``
+        (interface/mixin_local.py:50-69) without the time column."""
+        gc = _dev(grid_coords, device=self.device)
+        if gc.dim() == 1:
+            gc = gc[:, None]
+        if gc.shape[1] != self.metric.n_coord:
+            raise ValueError("metric expects {0} coordinate column(s), got {1}".format(self.metric.n_coord, gc.shape[1]))
+        soa = gc.t().contiguous()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_set_grid(self._plan, _ptr(soa), gc.shape[0], _stream()))
+        self.n_grid = int(gc.shape[0])
+        self.n_blocks = int(self.lib.b200da_num_blocks(self._plan))
+        return self
+
+    def bin_obs(self, obs_coords, normed_perts, normed_obs):
+        """obs_coords (M, n_coord); normed_perts (k, M); normed_obs (M,) — interface/base.py:359-379 outputs."""
+        yn = _dev(normed_perts, device=self.device)
+        d = _dev(normed_obs, device=self.device).reshape(-1)
+        if yn.dim() != 2 or yn.shape[0] != self.k:
+            raise ValueError("normed_perts must be (ens_size, n_obs)")
+        if yn.shape[-1] != d.shape[-1]:                          # pytassim/core/base.py:28-38
+            raise ValueError('Observational size between ensemble ({0:d}) and observations '
+                             '({1:d}) do not match!'.format(yn.shape[-1], d.shape[-1]))
+        oc = _dev(obs_coords, device=self.device)
+        if oc.dim() == 1:
+            oc = oc[:, None]
+        if oc.shape[0] != d.shape[0]:
+            raise ValueError("obs_coords and normed_obs disagree on the number of observations")
+        soa = oc.t().contiguous()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_bin_obs(self._plan, _ptr(soa), _ptr(yn), _ptr(d), d.shape[0], _stream()))
+        self.n_obs = int(d.shape[0])
+        return self
+
+    # -- hot path ----------------------------------------------------------------------------------------------
+    def analyse(self, state, out=None, return_weights=False, blocks=None, count_ambiguous=False):
+        """state (n_slices, k, N) on the device -> analysis of the same shape (interface/base.py:257-278)."""
+        x = _dev(state, device=self.device).reshape(self.n_slices, self.k, self.n_grid)
+        xa = torch.empty_like(x) if out is None else out
+        w = torch.empty((self.n_grid, self.k, self.k), dtype=torch.float64, device=self.device) if return_weights else None
+        amb = torch.zeros(1, dtype=torch.int64, device=self.device) if count_ambiguous else None
+        b0, b1 = (0, self.n_blocks) if blocks is None else blocks
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_letkf(self._plan, _ptr(x), _ptr(xa), _ptr(w), b0, b1, _ptr(amb), _stream()))
+        res = [xa]
+        if return_weights:
+            res.append(w)
+        if count_ambiguous:
+            res.append(int(amb.item()))
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def analyse_host(self, state, obs_coords, normed_perts, normed_obs, out=None):
+        """End-to-end call with HOST arrays (numpy or pinned CPU tensors): upload, bin, analyse, download."""
+        x = np.ascontiguousarray(state, dtype=np.float64) if not isinstance(state, torch.Tensor) else state
+        yn = np.ascontiguousarray(normed_perts, dtype=np.float64) if not isinstance(normed_perts, torch.Tensor) else normed_perts
+        d = np.ascontiguousarray(normed_obs, dtype=np.float64) if not isinstance(normed_obs, torch.Tensor) else normed_obs
+        oc = obs_coords
+        if isinstance(oc, torch.Tensor):
+            oc_soa = oc if oc.shape[0] == self.metric.n_coord and oc.dim() == 2 and oc.shape[1] != self.metric.n_coord \
+                else oc.reshape(-1, self.metric.n_coord).t().contiguous()
+        else:
+            oc_soa = np.ascontiguousarray(np.asarray(oc, dtype=np.float64).reshape(-1, self.metric.n_coord).T)
+        m = int(d.shape[-1])
+        if yn.shape[-1] != m:
+            raise ValueError('Observational size between ensemble ({0:d}) and observations '
+                             '({1:d}) do not match!'.format(yn.shape[-1], m))
+        if out is None:
+            out = np.empty(x.shape, dtype=np.float64) if not isinstance(x, torch.Tensor) else torch.empty_like(x)
+
+        def hp(a):
+            return ctypes.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else ctypes.c_void_p(a.ctypes.data)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_letkf_host(self._plan, hp(oc_soa), hp(yn), hp(d), m, hp(x), hp(out), _stream()))
+        self.n_obs = m
+        return out
+
+    # -- neighbour lists -----------------------------------------------------------------------------------------
+    def neighbour_lists(self, with_weights=True):
+        """CSR (offsets int64[N+1], idx int32[nnz], w float64[nnz], ambiguous uint8[nnz], n_ambiguous) of the
+        local observations of every grid point, ascending obs index = ``np.nonzero(use_obs)[0]``
+        (localization/gaspari_cohn.py:135)."""
+        counts = torch.zeros(self.n_grid, dtype=torch.int64, device=self.device)
+        namb = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_neighbour_count(self._plan, _ptr(counts), _ptr(namb), _stream()))
+            offsets = torch.zeros(self.n_grid + 1, dtype=torch.int64, device=self.device)
+            offsets[1:] = torch.cumsum(counts, 0)
+            nnz = int(offsets[-1].item())
+            idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=self.device)
+            w = torch.empty(max(nnz, 1), dtype=torch.float64, device=self.device) if with_weights else None
+            amb = torch.zeros(max(nnz, 1), dtype=torch.uint8, device=self.device)
+            _cabi.check(self.lib.b200da_neighbour_fill(self._plan, _ptr(offsets), _ptr(idx), _ptr(w), _ptr(amb), _stream()))
+        return offsets, idx[:nnz], (w[:nnz] if with_weights else None), amb[:nnz], int(namb.item())
+
+    def ambiguous_pairs(self, capacity=4096):
+        """(grid index, obs index, taper value) of every pair whose taper value is within 1e-13 of epsilon."""
+        gi = torch.empty(capacity, dtype=torch.int64, device=self.device)
+        oi = torch.empty(capacity, dtype=torch.int64, device=self.device)
+        w = torch.empty(capacity, dtype=torch.float64, device=self.device)
+        n = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_neighbour_ambiguous(self._plan, capacity, _ptr(gi), _ptr(oi), _ptr(w), _ptr(n), _stream()))
+        nf = min(int(n.item()), capacity)
+        return gi[:nf], oi[:nf], w[:nf], int(n.item())
+
+    # -- global ETKF ------------------------------------------------------------------------------------------
+    def etkf_weights(self, normed_perts, normed_obs):
+        """``ETKFModule.forward`` on the device (core/etkf.py:79-103) -> W (k, k)."""
+        yn = _dev(normed_perts, device=self.device)
+        d = _dev(normed_obs, device=self.device).reshape(-1)
+        if yn.shape[-1] != d.shape[-1]:
+            raise ValueError('Observational size between ensemble ({0:d}) and observations '
+                             '({1:d}) do not match!'.format(yn.shape[-1], d.shape[-1]))
+        w = torch.empty((self.k, self.k), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_etkf_weights(self._plan, _ptr(yn), _ptr(d), d.shape[0], _ptr(w), _stream()))
+        return w
+
+    def apply_weights(self, state, weights, out=None):
+        """``_apply_weights`` (interface/base.py:257-278): weights (k, k) or (N, k, k)."""
+        x = _dev(state, device=self.device)
+        n_grid = x.shape[-1]
+        x = x.reshape(self.n_slices, self.k, n_grid)
+        w = _dev(weights, device=self.device)
+        per_grid = 1 if w.dim() == 3 else 0
+        xa = torch.empty_like(x) if out is None else out
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_apply_weights(self._plan, _ptr(x), _ptr(w), per_grid, n_grid, _ptr(xa), _stream()))
+        return xa
+
+    # -- multi-GPU helpers --------------------------------------------------------------------------------------
+    def block_offset(self, block):
+        return int(self.lib.b200da_block_offset(self._plan, int(block)))
+
+    def pack_columns(self, xa, b0, b1):
+        ncols = self.block_offset(b1) - self.block_offset(b0)
+        packed = torch.empty((self.n_slices * self.k, ncols), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_pack_columns(self._plan, _ptr(xa), b0, b1, _ptr(packed), _stream()))
+        return packed
+
+    def unpack_columns(self, packed, b0, b1, xa):
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_unpack_columns(self._plan, _ptr(packed), b0, b1, _ptr(xa), _stream()))
+        return xa
+
+    # -- introspection ---------------------------------------------------------------------------------------------
+    @property
+    def kernel_name(self):
+        return self.lib.b200da_kernel_name(self._plan).decode()
+
+    def enable_timing(self, on=True):
+        _cabi.check(self.lib.b200da_enable_timing(self._plan, 1 if on else 0))
+
+    def last_kernel_ms(self):
+        return float(self.lib.b200da_last_kernel_ms(self._plan))
+
+
+def launch_count():
+    return int(_cabi.load().b200da_launch_count())
