@@ -159,6 +159,12 @@ const char* b200da_kernel_name(const b200da_plan* plan);
 int b200da_enable_timing(b200da_plan* plan, int on);
 float b200da_last_kernel_ms(b200da_plan* plan);
 
+/* Per-launch phase statistics of the fused kernel (diagnostics; small atomics overhead when enabled):
+ * out8 = {sum of Gram-phase cycles over CTAs, sum of EVD+transform+update cycles, Jacobi sweeps, EVDs,
+ *         set-up cycles, staged tiles, 0, 0}.  b200da_get_stats synchronises the device. */
+int b200da_collect_stats(b200da_plan* plan, int on);
+int b200da_get_stats(b200da_plan* plan, int64_t* out8);
+
 #ifdef __cplusplus
 }
 #endif

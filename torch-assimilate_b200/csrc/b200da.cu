@@ -207,7 +207,7 @@ void b200da_plan_destroy(b200da_plan* pl) {
     DevBuf* bufs[] = {&pl->gpos, &pl->gorder, &pl->block_off, &pl->opos, &pl->cell_start, &pl->ys, &pl->tmp_keys,
                       &pl->tmp_cell, &pl->tmp_count, &pl->tmp_a, &pl->tmp_b, &pl->tmp_pos, &pl->host_stage_obs,
                       &pl->host_stage_y, &pl->host_stage_d, &pl->host_stage_x, &pl->host_stage_xa, &pl->etkf_partial,
-                      &pl->etkf_w};
+                      &pl->etkf_w, &pl->stats};
     for (DevBuf* b : bufs) b->release();
     if (pl->ev0) cudaEventDestroy(pl->ev0);
     if (pl->ev1) cudaEventDestroy(pl->ev1);
@@ -256,6 +256,13 @@ int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t 
     P.block_begin = (int)block_begin;
     P.k = pl->k; P.n_slices = pl->n_slices; P.rho = pl->rho;
     P.cut_pad = pl->geom.cut_bin * (1.0 + 1e-9) + 1e-300;
+    P.stats = nullptr;
+    if (pl->collect_stats) {
+        int rc = pl->stats.ensure(sizeof(unsigned long long) * 8);
+        if (rc) return rc;
+        B200DA_CUDA(cudaMemsetAsync(pl->stats.p, 0, sizeof(unsigned long long) * 8, (cudaStream_t)stream));
+        P.stats = pl->stats.as<unsigned long long>();
+    }
     return dispatch_fused(pl, P, (int)(block_end - block_begin), (cudaStream_t)stream);
 }
 
@@ -390,6 +397,16 @@ int b200da_pack_columns(b200da_plan* pl, const void* Xa, int64_t b0, int64_t b1,
 }
 int b200da_unpack_columns(b200da_plan* pl, const void* packed, int64_t b0, int64_t b1, void* Xa, void* stream) {
     return pack_impl(pl, Xa, b0, b1, const_cast<void*>(packed), 1, (cudaStream_t)stream);
+}
+
+int b200da_collect_stats(b200da_plan* pl, int on) { if (!pl) return B200DA_ERR_INVALID; pl->collect_stats = on != 0; return B200DA_OK; }
+int b200da_get_stats(b200da_plan* pl, int64_t* out8) {
+    if (!pl || !out8) return B200DA_ERR_INVALID;
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    if (!pl->stats.p) return B200DA_OK;
+    B200DA_CUDA(cudaDeviceSynchronize());
+    B200DA_CUDA(cudaMemcpy(out8, pl->stats.p, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost));
+    return B200DA_OK;
 }
 
 const char* b200da_kernel_name(const b200da_plan* pl) { return pl ? pl->kernel_name.c_str() : ""; }

@@ -37,6 +37,7 @@ struct LetkfParams {
     double* xa;
     double* w_out;             // (N, k, k) or null
     unsigned long long* n_ambiguous;   // or null
+    unsigned long long* stats;         // or null: [0] gram cycles [1] evd cycles [2] sweeps [3] evds [4] setup cycles [5] tiles
     int64_t n_grid;
     int64_t n_obs;
     int block_begin;
@@ -124,8 +125,8 @@ struct JacobiScratch {
     int* flag;      // [2]
 };
 
-__device__ void jacobi_evd(double* __restrict__ A, double* __restrict__ V, int k, int lda, double shift,
-                           const JacobiScratch sc, int gtid, int gthreads, int bar_id) {
+__device__ int jacobi_evd(double* __restrict__ A, double* __restrict__ V, int k, int lda, double shift,
+                          const JacobiScratch sc, int gtid, int gthreads, int bar_id) {
     const int ne = (k + 1) & ~1;
     const int n2 = ne >> 1;
     const double tol = 1e-15;
@@ -135,8 +136,9 @@ __device__ void jacobi_evd(double* __restrict__ A, double* __restrict__ V, int k
     }
     if (gtid == 0) { sc.flag[0] = 0; sc.flag[1] = 0; }
     group_barrier(bar_id, gthreads);
-    if (k < 2) return;
-    for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
+    if (k < 2) return 0;
+    int sweep = 0;
+    for (; sweep < kMaxSweeps; ++sweep) {
         for (int step = 0; step < ne - 1; ++step) {
             // phase 1: rotation parameters of the n2 disjoint pairs
             if (gtid < n2) {
@@ -205,6 +207,7 @@ __device__ void jacobi_evd(double* __restrict__ A, double* __restrict__ V, int k
         group_barrier(bar_id, gthreads);
         if (!rotated) break;
     }
+    return sweep + 1;
 }
 
 // ---- transform: A (diagonalised), V, b -> W = w_mean 1^T + W_p written over V ---------------------------------------
@@ -380,8 +383,10 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_fused(const LetkfPara
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int my_g = warp / WPG, my_sub = warp % WPG;
     const int blk = P.block_begin + blockIdx.x;
+    const long long t_start = clock64();
     setup_block<G>(H, g, P.gpos, P.block_off, P.cell_start, P.n_obs, P.cut_pad, blk);
     const int ng = H.ng;
+    const long long t_setup = clock64();
 
     double acc[ACC][2];
 #pragma unroll
@@ -499,6 +504,7 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_fused(const LetkfPara
         if (P.n_ambiguous && my_amb) atomicAdd(P.n_ambiguous, my_amb);
     }
     __syncthreads();
+    const long long t_gram = clock64();
 
     // ------------------------------------------------------------------------------------------------------------
     // EVD + transform + update, evd_conc grid points at a time (the shared memory of the Gram phase is reused)
@@ -554,12 +560,20 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_fused(const LetkfPara
         const int gp_idx = round * E + grp;
         if (gp_idx < ng) {
             const int bar_id = 1 + grp;
-            jacobi_evd(A, V, k, lda, shift, sc, gtid, gthreads, bar_id);
+            const int nsw = jacobi_evd(A, V, k, lda, shift, sc, gtid, gthreads, bar_id);
+            if (P.stats && gtid == 0) { atomicAdd(P.stats + 2, (unsigned long long)nsw); atomicAdd(P.stats + 3, 1ull); }
             etkf_transform(A, V, bvec, vec, k, lda, P.rho, gtid, gthreads, bar_id);
             apply_point(V, lda, k, P.n_slices, P.n_grid, H.gp[gp_idx].id, P.x, P.xa, P.w_out, xbuf, gtid, gthreads,
                         bar_id);
         }
         __syncthreads();
+    }
+    if (P.stats && tid == 0) {
+        const long long t_end = clock64();
+        atomicAdd(P.stats + 0, (unsigned long long)(t_gram - t_setup));
+        atomicAdd(P.stats + 1, (unsigned long long)(t_end - t_gram));
+        atomicAdd(P.stats + 4, (unsigned long long)(t_setup - t_start));
+        atomicAdd(P.stats + 5, (unsigned long long)produced);
     }
 }
 

@@ -225,6 +225,15 @@ class LETKFEngine(object):
     def enable_timing(self, on=True):
         _cabi.check(self.lib.b200da_enable_timing(self._plan, 1 if on else 0))
 
+    def collect_stats(self, on=True):
+        _cabi.check(self.lib.b200da_collect_stats(self._plan, 1 if on else 0))
+
+    def stats(self):
+        out = (ctypes.c_int64 * 8)()
+        _cabi.check(self.lib.b200da_get_stats(self._plan, out))
+        v = list(out)
+        return dict(gram_cycles=v[0], evd_cycles=v[1], sweeps=v[2], evds=v[3], setup_cycles=v[4], tiles=v[5])
+
     def last_kernel_ms(self):
         return float(self.lib.b200da_last_kernel_ms(self._plan))
 
