@@ -152,16 +152,18 @@ const char* b200da_last_cuda_error(void);
 int b200da_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t b200da_launch_count(void);
-/* name of the CUDA event-timed kernel configuration chosen for the plan, e.g. "letkf_f64_kt7_g8_w2" */
+/* name of the Gram kernel configuration chosen for the plan, e.g. "letkf_gram_f64_kt7_g8_w2" */
 const char* b200da_kernel_name(const b200da_plan* plan);
 /* device time (ms) of the last b200da_letkf main-kernel launch on this plan, measured with CUDA events on
  * the launch stream when timing was enabled with b200da_enable_timing(plan, 1); synchronises. */
 int b200da_enable_timing(b200da_plan* plan, int on);
 float b200da_last_kernel_ms(b200da_plan* plan);
+/* after b200da_last_kernel_ms: summed device time of the Gram kernels (which = 0) / solve kernels (which = 1) */
+float b200da_last_phase_ms(b200da_plan* plan, int which);
 
 /* Per-launch phase statistics of the fused kernel (diagnostics; small atomics overhead when enabled):
- * out8 = {sum of Gram-phase cycles over CTAs, sum of EVD+transform+update cycles, Jacobi sweeps, EVDs,
- *         set-up cycles, staged tiles, 0, 0}.  b200da_get_stats synchronises the device. */
+ * out16 = {sum of Gram-phase cycles over CTAs, sum of EVD+transform+update cycles, Jacobi sweeps, EVDs,
+ *         set-up cycles, staged tiles, 0, 0, Jacobi step profile x5, 0, 0, 0}.  b200da_get_stats synchronises the device. */
 int b200da_collect_stats(b200da_plan* plan, int on);
 int b200da_get_stats(b200da_plan* plan, int64_t* out8);
 

@@ -21,8 +21,8 @@ eng.collect_stats(True)
 eng.analyse(x); torch.cuda.synchronize()
 st = eng.stats(); ms = eng.last_kernel_ms()
 nb = eng.n_blocks
-out = dict(workload=name, kernel=eng.kernel_name, kernel_ms=ms, blocks=nb,
+out = dict(workload=name, kernel=eng.kernel_name, kernel_ms=ms, blocks=nb, n_grid=data["state"].shape[-1],
            gram_cycles_per_cta=st["gram_cycles"] / nb, evd_cycles_per_cta=st["evd_cycles"] / nb,
            setup_cycles_per_cta=st["setup_cycles"] / nb, sweeps_per_evd=st["sweeps"] / max(st["evds"], 1),
-           tiles_per_cta=st["tiles"] / nb)
+           tiles_per_cta=st["tiles"] / nb, phase_ms=eng.last_phase_ms(), jacobi_prof_cycles_per_step=[c / max(1.0, st["sweeps"] / max(st["evds"], 1) * ((k + 1) // 2 * 2 - 1) * max(1, -(-data["state"].shape[-1] // (148 * 64)))) for c in st["jacobi_prof"]])
 print(json.dumps(out))

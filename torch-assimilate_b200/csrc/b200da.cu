@@ -49,20 +49,12 @@ constexpr size_t kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
 template <int KT, int G, int WPG>
 static int launch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st) {
     const size_t hdr = (sizeof(BlockHeader<G>) + 31) & ~size_t(31);
-    const size_t per = (evd_smem_bytes_per_matrix(pl->k) + 31) & ~size_t(31);
-    int E = G;
-    while (E > 1 && hdr + (size_t)E * per > kMaxSmem) E >>= 1;
-    if (hdr + (size_t)E * per > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
-    const size_t smem = hdr + std::max(gram_smem_bytes<KT, G, WPG>(), (size_t)E * per);
+    const size_t smem = hdr + gram_smem_bytes<KT, G, WPG>();
     if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
-    LetkfParams Q = P;
-    Q.evd_conc = E;
-    auto kern = k_letkf_fused<KT, G, WPG>;
+    auto kern = k_letkf_gram<KT, G, WPG>;
     B200DA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (pl->timing) B200DA_CUDA(cudaEventRecord(pl->ev0, st));
-    kern<<<nblocks, G * WPG * 32, smem, st>>>(Q);
+    kern<<<nblocks, G * WPG * 32, smem, st>>>(P);
     B200DA_LAUNCH_CHECK();
-    if (pl->timing) B200DA_CUDA(cudaEventRecord(pl->ev1, st));
     return B200DA_OK;
 }
 
@@ -171,7 +163,7 @@ int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int
     pl->kt = kt; pl->kp = kt * 8;
     const KernelConfig cfg = config_for_kt(kt);
     pl->gpb = cfg.g;
-    pl->kernel_name = "letkf_f64_kt" + std::to_string(kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
+    pl->kernel_name = "letkf_gram_f64_kt" + std::to_string(kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
     Geometry& g = pl->geom;
     g.metric = metric; g.taper = taper; g.n_coord = n_coord; g.periodic = 0;
     g.radius = radius[0]; g.eps = epsilon; g.period = 0.0; g.sphere_r = 1.0;
@@ -207,7 +199,8 @@ void b200da_plan_destroy(b200da_plan* pl) {
     DevBuf* bufs[] = {&pl->gpos, &pl->gorder, &pl->block_off, &pl->opos, &pl->cell_start, &pl->ys, &pl->tmp_keys,
                       &pl->tmp_cell, &pl->tmp_count, &pl->tmp_a, &pl->tmp_b, &pl->tmp_pos, &pl->host_stage_obs,
                       &pl->host_stage_y, &pl->host_stage_d, &pl->host_stage_x, &pl->host_stage_xa, &pl->etkf_partial,
-                      &pl->etkf_w, &pl->stats};
+                      &pl->etkf_w, &pl->stats, &pl->cmat};
+    for (cudaEvent_t ev : pl->ev_pool) cudaEventDestroy(ev);
     for (DevBuf* b : bufs) b->release();
     if (pl->ev0) cudaEventDestroy(pl->ev0);
     if (pl->ev1) cudaEventDestroy(pl->ev1);
@@ -258,12 +251,53 @@ int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t 
     P.cut_pad = pl->geom.cut_bin * (1.0 + 1e-9) + 1e-300;
     P.stats = nullptr;
     if (pl->collect_stats) {
-        int rc = pl->stats.ensure(sizeof(unsigned long long) * 8);
+        int rc = pl->stats.ensure(sizeof(unsigned long long) * 16);
         if (rc) return rc;
-        B200DA_CUDA(cudaMemsetAsync(pl->stats.p, 0, sizeof(unsigned long long) * 8, (cudaStream_t)stream));
+        B200DA_CUDA(cudaMemsetAsync(pl->stats.p, 0, sizeof(unsigned long long) * 16, (cudaStream_t)stream));
         P.stats = pl->stats.as<unsigned long long>();
     }
-    return dispatch_fused(pl, P, (int)(block_end - block_begin), (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k = pl->k;
+    const size_t per_slot = sizeof(double) * (size_t)(k + 1) * k;
+    const size_t smem_solve = solve_smem_bytes(k);
+    if (smem_solve > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
+    const bool big = k > 64;
+    if (big) B200DA_CUDA(cudaFuncSetAttribute(k_letkf_solve<512, 1, 2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    else B200DA_CUDA(cudaFuncSetAttribute(k_letkf_solve<256, 2, 1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    // chunk the block range so that the Gram scratch stays below ~2 GiB
+    const int64_t max_slots = std::max<int64_t>(pl->gpb, (int64_t)((size_t(2) << 30) / per_slot));
+    if (pl->timing) { B200DA_CUDA(cudaEventRecord(pl->ev0, st)); pl->gram_ms = 0.f; pl->solve_ms = 0.f; pl->n_ev = 0; }
+    int64_t b = block_begin;
+    while (b < block_end) {
+        int64_t e = b;
+        const int64_t s0 = pl->block_off_host[(size_t)b];
+        while (e < block_end && pl->block_off_host[(size_t)e + 1] - s0 <= max_slots) ++e;
+        if (e == b) ++e;
+        const int64_t n_slots = pl->block_off_host[(size_t)e] - s0;
+        int rc = pl->cmat.ensure(per_slot * (size_t)n_slots);
+        if (rc) return rc;
+        P.cmat = pl->cmat.as<double>();
+        P.slot_base = s0;
+        P.block_begin = (int)b;
+        cudaEvent_t ea = nullptr, eb = nullptr, ec = nullptr;
+        if (pl->timing) {
+            if ((rc = pl->next_events(&ea, &eb, &ec))) return rc;
+            B200DA_CUDA(cudaEventRecord(ea, st));
+        }
+        if ((rc = dispatch_fused(pl, P, (int)(e - b), st))) return rc;
+        if (pl->timing) B200DA_CUDA(cudaEventRecord(eb, st));
+        SolveParams S{};
+        S.cmat = P.cmat; S.gpos = P.gpos; S.x = P.x; S.xa = P.xa; S.w_out = P.w_out; S.stats = P.stats;
+        S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = pl->rho;
+        const int grid = (int)std::min<int64_t>(n_slots, 148 * 64);
+        if (big) k_letkf_solve<512, 1, 2, 4, 4><<<grid, 512, smem_solve, st>>>(S);
+        else k_letkf_solve<256, 2, 1, 4, 2><<<grid, 256, smem_solve, st>>>(S);
+        B200DA_LAUNCH_CHECK();
+        if (pl->timing) B200DA_CUDA(cudaEventRecord(ec, st));
+        b = e;
+    }
+    if (pl->timing) B200DA_CUDA(cudaEventRecord(pl->ev1, st));
+    return B200DA_OK;
 }
 
 int b200da_letkf_host(b200da_plan* pl, const double* obs_coord_host, const void* Yn_host, const void* d_host, int64_t m,
@@ -357,7 +391,7 @@ int b200da_etkf_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t 
         if ((rc = dispatch_etkf_gram(pl->kt, (const double*)Yn, (const double*)d, m, k, ncta, chunk,
                                      pl->etkf_partial.as<double>(), st))) return rc;
     }
-    const size_t smem = evd_smem_bytes_per_matrix(k) + 64;
+    const size_t smem = solve_smem_bytes(k);
     if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
     B200DA_CUDA(cudaFuncSetAttribute(k_etkf_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_etkf_solve<<<1, 512, smem, st>>>(pl->etkf_partial.as<double>(), m > 0 ? ncta : 0, kp, k, pl->rho, (double*)W);
@@ -402,10 +436,10 @@ int b200da_unpack_columns(b200da_plan* pl, const void* packed, int64_t b0, int64
 int b200da_collect_stats(b200da_plan* pl, int on) { if (!pl) return B200DA_ERR_INVALID; pl->collect_stats = on != 0; return B200DA_OK; }
 int b200da_get_stats(b200da_plan* pl, int64_t* out8) {
     if (!pl || !out8) return B200DA_ERR_INVALID;
-    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    for (int i = 0; i < 16; ++i) out8[i] = 0;
     if (!pl->stats.p) return B200DA_OK;
     B200DA_CUDA(cudaDeviceSynchronize());
-    B200DA_CUDA(cudaMemcpy(out8, pl->stats.p, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost));
+    B200DA_CUDA(cudaMemcpy(out8, pl->stats.p, sizeof(int64_t) * 16, cudaMemcpyDeviceToHost));
     return B200DA_OK;
 }
 
@@ -416,7 +450,19 @@ float b200da_last_kernel_ms(b200da_plan* pl) {
     if (cudaEventSynchronize(pl->ev1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
     float ms = -1.f;
     if (cudaEventElapsedTime(&ms, pl->ev0, pl->ev1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    pl->gram_ms = 0.f; pl->solve_ms = 0.f;
+    for (int i = 0; i + 2 < pl->n_ev; i += 3) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, pl->ev_pool[i], pl->ev_pool[i + 1]);
+        cudaEventElapsedTime(&b, pl->ev_pool[i + 1], pl->ev_pool[i + 2]);
+        pl->gram_ms += a; pl->solve_ms += b;
+    }
     return ms;
+}
+/* after b200da_last_kernel_ms: device time of the Gram kernels (which = 0) or the solve kernels (which = 1) */
+float b200da_last_phase_ms(b200da_plan* pl, int which) {
+    if (!pl) return -1.f;
+    return which == 0 ? pl->gram_ms : pl->solve_ms;
 }
 
 }  // extern "C"

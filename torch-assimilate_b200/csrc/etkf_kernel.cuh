@@ -66,32 +66,26 @@ __global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const double* __r
 }
 
 // Sum the partial Grams in a fixed order, eigendecompose, transform; W (k x k) row-major to global memory.
-__global__ void __launch_bounds__(512) k_etkf_solve(const double* __restrict__ partial, int n_partial, int kp, int k,
+__global__ void __launch_bounds__(512, 1) k_etkf_solve(const double* __restrict__ partial, int n_partial, int kp, int k,
                                                     double rho, double* __restrict__ w_out) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    const int lda = k | 1, n2 = (k + 1) / 2;
-    double* A = reinterpret_cast<double*>(smem_raw);
-    double* V = A + (size_t)k * lda;
-    double* bvec = V + (size_t)k * lda;
-    double* vec = bvec + k;
-    double* xbuf = vec + 3 * k;
-    JacobiScratch sc;
-    sc.cs = xbuf + k;
-    sc.pq = reinterpret_cast<int*>(sc.cs + 2 * n2 + 2);
-    sc.flag = sc.pq + 2 * n2;
+    const SolveSmem S = carve_solve_smem(smem_raw, k);
     const int tid = threadIdx.x, nt = blockDim.x;
+    for (int x = tid; x < S.ne * S.lda; x += nt) S.A[x] = 0.0;
+    if (tid < S.ne) S.bvec[tid] = 0.0;
+    __syncthreads();
     for (int x = tid; x < (k + 1) * k; x += nt) {
         const int r = x / k, c = x % k;
         if (r < k && c > r) continue;
         double s = 0.0;
         for (int p = 0; p < n_partial; ++p) s += partial[(size_t)p * kp * kp + r * kp + c];
-        if (r < k) { A[r * lda + c] = s; A[c * lda + r] = s; }
-        else bvec[c] = s;
+        if (r < k) { S.A[r * S.lda + c] = s; S.A[c * S.lda + r] = s; }
+        else S.bvec[c] = s;
     }
     __syncthreads();
-    jacobi_evd(A, V, k, lda, (double)(k - 1) / rho, sc, tid, nt, 0);
-    etkf_transform(A, V, bvec, vec, k, lda, rho, tid, nt, 0);
-    for (int x = tid; x < k * k; x += nt) w_out[x] = V[(x / k) * lda + (x % k)];
+    jacobi_evd<2, 4, 4>(S.A, S.Vt, S.ne, S.lda, S.ldv, (double)(k - 1) / rho, tid, nt, 0);
+    etkf_transform(S.A, S.Vt, S.bvec, S.vec, k, S.ne, S.lda, S.ldv, rho, tid, nt, 0);
+    for (int x = tid; x < k * k; x += nt) w_out[x] = S.A[(x / k) * S.lda + (x % k)];
 }
 
 // Xa = mean + (X - mean) W.  One thread per grid point (coalesced along the grid axis), 8 output members per

@@ -18,13 +18,13 @@
 // (w y)(y)^T equals (sqrt(w) y)(sqrt(w) y)^T of the reference up to rounding.
 #pragma once
 #include "plan.cuh"
+#include "solve_kernel.cuh"
 
 namespace b200da {
 
 constexpr int kTileObs = 64;      // observations per staged tile
 constexpr int kStages = 3;
 constexpr int kRing = 2048;       // survivor ring (sorted obs slots), power of two
-constexpr int kMaxSweeps = 40;
 
 struct LetkfParams {
     Geometry g;
@@ -38,12 +38,13 @@ struct LetkfParams {
     double* w_out;             // (N, k, k) or null
     unsigned long long* n_ambiguous;   // or null
     unsigned long long* stats;         // or null: [0] gram cycles [1] evd cycles [2] sweeps [3] evds [4] setup cycles [5] tiles
+    double* cmat;                      // scratch: per grid slot the augmented Gram [(k+1)][k], lower triangle + row k = b
+    int64_t slot_base;                 // first grid slot of the chunk held in cmat
     int64_t n_grid;
     int64_t n_obs;
     int block_begin;
     int k;
     int n_slices;
-    int evd_conc;              // EVDs resident in shared memory at once (power of two, <= G)
     double rho;
     double cut_pad;            // padded cutoff in bin space
 };
@@ -59,9 +60,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
-__device__ __forceinline__ void group_barrier(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
-}
 
 // ---- Gram tile: acc += (w .* Y_tile) Y_tile^T for the tiles owned by warp SUB of the grid point ------------------
 template <int KT, int WPG, int SUB>
@@ -115,164 +113,26 @@ __device__ __forceinline__ void dump_tiles(const double (&acc)[(KT * (KT + 1) / 
     }
 }
 
-// ---- parallel cyclic Jacobi (two-sided, round-robin ordering) on a group of threads ---------------------------------
-// A (k x k symmetric, full storage) is diagonalised in place, V accumulates the rotations (columns = eigenvectors).
-// Rotations are skipped when |a_pq| <= tol * sqrt((a_pp + shift)(a_qq + shift)): the criterion of a relative-accuracy
-// Jacobi on A + shift*I, which is the matrix whose functions the transform needs (core/utils.py:58-60).
-struct JacobiScratch {
-    double* cs;     // [n2][2]
-    int* pq;        // [n2][2]
-    int* flag;      // [2]
-};
-
-__device__ int jacobi_evd(double* __restrict__ A, double* __restrict__ V, int k, int lda, double shift,
-                          const JacobiScratch sc, int gtid, int gthreads, int bar_id) {
-    const int ne = (k + 1) & ~1;
-    const int n2 = ne >> 1;
-    const double tol = 1e-15;
-    for (int i = gtid; i < k * k; i += gthreads) {
-        const int r = i / k, c = i % k;
-        V[r * lda + c] = (r == c) ? 1.0 : 0.0;
-    }
-    if (gtid == 0) { sc.flag[0] = 0; sc.flag[1] = 0; }
-    group_barrier(bar_id, gthreads);
-    if (k < 2) return 0;
-    int sweep = 0;
-    for (; sweep < kMaxSweeps; ++sweep) {
-        for (int step = 0; step < ne - 1; ++step) {
-            // phase 1: rotation parameters of the n2 disjoint pairs
-            if (gtid < n2) {
-                int a, b;
-                if (gtid == 0) { a = ne - 1; b = step; }
-                else { a = (step + gtid) % (ne - 1); b = (step - gtid + (ne - 1)) % (ne - 1); }
-                const int p = min(a, b), q = max(a, b);
-                double c = 1.0, s = 0.0;
-                if (q < k) {
-                    const double apq = A[p * lda + q];
-                    const double app = A[p * lda + p], aqq = A[q * lda + q];
-                    if (fabs(apq) > tol * sqrt(fabs((app + shift) * (aqq + shift)))) {
-                        const double tau = (aqq - app) / (2.0 * apq);
-                        const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
-                        c = rsqrt(fma(t, t, 1.0));
-                        s = t * c;
-                        sc.flag[sweep & 1] = 1;
-                    }
+// accumulators -> global scratch: C[(k+1)][k] row-major per grid slot (rows 0..k-1 lower triangle, row k = b)
+template <int KT, int WPG, int SUB>
+__device__ __forceinline__ void dump_tiles_global(const double (&acc)[(KT * (KT + 1) / 2 + WPG - 1) / WPG][2],
+                                                  double* __restrict__ C, int k, int lane) {
+    int idx = 0, n = 0;
+#pragma unroll
+    for (int mt = 0; mt < KT; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt <= mt; ++nt) {
+            if (idx % WPG == SUB) {
+                const int r = mt * 8 + (lane >> 2);
+                const int c = nt * 8 + (lane & 3) * 2;
+                if (r <= k) {
+                    if (c < k) C[(size_t)r * k + c] = acc[n][0];
+                    if (c + 1 < k) C[(size_t)r * k + c + 1] = acc[n][1];
                 }
-                sc.pq[2 * gtid] = p; sc.pq[2 * gtid + 1] = (q < k) ? q : -1;
-                sc.cs[2 * gtid] = c; sc.cs[2 * gtid + 1] = s;
+                ++n;
             }
-            group_barrier(bar_id, gthreads);
-            // phase 2: A <- J^T A J on independent 2x2 blocks (lower triangle of pair-pairs, mirrored), V <- V J
-            const int nblk = n2 * (n2 + 1) / 2;
-            for (int x = gtid; x < nblk; x += gthreads) {
-                int ti = (int)((sqrtf(8.0f * (float)x + 1.0f) - 1.0f) * 0.5f);
-                while (ti * (ti + 1) / 2 > x) --ti;
-                while ((ti + 1) * (ti + 2) / 2 <= x) ++ti;
-                const int tj = x - ti * (ti + 1) / 2;
-                const int pi = sc.pq[2 * ti], qi = sc.pq[2 * ti + 1];
-                const int pj = sc.pq[2 * tj], qj = sc.pq[2 * tj + 1];
-                const double ci = sc.cs[2 * ti], si = sc.cs[2 * ti + 1];
-                const double cj = sc.cs[2 * tj], sj = sc.cs[2 * tj + 1];
-                if (qi < 0 && qj < 0) continue;
-                // rows (pi, qi) x cols (pj, qj); a dummy partner (q < 0) has identity rotation and no storage
-                const double b00 = A[pi * lda + pj];
-                const double b01 = qj >= 0 ? A[pi * lda + qj] : 0.0;
-                const double b10 = qi >= 0 ? A[qi * lda + pj] : 0.0;
-                const double b11 = (qi >= 0 && qj >= 0) ? A[qi * lda + qj] : 0.0;
-                // left: rows' = J_i^T rows
-                const double r00 = ci * b00 - si * b10, r01 = ci * b01 - si * b11;
-                const double r10 = si * b00 + ci * b10, r11 = si * b01 + ci * b11;
-                // right: cols' = cols J_j
-                double n00 = cj * r00 - sj * r01, n01 = sj * r00 + cj * r01;
-                double n10 = cj * r10 - sj * r11, n11 = sj * r10 + cj * r11;
-                if (ti == tj) { n01 = 0.0; n10 = 0.0; }
-                A[pi * lda + pj] = n00; A[pj * lda + pi] = n00;
-                if (qj >= 0) { A[pi * lda + qj] = n01; A[qj * lda + pi] = n01; }
-                if (qi >= 0) { A[qi * lda + pj] = n10; A[pj * lda + qi] = n10; }
-                if (qi >= 0 && qj >= 0) { A[qi * lda + qj] = n11; A[qj * lda + qi] = n11; }
-            }
-            for (int x = gtid; x < n2 * k; x += gthreads) {
-                const int t = x / k, r = x % k;
-                const int p = sc.pq[2 * t], q = sc.pq[2 * t + 1];
-                if (q < 0) continue;
-                const double c = sc.cs[2 * t], s = sc.cs[2 * t + 1];
-                const double vp = V[r * lda + p], vq = V[r * lda + q];
-                V[r * lda + p] = c * vp - s * vq;
-                V[r * lda + q] = s * vp + c * vq;
-            }
-            group_barrier(bar_id, gthreads);
+            ++idx;
         }
-        const int rotated = sc.flag[sweep & 1];
-        if (gtid == 0) sc.flag[(sweep + 1) & 1] = 0;
-        group_barrier(bar_id, gthreads);
-        if (!rotated) break;
-    }
-    return sweep + 1;
-}
-
-// ---- transform: A (diagonalised), V, b -> W = w_mean 1^T + W_p written over V ---------------------------------------
-// core/utils.py:58-60 (clamp, + (k-1)/rho, reciprocal), core/etkf.py:70-77,102.
-__device__ void etkf_transform(double* __restrict__ A, double* __restrict__ V, const double* __restrict__ bvec,
-                               double* __restrict__ vec, int k, int lda, double rho, int gtid, int gthreads, int bar_id) {
-    double* inv = vec;            // [k] 1 / (max(lambda, 0) + (k-1)/rho)
-    double* z = vec + k;          // [k]
-    double* wbar = vec + 2 * k;   // [k]
-    const double reg = (double)(k - 1) / rho;
-    for (int m = gtid; m < k; m += gthreads) {
-        const double ev = fmax(A[m * lda + m], 0.0) + reg;
-        const double iv = 1.0 / ev;
-        inv[m] = iv;
-        double acc = 0.0;                                   // z = L^-1 U^T b
-        for (int i = 0; i < k; ++i) acc = fma(V[i * lda + m], bvec[i], acc);
-        z[m] = acc * iv;
-    }
-    group_barrier(bar_id, gthreads);
-    for (int i = gtid; i < k; i += gthreads) {              // w_mean = U z
-        double acc = 0.0;
-        for (int m = 0; m < k; ++m) acc = fma(V[i * lda + m], z[m], acc);
-        wbar[i] = acc;
-    }
-    // B = U diag(((k-1) inv)^(1/4)) so that W_p = B B^T; B overwrites A
-    for (int x = gtid; x < k * k; x += gthreads) {
-        const int i = x / k, m = x % k;
-        A[i * lda + m] = V[i * lda + m] * sqrt(sqrt((double)(k - 1) * inv[m]));
-    }
-    group_barrier(bar_id, gthreads);
-    for (int x = gtid; x < k * (k + 1) / 2; x += gthreads) {
-        int i = (int)((sqrtf(8.0f * (float)x + 1.0f) - 1.0f) * 0.5f);
-        while (i * (i + 1) / 2 > x) --i;
-        while ((i + 1) * (i + 2) / 2 <= x) ++i;
-        const int j = x - i * (i + 1) / 2;
-        double acc = 0.0;
-        for (int m = 0; m < k; ++m) acc = fma(A[i * lda + m], A[j * lda + m], acc);
-        V[i * lda + j] = acc + wbar[i];                     // W[i][j] = w_mean[i] + W_p[i][j]  (core/etkf.py:102)
-        if (i != j) V[j * lda + i] = acc + wbar[j];
-    }
-    group_barrier(bar_id, gthreads);
-}
-
-// ---- update: x_a[s, j, g] = mean + sum_i (x[s, i, g] - mean) W[i][j]  (interface/base.py:257-278) ------------------
-__device__ void apply_point(const double* __restrict__ W, int lda, int k, int n_slices, int64_t n_grid, int64_t gi,
-                            const double* __restrict__ x, double* __restrict__ xa, double* __restrict__ w_out,
-                            double* __restrict__ xbuf, int gtid, int gthreads, int bar_id) {
-    if (w_out) {
-        double* dst = w_out + gi * (int64_t)k * k;
-        for (int i = gtid; i < k * k; i += gthreads) dst[i] = W[(i / k) * lda + (i % k)];
-    }
-    for (int s = 0; s < n_slices; ++s) {
-        const double* xs = x + (int64_t)s * k * n_grid + gi;
-        double* xo = xa + (int64_t)s * k * n_grid + gi;
-        for (int i = gtid; i < k; i += gthreads) xbuf[i] = xs[(int64_t)i * n_grid];
-        group_barrier(bar_id, gthreads);
-        double mean = 0.0;
-        for (int i = 0; i < k; ++i) mean += xbuf[i];       // same order for every thread
-        mean /= (double)k;
-        for (int j = gtid; j < k; j += gthreads) {
-            double acc = 0.0;
-            for (int i = 0; i < k; ++i) acc = fma(xbuf[i] - mean, W[i * lda + j], acc);
-            xo[(int64_t)j * n_grid] = mean + acc;
-        }
-        group_barrier(bar_id, gthreads);
     }
 }
 
@@ -362,13 +222,9 @@ template <int KT, int G, int WPG>
 constexpr size_t gram_smem_bytes() {
     return sizeof(double) * ((size_t)kStages * kTileObs * (KT * 8 + 4) + (size_t)kStages * G * kTileObs);
 }
-__host__ __device__ inline size_t evd_smem_bytes_per_matrix(int k) {
-    const int lda = k | 1, n2 = (k + 1) / 2;
-    return sizeof(double) * ((size_t)2 * k * lda + 5 * (size_t)k + 2 * (size_t)n2 + 2) + sizeof(int) * (2 * (size_t)n2 + 4);
-}
 
 template <int KT, int G, int WPG>
-__global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_fused(const LetkfParams P) {
+__global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParams P) {
     constexpr int NT = G * WPG * 32;
     constexpr int KP = KT * 8, LDY = KP + 4;
     constexpr int NTILES = KT * (KT + 1) / 2;
@@ -507,71 +363,39 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_fused(const LetkfPara
     const long long t_gram = clock64();
 
     // ------------------------------------------------------------------------------------------------------------
-    // EVD + transform + update, evd_conc grid points at a time (the shared memory of the Gram phase is reused)
+    // hand the augmented Gram matrices to the solve kernel through the (L2-resident) scratch
     // ------------------------------------------------------------------------------------------------------------
-    const int k = P.k, lda = k | 1, n2 = (k + 1) / 2;
-    const int E = P.evd_conc;
-    const int gthreads = NT / E;
-    const int grp = tid / gthreads, gtid = tid % gthreads;
-    const size_t per = (evd_smem_bytes_per_matrix(k) + 31) & ~size_t(31);
-    unsigned char* mine = work + (size_t)grp * per;
-    double* A = reinterpret_cast<double*>(mine);
-    double* V = A + (size_t)k * lda;
-    double* bvec = V + (size_t)k * lda;          // [k]
-    double* vec = bvec + k;                      // [3k] inv, z, wbar
-    double* xbuf = vec + 3 * k;                  // [k]
-    JacobiScratch sc;
-    sc.cs = xbuf + k;                            // [2 n2]
-    sc.pq = reinterpret_cast<int*>(sc.cs + 2 * n2 + 2);
-    sc.flag = sc.pq + 2 * n2;
-    const double shift = (double)(k - 1) / P.rho;
-
-    for (int round = 0; round * E < ng; ++round) {
-        // warps owning a grid point of this round dump their tiles into that group's A / b
-        if (my_g >= round * E && my_g < (round + 1) * E && my_g < ng) {
-            unsigned char* dst = work + (size_t)(my_g - round * E) * per;
-            double* Ad = reinterpret_cast<double*>(dst);
-            double* bd = Ad + (size_t)2 * k * lda;
-            if constexpr (WPG == 1) dump_tiles<KT, WPG, 0>(acc, Ad, lda, bd, k, lane);
-            else if constexpr (WPG == 2) {
-                if (my_sub == 0) dump_tiles<KT, WPG, 0>(acc, Ad, lda, bd, k, lane);
-                else dump_tiles<KT, WPG, 1>(acc, Ad, lda, bd, k, lane);
-            } else if constexpr (WPG == 4) {
-                switch (my_sub) {
-                    case 0: dump_tiles<KT, WPG, 0>(acc, Ad, lda, bd, k, lane); break;
-                    case 1: dump_tiles<KT, WPG, 1>(acc, Ad, lda, bd, k, lane); break;
-                    case 2: dump_tiles<KT, WPG, 2>(acc, Ad, lda, bd, k, lane); break;
-                    default: dump_tiles<KT, WPG, 3>(acc, Ad, lda, bd, k, lane); break;
-                }
-            } else {
-                switch (my_sub) {
-                    case 0: dump_tiles<KT, WPG, 0>(acc, Ad, lda, bd, k, lane); break;
-                    case 1: dump_tiles<KT, WPG, 1>(acc, Ad, lda, bd, k, lane); break;
-                    case 2: dump_tiles<KT, WPG, 2>(acc, Ad, lda, bd, k, lane); break;
-                    case 3: dump_tiles<KT, WPG, 3>(acc, Ad, lda, bd, k, lane); break;
-                    case 4: dump_tiles<KT, WPG, 4>(acc, Ad, lda, bd, k, lane); break;
-                    case 5: dump_tiles<KT, WPG, 5>(acc, Ad, lda, bd, k, lane); break;
-                    case 6: dump_tiles<KT, WPG, 6>(acc, Ad, lda, bd, k, lane); break;
-                    default: dump_tiles<KT, WPG, 7>(acc, Ad, lda, bd, k, lane); break;
-                }
+    if (my_g < ng) {
+        const int k = P.k;
+        double* C = P.cmat + (size_t)((int64_t)P.block_off[blk] + my_g - P.slot_base) * (size_t)(k + 1) * k;
+        if constexpr (WPG == 1) dump_tiles_global<KT, WPG, 0>(acc, C, k, lane);
+        else if constexpr (WPG == 2) {
+            if (my_sub == 0) dump_tiles_global<KT, WPG, 0>(acc, C, k, lane);
+            else dump_tiles_global<KT, WPG, 1>(acc, C, k, lane);
+        } else if constexpr (WPG == 4) {
+            switch (my_sub) {
+                case 0: dump_tiles_global<KT, WPG, 0>(acc, C, k, lane); break;
+                case 1: dump_tiles_global<KT, WPG, 1>(acc, C, k, lane); break;
+                case 2: dump_tiles_global<KT, WPG, 2>(acc, C, k, lane); break;
+                default: dump_tiles_global<KT, WPG, 3>(acc, C, k, lane); break;
+            }
+        } else {
+            switch (my_sub) {
+                case 0: dump_tiles_global<KT, WPG, 0>(acc, C, k, lane); break;
+                case 1: dump_tiles_global<KT, WPG, 1>(acc, C, k, lane); break;
+                case 2: dump_tiles_global<KT, WPG, 2>(acc, C, k, lane); break;
+                case 3: dump_tiles_global<KT, WPG, 3>(acc, C, k, lane); break;
+                case 4: dump_tiles_global<KT, WPG, 4>(acc, C, k, lane); break;
+                case 5: dump_tiles_global<KT, WPG, 5>(acc, C, k, lane); break;
+                case 6: dump_tiles_global<KT, WPG, 6>(acc, C, k, lane); break;
+                default: dump_tiles_global<KT, WPG, 7>(acc, C, k, lane); break;
             }
         }
-        __syncthreads();
-        const int gp_idx = round * E + grp;
-        if (gp_idx < ng) {
-            const int bar_id = 1 + grp;
-            const int nsw = jacobi_evd(A, V, k, lda, shift, sc, gtid, gthreads, bar_id);
-            if (P.stats && gtid == 0) { atomicAdd(P.stats + 2, (unsigned long long)nsw); atomicAdd(P.stats + 3, 1ull); }
-            etkf_transform(A, V, bvec, vec, k, lda, P.rho, gtid, gthreads, bar_id);
-            apply_point(V, lda, k, P.n_slices, P.n_grid, H.gp[gp_idx].id, P.x, P.xa, P.w_out, xbuf, gtid, gthreads,
-                        bar_id);
-        }
-        __syncthreads();
     }
     if (P.stats && tid == 0) {
         const long long t_end = clock64();
         atomicAdd(P.stats + 0, (unsigned long long)(t_gram - t_setup));
-        atomicAdd(P.stats + 1, (unsigned long long)(t_end - t_gram));
+        atomicAdd(P.stats + 6, (unsigned long long)(t_end - t_gram));
         atomicAdd(P.stats + 4, (unsigned long long)(t_setup - t_start));
         atomicAdd(P.stats + 5, (unsigned long long)produced);
     }

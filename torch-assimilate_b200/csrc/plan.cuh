@@ -76,11 +76,23 @@ struct b200da_plan {
     // scratch
     b200da::DevBuf tmp_keys, tmp_cell, tmp_count, tmp_a, tmp_b, tmp_pos;
     b200da::DevBuf host_stage_obs, host_stage_y, host_stage_d, host_stage_x, host_stage_xa;
-    b200da::DevBuf etkf_partial, etkf_w, stats;
+    b200da::DevBuf etkf_partial, etkf_w, stats, cmat;
     bool collect_stats = false;
     // timing
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_ms = -1.f;
+    float last_ms = -1.f, gram_ms = 0.f, solve_ms = 0.f;
+    std::vector<cudaEvent_t> ev_pool;
+    int n_ev = 0;
+    int next_events(cudaEvent_t* a, cudaEvent_t* b, cudaEvent_t* c) {
+        while ((int)ev_pool.size() < n_ev + 3) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return B200DA_ERR_CUDA;
+            ev_pool.push_back(e);
+        }
+        *a = ev_pool[n_ev]; *b = ev_pool[n_ev + 1]; *c = ev_pool[n_ev + 2];
+        n_ev += 3;
+        return B200DA_OK;
+    }
     std::string kernel_name;
 };

@@ -48,6 +48,7 @@ SIGNATURES = {
     "b200da_kernel_name": (_c.c_char_p, [_vp]),
     "b200da_enable_timing": (_i, [_vp, _i]),
     "b200da_last_kernel_ms": (_c.c_float, [_vp]),
+    "b200da_last_phase_ms": (_c.c_float, [_vp, _i]),
     "b200da_collect_stats": (_i, [_vp, _i]),
     "b200da_get_stats": (_i, [_vp, _c.POINTER(_c.c_int64)]),
 }

@@ -225,14 +225,18 @@ class LETKFEngine(object):
     def enable_timing(self, on=True):
         _cabi.check(self.lib.b200da_enable_timing(self._plan, 1 if on else 0))
 
+    def last_phase_ms(self):
+        """(gram_ms, solve_ms) of the last analyse(); call last_kernel_ms() first."""
+        return float(self.lib.b200da_last_phase_ms(self._plan, 0)), float(self.lib.b200da_last_phase_ms(self._plan, 1))
+
     def collect_stats(self, on=True):
         _cabi.check(self.lib.b200da_collect_stats(self._plan, 1 if on else 0))
 
     def stats(self):
-        out = (ctypes.c_int64 * 8)()
+        out = (ctypes.c_int64 * 16)()
         _cabi.check(self.lib.b200da_get_stats(self._plan, out))
         v = list(out)
-        return dict(gram_cycles=v[0], evd_cycles=v[1], sweeps=v[2], evds=v[3], setup_cycles=v[4], tiles=v[5])
+        return dict(gram_cycles=v[0], evd_cycles=v[1], sweeps=v[2], evds=v[3], setup_cycles=v[4], tiles=v[5], jacobi_prof=v[8:13])
 
     def last_kernel_ms(self):
         return float(self.lib.b200da_last_kernel_ms(self._plan))
