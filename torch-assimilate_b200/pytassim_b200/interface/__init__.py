@@ -1,0 +1,3 @@
+from .etkf import ETKF  # noqa: F401
+from .letkf import LETKF  # noqa: F401
+from .base import StateError, ObservationError  # noqa: F401

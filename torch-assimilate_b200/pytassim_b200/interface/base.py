@@ -1,0 +1,247 @@
+"""``BaseAssimilation`` / ``FilterAssimilation`` of the B200 engine: the reference's ``assimilate`` driver
+(pytassim/interface/base.py:419-512) and ``update_state`` (pytassim/interface/filter.py:96-165) with the same
+signatures, validation and error behaviour; everything between "obs-space variables are ready" and "analysis is
+assembled" runs on the GPU (include/b200da.h).
+
+Inputs are duck-typed (see :mod:`pytassim_b200.xrlite`): real ``xarray`` objects when xarray is installed, the
+light-weight stand-ins otherwise.
+"""
+import abc
+import logging
+import time
+import warnings
+
+import numpy as np
+import pandas as pd
+import torch
+
+logger = logging.getLogger(__name__)
+
+
+class StateError(Exception):            # pytassim/state.py:44-49
+    pass
+
+
+class ObservationError(Exception):      # pytassim/observation.py:42-47
+    pass
+
+
+def _is_state_like(obj):
+    return all(hasattr(obj, a) for a in ("values", "dims", "indexes"))
+
+
+def _is_obs_like(obj):
+    return hasattr(obj, "obs") and hasattr(obj, "__getitem__")
+
+
+def dtindex_to_total_seconds(index):
+    """pytassim/utilities/pandas.py:28-45."""
+    index = pd.DatetimeIndex(index)
+    return np.asarray((index - pd.Timestamp(1970, 1, 1)).total_seconds(), dtype=np.float64)
+
+
+def index_to_array(index):
+    """pytassim/utilities/pandas.py:70-102: any index (incl. MultiIndex of tuples) -> float (n, n_coord) array."""
+    if isinstance(index, pd.MultiIndex):
+        return np.stack([np.asarray(index.get_level_values(i), dtype=np.float64) for i in range(index.nlevels)], axis=1)
+    raw = np.atleast_1d(np.asarray(getattr(index, "values", index)))
+    if raw.dtype == object and len(raw) and isinstance(raw[0], tuple):
+        return np.asarray([list(t) for t in raw], dtype=np.float64)
+    if raw.ndim > 1:
+        return raw.astype(np.float64)
+    return raw.astype(np.float64).reshape(-1, 1)
+
+
+def _time_coord(obj):
+    t = obj.indexes['time']
+    return pd.DatetimeIndex(t) if not isinstance(t, pd.DatetimeIndex) else t
+
+
+class BaseAssimilation(object):
+    """Reference: pytassim/interface/base.py:51-512."""
+
+    def __init__(self, smoother=False, gpu=False, pre_transform=None, post_transform=None, weight_save_path=None,
+                 forward_model=None):
+        self._dtype = torch.float32
+        self.smoother = smoother
+        self.gpu = gpu                    # accepted for signature compatibility; the engine always runs on the GPU
+        self.pre_transform = pre_transform
+        self.post_transform = post_transform
+        self.dtype = torch.float64
+        if weight_save_path is not None:
+            raise NotImplementedError("weight_save_path (netCDF weight store) is outside the B200 hot path")
+        self.weight_save_path = None
+        self.forward_model = forward_model
+
+    # -- properties (base.py:86-126) ---------------------------------------------------------------------------
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @dtype.setter
+    def dtype(self, new_type):
+        if isinstance(new_type, torch.dtype):
+            self._dtype = new_type
+        else:
+            raise TypeError('Given object is not a valid torch.dtype, instead it has as type: {0}'.format(type(new_type)))
+
+    @property
+    def device(self):
+        return torch.device("cuda")
+
+    @property
+    def chunks(self):
+        return None
+
+    # -- validation (base.py:129-151) ------------------------------------------------------------------------------
+    @staticmethod
+    def _validate_state(state):
+        if not _is_state_like(state):
+            raise TypeError('*** Given state is not a valid ``xarray.DataArray`` ***\n{0}'.format(type(state)))
+        if tuple(state.dims) != ('var_name', 'time', 'ensemble', 'grid'):          # state.py:114-115
+            raise StateError('*** Given state is not a valid state ***\n{0:s}'.format(str(state.dims)))
+
+    @staticmethod
+    def _validate_observations(observations):
+        for obs in observations:
+            if not _is_obs_like(obs):
+                raise TypeError('*** Given observation is not a valid ``xarray.Dataset`` ***\n{0}'.format(type(obs)))
+            if not obs.obs.valid:
+                raise ObservationError('*** Given observation is not a valid observation ***\n{0:s}'.format(str(obs)))
+
+    @staticmethod
+    def _get_analysis_time(state, analysis_time=None):
+        """base.py:154-178: None -> last time; exact match; else nearest with a UserWarning."""
+        times = _time_coord(state)
+        if analysis_time is None:
+            return pd.Timestamp(times[-1])
+        analysis_time = pd.to_datetime(analysis_time)
+        if analysis_time in times:
+            return pd.Timestamp(analysis_time)
+        nearest = times[np.argmin(np.abs((times - analysis_time).total_seconds()))]
+        warnings.warn('Given analysis time {0:s} is not within state, used instead nearest neighbor {1:s}'.format(
+            str(analysis_time), str(nearest)), category=UserWarning)
+        return pd.Timestamp(nearest)
+
+    @staticmethod
+    def _apply_obs_operator(pseudo_state, observations):
+        """base.py:181-220: datasets whose operator raises NotImplementedError are dropped."""
+        obs_equivalent, filtered = [], []
+        for obs in observations:
+            try:
+                obs_equivalent.append(obs.obs.operator(obs, pseudo_state))
+                filtered.append(obs)
+            except NotImplementedError:
+                pass
+        return obs_equivalent, filtered
+
+    def get_pseudo_state(self, pseudo_state, state):
+        """base.py:342-357 without the forward-model propagation (outside the hot path)."""
+        if pseudo_state is None and self.forward_model is not None:
+            raise NotImplementedError("forward_model propagation is outside the B200 hot path")
+        return state if pseudo_state is None else pseudo_state
+
+    # -- obs-space variables (base.py:359-379, 223-241; observation.py:241-295) ---------------------------------------
+    @staticmethod
+    def _get_obs_space_variables(ens_obs, observations):
+        """Returns (innovations (M,), perturbations (k, M), obs_info (M, 1+nc) = [t_unix, coords...]) stacked
+        dataset-major, time-major, obs_grid_1-minor."""
+        innovations, perts, infos = [], [], []
+        for hx, obs in zip(ens_obs, observations):
+            hxv = hx.transpose('ensemble', 'time', 'obs_grid_1').values.astype(np.float64) \
+                if tuple(hx.dims) != ('ensemble', 'time', 'obs_grid_1') else np.asarray(hx.values, dtype=np.float64)
+            y = np.asarray(obs['observations'].values, dtype=np.float64)
+            cov = obs['covariance']
+            covv = np.asarray(cov.values, dtype=np.float64)
+            mean = hxv.mean(axis=0)                                     # state.py:160-161
+            pert = hxv - mean[None]
+            innov = y - mean
+            if 'obs_grid_2' in cov.dims:                                # observation.py:247-275
+                if 'time' in cov.dims:
+                    cinv = np.stack([np.linalg.inv(np.linalg.cholesky(c).T) for c in covv], axis=0)
+                    innov = np.einsum('to,top->tp', innov, cinv)
+                    pert = np.einsum('kto,top->ktp', pert, cinv)
+                else:
+                    cinv = np.linalg.inv(np.linalg.cholesky(covv).T)
+                    innov = innov @ cinv
+                    pert = pert @ cinv
+            else:                                                       # observation.py:241-245,277-279
+                rc = 1 / np.sqrt(covv)
+                innov = innov * rc
+                pert = pert * rc
+            t_unix = dtindex_to_total_seconds(_time_coord(obs['observations']))
+            coords = index_to_array(obs['observations'].indexes['obs_grid_1'])
+            n_t, n_o = y.shape
+            info = np.concatenate([np.repeat(t_unix, n_o)[:, None], np.tile(coords, (n_t, 1))], axis=1)
+            innovations.append(innov.reshape(-1))
+            perts.append(pert.reshape(pert.shape[0], -1))
+            infos.append(info)
+        return np.concatenate(innovations), np.concatenate(perts, axis=1), np.concatenate(infos, axis=0)
+
+    @abc.abstractmethod
+    def update_state(self, state, observations, pseudo_state, analysis_time):
+        pass
+
+    def assimilate(self, state, observations, pseudo_state=None, analysis_time=None):
+        """Reference: pytassim/interface/base.py:419-512 (same signature, warnings and exceptions)."""
+        start_time = time.time()
+        logger.info('Starting assimilation')
+        if not observations:
+            warnings.warn('No observation is given, I will return the background state!', UserWarning)
+            return state
+        if not isinstance(observations, (list, set, tuple)):
+            observations = (observations, )
+        self._validate_state(state)
+        self._validate_observations(observations)
+        analysis_time = self._get_analysis_time(state, analysis_time)
+        if self.pre_transform:
+            for trans in self.pre_transform:
+                state, observations, pseudo_state = trans.pre(state, observations, pseudo_state)
+        analysis = self.update_state(state, observations, pseudo_state, analysis_time)
+        if self.post_transform:
+            for trans in self.post_transform:
+                analysis = trans.post(analysis, state, observations, pseudo_state)
+        self._validate_state(analysis)
+        logger.info('Finished assimilation after {0:.2f} s'.format(time.time() - start_time))
+        return analysis
+
+
+class FilterAssimilation(BaseAssimilation):
+    """Reference: pytassim/interface/filter.py:29-165."""
+
+    @staticmethod
+    def _slice_analysis(analysis_time, state, observations, pseudo_state):
+        """filter.py:39-54: state / pseudo state / observations at the analysis time only."""
+        def pick(obj):
+            times = _time_coord(obj)
+            hit = np.nonzero(times == analysis_time)[0]
+            if len(hit) == 0:
+                raise KeyError(analysis_time)
+            return hit[:1]
+        state = state.isel(time=pick(state))
+        pseudo_state = pseudo_state.isel(time=pick(pseudo_state))
+        sel_obs = []
+        for obs in observations:
+            tmp = obs.isel(time=pick(obs['observations']))
+            tmp.obs.operator = obs.obs.operator
+            sel_obs.append(tmp)
+        return state, sel_obs, pseudo_state
+
+    @abc.abstractmethod
+    def _analyse_arrays(self, state, x, innov, perts, obs_info):
+        """x (n_slices, k, N) host array -> analysed (n_slices, k, N) host array."""
+
+    def update_state(self, state, observations, pseudo_state, analysis_time):
+        pseudo_state = self.get_pseudo_state(pseudo_state, state)
+        self._validate_state(pseudo_state)
+        if not self.smoother:
+            state, observations, pseudo_state = self._slice_analysis(analysis_time, state, observations, pseudo_state)
+        ens_obs, filtered_obs = self._apply_obs_operator(pseudo_state, observations)
+        if not filtered_obs:
+            warnings.warn('No observation is given, I will return the background state!', UserWarning)
+            return state
+        innov, perts, obs_info = self._get_obs_space_variables(ens_obs, filtered_obs)
+        values = np.ascontiguousarray(state.values, dtype=np.float64)
+        n_var, n_t, k, n_grid = values.shape
+        xa = self._analyse_arrays(state, values.reshape(n_var * n_t, k, n_grid), innov, perts, obs_info)
+        return state.copy(data=np.asarray(xa).reshape(values.shape).astype(state.values.dtype, copy=False))

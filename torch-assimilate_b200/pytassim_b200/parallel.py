@@ -1,0 +1,61 @@
+"""Grid-point sharding of one LETKF analysis over the GPUs of one node (one process per GPU, torch.distributed).
+
+The reference's only parallelism is data-parallel over grid points with the observation arrays handed to every task
+(pytassim/interface/letkf.py:121-143: ``state_info.chunk({'grid': chunksize})``, obs arrays one chunk).  The B200
+equivalent: rank 0 broadcasts the observation-space arrays once, every rank bins them and analyses a contiguous range
+of grid-point blocks, and the analysed columns are all-gathered (NCCL over NVLink on GPUs; the same code runs on gloo /
+CPU tensors for the host-logic tests).  Grid points are independent given the observations, so there is no other
+data-path collective.
+
+``engine`` is duck-typed: ``n_blocks``, ``block_offset(b)``, ``analyse(x, out=, blocks=(b0, b1))``,
+``pack_columns(xa, b0, b1) -> (rows, ncols)`` and ``unpack_columns(packed, b0, b1, xa)``.
+"""
+import torch
+import torch.distributed as dist
+
+__all__ = ["block_range", "ShardedAnalysis"]
+
+
+def block_range(n_blocks, world_size, rank):
+    """Contiguous, balanced split of the block-sorted grid (blocks are spatially ordered and equally sized, so equal
+    block counts are equal work for a uniform observation density)."""
+    return (n_blocks * rank) // world_size, (n_blocks * (rank + 1)) // world_size
+
+
+class ShardedAnalysis(object):
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        nb = engine.n_blocks
+        self.ranges = [block_range(nb, self.world, r) for r in range(self.world)]
+        self.ncols = [engine.block_offset(b1) - engine.block_offset(b0) for b0, b1 in self.ranges]
+        self._send = None
+        self._recv = None
+
+    def broadcast_inputs(self, tensors, src=0):
+        """Observation-space arrays (and the state) live on ``src``; one broadcast each per analysis."""
+        if self.world > 1:
+            for t in tensors:
+                dist.broadcast(t, src, group=self.group)
+
+    def run(self, x, out):
+        """Analyse this rank's blocks of ``x`` (n_slices, k, N) into ``out`` and fill in every other rank's columns."""
+        b0, b1 = self.ranges[self.rank]
+        self.engine.analyse(x, out=out, blocks=(b0, b1))
+        if self.world == 1:
+            return out
+        rows = out.shape[0] * out.shape[1]
+        maxc = max(self.ncols)
+        if self._send is None or self._send.shape != (rows, maxc) or self._send.device != out.device:
+            self._send = torch.zeros((rows, maxc), dtype=out.dtype, device=out.device)
+            self._recv = torch.empty((self.world * rows, maxc), dtype=out.dtype, device=out.device)
+        packed = self.engine.pack_columns(out, b0, b1)
+        self._send[:, :packed.shape[1]] = packed
+        dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+        recv = self._recv.view(self.world, rows, maxc)
+        for r, (rb0, rb1) in enumerate(self.ranges):
+            if r != self.rank and self.ncols[r] > 0:
+                self.engine.unpack_columns(recv[r, :, :self.ncols[r]].contiguous(), rb0, rb1, out)
+        return out
