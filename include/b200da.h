@@ -65,6 +65,13 @@ typedef enum {
 
 typedef enum { B200DA_F64 = 0, B200DA_F32 = 1 } b200da_dtype;
 
+/* How the k x k ensemble-space problem of every grid point is solved (both replace core/utils.py:26-93 +
+ * core/etkf.py:57-77 and agree to rounding):
+ *   NEWTON_SCHULZ  (default) (C + aI)^(-1/2) by a scaled coupled Newton-Schulz iteration: k x k x k products on the
+ *                  FP64 tensor pipe, one warp per matrix up to k = 56;
+ *   JACOBI         shared-memory parallel cyclic-Jacobi eigendecomposition (k <= 111). */
+typedef enum { B200DA_SOLVER_NEWTON_SCHULZ = 0, B200DA_SOLVER_JACOBI = 1 } b200da_solver;
+
 /* ---- plan ------------------------------------------------------------------------------------------------ */
 
 /* Replaces the constructor state of LETKF(localization=GaspariCohn(length_scale, dist_func, epsilon),
@@ -165,6 +172,8 @@ float b200da_last_phase_ms(b200da_plan* plan, int which);
  * out16 = {sum of Gram-phase cycles over CTAs, sum of EVD+transform+update cycles, Jacobi sweeps, EVDs,
  *         set-up cycles, staged tiles, 0, 0, Jacobi step profile x5, 0, 0, 0}.  b200da_get_stats synchronises the device. */
 int b200da_collect_stats(b200da_plan* plan, int on);
+/* choose the ensemble-space solver of b200da_letkf (b200da_solver) */
+int b200da_set_solver(b200da_plan* plan, int solver);
 int b200da_get_stats(b200da_plan* plan, int64_t* out8);
 
 #ifdef __cplusplus

@@ -28,11 +28,12 @@ def _metrics():
     return metrics
 
 
-def _run(data, metric, radius, rho, taper="gc", eps=1e-5, weights=False):
+def _run(data, metric, radius, rho, taper="gc", eps=1e-5, weights=False, solver="newton"):
     st = data["state"]
     n_slices = st.shape[0] * st.shape[1]
     k = st.shape[2]
     eng = _engine(k, n_slices, metric, radius, inf_factor=rho, taper=taper, epsilon=eps)
+    eng.set_solver(solver)
     eng.set_grid(data["grid_rows"][:, 1:])
     eng.bin_obs(data["obs_rows"][:, 1:], data["normed_perts"], data["normed_obs"])
     x = torch.as_tensor(st.reshape(n_slices, k, -1)).cuda()
@@ -139,13 +140,15 @@ SYNTH = {
 }
 
 
+@pytest.mark.parametrize("solver", ["newton", "jacobi"])
 @pytest.mark.parametrize("name", sorted(SYNTH))
-def test_synthetic_configs_against_reference(golden, name):
-    """BASELINE.json configurations (scaled) against outputs of the reference's own hot loop."""
+def test_synthetic_configs_against_reference(golden, name, solver):
+    """BASELINE.json configurations (scaled) against outputs of the reference's own hot loop, for both ensemble-space
+    solvers (tensor-core Newton-Schulz inverse square root, shared-memory Jacobi eigendecomposition)."""
     g = golden(name)
     data, metric = SYNTH[name](g, _metrics())
     sel = g["sel"]
-    eng, xa, w, namb = _run(data, metric, float(g["radius"]), float(g["rho"]), weights=True)
+    eng, xa, w, namb = _run(data, metric, float(g["radius"]), float(g["rho"]), weights=True, solver=solver)
     assert namb == 0
     np.testing.assert_allclose(xa[..., sel], g["analysis"], rtol=RTOL, atol=ATOL)
     nw = g["weights"].shape[0]
@@ -153,13 +156,18 @@ def test_synthetic_configs_against_reference(golden, name):
     _check_lists(eng, g["csr_off"], g["csr_idx"], sel=sel, w_ref=g["csr_w"])
 
 
-@pytest.mark.parametrize("k,n_grid,stride,radius", [(3, 64, 1, 2.5), (8, 300, 3, 4.0), (23, 500, 2, 7.0),
-                                                    (32, 257, 1, 30.0), (64, 300, 1, 12.0), (100, 96, 1, 6.0)])
-def test_ensemble_sizes_against_oracle(k, n_grid, stride, radius):
-    """Every kernel configuration (tiles 1..13, 1/2/4/8 warps per grid point) against the oracle."""
+@pytest.mark.parametrize("solver", ["newton", "jacobi"])
+@pytest.mark.parametrize("k,n_grid,stride,radius", [(2, 40, 1, 3.0), (3, 64, 1, 2.5), (8, 300, 3, 4.0), (16, 200, 1, 9.0),
+                                                    (23, 500, 2, 7.0), (32, 257, 1, 30.0), (40, 300, 2, 20.0),
+                                                    (56, 200, 1, 10.0), (57, 200, 1, 10.0), (64, 300, 1, 12.0),
+                                                    (72, 150, 1, 15.0), (80, 120, 1, 11.0), (88, 100, 1, 9.0),
+                                                    (100, 96, 1, 6.0), (111, 64, 1, 8.0)])
+def test_ensemble_sizes_against_oracle(k, n_grid, stride, radius, solver):
+    """Every kernel configuration (tiles 1..14; 1/2/4/8 Gram warps per grid point; 1/2/4 solve warps per matrix) against
+    the oracle, for both ensemble-space solvers."""
     m = _metrics()
     data = syn.lorenz96_1d(n_grid, k, stride, seed=100 + k)
-    eng, xa, w, namb = _run(data, m.PeriodicDistance1D(float(n_grid)), radius, 1.07, weights=True)
+    eng, xa, w, namb = _run(data, m.PeriodicDistance1D(float(n_grid)), radius, 1.07, weights=True, solver=solver)
     ref, wref, lists = orc.letkf_analysis(data["state"], data["normed_perts"], data["normed_obs"], data["grid_rows"],
                                           data["obs_rows"], orc.make_dist_periodic1d(float(n_grid)), radius,
                                           inf_factor=1.07, return_lists=True)
@@ -241,3 +249,18 @@ def test_full_size_properties_cfg2():
     rolled["normed_obs"] = np.roll(data["normed_obs"], 1)
     _, xar, _, _ = _run(rolled, m.PeriodicDistance1D(100_000.0), 20.0, 1.1)
     np.testing.assert_allclose(np.roll(xar, -2, axis=-1), xa, rtol=1e-11, atol=1e-11)
+
+
+def test_analysis_is_deterministic():
+    """Two runs on the same inputs are bit-identical (no order-dependent reductions, no races): 20k grid points on the
+    sphere so that many CTAs of both kernels are in flight."""
+    m = _metrics()
+    data = syn.sphere_latlon(100, 200, 50, 20_000, seed=5)
+    _, xa1, w1, _ = _run(data, m.HaversineDistance(6371.0), 1000.0, 1.1, weights=True)
+    _, xa2, w2, _ = _run(data, m.HaversineDistance(6371.0), 1000.0, 1.1, weights=True)
+    np.testing.assert_array_equal(xa1, xa2)
+    np.testing.assert_array_equal(w1, w2)
+    sel = np.arange(0, 20_000, 1999)
+    ref, _ = orc.letkf_analysis(data["state"], data["normed_perts"], data["normed_obs"], data["grid_rows"],
+                                data["obs_rows"], orc.make_dist_haversine(6371.0), 1000.0, inf_factor=1.1, grid_subset=sel)
+    np.testing.assert_allclose(xa1[..., sel], ref, rtol=RTOL, atol=ATOL)

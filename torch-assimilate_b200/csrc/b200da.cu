@@ -5,6 +5,8 @@
 #include "etkf_kernel.cuh"
 #include "letkf_kernel.cuh"
 #include "neighbour_kernel.cuh"
+#include "ns_solve_kernel.cuh"
+#include "launch.cuh"
 
 namespace b200da {
 thread_local std::string g_last_cuda_error;
@@ -44,30 +46,6 @@ static KernelConfig config_for_kt(int kt) {
     return {2, 8};
 }
 constexpr int kMaxKt = 14;
-constexpr size_t kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
-
-template <int KT, int G, int WPG>
-static int launch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st) {
-    const size_t hdr = (sizeof(BlockHeader<G>) + 31) & ~size_t(31);
-    const size_t smem = hdr + gram_smem_bytes<KT, G, WPG>();
-    if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
-    auto kern = k_letkf_gram<KT, G, WPG>;
-    B200DA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<nblocks, G * WPG * 32, smem, st>>>(P);
-    B200DA_LAUNCH_CHECK();
-    return B200DA_OK;
-}
-
-#define B200DA_KT_CASE(KT, G, WPG) case KT: return launch_fused<KT, G, WPG>(pl, P, nblocks, st);
-static int dispatch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st) {
-    switch (pl->kt) {
-        B200DA_KT_CASE(1, 8, 1) B200DA_KT_CASE(2, 8, 1) B200DA_KT_CASE(3, 8, 1) B200DA_KT_CASE(4, 8, 1)
-        B200DA_KT_CASE(5, 8, 1) B200DA_KT_CASE(6, 8, 2) B200DA_KT_CASE(7, 8, 2) B200DA_KT_CASE(8, 4, 4)
-        B200DA_KT_CASE(9, 4, 4) B200DA_KT_CASE(10, 4, 4) B200DA_KT_CASE(11, 2, 8) B200DA_KT_CASE(12, 2, 8)
-        B200DA_KT_CASE(13, 2, 8) B200DA_KT_CASE(14, 2, 8)
-        default: return B200DA_ERR_UNSUPPORTED;
-    }
-}
 
 template <int KT>
 static int launch_etkf_gram(const double* yn, const double* d, int64_t m, int k, int ncta, int64_t chunk, double* partial,
@@ -199,7 +177,7 @@ void b200da_plan_destroy(b200da_plan* pl) {
     DevBuf* bufs[] = {&pl->gpos, &pl->gorder, &pl->block_off, &pl->opos, &pl->cell_start, &pl->ys, &pl->tmp_keys,
                       &pl->tmp_cell, &pl->tmp_count, &pl->tmp_a, &pl->tmp_b, &pl->tmp_pos, &pl->host_stage_obs,
                       &pl->host_stage_y, &pl->host_stage_d, &pl->host_stage_x, &pl->host_stage_xa, &pl->etkf_partial,
-                      &pl->etkf_w, &pl->stats, &pl->cmat};
+                      &pl->etkf_w, &pl->stats, &pl->cmat, &pl->counter};
     for (cudaEvent_t ev : pl->ev_pool) cudaEventDestroy(ev);
     for (DevBuf* b : bufs) b->release();
     if (pl->ev0) cudaEventDestroy(pl->ev0);
@@ -258,12 +236,19 @@ int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t 
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int k = pl->k;
-    const size_t per_slot = sizeof(double) * (size_t)(k + 1) * k;
+    const int64_t slot_stride = (int64_t)tri_tiles(pl->kt) * 64;           // doubles per grid slot of the Gram scratch
+    const size_t per_slot = sizeof(double) * (size_t)slot_stride;
+    const bool jacobi = pl->solver == B200DA_SOLVER_JACOBI;
     const size_t smem_solve = solve_smem_bytes(k);
-    if (smem_solve > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
     const bool big = k > 64;
-    if (big) B200DA_CUDA(cudaFuncSetAttribute(k_letkf_solve<512, 1, 2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
-    else B200DA_CUDA(cudaFuncSetAttribute(k_letkf_solve<256, 2, 1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    if (jacobi) {
+        if (smem_solve > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
+        if (big) B200DA_CUDA(cudaFuncSetAttribute(k_letkf_solve<512, 1, 2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+        else B200DA_CUDA(cudaFuncSetAttribute(k_letkf_solve<256, 2, 1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    } else {
+        int rc = pl->counter.ensure(sizeof(unsigned int) * 4);
+        if (rc) return rc;
+    }
     // chunk the block range so that the Gram scratch stays below ~2 GiB
     const int64_t max_slots = std::max<int64_t>(pl->gpb, (int64_t)((size_t(2) << 30) / per_slot));
     if (pl->timing) { B200DA_CUDA(cudaEventRecord(pl->ev0, st)); pl->gram_ms = 0.f; pl->solve_ms = 0.f; pl->n_ev = 0; }
@@ -286,13 +271,22 @@ int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t 
         }
         if ((rc = dispatch_fused(pl, P, (int)(e - b), st))) return rc;
         if (pl->timing) B200DA_CUDA(cudaEventRecord(eb, st));
-        SolveParams S{};
-        S.cmat = P.cmat; S.gpos = P.gpos; S.x = P.x; S.xa = P.xa; S.w_out = P.w_out; S.stats = P.stats;
-        S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = pl->rho;
-        const int grid = (int)std::min<int64_t>(n_slots, 148 * 64);
-        if (big) k_letkf_solve<512, 1, 2, 4, 4><<<grid, 512, smem_solve, st>>>(S);
-        else k_letkf_solve<256, 2, 1, 4, 2><<<grid, 256, smem_solve, st>>>(S);
-        B200DA_LAUNCH_CHECK();
+        if (jacobi) {
+            SolveParams S{};
+            S.cmat = P.cmat; S.slot_stride = slot_stride; S.gpos = P.gpos; S.x = P.x; S.xa = P.xa; S.w_out = P.w_out; S.stats = P.stats;
+            S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = pl->rho;
+            const int grid = (int)std::min<int64_t>(n_slots, 148 * 64);
+            if (big) k_letkf_solve<512, 1, 2, 4, 4><<<grid, 512, smem_solve, st>>>(S);
+            else k_letkf_solve<256, 2, 1, 4, 2><<<grid, 256, smem_solve, st>>>(S);
+            B200DA_LAUNCH_CHECK();
+        } else {
+            B200DA_CUDA(cudaMemsetAsync(pl->counter.p, 0, sizeof(unsigned int) * 4, st));
+            NsParams S{};
+            S.cmat = P.cmat; S.slot_stride = slot_stride; S.gpos = P.gpos; S.x = P.x; S.xa = P.xa; S.w_out = P.w_out; S.stats = P.stats;
+            S.counter = pl->counter.as<unsigned int>();
+            S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = pl->rho;
+            if ((rc = dispatch_ns((k + 7) / 8, S, st))) return rc;
+        }
         if (pl->timing) B200DA_CUDA(cudaEventRecord(ec, st));
         b = e;
     }
@@ -431,6 +425,13 @@ int b200da_pack_columns(b200da_plan* pl, const void* Xa, int64_t b0, int64_t b1,
 }
 int b200da_unpack_columns(b200da_plan* pl, const void* packed, int64_t b0, int64_t b1, void* Xa, void* stream) {
     return pack_impl(pl, Xa, b0, b1, const_cast<void*>(packed), 1, (cudaStream_t)stream);
+}
+
+int b200da_set_solver(b200da_plan* pl, int solver) {
+    if (!pl) return B200DA_ERR_INVALID;
+    if (solver != B200DA_SOLVER_NEWTON_SCHULZ && solver != B200DA_SOLVER_JACOBI) return B200DA_ERR_UNSUPPORTED;
+    pl->solver = solver;
+    return B200DA_OK;
 }
 
 int b200da_collect_stats(b200da_plan* pl, int on) { if (!pl) return B200DA_ERR_INVALID; pl->collect_stats = on != 0; return B200DA_OK; }

@@ -187,4 +187,14 @@ __device__ __forceinline__ double pair_weight(const Geometry& g, double gx, doub
     return (w > g.eps) ? w : 0.0;                          // gaspari_cohn.py:135
 }
 
+// ---- tile-packed symmetric matrices ----------------------------------------------------------------------------
+// Lower-triangle 8x8 tiles, tile (mt, nt), nt <= mt, at ((mt (mt+1))/2 + nt) * 64 doubles; element (r, c) of a tile at
+// r * 8 + (c ^ ((r & 2) << 1)).  The XOR makes both the direct and the transposed DMMA fragment reads of a tile
+// bank-conflict free.  This is the hand-over format between the Gram kernel and the solve kernels.
+__host__ __device__ constexpr int tri_tiles(int kt) { return kt * (kt + 1) / 2; }
+__host__ __device__ constexpr int tile_off(int mt, int nt) { return (mt * (mt + 1) / 2 + nt) * 64; }   // nt <= mt
+__host__ __device__ constexpr int tile_elem(int r, int c) { return r * 8 + (c ^ ((r & 2) << 1)); }
+// offset of element (i, j), j <= i
+__host__ __device__ constexpr int sym_off(int i, int j) { return tile_off(i >> 3, j >> 3) + tile_elem(i & 7, j & 7); }
+
 }  // namespace b200da

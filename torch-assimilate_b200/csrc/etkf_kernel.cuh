@@ -3,6 +3,7 @@
 // interface/base.py:257-278 (update).
 #pragma once
 #include "letkf_kernel.cuh"
+#include "solve_kernel.cuh"
 
 namespace b200da {
 

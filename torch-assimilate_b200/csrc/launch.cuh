@@ -1,0 +1,14 @@
+// Kernel dispatchers that live in their own translation units (gram_launch.cu, ns_launch.cu).
+#pragma once
+#include "plan.cuh"
+
+namespace b200da {
+
+constexpr size_t kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
+
+struct LetkfParams;
+struct NsParams;
+int dispatch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st);
+int dispatch_ns(int kts, const NsParams& P, cudaStream_t st);
+
+}  // namespace b200da

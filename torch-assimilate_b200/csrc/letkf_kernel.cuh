@@ -18,7 +18,6 @@
 // (w y)(y)^T equals (sqrt(w) y)(sqrt(w) y)^T of the reference up to rounding.
 #pragma once
 #include "plan.cuh"
-#include "solve_kernel.cuh"
 
 namespace b200da {
 
@@ -38,7 +37,7 @@ struct LetkfParams {
     double* w_out;             // (N, k, k) or null
     unsigned long long* n_ambiguous;   // or null
     unsigned long long* stats;         // or null: [0] gram cycles [1] evd cycles [2] sweeps [3] evds [4] setup cycles [5] tiles
-    double* cmat;                      // scratch: per grid slot the augmented Gram [(k+1)][k], lower triangle + row k = b
+    double* cmat;                      // scratch: per grid slot the tile-packed augmented Gram (rows 0..k-1 = C, row k = b)
     int64_t slot_base;                 // first grid slot of the chunk held in cmat
     int64_t n_grid;
     int64_t n_obs;
@@ -113,22 +112,19 @@ __device__ __forceinline__ void dump_tiles(const double (&acc)[(KT * (KT + 1) / 
     }
 }
 
-// accumulators -> global scratch: C[(k+1)][k] row-major per grid slot (rows 0..k-1 lower triangle, row k = b)
+// accumulators -> global scratch in the tile-packed layout (common.cuh): one 512-byte tile per accumulator pair set,
+// rows 0..k-1 = C (diagonal tiles hold the full 8x8 product), row k = b
 template <int KT, int WPG, int SUB>
 __device__ __forceinline__ void dump_tiles_global(const double (&acc)[(KT * (KT + 1) / 2 + WPG - 1) / WPG][2],
-                                                  double* __restrict__ C, int k, int lane) {
+                                                  double* __restrict__ C, int lane) {
+    const int r = lane >> 2, c = (lane & 3) * 2;
     int idx = 0, n = 0;
 #pragma unroll
     for (int mt = 0; mt < KT; ++mt) {
 #pragma unroll
         for (int nt = 0; nt <= mt; ++nt) {
             if (idx % WPG == SUB) {
-                const int r = mt * 8 + (lane >> 2);
-                const int c = nt * 8 + (lane & 3) * 2;
-                if (r <= k) {
-                    if (c < k) C[(size_t)r * k + c] = acc[n][0];
-                    if (c + 1 < k) C[(size_t)r * k + c + 1] = acc[n][1];
-                }
+                *reinterpret_cast<double2*>(C + tile_off(mt, nt) + tile_elem(r, c)) = make_double2(acc[n][0], acc[n][1]);
                 ++n;
             }
             ++idx;
@@ -366,29 +362,28 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
     // hand the augmented Gram matrices to the solve kernel through the (L2-resident) scratch
     // ------------------------------------------------------------------------------------------------------------
     if (my_g < ng) {
-        const int k = P.k;
-        double* C = P.cmat + (size_t)((int64_t)P.block_off[blk] + my_g - P.slot_base) * (size_t)(k + 1) * k;
-        if constexpr (WPG == 1) dump_tiles_global<KT, WPG, 0>(acc, C, k, lane);
+        double* C = P.cmat + (size_t)((int64_t)P.block_off[blk] + my_g - P.slot_base) * (size_t)(NTILES * 64);
+        if constexpr (WPG == 1) dump_tiles_global<KT, WPG, 0>(acc, C, lane);
         else if constexpr (WPG == 2) {
-            if (my_sub == 0) dump_tiles_global<KT, WPG, 0>(acc, C, k, lane);
-            else dump_tiles_global<KT, WPG, 1>(acc, C, k, lane);
+            if (my_sub == 0) dump_tiles_global<KT, WPG, 0>(acc, C, lane);
+            else dump_tiles_global<KT, WPG, 1>(acc, C, lane);
         } else if constexpr (WPG == 4) {
             switch (my_sub) {
-                case 0: dump_tiles_global<KT, WPG, 0>(acc, C, k, lane); break;
-                case 1: dump_tiles_global<KT, WPG, 1>(acc, C, k, lane); break;
-                case 2: dump_tiles_global<KT, WPG, 2>(acc, C, k, lane); break;
-                default: dump_tiles_global<KT, WPG, 3>(acc, C, k, lane); break;
+                case 0: dump_tiles_global<KT, WPG, 0>(acc, C, lane); break;
+                case 1: dump_tiles_global<KT, WPG, 1>(acc, C, lane); break;
+                case 2: dump_tiles_global<KT, WPG, 2>(acc, C, lane); break;
+                default: dump_tiles_global<KT, WPG, 3>(acc, C, lane); break;
             }
         } else {
             switch (my_sub) {
-                case 0: dump_tiles_global<KT, WPG, 0>(acc, C, k, lane); break;
-                case 1: dump_tiles_global<KT, WPG, 1>(acc, C, k, lane); break;
-                case 2: dump_tiles_global<KT, WPG, 2>(acc, C, k, lane); break;
-                case 3: dump_tiles_global<KT, WPG, 3>(acc, C, k, lane); break;
-                case 4: dump_tiles_global<KT, WPG, 4>(acc, C, k, lane); break;
-                case 5: dump_tiles_global<KT, WPG, 5>(acc, C, k, lane); break;
-                case 6: dump_tiles_global<KT, WPG, 6>(acc, C, k, lane); break;
-                default: dump_tiles_global<KT, WPG, 7>(acc, C, k, lane); break;
+                case 0: dump_tiles_global<KT, WPG, 0>(acc, C, lane); break;
+                case 1: dump_tiles_global<KT, WPG, 1>(acc, C, lane); break;
+                case 2: dump_tiles_global<KT, WPG, 2>(acc, C, lane); break;
+                case 3: dump_tiles_global<KT, WPG, 3>(acc, C, lane); break;
+                case 4: dump_tiles_global<KT, WPG, 4>(acc, C, lane); break;
+                case 5: dump_tiles_global<KT, WPG, 5>(acc, C, lane); break;
+                case 6: dump_tiles_global<KT, WPG, 6>(acc, C, lane); break;
+                default: dump_tiles_global<KT, WPG, 7>(acc, C, lane); break;
             }
         }
     }

@@ -1,0 +1,381 @@
+// K3b — ETKF transform by a tensor-core matrix iteration, then the state update.
+//
+// The reference obtains P~a = (C + aI)^-1 and W_p = ((k-1) (C + aI)^-1)^(1/2), a = (k-1)/rho, from a symmetric
+// eigendecomposition of C (pytassim/core/utils.py:26-93, core/etkf.py:57-77).  Only these two symmetric functions
+// of C are used, so this kernel computes Z = (C + aI)^(-1/2) directly with the coupled Newton-Schulz iteration
+//
+//     M = Z Y,  T = (3 I - g M) / 2,  Z <- sqrt(g) T Z,  Y <- sqrt(g) Y T        (Y0 = A / s, Z0 = I, A = C + aI)
+//
+// (Higham, Functions of Matrices, eq. 6.35, with the scaling g chosen from a tracked spectral interval), which is
+// nothing but k x k x k matrix products: they run on the FP64 tensor pipe (DMMA m8n8k4) instead of the
+// shared-memory-bandwidth-bound rotations of a Jacobi sweep.  Then
+//
+//     w_mean = Z (Z b) / s,  W_p = sqrt((k-1) / s) Z,  W = w_mean 1^T + W_p     (core/etkf.py:72-77,102)
+//     x_a = mean + (x - mean) W                                                   (interface/base.py:257-278)
+//
+// Spectrum.  C is a Gram matrix, so eig(A) lies in [a, s] with s = min(||A||_F, ||A||_inf); the reference's
+// clamp(min=0) (core/utils.py:58) only removes rounding noise of the same size as this kernel's own rounding.
+// With mu = eig(g M) in [g lo, g], g = 3 / (1 + sqrt(lo) + lo) equalises f(g lo) = f(g), f(mu) = mu (3 - mu)^2 / 4,
+// which is the largest lower bound reachable in one step; lo <- f(g lo).  The iteration count follows from the
+// bound alone (no data-dependent test): it stops when 1 - lo < 2e-8, i.e. when the next step leaves an error
+// of order (1 - lo)^2 below the FP64 rounding level.
+//
+// Layout.  Every matrix of the iteration is a polynomial in A, hence symmetric: only the lower-triangle 8x8
+// tiles are stored (tile (mt, nt), nt <= mt, at ((mt (mt+1))/2 + nt) * 64 doubles; element (r, c) of a tile at
+// r * 8 + (c ^ ((r & 2) << 1)): the XOR makes both the direct and the transposed DMMA fragment reads
+// bank-conflict free).  The Gram kernel writes its accumulators to global memory in exactly this layout, so
+// loading a matrix is a flat copy.  One group of WPM warps owns one matrix (WPM = 1 up to k = 56: no CTA-wide
+// barrier anywhere in the iteration); a CTA holds several groups, each fetching grid slots from an atomic counter.
+#pragma once
+#include "plan.cuh"
+
+namespace b200da {
+
+__device__ __forceinline__ double sym_get(const double* __restrict__ S, int i, int j) {
+    return i >= j ? S[sym_off(i, j)] : S[sym_off(j, i)];
+}
+
+__device__ __forceinline__ void dmma884_ns(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct FragOff { int d0, d1, t0, t1; };      // per-lane offsets inside a tile: direct / transposed, k-step 0 / 1
+__device__ __forceinline__ FragOff make_frag_off(int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    FragOff f;
+    f.d0 = tile_elem(r, q); f.d1 = tile_elem(r, 4 + q);
+    f.t0 = tile_elem(q, r); f.t1 = tile_elem(4 + q, r);
+    return f;
+}
+
+template <int KT, int WPM>
+struct NsCfg {
+    static constexpr int NT = tri_tiles(KT);
+    static constexpr int OWN = (NT + WPM - 1) / WPM;           // accumulator tiles per warp
+    static constexpr int KP = KT * 8;
+    static constexpr int MAT = NT * 64;                        // doubles per matrix
+    static constexpr int LDW = KP + 1;                         // dense W overlay (odd: conflict-free rows and columns)
+    static constexpr int VEC = 4 * KP + 8;                     // b, u, w_mean, xbuf (+ reduction scratch)
+    static constexpr size_t GROUP_BYTES = sizeof(double) * (3 * (size_t)MAT + VEC);
+    static_assert(2 * MAT >= KP * LDW, "dense overlay must fit in two tile-packed matrices");
+};
+
+template <int KT, int WPM, int SUB>
+__device__ __forceinline__ constexpr bool tile_owned(int idx) {
+    return idx >= tri_tiles(KT) * SUB / WPM && idx < tri_tiles(KT) * (SUB + 1) / WPM;
+}
+
+// rows [t*8, t*8+8) x columns [kt*8 + ks*4, +4) of the symmetric matrix S as a DMMA A-fragment (equally the
+// B-fragment of S used as right operand, because S is symmetric): read directly from tile (t, kt) when kt <= t,
+// transposed from tile (kt, t) otherwise.  t is a compile-time constant after unrolling, kt a loop variable.
+template <int KS>
+__device__ __forceinline__ double sym_frag(const double* __restrict__ S, int t, int kt, const FragOff& fo) {
+    const int off = kt <= t ? tile_off(t, kt) + (KS ? fo.d1 : fo.d0) : tile_off(kt, t) + (KS ? fo.t1 : fo.t0);
+    return S[off];
+}
+
+template <int KT, int WPM, int SUB, int KS>
+__device__ __forceinline__ void gemm_kstep(const double* __restrict__ L, const double* __restrict__ R, int kt,
+                                           const FragOff& fo, double (&acc)[NsCfg<KT, WPM>::OWN][2]) {
+    double fl[KT], fr[KT];
+#pragma unroll
+    for (int t = 0; t < KT; ++t) {            // fragments of rows / columns this warp does not own are dead code
+        fl[t] = sym_frag<KS>(L, t, kt, fo);
+        fr[t] = sym_frag<KS>(R, t, kt, fo);
+    }
+    int idx = 0, n = 0;
+#pragma unroll
+    for (int mt = 0; mt < KT; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt <= mt; ++nt) {
+            if (tile_owned<KT, WPM, SUB>(idx)) { dmma884_ns(acc[n][0], acc[n][1], fl[mt], fr[nt]); ++n; }
+            ++idx;
+        }
+    }
+}
+
+// acc = lower-triangle tiles (owned by warp SUB of the group) of L R for symmetric, commuting L and R
+template <int KT, int WPM, int SUB>
+__device__ __forceinline__ void sym_gemm_sub(const double* __restrict__ L, const double* __restrict__ R, const FragOff& fo,
+                                             double (&acc)[NsCfg<KT, WPM>::OWN][2]) {
+#pragma unroll
+    for (int i = 0; i < NsCfg<KT, WPM>::OWN; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+#pragma unroll 1
+    for (int kt = 0; kt < KT; ++kt) {
+        gemm_kstep<KT, WPM, SUB, 0>(L, R, kt, fo, acc);
+        gemm_kstep<KT, WPM, SUB, 1>(L, R, kt, fo, acc);
+    }
+}
+
+template <int KT, int WPM>
+__device__ __forceinline__ void sym_gemm(int sub, const double* __restrict__ L, const double* __restrict__ R,
+                                         const FragOff& fo, double (&acc)[NsCfg<KT, WPM>::OWN][2]) {
+    if constexpr (WPM == 1) sym_gemm_sub<KT, 1, 0>(L, R, fo, acc);
+    else if constexpr (WPM == 2) {
+        if (sub == 0) sym_gemm_sub<KT, 2, 0>(L, R, fo, acc); else sym_gemm_sub<KT, 2, 1>(L, R, fo, acc);
+    } else {
+        switch (sub) {
+            case 0: sym_gemm_sub<KT, 4, 0>(L, R, fo, acc); break;
+            case 1: sym_gemm_sub<KT, 4, 1>(L, R, fo, acc); break;
+            case 2: sym_gemm_sub<KT, 4, 2>(L, R, fo, acc); break;
+            default: sym_gemm_sub<KT, 4, 3>(L, R, fo, acc); break;
+        }
+    }
+}
+
+// S <- scale * acc + diag * I over the warp's tiles; diagonal tiles are written symmetrically from their lower half
+template <int KT, int WPM, int SUB>
+__device__ __forceinline__ void store_tiles_sub(double* __restrict__ S, const double (&acc)[NsCfg<KT, WPM>::OWN][2],
+                                            double scale, double diag, int lane) {
+    const int r = lane >> 2, c = (lane & 3) * 2;
+    int idx = 0, n = 0;
+#pragma unroll
+    for (int mt = 0; mt < KT; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt <= mt; ++nt) {
+            if (tile_owned<KT, WPM, SUB>(idx)) {
+                double* tp = S + tile_off(mt, nt);
+                const double v0 = acc[n][0] * scale, v1 = acc[n][1] * scale;
+                if (mt != nt) {
+                    *reinterpret_cast<double2*>(tp + tile_elem(r, c)) = make_double2(v0, v1);
+                } else {
+                    if (c < r) { tp[tile_elem(r, c)] = v0; tp[tile_elem(c, r)] = v0; }
+                    else if (c == r) tp[tile_elem(r, c)] = v0 + diag;
+                    if (c + 1 < r) { tp[tile_elem(r, c + 1)] = v1; tp[tile_elem(c + 1, r)] = v1; }
+                    else if (c + 1 == r) tp[tile_elem(r, c + 1)] = v1 + diag;
+                }
+                ++n;
+            }
+            ++idx;
+        }
+    }
+}
+
+template <int KT, int WPM>
+__device__ __forceinline__ void store_tiles(int sub, double* __restrict__ S, const double (&acc)[NsCfg<KT, WPM>::OWN][2],
+                                            double scale, double diag, int lane) {
+    if constexpr (WPM == 1) store_tiles_sub<KT, 1, 0>(S, acc, scale, diag, lane);
+    else if constexpr (WPM == 2) {
+        if (sub == 0) store_tiles_sub<KT, 2, 0>(S, acc, scale, diag, lane); else store_tiles_sub<KT, 2, 1>(S, acc, scale, diag, lane);
+    } else {
+        switch (sub) {
+            case 0: store_tiles_sub<KT, 4, 0>(S, acc, scale, diag, lane); break;
+            case 1: store_tiles_sub<KT, 4, 1>(S, acc, scale, diag, lane); break;
+            case 2: store_tiles_sub<KT, 4, 2>(S, acc, scale, diag, lane); break;
+            default: store_tiles_sub<KT, 4, 3>(S, acc, scale, diag, lane); break;
+        }
+    }
+}
+
+struct NsParams {
+    const double* cmat;        // [n_slots][slot_stride]: tile-packed augmented Gram (rows 0..k-1 = C, row k = b)
+    const Pos4* gpos;          // block-sorted grid positions (id = original index)
+    const double* x;
+    double* xa;
+    double* w_out;
+    unsigned int* counter;     // zeroed before the launch: next slot to solve
+    unsigned long long* stats; // or null: [1] solve cycles [2] iterations [3] solves
+    int64_t slot_base;
+    int64_t n_slots;
+    int64_t n_grid;
+    int64_t slot_stride;       // doubles per slot in cmat
+    int k;
+    int n_slices;
+    double rho;
+};
+
+template <int WPM>
+__device__ __forceinline__ void ns_sync(int bar_id) {
+    if constexpr (WPM == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(WPM * 32) : "memory");
+}
+
+// One matrix: everything between "augmented Gram in global memory" and "analysis columns written".
+template <int KT, int WPM>
+__device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict__ Z, double* __restrict__ Y,
+                             double* __restrict__ T, double* __restrict__ vec, int gtid, int sub, int lane, int bar_id) {
+    using Cfg = NsCfg<KT, WPM>;
+    constexpr int GT = WPM * 32, KP = Cfg::KP, MAT = Cfg::MAT, LDW = Cfg::LDW;
+    const int k = P.k;
+    double* bvec = vec;                 // [KP]
+    double* uvec = vec + KP;            // [KP]
+    double* wbar = vec + 2 * KP;        // [KP]
+    double* xbuf = vec + 3 * KP;        // [KP]
+    double* red = vec + 4 * KP;         // [8] cross-warp reduction scratch
+    const double* gC = P.cmat + (size_t)slot * (size_t)P.slot_stride;
+    const double alpha = (double)(k - 1) / P.rho;
+    const FragOff fo = make_frag_off(lane);
+
+    // ---- load: flat copy of the lower-triangle tiles, b from row k ---------------------------------------------------
+    for (int e = gtid * 2; e < MAT; e += GT * 2)
+        *reinterpret_cast<double2*>(Y + e) = *reinterpret_cast<const double2*>(gC + e);
+    for (int c = gtid; c < KP; c += GT) bvec[c] = c < k ? gC[sym_off(k, c)] : 0.0;
+    ns_sync<WPM>(bar_id);
+    // ---- fix-up: zero the padding (and the b row if it shares the last tile row), mirror diagonal tiles, add a I -------
+    if ((k & 7) != 0) {
+        constexpr int MT = KT - 1;
+        for (int e = gtid; e < KT * 64; e += GT) {
+            const int nt = e >> 6, r = (e >> 3) & 7, c = e & 7;
+            if (MT * 8 + r >= k || nt * 8 + c >= k) Y[tile_off(MT, nt) + tile_elem(r, c)] = 0.0;
+        }
+        ns_sync<WPM>(bar_id);
+    }
+    for (int e = gtid; e < KT * 64; e += GT) {
+        const int mt = e >> 6, r = (e >> 3) & 7, c = e & 7;
+        double* tp = Y + tile_off(mt, mt);
+        if (c > r) tp[tile_elem(r, c)] = tp[tile_elem(c, r)];
+        else if (c == r && mt * 8 + r < k) tp[tile_elem(r, c)] += alpha;
+    }
+    ns_sync<WPM>(bar_id);
+    // ---- s = min(||A||_F, ||A||_inf) -------------------------------------------------------------------------------
+    double rs_max = 0.0, sq = 0.0;
+    for (int i = gtid; i < k; i += GT) {
+        double rs = 0.0;
+        for (int j = 0; j < k; ++j) { const double a = sym_get(Y, i, j); rs += fabs(a); sq = fma(a, a, sq); }
+        rs_max = fmax(rs_max, rs);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        rs_max = fmax(rs_max, __shfl_xor_sync(0xffffffffu, rs_max, off));
+        sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    }
+    if constexpr (WPM > 1) {
+        if (lane == 0) { red[sub] = rs_max; red[4 + sub] = sq; }
+        ns_sync<WPM>(bar_id);
+        rs_max = red[0]; sq = red[4];
+#pragma unroll
+        for (int w = 1; w < WPM; ++w) { rs_max = fmax(rs_max, red[w]); sq += red[4 + w]; }
+    }
+    const double s = fmin(sqrt(sq), rs_max) * (1.0 + 1e-12);
+    const double inv_s = 1.0 / s;
+    // ---- iteration 0 (Z0 = I): T = (3 I - g Y0) / 2, Z1 = sqrt(g) T, Y1 = sqrt(g) Y0 T ---------------------------------
+    double lo = fmin(alpha * inv_s, 1.0);
+    double g = 3.0 / (1.0 + sqrt(lo) + lo);
+    double sg = sqrt(g);
+    for (int e = gtid; e < MAT; e += GT) {
+        const int tile = e >> 6, r = (e >> 3) & 7, c = (e & 7) ^ ((r & 2) << 1);   // e = tile*64 + tile_elem(r, c)
+        // tile -> (mt, nt): diagonal tiles sit at mt (mt + 3) / 2
+        int mt = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
+        while (mt * (mt + 1) / 2 > tile) --mt;
+        while ((mt + 1) * (mt + 2) / 2 <= tile) ++mt;
+        const int nt = tile - mt * (mt + 1) / 2;
+        const bool on_diag = (mt == nt) && (r == c);
+        double y = Y[e] * inv_s;
+        if (on_diag && mt * 8 + r >= k) y = 1.0;                 // padding: decoupled unit eigenvalues
+        const double t = fma(-0.5 * g, y, on_diag ? 1.5 : 0.0);
+        Y[e] = y; T[e] = t; Z[e] = sg * t;
+    }
+    ns_sync<WPM>(bar_id);
+    double acc[Cfg::OWN][2];
+    int iters = 1;
+    {
+        sym_gemm<KT, WPM>(sub, Y, T, fo, acc);
+        ns_sync<WPM>(bar_id);
+        store_tiles<KT, WPM>(sub, Y, acc, sg, 0.0, lane);
+        ns_sync<WPM>(bar_id);
+        const double m = g * lo;
+        lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
+    }
+    // ---- iterations 1.. ----------------------------------------------------------------------------------------------
+    for (; iters < 64; ++iters) {
+        const bool last = (1.0 - lo) < 2e-8;
+        g = 3.0 / (1.0 + sqrt(lo) + lo);
+        sg = sqrt(g);
+        sym_gemm<KT, WPM>(sub, Z, Y, fo, acc);                    // M = Z Y
+        store_tiles<KT, WPM>(sub, T, acc, -0.5 * g, 1.5, lane);   // T = (3 I - g M) / 2
+        ns_sync<WPM>(bar_id);
+        sym_gemm<KT, WPM>(sub, T, Z, fo, acc);                    // Z' = sqrt(g) T Z
+        ns_sync<WPM>(bar_id);
+        store_tiles<KT, WPM>(sub, Z, acc, sg, 0.0, lane);
+        if (last) break;
+        sym_gemm<KT, WPM>(sub, Y, T, fo, acc);                    // Y' = sqrt(g) Y T
+        ns_sync<WPM>(bar_id);
+        store_tiles<KT, WPM>(sub, Y, acc, sg, 0.0, lane);
+        ns_sync<WPM>(bar_id);
+        const double m = g * lo;
+        lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
+    }
+    ns_sync<WPM>(bar_id);
+    if (P.stats && gtid == 0) { atomicAdd(P.stats + 2, (unsigned long long)(iters + 1)); atomicAdd(P.stats + 3, 1ull); }
+    // ---- D = A^(-1/2) = Z / sqrt(s), dense, over the Y | T buffers -------------------------------------------------------
+    double* D = Y;
+    const double zs = sqrt(inv_s);
+    for (int e = gtid; e < k * k; e += GT) {
+        const int i = e / k, j = e - i * k;
+        D[i * LDW + j] = sym_get(Z, i, j) * zs;
+    }
+    ns_sync<WPM>(bar_id);
+    for (int i = gtid; i < k; i += GT) {                          // u = D b
+        double a = 0.0;
+        for (int j = 0; j < k; ++j) a = fma(D[i * LDW + j], bvec[j], a);
+        uvec[i] = a;
+    }
+    ns_sync<WPM>(bar_id);
+    for (int i = gtid; i < k; i += GT) {                          // w_mean = D u = A^-1 b        core/etkf.py:72-73
+        double a = 0.0;
+        for (int j = 0; j < k; ++j) a = fma(D[i * LDW + j], uvec[j], a);
+        wbar[i] = a;
+    }
+    ns_sync<WPM>(bar_id);
+    const double sk = sqrt((double)(k - 1));
+    const int64_t gi = P.gpos[P.slot_base + slot].id;
+    double* wdst = P.w_out ? P.w_out + gi * (int64_t)k * k : nullptr;
+    for (int e = gtid; e < k * k; e += GT) {                      // W = w_mean 1^T + sqrt(k-1) D     core/etkf.py:75-76,102
+        const int i = e / k, j = e - i * k;
+        const double w = fma(sk, D[i * LDW + j], wbar[i]);
+        D[i * LDW + j] = w;
+        if (wdst) wdst[e] = w;
+    }
+    ns_sync<WPM>(bar_id);
+    // ---- x_a[s, j, g] = mean + sum_i (x[s, i, g] - mean) W[i][j]                                interface/base.py:257-278
+    for (int sl = 0; sl < P.n_slices; ++sl) {
+        const double* xs = P.x + (int64_t)sl * k * P.n_grid + gi;
+        double* xo = P.xa + (int64_t)sl * k * P.n_grid + gi;
+        for (int i = gtid; i < k; i += GT) xbuf[i] = xs[(int64_t)i * P.n_grid];
+        ns_sync<WPM>(bar_id);
+        double mean = 0.0;
+        for (int i = 0; i < k; ++i) mean += xbuf[i];              // same order in every thread
+        mean /= (double)k;
+        for (int j = gtid; j < k; j += GT) {
+            double a = 0.0;
+            for (int i = 0; i < k; ++i) a = fma(xbuf[i] - mean, D[i * LDW + j], a);
+            xo[(int64_t)j * P.n_grid] = mean + a;
+        }
+        ns_sync<WPM>(bar_id);
+    }
+}
+
+template <int KT, int WPM, int GROUPS>
+__global__ void __launch_bounds__(GROUPS * WPM * 32, 1) k_letkf_solve_ns(const NsParams P) {
+    using Cfg = NsCfg<KT, WPM>;
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    __shared__ long long next_slot[GROUPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int group = warp / WPM, sub = warp % WPM, gtid = tid - group * WPM * 32;
+    double* base = reinterpret_cast<double*>(smem_raw + (size_t)group * Cfg::GROUP_BYTES);
+    double* Z = base;
+    double* Y = base + Cfg::MAT;
+    double* T = base + 2 * Cfg::MAT;
+    double* vec = base + 3 * Cfg::MAT;
+    const int bar_id = 1 + group;
+    const long long t0 = clock64();
+    while (true) {
+        long long slot;
+        if constexpr (WPM == 1) {
+            unsigned int v = 0;
+            if (lane == 0) v = atomicAdd(P.counter, 1u);
+            slot = (long long)__shfl_sync(0xffffffffu, v, 0);
+        } else {
+            if (gtid == 0) next_slot[group] = (long long)atomicAdd(P.counter, 1u);
+            ns_sync<WPM>(bar_id);
+            slot = next_slot[group];
+            ns_sync<WPM>(bar_id);
+        }
+        if (slot >= P.n_slots) break;
+        ns_solve_one<KT, WPM>(P, slot, Z, Y, T, vec, gtid, sub, lane, bar_id);
+    }
+    if (P.stats && tid == 0) atomicAdd(P.stats + 1, (unsigned long long)(clock64() - t0));
+}
+
+}  // namespace b200da

@@ -76,7 +76,8 @@ struct b200da_plan {
     // scratch
     b200da::DevBuf tmp_keys, tmp_cell, tmp_count, tmp_a, tmp_b, tmp_pos;
     b200da::DevBuf host_stage_obs, host_stage_y, host_stage_d, host_stage_x, host_stage_xa;
-    b200da::DevBuf etkf_partial, etkf_w, stats, cmat;
+    b200da::DevBuf etkf_partial, etkf_w, stats, cmat, counter;
+    int solver = B200DA_SOLVER_NEWTON_SCHULZ;
     bool collect_stats = false;
     // timing
     bool timing = false;

@@ -186,7 +186,7 @@ __device__ int jacobi_evd(double* __restrict__ A, double* __restrict__ Vt, int n
 // A (diagonal = eigenvalues per slot), Vt (row m = eigenvector of slot m), b -> W = w_mean 1^T + W_p as
 // [k][ldw] row-major written over A.  Sums run over all ne slots; the dummy slot of an odd ensemble size is a
 // decoupled eigenpair (0, e_dummy) that never touches the first k rows.
-__device__ void etkf_transform(double* __restrict__ A, double* __restrict__ Vt, const double* __restrict__ bvec,
+__device__ inline void etkf_transform(double* __restrict__ A, double* __restrict__ Vt, const double* __restrict__ bvec,
                                double* __restrict__ vec, int k, int ne, int lda, int ldv, double rho, int tid,
                                int nthreads, int bar_id) {
     double* inv = vec;             // [ne] 1 / (max(lambda, 0) + (k-1)/rho)        core/utils.py:58-60
@@ -206,6 +206,7 @@ __device__ void etkf_transform(double* __restrict__ A, double* __restrict__ Vt, 
         for (int m = 0; m < ne; ++m) acc = fma(Vt[m * ldv + i], z[m], acc);
         wbar[i] = acc;
     }
+    group_barrier(bar_id, nthreads);            // w_mean reads the unscaled Vt: finish before any thread scales it
     // scale row m of Vt by ((k-1) inv_m)^(1/4): W_p = B^T B with B = that matrix            core/etkf.py:75-76
     for (int x = tid; x < ne * ne; x += nthreads) {
         const int m = x / ne, i = x - m * ne;
@@ -226,7 +227,7 @@ __device__ void etkf_transform(double* __restrict__ A, double* __restrict__ Vt, 
 }
 
 // x_a[s, j, g] = mean + sum_i (x[s, i, g] - mean) W[i][j]                                     interface/base.py:257-278
-__device__ void apply_point(const double* __restrict__ W, int ldw, int k, int n_slices, int64_t n_grid, int64_t gi,
+__device__ inline void apply_point(const double* __restrict__ W, int ldw, int k, int n_slices, int64_t n_grid, int64_t gi,
                             const double* __restrict__ x, double* __restrict__ xa, double* __restrict__ w_out,
                             double* __restrict__ xbuf, int tid, int nthreads, int bar_id) {
     if (w_out) {
@@ -272,7 +273,8 @@ __device__ inline SolveSmem carve_solve_smem(unsigned char* base, int k) {
 }
 
 struct SolveParams {
-    const double* cmat;        // [n_slots][(k+1)][k]: rows 0..k-1 lower triangle of the Gram, row k = b
+    const double* cmat;        // [n_slots][slot_stride]: tile-packed augmented Gram (common.cuh), row k = b
+    int64_t slot_stride;
     const Pos4* gpos;          // block-sorted grid positions (id = original index)
     const double* x;
     double* xa;
@@ -295,14 +297,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_letkf_solve(const SolveParams
     const int tid = threadIdx.x;
     const long long t0 = clock64();
     for (int64_t s = blockIdx.x; s < P.n_slots; s += gridDim.x) {
-        const double* C = P.cmat + (size_t)s * (size_t)(k + 1) * k;
+        const double* C = P.cmat + (size_t)s * (size_t)P.slot_stride;
         for (int x = tid; x < S.ne * S.lda; x += THREADS) S.A[x] = 0.0;
         if (tid < S.ne) S.bvec[tid] = 0.0;
         __syncthreads();
         for (int x = tid; x < (k + 1) * k; x += THREADS) {
             const int r = x / k, c = x - r * k;
-            if (r < k) { if (c <= r) { const double v = C[x]; S.A[r * S.lda + c] = v; S.A[c * S.lda + r] = v; } }
-            else S.bvec[c] = C[x];
+            if (r < k) { if (c <= r) { const double v = C[sym_off(r, c)]; S.A[r * S.lda + c] = v; S.A[c * S.lda + r] = v; } }
+            else S.bvec[c] = C[sym_off(k, c)];
         }
         __syncthreads();
         const int nsw = jacobi_evd<NR, RW, NV>(S.A, S.Vt, S.ne, S.lda, S.ldv, (double)(k - 1) / P.rho, tid, THREADS, 0);

@@ -16,6 +16,7 @@ ERR_INVALID, ERR_SIZE, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_
 METRIC_ABS1D, METRIC_PERIODIC1D, METRIC_EUCLID, METRIC_HAVERSINE = 0, 1, 2, 3
 TAPER_GC, TAPER_GCINF = 0, 1
 F64, F32 = 0, 1
+SOLVER_NEWTON_SCHULZ, SOLVER_JACOBI = 0, 1
 
 _c = ctypes
 _vp, _i, _i64, _dbl = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
@@ -51,6 +52,7 @@ SIGNATURES = {
     "b200da_last_phase_ms": (_c.c_float, [_vp, _i]),
     "b200da_collect_stats": (_i, [_vp, _i]),
     "b200da_get_stats": (_i, [_vp, _c.POINTER(_c.c_int64)]),
+    "b200da_set_solver": (_i, [_vp, _i]),
 }
 
 _lib = None

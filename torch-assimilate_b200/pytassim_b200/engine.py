@@ -229,6 +229,11 @@ class LETKFEngine(object):
         """(gram_ms, solve_ms) of the last analyse(); call last_kernel_ms() first."""
         return float(self.lib.b200da_last_phase_ms(self._plan, 0)), float(self.lib.b200da_last_phase_ms(self._plan, 1))
 
+    def set_solver(self, name):
+        """'newton' (default: tensor-core Newton-Schulz inverse square root) or 'jacobi' (shared-memory Jacobi EVD)."""
+        _cabi.check(self.lib.b200da_set_solver(self._plan, {"newton": _cabi.SOLVER_NEWTON_SCHULZ, "jacobi": _cabi.SOLVER_JACOBI}[name]))
+        return self
+
     def collect_stats(self, on=True):
         _cabi.check(self.lib.b200da_collect_stats(self._plan, 1 if on else 0))
 
