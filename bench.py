@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="plan dtype (state / obs-space arrays in HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -248,19 +249,22 @@ def main():
         n_grid, n_obs, n_coord = data["state"].shape[-1], data["normed_obs"].shape[0], data["grid_rows"].shape[1] - 1
 
     f64 = torch.float64
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    ndt = np.float64 if args.dtype == "f64" else np.float32
+    esz = 8 if args.dtype == "f64" else 4
     if rank == 0:
-        x_host = torch.from_numpy(np.ascontiguousarray(data["state"].reshape(1, k, n_grid))).pin_memory()
-        y_host = torch.from_numpy(np.ascontiguousarray(data["normed_perts"])).pin_memory()
-        d_host = torch.from_numpy(np.ascontiguousarray(data["normed_obs"])).pin_memory()
+        x_host = torch.from_numpy(np.ascontiguousarray(data["state"].reshape(1, k, n_grid), dtype=ndt)).pin_memory()
+        y_host = torch.from_numpy(np.ascontiguousarray(data["normed_perts"], dtype=ndt)).pin_memory()
+        d_host = torch.from_numpy(np.ascontiguousarray(data["normed_obs"], dtype=ndt)).pin_memory()
         oc_host = torch.from_numpy(np.ascontiguousarray(data["obs_rows"][:, 1:].T)).pin_memory()     # (n_coord, M)
         gc_dev = torch.from_numpy(np.ascontiguousarray(data["grid_rows"][:, 1:])).to(dev)
         x_dev, y_dev, d_dev = x_host.to(dev), y_host.to(dev), d_host.to(dev)
         oc_dev = oc_host.to(dev).t().contiguous()                                                     # (M, n_coord)
     else:
         gc_dev = torch.empty((n_grid, n_coord), dtype=f64, device=dev)
-        x_dev = torch.empty((1, k, n_grid), dtype=f64, device=dev)
-        y_dev = torch.empty((k, n_obs), dtype=f64, device=dev)
-        d_dev = torch.empty((n_obs,), dtype=f64, device=dev)
+        x_dev = torch.empty((1, k, n_grid), dtype=tdt, device=dev)
+        y_dev = torch.empty((k, n_obs), dtype=tdt, device=dev)
+        d_dev = torch.empty((n_obs,), dtype=tdt, device=dev)
         oc_dev = torch.empty((n_obs, n_coord), dtype=f64, device=dev)
     if world > 1:
         dist.broadcast(gc_dev, 0)          # the grid is static: part of the plan, outside the timed region
@@ -277,7 +281,7 @@ def main():
         if rank != 0:
             metric = mm.HaversineDistance(float(mpar[0])) if int(mdesc[0]) == 3 else mm.PeriodicDistance1D(float(mpar[0]))
 
-    eng = LETKFEngine(k, 1, metric, w["radius"], inf_factor=w["rho"])
+    eng = LETKFEngine(k, 1, metric, w["radius"], inf_factor=w["rho"], dtype=tdt)
     eng.set_grid(gc_dev)
     eng.enable_timing(True)
     from pytassim_b200.parallel import ShardedAnalysis
@@ -362,8 +366,8 @@ def main():
             eng.analyse_host(x_host, oc_host, y_host, d_host, out=out_host)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.e2e_steps
-        h2d = x_host.numel() * 8 + y_host.numel() * 8 + d_host.numel() * 8 + oc_host.numel() * 8
-        e2e = {"value": n_grid / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.numel() * 8),
+        h2d = x_host.numel() * esz + y_host.numel() * esz + d_host.numel() * esz + oc_host.numel() * 8
+        e2e = {"value": n_grid / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.numel() * esz),
                "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "api": "LETKFEngine.analyse_host -> b200da_letkf_host"}
         # sanity: the e2e result equals the device-resident result
         e2e["max_abs_diff_vs_device_path"] = float((out_host - xa_dev.cpu()).abs().max())
@@ -376,7 +380,7 @@ def main():
             step()
             if rank == 0:
                 out_host.copy_(xa_dev, non_blocking=True)
-        out_host = torch.empty((1, k, n_grid), dtype=f64).pin_memory() if rank == 0 else None
+        out_host = torch.empty((1, k, n_grid), dtype=tdt).pin_memory() if rank == 0 else None
         e2e_step(); barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -387,8 +391,8 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt[0])
         if rank == 0:
-            h2d = x_host.numel() * 8 + y_host.numel() * 8 + d_host.numel() * 8 + oc_host.numel() * 8
-            e2e = {"value": n_grid / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n_grid * k * 8),
+            h2d = x_host.numel() * esz + y_host.numel() * esz + d_host.numel() * esz + oc_host.numel() * 8
+            e2e = {"value": n_grid / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n_grid * k * esz),
                    "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "api": "pinned host -> rank 0 -> NCCL broadcast -> analyse -> all-gather -> host"}
 
     if rank == 0:
@@ -406,12 +410,12 @@ def main():
         line = {
             "metric": metric_name, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "n_grid": n_grid, "n_obs": n_obs, "ens_size": k, "mean_local_obs": p_mean,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": w["desc"] if args.dtype == "f64" else w["desc"].replace("FP64", "FP32 arrays in HBM"), "n_grid": n_grid, "n_obs": n_obs, "ens_size": k, "mean_local_obs": p_mean,
                        "sharding": "grid-point blocks split contiguously over {0} GPU(s); obs broadcast from rank 0, "
                                    "analysis all-gathered".format(world),
                        "l2": "inputs exceed L2 (staged obs copy {0:.0f} MB + state {1:.0f} MB vs 126 MB)".format(
-                           n_obs * eng.k * 8 * 1.12 / 1e6, n_grid * k * 8 / 1e6) if n_obs * k * 8 > 2e8 else
+                           n_obs * eng.k * esz * 1.12 / 1e6, n_grid * k * esz / 1e6) if n_obs * k * esz > 2e8 else
                              "inputs fit in L2; no flush (workload is latency/compute bound, not DRAM bound)",
                        "kernel": eng.kernel_name},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s",

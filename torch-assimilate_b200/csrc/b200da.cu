@@ -48,14 +48,15 @@ static KernelConfig config_for_kt(int kt) {
 constexpr int kMaxKt = 14;
 
 template <int KT>
-static int launch_etkf_gram(const double* yn, const double* d, int64_t m, int k, int ncta, int64_t chunk, double* partial,
+static int launch_etkf_gram(int f32, const void* yn, const void* d, int64_t m, int k, int ncta, int64_t chunk, double* partial,
                             cudaStream_t st) {
-    k_etkf_gram<KT><<<ncta, kEtkfWarps * 32, 0, st>>>(yn, d, m, k, chunk, partial);
+    if (f32) k_etkf_gram<float, KT><<<ncta, kEtkfWarps * 32, 0, st>>>((const float*)yn, (const float*)d, m, k, chunk, partial);
+    else k_etkf_gram<double, KT><<<ncta, kEtkfWarps * 32, 0, st>>>((const double*)yn, (const double*)d, m, k, chunk, partial);
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
-#define B200DA_EG_CASE(KT) case KT: return launch_etkf_gram<KT>(yn, d, m, k, ncta, chunk, partial, st);
-static int dispatch_etkf_gram(int kt, const double* yn, const double* d, int64_t m, int k, int ncta, int64_t chunk,
+#define B200DA_EG_CASE(KT) case KT: return launch_etkf_gram<KT>(f32, yn, d, m, k, ncta, chunk, partial, st);
+static int dispatch_etkf_gram(int kt, int f32, const void* yn, const void* d, int64_t m, int k, int ncta, int64_t chunk,
                               double* partial, cudaStream_t st) {
     switch (kt) {
         B200DA_EG_CASE(1) B200DA_EG_CASE(2) B200DA_EG_CASE(3) B200DA_EG_CASE(4) B200DA_EG_CASE(5) B200DA_EG_CASE(6)
@@ -129,7 +130,7 @@ int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int
     *plan = nullptr;
     if (k < 2 || n_slices < 1 || !radius || n_radius < 1 || !(radius[0] > 0.0) || !(inf_factor > 0.0))
         return B200DA_ERR_INVALID;
-    if (dtype != B200DA_F64) return B200DA_ERR_UNSUPPORTED;
+    if (dtype != B200DA_F64 && dtype != B200DA_F32) return B200DA_ERR_UNSUPPORTED;
     if (taper != B200DA_TAPER_GC && taper != B200DA_TAPER_GCINF) return B200DA_ERR_UNSUPPORTED;
     const int kt = (k + 1 + 7) / 8;
     if (kt > kMaxKt) return B200DA_ERR_UNSUPPORTED;
@@ -141,7 +142,7 @@ int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int
     pl->kt = kt; pl->kp = kt * 8;
     const KernelConfig cfg = config_for_kt(kt);
     pl->gpb = cfg.g;
-    pl->kernel_name = "letkf_gram_f64_kt" + std::to_string(kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
+    pl->kernel_name = std::string("letkf_gram_") + (dtype == B200DA_F32 ? "f32in_f64dmma" : "f64") + "_kt" + std::to_string(kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
     Geometry& g = pl->geom;
     g.metric = metric; g.taper = taper; g.n_coord = n_coord; g.periodic = 0;
     g.radius = radius[0]; g.eps = epsilon; g.period = 0.0; g.sphere_r = 1.0;
@@ -190,6 +191,9 @@ int b200da_set_grid(b200da_plan* plan, const double* grid_coord, int64_t n_grid,
 }
 
 int b200da_bin_obs(b200da_plan* plan, const double* obs_coord, const void* Yn, const void* d, int64_t n_obs, void* stream) {
+    if (!plan) return B200DA_ERR_INVALID;
+    if (plan->dtype == B200DA_F32)
+        return bin_obs_impl<float>(plan, obs_coord, (const float*)Yn, (const float*)d, n_obs, (cudaStream_t)stream);
     return bin_obs_impl<double>(plan, obs_coord, (const double*)Yn, (const double*)d, n_obs, (cudaStream_t)stream);
 }
 
@@ -220,8 +224,9 @@ int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t 
     P.block_off = pl->block_off.as<int>();
     P.opos = pl->opos.as<Pos4>();
     P.cell_start = pl->cell_start.as<int>();
-    P.ys = pl->ys.as<double>();
-    P.x = (const double*)X; P.xa = (double*)Xa; P.w_out = (double*)W_opt;
+    P.ys = pl->ys.p;
+    P.x = X; P.xa = Xa; P.w_out = W_opt;
+    const int f32 = pl->dtype == B200DA_F32 ? 1 : 0;
     P.n_ambiguous = (unsigned long long*)n_ambiguous_opt;
     P.n_grid = pl->n_grid; P.n_obs = pl->n_obs;
     P.block_begin = (int)block_begin;
@@ -274,6 +279,7 @@ int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t 
         if (jacobi) {
             SolveParams S{};
             S.cmat = P.cmat; S.slot_stride = slot_stride; S.gpos = P.gpos; S.x = P.x; S.xa = P.xa; S.w_out = P.w_out; S.stats = P.stats;
+            S.io_f32 = f32;
             S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = pl->rho;
             const int grid = (int)std::min<int64_t>(n_slots, 148 * 64);
             if (big) k_letkf_solve<512, 1, 2, 4, 4><<<grid, 512, smem_solve, st>>>(S);
@@ -284,6 +290,7 @@ int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t 
             NsParams S{};
             S.cmat = P.cmat; S.slot_stride = slot_stride; S.gpos = P.gpos; S.x = P.x; S.xa = P.xa; S.w_out = P.w_out; S.stats = P.stats;
             S.counter = pl->counter.as<unsigned int>();
+            S.io_f32 = f32;
             S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = pl->rho;
             if ((rc = dispatch_ns((k + 7) / 8, S, st))) return rc;
         }
@@ -301,16 +308,17 @@ int b200da_letkf_host(b200da_plan* pl, const double* obs_coord_host, const void*
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     const size_t mm = (size_t)std::max<int64_t>(m, 1);
-    const size_t xbytes = sizeof(double) * (size_t)pl->n_slices * pl->k * (size_t)pl->n_grid;
+    const size_t es = pl->dtype == B200DA_F32 ? sizeof(float) : sizeof(double);
+    const size_t xbytes = es * (size_t)pl->n_slices * pl->k * (size_t)pl->n_grid;
     if ((rc = pl->host_stage_obs.ensure(sizeof(double) * mm * pl->n_coord))) return rc;
-    if ((rc = pl->host_stage_y.ensure(sizeof(double) * mm * pl->k))) return rc;
-    if ((rc = pl->host_stage_d.ensure(sizeof(double) * mm))) return rc;
+    if ((rc = pl->host_stage_y.ensure(es * mm * pl->k))) return rc;
+    if ((rc = pl->host_stage_d.ensure(es * mm))) return rc;
     if ((rc = pl->host_stage_x.ensure(xbytes))) return rc;
     if ((rc = pl->host_stage_xa.ensure(xbytes))) return rc;
     if (m > 0) {
         B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_obs.p, obs_coord_host, sizeof(double) * (size_t)m * pl->n_coord, cudaMemcpyHostToDevice, st));
-        B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_y.p, Yn_host, sizeof(double) * (size_t)m * pl->k, cudaMemcpyHostToDevice, st));
-        B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_d.p, d_host, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, st));
+        B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_y.p, Yn_host, es * (size_t)m * pl->k, cudaMemcpyHostToDevice, st));
+        B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_d.p, d_host, es * (size_t)m, cudaMemcpyHostToDevice, st));
     }
     B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_x.p, X_host, xbytes, cudaMemcpyHostToDevice, st));
     if ((rc = b200da_bin_obs(pl, pl->host_stage_obs.as<double>(), pl->host_stage_y.p, pl->host_stage_d.p, m, stream))) return rc;
@@ -382,13 +390,14 @@ int b200da_etkf_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t 
     int rc;
     if ((rc = pl->etkf_partial.ensure(sizeof(double) * (size_t)ncta * kp * kp))) return rc;
     if (m > 0) {
-        if ((rc = dispatch_etkf_gram(pl->kt, (const double*)Yn, (const double*)d, m, k, ncta, chunk,
+        if ((rc = dispatch_etkf_gram(pl->kt, pl->dtype == B200DA_F32, Yn, d, m, k, ncta, chunk,
                                      pl->etkf_partial.as<double>(), st))) return rc;
     }
     const size_t smem = solve_smem_bytes(k);
     if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
     B200DA_CUDA(cudaFuncSetAttribute(k_etkf_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_etkf_solve<<<1, 512, smem, st>>>(pl->etkf_partial.as<double>(), m > 0 ? ncta : 0, kp, k, pl->rho, (double*)W);
+    k_etkf_solve<<<1, 512, smem, st>>>(pl->etkf_partial.as<double>(), m > 0 ? ncta : 0, kp, k, pl->rho, W,
+                                       pl->dtype == B200DA_F32 ? 1 : 0);
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
@@ -399,9 +408,15 @@ int b200da_apply_weights(b200da_plan* pl, const void* X, const void* W, int per_
     const int k = pl->k;
     const size_t smem = per_grid ? 0 : sizeof(double) * (size_t)k * k;
     if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
-    B200DA_CUDA(cudaFuncSetAttribute(k_apply_weights<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-    k_apply_weights<8><<<grid1d(n_grid, 128), 128, smem, st>>>((const double*)X, (const double*)W, per_grid, k, pl->n_slices,
-                                                            n_grid, (double*)Xa);
+    if (pl->dtype == B200DA_F32) {
+        B200DA_CUDA(cudaFuncSetAttribute(k_apply_weights<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        k_apply_weights<float, 8><<<grid1d(n_grid, 128), 128, smem, st>>>((const float*)X, (const float*)W, per_grid, k,
+                                                                        pl->n_slices, n_grid, (float*)Xa);
+    } else {
+        B200DA_CUDA(cudaFuncSetAttribute(k_apply_weights<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        k_apply_weights<double, 8><<<grid1d(n_grid, 128), 128, smem, st>>>((const double*)X, (const double*)W, per_grid, k,
+                                                                         pl->n_slices, n_grid, (double*)Xa);
+    }
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
@@ -416,7 +431,10 @@ static int pack_impl(b200da_plan* pl, const void* xa, int64_t b0, int64_t b1, vo
     const int rows = pl->n_slices * pl->k;
     if (rows > 65535) return B200DA_ERR_UNSUPPORTED;
     dim3 grid((unsigned)grid1d(ncols, 256), (unsigned)rows);
-    k_pack_columns<<<grid, 256, 0, st>>>((const double*)xa, pl->gorder.as<int>(), s0, ncols, rows, pl->n_grid, (double*)packed, unpack);
+    if (pl->dtype == B200DA_F32)
+        k_pack_columns<float><<<grid, 256, 0, st>>>((const float*)xa, pl->gorder.as<int>(), s0, ncols, rows, pl->n_grid, (float*)packed, unpack);
+    else
+        k_pack_columns<double><<<grid, 256, 0, st>>>((const double*)xa, pl->gorder.as<int>(), s0, ncols, rows, pl->n_grid, (double*)packed, unpack);
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }

@@ -187,6 +187,16 @@ __device__ __forceinline__ double pair_weight(const Geometry& g, double gx, doub
     return (w > g.eps) ? w : 0.0;                          // gaspari_cohn.py:135
 }
 
+// ---- state / weight I/O in the plan's dtype --------------------------------------------------------------------
+// The ensemble-space algebra always runs in FP64; with an FP32 plan only the HBM-resident arrays (state, analysis,
+// observation-space staging copy, exported weights) are FP32.  `f32` is uniform over a launch.
+__device__ __forceinline__ double ld_io(const void* __restrict__ p, int64_t i, int f32) {
+    return f32 ? (double)reinterpret_cast<const float*>(p)[i] : reinterpret_cast<const double*>(p)[i];
+}
+__device__ __forceinline__ void st_io(void* __restrict__ p, int64_t i, double v, int f32) {
+    if (f32) reinterpret_cast<float*>(p)[i] = (float)v; else reinterpret_cast<double*>(p)[i] = v;
+}
+
 // ---- tile-packed symmetric matrices ----------------------------------------------------------------------------
 // Lower-triangle 8x8 tiles, tile (mt, nt), nt <= mt, at ((mt (mt+1))/2 + nt) * 64 doubles; element (r, c) of a tile at
 // r * 8 + (c ^ ((r & 2) << 1)).  The XOR makes both the direct and the transposed DMMA fragment reads of a tile

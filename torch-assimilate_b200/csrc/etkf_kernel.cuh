@@ -12,8 +12,8 @@ constexpr int kEtkfWarps = 8;
 // Partial Gram of [Yn; d] over a chunk of observations per CTA; the lower-triangle tiles are split over the
 // CTA's warps.  Yn is read in the reference layout (k, M) directly: a DMMA fragment is 4 consecutive
 // observations of 8 members = eight 32-byte sectors.
-template <int KT>
-__global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const double* __restrict__ yn, const double* __restrict__ d,
+template <typename T, int KT>
+__global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const T* __restrict__ yn, const T* __restrict__ d,
                                                                int64_t m_obs, int k, int64_t chunk,
                                                                double* __restrict__ partial) {
     constexpr int NTILES = KT * (KT + 1) / 2;
@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const double* __r
             const int mem = t * 8 + (lane >> 2);
             double v = 0.0;
             if (j < j1) {
-                if (mem < k) v = yn[(int64_t)mem * m_obs + j];
-                else if (mem == k) v = d[j];
+                if (mem < k) v = (double)yn[(int64_t)mem * m_obs + j];
+                else if (mem == k) v = (double)d[j];
             }
             f[t] = v;
         }
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const double* __r
 
 // Sum the partial Grams in a fixed order, eigendecompose, transform; W (k x k) row-major to global memory.
 __global__ void __launch_bounds__(512, 1) k_etkf_solve(const double* __restrict__ partial, int n_partial, int kp, int k,
-                                                    double rho, double* __restrict__ w_out) {
+                                                    double rho, void* __restrict__ w_out, int io_f32) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     const SolveSmem S = carve_solve_smem(smem_raw, k);
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -86,55 +86,57 @@ __global__ void __launch_bounds__(512, 1) k_etkf_solve(const double* __restrict_
     __syncthreads();
     jacobi_evd<2, 4, 4>(S.A, S.Vt, S.ne, S.lda, S.ldv, (double)(k - 1) / rho, tid, nt, 0);
     etkf_transform(S.A, S.Vt, S.bvec, S.vec, k, S.ne, S.lda, S.ldv, rho, tid, nt, 0);
-    for (int x = tid; x < k * k; x += nt) w_out[x] = S.A[(x / k) * S.lda + (x % k)];
+    for (int x = tid; x < k * k; x += nt) st_io(w_out, x, S.A[(x / k) * S.lda + (x % k)], io_f32);
 }
 
 // Xa = mean + (X - mean) W.  One thread per grid point (coalesced along the grid axis), 8 output members per
 // pass; W is staged in shared memory when it is global (per_grid = 0).
-template <int JB>
-__global__ void __launch_bounds__(128) k_apply_weights(const double* __restrict__ x, const double* __restrict__ w,
+template <typename T, int JB>
+__global__ void __launch_bounds__(128) k_apply_weights(const T* __restrict__ x, const T* __restrict__ w,
                                                        int per_grid, int k, int n_rows, int64_t n_grid,
-                                                       double* __restrict__ xa) {
-    extern __shared__ double wsm[];
+                                                       T* __restrict__ xa) {
+    extern __shared__ double wsm_raw[];
+    T* wsm = reinterpret_cast<T*>(wsm_raw);
     if (!per_grid) {
         for (int i = threadIdx.x; i < k * k; i += blockDim.x) wsm[i] = w[i];
         __syncthreads();
     }
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= n_grid) return;
-    const double* wg = per_grid ? (w + gi * (int64_t)k * k) : wsm;
+    const T* wg = per_grid ? (w + gi * (int64_t)k * k) : wsm;
     for (int s = 0; s < n_rows; ++s) {
-        const double* xs = x + (int64_t)s * k * n_grid + gi;
-        double* xo = xa + (int64_t)s * k * n_grid + gi;
+        const T* xs = x + (int64_t)s * k * n_grid + gi;
+        T* xo = xa + (int64_t)s * k * n_grid + gi;
         double mean = 0.0;
-        for (int i = 0; i < k; ++i) mean += xs[(int64_t)i * n_grid];
+        for (int i = 0; i < k; ++i) mean += (double)xs[(int64_t)i * n_grid];
         mean /= (double)k;
         for (int j0 = 0; j0 < k; j0 += JB) {
             double acc[JB];
 #pragma unroll
             for (int j = 0; j < JB; ++j) acc[j] = 0.0;
             for (int i = 0; i < k; ++i) {
-                const double p = xs[(int64_t)i * n_grid] - mean;
-                const double* wr = wg + i * k + j0;
+                const double p = (double)xs[(int64_t)i * n_grid] - mean;
+                const T* wr = wg + i * k + j0;
 #pragma unroll
                 for (int j = 0; j < JB; ++j)
-                    if (j0 + j < k) acc[j] = fma(p, wr[j], acc[j]);
+                    if (j0 + j < k) acc[j] = fma(p, (double)wr[j], acc[j]);
             }
 #pragma unroll
             for (int j = 0; j < JB; ++j)
-                if (j0 + j < k) xo[(int64_t)(j0 + j) * n_grid] = mean + acc[j];
+                if (j0 + j < k) xo[(int64_t)(j0 + j) * n_grid] = (T)(mean + acc[j]);
         }
     }
 }
 
 // (n_rows, N) <-> dense (n_rows, n_cols) in block-sorted order: the all-gather payload of the grid-sharded run
-__global__ void k_pack_columns(const double* __restrict__ xa, const int* __restrict__ order, int64_t slot0, int64_t n_cols,
-                               int n_rows, int64_t n_grid, double* __restrict__ packed, int unpack) {
+template <typename T>
+__global__ void k_pack_columns(const T* __restrict__ xa, const int* __restrict__ order, int64_t slot0, int64_t n_cols,
+                               int n_rows, int64_t n_grid, T* __restrict__ packed, int unpack) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (c >= n_cols || r >= n_rows) return;
     const int64_t gi = order[slot0 + c];
-    if (unpack) const_cast<double*>(xa)[(int64_t)r * n_grid + gi] = packed[(int64_t)r * n_cols + c];
+    if (unpack) const_cast<T*>(xa)[(int64_t)r * n_grid + gi] = packed[(int64_t)r * n_cols + c];
     else packed[(int64_t)r * n_cols + c] = xa[(int64_t)r * n_grid + gi];
 }
 

@@ -5,16 +5,22 @@
 
 namespace b200da {
 
-template <int KT, int G, int WPG>
-static int launch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st) {
+template <typename T, int KT, int G, int WPG>
+static int launch_fused_t(const LetkfParams& P, int nblocks, cudaStream_t st) {
     const size_t hdr = (sizeof(BlockHeader<G>) + 31) & ~size_t(31);
-    const size_t smem = hdr + gram_smem_bytes<KT, G, WPG>();
+    const size_t smem = hdr + gram_smem_bytes<T, KT, G, WPG>();
     if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
-    auto kern = k_letkf_gram<KT, G, WPG>;
+    auto kern = k_letkf_gram<T, KT, G, WPG>;
     B200DA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<nblocks, G * WPG * 32, smem, st>>>(P);
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
+}
+
+template <int KT, int G, int WPG>
+static int launch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st) {
+    return pl->dtype == B200DA_F32 ? launch_fused_t<float, KT, G, WPG>(P, nblocks, st)
+                                   : launch_fused_t<double, KT, G, WPG>(P, nblocks, st);
 }
 
 #define B200DA_KT_CASE(KT, G, WPG) case KT: return launch_fused<KT, G, WPG>(pl, P, nblocks, st);

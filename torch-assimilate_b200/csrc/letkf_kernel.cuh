@@ -31,10 +31,10 @@ struct LetkfParams {
     const int* block_off;
     const Pos4* opos;          // cell-sorted obs positions
     const int* cell_start;
-    const double* ys;          // [M][KP]
-    const double* x;           // (n_slices, k, N)
-    double* xa;
-    double* w_out;             // (N, k, k) or null
+    const void* ys;            // [M][KP] of the plan dtype
+    const void* x;             // (n_slices, k, N) of the plan dtype
+    void* xa;
+    void* w_out;               // (N, k, k) or null
     unsigned long long* n_ambiguous;   // or null
     unsigned long long* stats;         // or null: [0] gram cycles [1] evd cycles [2] sweeps [3] evds [4] setup cycles [5] tiles
     double* cmat;                      // scratch: per grid slot the tile-packed augmented Gram (rows 0..k-1 = C, row k = b)
@@ -61,19 +61,25 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
 
 // ---- Gram tile: acc += (w .* Y_tile) Y_tile^T for the tiles owned by warp SUB of the grid point ------------------
-template <int KT, int WPG, int SUB>
-__device__ __forceinline__ void gram_tile(const double* __restrict__ ytile, const double* __restrict__ wrow,
+// padded row length of the staged tile: conflict-free fragment reads (4 observations x 8 members per warp load)
+template <typename T, int KT>
+__host__ __device__ constexpr int tile_ld() {
+    return sizeof(T) == 8 ? KT * 8 + 4 : KT * 8 + ((8 - (KT * 8) % 32 + 32) % 32);
+}
+
+template <typename T, int KT, int WPG, int SUB>
+__device__ __forceinline__ void gram_tile(const T* __restrict__ ytile, const double* __restrict__ wrow,
                                           double (&acc)[(KT * (KT + 1) / 2 + WPG - 1) / WPG][2], int lane) {
-    constexpr int LDY = KT * 8 + 4;
+    constexpr int LDY = tile_ld<T, KT>();
 #pragma unroll 2
     for (int ks = 0; ks < kTileObs / 4; ++ks) {
         const int j = ks * 4 + (lane & 3);
         const double w = wrow[j];
         if (__all_sync(0xffffffffu, w == 0.0)) continue;
-        const double* yr = ytile + j * LDY + (lane >> 2);
+        const T* yr = ytile + j * LDY + (lane >> 2);
         double f[KT];
 #pragma unroll
-        for (int t = 0; t < KT; ++t) f[t] = yr[t * 8];
+        for (int t = 0; t < KT; ++t) f[t] = (double)yr[t * 8];
         int idx = 0, n = 0;
 #pragma unroll
         for (int mt = 0; mt < KT; ++mt) {
@@ -214,22 +220,23 @@ __device__ void setup_block(BlockHeader<G>& H, const Geometry& g, const Pos4* __
 
 }
 
-template <int KT, int G, int WPG>
-constexpr size_t gram_smem_bytes() {
-    return sizeof(double) * ((size_t)kStages * kTileObs * (KT * 8 + 4) + (size_t)kStages * G * kTileObs);
+template <typename T, int KT, int G, int WPG>
+__host__ __device__ constexpr size_t gram_smem_bytes() {
+    return sizeof(double) * ((size_t)kStages * G * kTileObs) + sizeof(T) * ((size_t)kStages * kTileObs * tile_ld<T, KT>());
 }
 
-template <int KT, int G, int WPG>
+template <typename T, int KT, int G, int WPG>
 __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParams P) {
     constexpr int NT = G * WPG * 32;
-    constexpr int KP = KT * 8, LDY = KP + 4;
+    constexpr int KP = KT * 8, LDY = tile_ld<T, KT>();
     constexpr int NTILES = KT * (KT + 1) / 2;
     constexpr int ACC = (NTILES + WPG - 1) / WPG;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     BlockHeader<G>& H = *reinterpret_cast<BlockHeader<G>*>(smem_raw);
     unsigned char* work = smem_raw + ((sizeof(BlockHeader<G>) + 31) & ~size_t(31));
-    double* ybuf = reinterpret_cast<double*>(work);                       // [S][TS][LDY]
-    double* wbuf = ybuf + (size_t)kStages * kTileObs * LDY;               // [S][G][TS]
+    double* wbuf = reinterpret_cast<double*>(work);                       // [S][G][TS]
+    T* ybuf = reinterpret_cast<T*>(wbuf + (size_t)kStages * G * kTileObs);   // [S][TS][LDY]
+    const T* ys = reinterpret_cast<const T*>(P.ys);
 
     const Geometry& g = P.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -302,12 +309,13 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
             wst[q] = w;
         }
         // 3. asynchronous copy of the observation rows; padded slots re-read the first row with weight 0
-        double* yst = ybuf + (size_t)stage * kTileObs * LDY;
-        constexpr int CH = KP / 2;                   // 16-byte chunks per row
+        T* yst = ybuf + (size_t)stage * kTileObs * LDY;
+        constexpr int EPC = 16 / sizeof(T);          // elements per 16-byte chunk
+        constexpr int CH = KP / EPC;                 // 16-byte chunks per row
         for (int q = tid; q < kTileObs * CH; q += NT) {
             const int slot = q / CH, ch = q % CH;
             const int s = H.ring[(ring_head + (slot < n_tile ? slot : 0)) & (kRing - 1)];
-            cp_async16(yst + slot * LDY + ch * 2, P.ys + (size_t)s * KP + ch * 2);
+            cp_async16(yst + slot * LDY + ch * EPC, ys + (size_t)s * KP + ch * EPC);
         }
         ring_head += n_tile;
         ++produced;
@@ -324,29 +332,29 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
             cp_async_commit();                        // one group per iteration, possibly empty
             if (my_g < ng) {
                 const int stage = consumed % kStages;
-                const double* yst = ybuf + (size_t)stage * kTileObs * LDY;
+                const T* yst = ybuf + (size_t)stage * kTileObs * LDY;
                 const double* wrow = wbuf + ((size_t)stage * G + my_g) * kTileObs;
-                if constexpr (WPG == 1) gram_tile<KT, WPG, 0>(yst, wrow, acc, lane);
+                if constexpr (WPG == 1) gram_tile<T, KT, WPG, 0>(yst, wrow, acc, lane);
                 else if constexpr (WPG == 2) {
-                    if (my_sub == 0) gram_tile<KT, WPG, 0>(yst, wrow, acc, lane);
-                    else gram_tile<KT, WPG, 1>(yst, wrow, acc, lane);
+                    if (my_sub == 0) gram_tile<T, KT, WPG, 0>(yst, wrow, acc, lane);
+                    else gram_tile<T, KT, WPG, 1>(yst, wrow, acc, lane);
                 } else if constexpr (WPG == 4) {
                     switch (my_sub) {
-                        case 0: gram_tile<KT, WPG, 0>(yst, wrow, acc, lane); break;
-                        case 1: gram_tile<KT, WPG, 1>(yst, wrow, acc, lane); break;
-                        case 2: gram_tile<KT, WPG, 2>(yst, wrow, acc, lane); break;
-                        default: gram_tile<KT, WPG, 3>(yst, wrow, acc, lane); break;
+                        case 0: gram_tile<T, KT, WPG, 0>(yst, wrow, acc, lane); break;
+                        case 1: gram_tile<T, KT, WPG, 1>(yst, wrow, acc, lane); break;
+                        case 2: gram_tile<T, KT, WPG, 2>(yst, wrow, acc, lane); break;
+                        default: gram_tile<T, KT, WPG, 3>(yst, wrow, acc, lane); break;
                     }
                 } else {
                     switch (my_sub) {
-                        case 0: gram_tile<KT, WPG, 0>(yst, wrow, acc, lane); break;
-                        case 1: gram_tile<KT, WPG, 1>(yst, wrow, acc, lane); break;
-                        case 2: gram_tile<KT, WPG, 2>(yst, wrow, acc, lane); break;
-                        case 3: gram_tile<KT, WPG, 3>(yst, wrow, acc, lane); break;
-                        case 4: gram_tile<KT, WPG, 4>(yst, wrow, acc, lane); break;
-                        case 5: gram_tile<KT, WPG, 5>(yst, wrow, acc, lane); break;
-                        case 6: gram_tile<KT, WPG, 6>(yst, wrow, acc, lane); break;
-                        default: gram_tile<KT, WPG, 7>(yst, wrow, acc, lane); break;
+                        case 0: gram_tile<T, KT, WPG, 0>(yst, wrow, acc, lane); break;
+                        case 1: gram_tile<T, KT, WPG, 1>(yst, wrow, acc, lane); break;
+                        case 2: gram_tile<T, KT, WPG, 2>(yst, wrow, acc, lane); break;
+                        case 3: gram_tile<T, KT, WPG, 3>(yst, wrow, acc, lane); break;
+                        case 4: gram_tile<T, KT, WPG, 4>(yst, wrow, acc, lane); break;
+                        case 5: gram_tile<T, KT, WPG, 5>(yst, wrow, acc, lane); break;
+                        case 6: gram_tile<T, KT, WPG, 6>(yst, wrow, acc, lane); break;
+                        default: gram_tile<T, KT, WPG, 7>(yst, wrow, acc, lane); break;
                     }
                 }
             }

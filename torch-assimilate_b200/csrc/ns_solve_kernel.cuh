@@ -171,9 +171,10 @@ __device__ __forceinline__ void store_tiles(int sub, double* __restrict__ S, con
 struct NsParams {
     const double* cmat;        // [n_slots][slot_stride]: tile-packed augmented Gram (rows 0..k-1 = C, row k = b)
     const Pos4* gpos;          // block-sorted grid positions (id = original index)
-    const double* x;
-    double* xa;
-    double* w_out;
+    const void* x;             // state / analysis / exported weights in the plan dtype (io_f32)
+    void* xa;
+    void* w_out;
+    int io_f32;
     unsigned int* counter;     // zeroed before the launch: next slot to solve
     unsigned long long* stats; // or null: [1] solve cycles [2] iterations [3] solves
     int64_t slot_base;
@@ -320,19 +321,18 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
     ns_sync<WPM>(bar_id);
     const double sk = sqrt((double)(k - 1));
     const int64_t gi = P.gpos[P.slot_base + slot].id;
-    double* wdst = P.w_out ? P.w_out + gi * (int64_t)k * k : nullptr;
+    const int f32 = P.io_f32;
     for (int e = gtid; e < k * k; e += GT) {                      // W = w_mean 1^T + sqrt(k-1) D     core/etkf.py:75-76,102
         const int i = e / k, j = e - i * k;
         const double w = fma(sk, D[i * LDW + j], wbar[i]);
         D[i * LDW + j] = w;
-        if (wdst) wdst[e] = w;
+        if (P.w_out) st_io(P.w_out, gi * (int64_t)k * k + e, w, f32);
     }
     ns_sync<WPM>(bar_id);
     // ---- x_a[s, j, g] = mean + sum_i (x[s, i, g] - mean) W[i][j]                                interface/base.py:257-278
     for (int sl = 0; sl < P.n_slices; ++sl) {
-        const double* xs = P.x + (int64_t)sl * k * P.n_grid + gi;
-        double* xo = P.xa + (int64_t)sl * k * P.n_grid + gi;
-        for (int i = gtid; i < k; i += GT) xbuf[i] = xs[(int64_t)i * P.n_grid];
+        const int64_t base = (int64_t)sl * k * P.n_grid + gi;
+        for (int i = gtid; i < k; i += GT) xbuf[i] = ld_io(P.x, base + (int64_t)i * P.n_grid, f32);
         ns_sync<WPM>(bar_id);
         double mean = 0.0;
         for (int i = 0; i < k; ++i) mean += xbuf[i];              // same order in every thread
@@ -340,7 +340,7 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         for (int j = gtid; j < k; j += GT) {
             double a = 0.0;
             for (int i = 0; i < k; ++i) a = fma(xbuf[i] - mean, D[i * LDW + j], a);
-            xo[(int64_t)j * P.n_grid] = mean + a;
+            st_io(P.xa, base + (int64_t)j * P.n_grid, mean + a, f32);
         }
         ns_sync<WPM>(bar_id);
     }

@@ -228,16 +228,14 @@ __device__ inline void etkf_transform(double* __restrict__ A, double* __restrict
 
 // x_a[s, j, g] = mean + sum_i (x[s, i, g] - mean) W[i][j]                                     interface/base.py:257-278
 __device__ inline void apply_point(const double* __restrict__ W, int ldw, int k, int n_slices, int64_t n_grid, int64_t gi,
-                            const double* __restrict__ x, double* __restrict__ xa, double* __restrict__ w_out,
+                            const void* __restrict__ x, void* __restrict__ xa, void* __restrict__ w_out, int f32,
                             double* __restrict__ xbuf, int tid, int nthreads, int bar_id) {
     if (w_out) {
-        double* dst = w_out + gi * (int64_t)k * k;
-        for (int i = tid; i < k * k; i += nthreads) dst[i] = W[(i / k) * ldw + (i % k)];
+        for (int i = tid; i < k * k; i += nthreads) st_io(w_out, gi * (int64_t)k * k + i, W[(i / k) * ldw + (i % k)], f32);
     }
     for (int s = 0; s < n_slices; ++s) {
-        const double* xs = x + (int64_t)s * k * n_grid + gi;
-        double* xo = xa + (int64_t)s * k * n_grid + gi;
-        for (int i = tid; i < k; i += nthreads) xbuf[i] = xs[(int64_t)i * n_grid];
+        const int64_t base = (int64_t)s * k * n_grid + gi;
+        for (int i = tid; i < k; i += nthreads) xbuf[i] = ld_io(x, base + (int64_t)i * n_grid, f32);
         group_barrier(bar_id, nthreads);
         double mean = 0.0;
         for (int i = 0; i < k; ++i) mean += xbuf[i];       // same order for every thread
@@ -245,7 +243,7 @@ __device__ inline void apply_point(const double* __restrict__ W, int ldw, int k,
         for (int j = tid; j < k; j += nthreads) {
             double acc = 0.0;
             for (int i = 0; i < k; ++i) acc = fma(xbuf[i] - mean, W[i * ldw + j], acc);
-            xo[(int64_t)j * n_grid] = mean + acc;
+            st_io(xa, base + (int64_t)j * n_grid, mean + acc, f32);
         }
         group_barrier(bar_id, nthreads);
     }
@@ -276,9 +274,10 @@ struct SolveParams {
     const double* cmat;        // [n_slots][slot_stride]: tile-packed augmented Gram (common.cuh), row k = b
     int64_t slot_stride;
     const Pos4* gpos;          // block-sorted grid positions (id = original index)
-    const double* x;
-    double* xa;
-    double* w_out;
+    const void* x;             // state / analysis / exported weights in the plan dtype (io_f32)
+    void* xa;
+    void* w_out;
+    int io_f32;
     unsigned long long* stats;
     int64_t slot_base;
     int64_t n_slots;
@@ -310,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_letkf_solve(const SolveParams
         const int nsw = jacobi_evd<NR, RW, NV>(S.A, S.Vt, S.ne, S.lda, S.ldv, (double)(k - 1) / P.rho, tid, THREADS, 0);
         if (P.stats && tid == 0) { atomicAdd(P.stats + 2, (unsigned long long)nsw); atomicAdd(P.stats + 3, 1ull); }
         etkf_transform(S.A, S.Vt, S.bvec, S.vec, k, S.ne, S.lda, S.ldv, P.rho, tid, THREADS, 0);
-        apply_point(S.A, S.lda, k, P.n_slices, P.n_grid, P.gpos[P.slot_base + s].id, P.x, P.xa, P.w_out, S.xbuf, tid,
+        apply_point(S.A, S.lda, k, P.n_slices, P.n_grid, P.gpos[P.slot_base + s].id, P.x, P.xa, P.w_out, P.io_f32, S.xbuf, tid,
                     THREADS, 0);
         __syncthreads();
     }

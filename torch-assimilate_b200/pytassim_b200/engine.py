@@ -40,8 +40,10 @@ class LETKFEngine(object):
                  dtype=torch.float64, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("pytassim_b200 needs a CUDA device (sm_100); there is no CPU fallback")
-        if dtype != torch.float64:
-            raise NotImplementedError("only float64 is implemented in this round")
+        if dtype not in (torch.float64, torch.float32):
+            raise NotImplementedError("the engine computes in float64 or float32, got {0}".format(dtype))
+        self.dtype = dtype
+        self._np_dtype = np.float64 if dtype == torch.float64 else np.float32
         self.lib = _cabi.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.k, self.n_slices = int(ens_size), int(n_slices)
@@ -54,7 +56,7 @@ class LETKFEngine(object):
                 ctypes.byref(handle), self.k, self.n_slices, int(metric.n_coord), int(metric.metric_id),
                 params.ctypes.data_as(_cabi._dp), len(metric.params),
                 radius.ctypes.data_as(_cabi._dp), int(radius.size), float(epsilon), float(inf_factor),
-                _cabi.F64, _TAPERS[taper]))
+                _cabi.F64 if dtype == torch.float64 else _cabi.F32, _TAPERS[taper]))
         self._plan = handle
         self.n_grid = 0
         self.n_obs = 0
@@ -87,8 +89,8 @@ class LETKFEngine(object):
 
     def bin_obs(self, obs_coords, normed_perts, normed_obs):
         """obs_coords (M, n_coord); normed_perts (k, M); normed_obs (M,) — interface/base.py:359-379 outputs."""
-        yn = _dev(normed_perts, device=self.device)
-        d = _dev(normed_obs, device=self.device).reshape(-1)
+        yn = _dev(normed_perts, dtype=self.dtype, device=self.device)
+        d = _dev(normed_obs, dtype=self.dtype, device=self.device).reshape(-1)
         if yn.dim() != 2 or yn.shape[0] != self.k:
             raise ValueError("normed_perts must be (ens_size, n_obs)")
         if yn.shape[-1] != d.shape[-1]:                          # pytassim/core/base.py:28-38
@@ -108,9 +110,11 @@ class LETKFEngine(object):
     # -- hot path ----------------------------------------------------------------------------------------------
     def analyse(self, state, out=None, return_weights=False, blocks=None, count_ambiguous=False):
         """state (n_slices, k, N) on the device -> analysis of the same shape (interface/base.py:257-278)."""
-        x = _dev(state, device=self.device).reshape(self.n_slices, self.k, self.n_grid)
+        x = _dev(state, dtype=self.dtype, device=self.device).reshape(self.n_slices, self.k, self.n_grid)
         xa = torch.empty_like(x) if out is None else out
-        w = torch.empty((self.n_grid, self.k, self.k), dtype=torch.float64, device=self.device) if return_weights else None
+        if xa.dtype != self.dtype or not xa.is_contiguous():
+            raise ValueError("out must be a contiguous {0} tensor".format(self.dtype))
+        w = torch.empty((self.n_grid, self.k, self.k), dtype=self.dtype, device=self.device) if return_weights else None
         amb = torch.zeros(1, dtype=torch.int64, device=self.device) if count_ambiguous else None
         b0, b1 = (0, self.n_blocks) if blocks is None else blocks
         with torch.cuda.device(self.device):
@@ -124,9 +128,15 @@ class LETKFEngine(object):
 
     def analyse_host(self, state, obs_coords, normed_perts, normed_obs, out=None):
         """End-to-end call with HOST arrays (numpy or pinned CPU tensors): upload, bin, analyse, download."""
-        x = np.ascontiguousarray(state, dtype=np.float64) if not isinstance(state, torch.Tensor) else state
-        yn = np.ascontiguousarray(normed_perts, dtype=np.float64) if not isinstance(normed_perts, torch.Tensor) else normed_perts
-        d = np.ascontiguousarray(normed_obs, dtype=np.float64) if not isinstance(normed_obs, torch.Tensor) else normed_obs
+        nd = self._np_dtype
+
+        def host(a):
+            if isinstance(a, torch.Tensor):
+                if a.dtype != self.dtype or not a.is_contiguous() or a.is_cuda:
+                    raise ValueError("host tensors must be contiguous CPU tensors of dtype {0}".format(self.dtype))
+                return a
+            return np.ascontiguousarray(a, dtype=nd)
+        x, yn, d = host(state), host(normed_perts), host(normed_obs)
         oc = obs_coords
         if isinstance(oc, torch.Tensor):
             oc_soa = oc if oc.shape[0] == self.metric.n_coord and oc.dim() == 2 and oc.shape[1] != self.metric.n_coord \
@@ -138,7 +148,7 @@ class LETKFEngine(object):
             raise ValueError('Observational size between ensemble ({0:d}) and observations '
                              '({1:d}) do not match!'.format(yn.shape[-1], m))
         if out is None:
-            out = np.empty(x.shape, dtype=np.float64) if not isinstance(x, torch.Tensor) else torch.empty_like(x)
+            out = np.empty(x.shape, dtype=nd) if not isinstance(x, torch.Tensor) else torch.empty_like(x)
 
         def hp(a):
             return ctypes.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else ctypes.c_void_p(a.ctypes.data)
@@ -179,22 +189,22 @@ class LETKFEngine(object):
     # -- global ETKF ------------------------------------------------------------------------------------------
     def etkf_weights(self, normed_perts, normed_obs):
         """``ETKFModule.forward`` on the device (core/etkf.py:79-103) -> W (k, k)."""
-        yn = _dev(normed_perts, device=self.device)
-        d = _dev(normed_obs, device=self.device).reshape(-1)
+        yn = _dev(normed_perts, dtype=self.dtype, device=self.device)
+        d = _dev(normed_obs, dtype=self.dtype, device=self.device).reshape(-1)
         if yn.shape[-1] != d.shape[-1]:
             raise ValueError('Observational size between ensemble ({0:d}) and observations '
                              '({1:d}) do not match!'.format(yn.shape[-1], d.shape[-1]))
-        w = torch.empty((self.k, self.k), dtype=torch.float64, device=self.device)
+        w = torch.empty((self.k, self.k), dtype=self.dtype, device=self.device)
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.b200da_etkf_weights(self._plan, _ptr(yn), _ptr(d), d.shape[0], _ptr(w), _stream()))
         return w
 
     def apply_weights(self, state, weights, out=None):
         """``_apply_weights`` (interface/base.py:257-278): weights (k, k) or (N, k, k)."""
-        x = _dev(state, device=self.device)
+        x = _dev(state, dtype=self.dtype, device=self.device)
         n_grid = x.shape[-1]
         x = x.reshape(self.n_slices, self.k, n_grid)
-        w = _dev(weights, device=self.device)
+        w = _dev(weights, dtype=self.dtype, device=self.device)
         per_grid = 1 if w.dim() == 3 else 0
         xa = torch.empty_like(x) if out is None else out
         with torch.cuda.device(self.device):
@@ -207,7 +217,7 @@ class LETKFEngine(object):
 
     def pack_columns(self, xa, b0, b1):
         ncols = self.block_offset(b1) - self.block_offset(b0)
-        packed = torch.empty((self.n_slices * self.k, ncols), dtype=torch.float64, device=self.device)
+        packed = torch.empty((self.n_slices * self.k, ncols), dtype=self.dtype, device=self.device)
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.b200da_pack_columns(self._plan, _ptr(xa), b0, b1, _ptr(packed), _stream()))
         return packed

@@ -34,9 +34,10 @@ class ETKF(FilterAssimilation):
         self._engines = {}
 
     def _global_engine(self, k, n_slices):
-        key = ('global', k, n_slices, float(self.inf_factor))
+        key = ('global', k, n_slices, float(self.inf_factor), self.dtype)
         if key not in self._engines:
-            self._engines[key] = LETKFEngine(k, n_slices, AbsDistance1D(), 1.0, inf_factor=float(self.inf_factor))
+            self._engines[key] = LETKFEngine(k, n_slices, AbsDistance1D(), 1.0, inf_factor=float(self.inf_factor),
+                                             dtype=self.dtype)
         return self._engines[key]
 
     def _analyse_arrays(self, state, x, innov, perts, obs_info):

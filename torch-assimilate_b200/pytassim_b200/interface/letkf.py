@@ -33,12 +33,12 @@ class LETKF(ETKF):
 
     def _local_engine(self, k, n_slices, grid_coords):
         loc = self.localization
-        key = ('local', k, n_slices, float(self.inf_factor), type(loc).__name__, repr(loc.dist_func),
+        key = ('local', k, n_slices, float(self.inf_factor), self.dtype, type(loc).__name__, repr(loc.dist_func),
                tuple(np.atleast_1d(loc.radius).tolist()), float(loc.epsilon))
         if key not in self._engines:
             self._engines = {kk: v for kk, v in self._engines.items() if kk[0] != 'local'}
             self._engines[key] = LETKFEngine(k, n_slices, loc.dist_func, loc.radius, epsilon=loc.epsilon,
-                                             inf_factor=float(self.inf_factor), taper=loc.taper)
+                                             inf_factor=float(self.inf_factor), taper=loc.taper, dtype=self.dtype)
             self._grid_cache = None
         eng = self._engines[key]
         if self._grid_cache is None or self._grid_cache.shape != grid_coords.shape or \
