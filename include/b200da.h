@@ -114,6 +114,12 @@ int b200da_grid_order(const b200da_plan* plan, int32_t* order_out, void* stream)
 int b200da_letkf(b200da_plan* plan, const void* X, void* Xa, void* W_opt, int64_t block_begin,
                  int64_t block_end, int64_t* n_ambiguous_opt, void* stream);
 
+/* The first half of b200da_letkf alone: the localization-weighted augmented Gram matrix of every grid point of the
+ * blocks, G_g = sum_j w_gj [y_j; d_j][y_j; d_j]^T (rows 0..k-1: C = Y~ Y~^T of core/etkf.py:68 after the sqrt(w) gather of
+ * interface/wrapper.py:91-97; row k: b = Y~ d~^T of core/etkf.py:72), dense (N, k+1, k+1) FP64 in original grid order,
+ * lower triangle filled, element (k, k) and the upper triangle zero.  Parity hook for the Gram kernels. */
+int b200da_letkf_gram(b200da_plan* plan, double* gram_out, int64_t block_begin, int64_t block_end, void* stream);
+
 /* Host-buffer convenience used for end-to-end timing: uploads (obs_coord, Yn, d, X), bins, analyses all
  * blocks, downloads Xa.  All pointers are HOST pointers (pinned memory makes the copies asynchronous).
  * The grid must have been set with b200da_set_grid. */

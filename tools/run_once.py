@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=1)
     ap.add_argument("--stats", action="store_true")
     ap.add_argument("--solver", default="newton", choices=["newton", "jacobi"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -29,14 +30,15 @@ def main():
     metric = bench.make_metric(w, data)
     k = w["k"]
     n_grid = data["state"].shape[-1]
-    eng = LETKFEngine(k, 1, metric, w["radius"], inf_factor=w["rho"])
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    eng = LETKFEngine(k, 1, metric, w["radius"], inf_factor=w["rho"], dtype=tdt)
     eng.set_grid(data["grid_rows"][:, 1:])
     eng.bin_obs(data["obs_rows"][:, 1:], data["normed_perts"], data["normed_obs"])
     eng.enable_timing(True)
     eng.set_solver(args.solver)
     if args.stats:
         eng.collect_stats(True)
-    x = torch.as_tensor(np.ascontiguousarray(data["state"].reshape(1, k, n_grid))).cuda()
+    x = torch.as_tensor(np.ascontiguousarray(data["state"].reshape(1, k, n_grid)), dtype=tdt).cuda()
     xa = torch.zeros_like(x)
     blocks = None
     if args.blocks:

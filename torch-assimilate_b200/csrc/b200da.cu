@@ -38,6 +38,19 @@ static double cutoff_radius(int taper, double eps) {
     return std::min(2.0, hi * (1.0 + 1e-7) + 1e-9);
 }
 
+// tile-packed augmented Gram of the chunk's grid slots -> dense (N, k+1, k+1) in original grid order (lower triangle)
+__global__ void k_unpack_gram(const double* __restrict__ cmat, const Pos4* __restrict__ gpos, int64_t slot_base, int64_t n_slots,
+                              int64_t slot_stride, int k1, double* __restrict__ out) {
+    for (int64_t s = blockIdx.x; s < n_slots; s += gridDim.x) {
+        const double* C = cmat + (size_t)s * (size_t)slot_stride;
+        double* o = out + (size_t)gpos[slot_base + s].id * (size_t)k1 * k1;
+        for (int e = threadIdx.x; e < k1 * k1; e += blockDim.x) {
+            const int r = e / k1, c = e - r * k1;
+            o[e] = (c <= r && !(r == k1 - 1 && c == k1 - 1)) ? C[sym_off(r, c)] : 0.0;
+        }
+    }
+}
+
 struct KernelConfig { int g, wpg; };
 static KernelConfig config_for_kt(int kt) {
     if (kt <= 5) return {8, 1};
@@ -91,6 +104,7 @@ template <int MODE>
 static int launch_neighbours(const b200da_plan* pl, const NeighbourParams& P, cudaStream_t st) {
     if (pl->n_blocks == 0) return B200DA_OK;
     switch (pl->gpb) {
+        case 128: k_neighbours<128, MODE><<<(int)pl->n_blocks, 256, 0, st>>>(P); break;
         case 8: k_neighbours<8, MODE><<<(int)pl->n_blocks, 256, 0, st>>>(P); break;
         case 4: k_neighbours<4, MODE><<<(int)pl->n_blocks, 256, 0, st>>>(P); break;
         default: k_neighbours<2, MODE><<<(int)pl->n_blocks, 256, 0, st>>>(P); break;
@@ -142,7 +156,14 @@ int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int
     pl->kt = kt; pl->kp = kt * 8;
     const KernelConfig cfg = config_for_kt(kt);
     pl->gpb = cfg.g;
+    pl->use_tc = (dtype == B200DA_F32 && k >= 32);
     pl->kernel_name = std::string("letkf_gram_") + (dtype == B200DA_F32 ? "f32in_f64dmma" : "f64") + "_kt" + std::to_string(kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
+    if (pl->use_tc) {
+        int n_cols, n_chunks, nc;
+        tc_chunking(k, &n_cols, &n_chunks, &nc);
+        pl->gpb = 128;
+        pl->kernel_name = "letkf_gram_tcgen05_bf16x3_k" + std::to_string(k) + "_m128_n" + std::to_string(nc) + "x" + std::to_string(n_chunks);
+    }
     Geometry& g = pl->geom;
     g.metric = metric; g.taper = taper; g.n_coord = n_coord; g.periodic = 0;
     g.radius = radius[0]; g.eps = epsilon; g.period = 0.0; g.sphere_r = 1.0;
@@ -212,9 +233,9 @@ int b200da_grid_order(const b200da_plan* plan, int32_t* order_out, void* stream)
     return B200DA_OK;
 }
 
-int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t block_begin, int64_t block_end,
-                 int64_t* n_ambiguous_opt, void* stream) {
-    if (!pl || !X || !Xa) return B200DA_ERR_INVALID;
+static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t block_begin, int64_t block_end,
+                      int64_t* n_ambiguous_opt, double* gram_out, void* stream) {
+    if (!pl || (!gram_out && (!X || !Xa))) return B200DA_ERR_INVALID;
     if (!pl->have_grid || !pl->have_obs) return B200DA_ERR_STATE;
     if (block_begin < 0 || block_end > pl->n_blocks || block_begin > block_end) return B200DA_ERR_INVALID;
     if (block_begin == block_end) return B200DA_OK;
@@ -274,9 +295,13 @@ int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t 
             if ((rc = pl->next_events(&ea, &eb, &ec))) return rc;
             B200DA_CUDA(cudaEventRecord(ea, st));
         }
-        if ((rc = dispatch_fused(pl, P, (int)(e - b), st))) return rc;
+        if (pl->use_tc) { if ((rc = launch_tc_gram(pl, P, (int)(e - b), st))) return rc; }
+        else if ((rc = dispatch_fused(pl, P, (int)(e - b), st))) return rc;
         if (pl->timing) B200DA_CUDA(cudaEventRecord(eb, st));
-        if (jacobi) {
+        if (gram_out) {
+            k_unpack_gram<<<(int)std::min<int64_t>(n_slots, 148 * 16), 128, 0, st>>>(P.cmat, P.gpos, s0, n_slots, slot_stride, k + 1, gram_out);
+            B200DA_LAUNCH_CHECK();
+        } else if (jacobi) {
             SolveParams S{};
             S.cmat = P.cmat; S.slot_stride = slot_stride; S.gpos = P.gpos; S.x = P.x; S.xa = P.xa; S.w_out = P.w_out; S.stats = P.stats;
             S.io_f32 = f32;
@@ -299,6 +324,16 @@ int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t 
     }
     if (pl->timing) B200DA_CUDA(cudaEventRecord(pl->ev1, st));
     return B200DA_OK;
+}
+
+int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t block_begin, int64_t block_end,
+                 int64_t* n_ambiguous_opt, void* stream) {
+    return letkf_impl(pl, X, Xa, W_opt, block_begin, block_end, n_ambiguous_opt, nullptr, stream);
+}
+
+int b200da_letkf_gram(b200da_plan* pl, double* gram_out, int64_t block_begin, int64_t block_end, void* stream) {
+    if (!gram_out) return B200DA_ERR_INVALID;
+    return letkf_impl(pl, nullptr, nullptr, nullptr, block_begin, block_end, nullptr, gram_out, stream);
 }
 
 int b200da_letkf_host(b200da_plan* pl, const double* obs_coord_host, const void* Yn_host, const void* d_host, int64_t m,

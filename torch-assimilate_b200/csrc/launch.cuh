@@ -10,5 +10,7 @@ struct LetkfParams;
 struct NsParams;
 int dispatch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st);
 int dispatch_ns(int kts, const NsParams& P, cudaStream_t st);
+void tc_chunking(int k, int* n_cols, int* n_chunks, int* nc);
+int launch_tc_gram(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st);
 
 }  // namespace b200da

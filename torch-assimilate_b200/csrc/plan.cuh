@@ -59,6 +59,7 @@ struct b200da_plan {
     int kt = 0;            // 8-row tiles of the augmented [Yn; d] matrix: ceil((k + 1) / 8)
     int kp = 0;            // padded row length of the staging copy: 8 * kt
     int gpb = 8;           // grid points per block (CTA) of the fused kernel
+    bool use_tc = false;   // FP32 plan with k >= 32: tcgen05 Gram kernel, 128 grid points per block
     double rho = 1.0;
     b200da::Geometry geom{};
     // grid side

@@ -1,0 +1,32 @@
+// Launch of the tcgen05 Gram kernel (tc_gram_kernel.cuh): its own translation unit so that the library builds in parallel.
+#include "launch.cuh"
+#include "tc_gram_kernel.cuh"
+
+namespace b200da {
+
+// column chunking of the (k + 1)(k + 2) / 2 pair columns: as few chunks as fit 512 tensor-memory columns each
+void tc_chunking(int k, int* n_cols, int* n_chunks, int* nc) {
+    *n_cols = (k + 1) * (k + 2) / 2;
+    *n_chunks = (*n_cols + kTcMaxCols - 1) / kTcMaxCols;
+    const int per = (*n_cols + *n_chunks - 1) / *n_chunks;
+    *nc = (per + 31) / 32 * 32;
+}
+
+int launch_tc_gram(b200da_plan* pl, const LetkfParams& L, int nblocks, cudaStream_t st) {
+    TcParams P{};
+    P.L = L;
+    tc_chunking(pl->k, &P.n_cols, &P.n_chunks, &P.nc);
+    P.kp = pl->kp;
+    const Geometry& g = pl->geom;
+    P.r_scale = (float)(g.metric == B200DA_METRIC_HAVERSINE ? 2.0 * g.sphere_r / g.radius : 1.0 / g.radius);
+    P.eps = (float)g.eps;
+    P.period = (float)g.period;
+    const size_t smem = tc_smem_bytes(P.kp, P.nc);
+    if (smem > kMaxSmem || (pl->kp >> 2) * kTcObs > kTcMaxYItems * kTcThreads) return B200DA_ERR_UNSUPPORTED;
+    B200DA_CUDA(cudaFuncSetAttribute(k_tc_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tc_gram<<<nblocks * P.n_chunks, kTcThreads, smem, st>>>(P);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
+}  // namespace b200da

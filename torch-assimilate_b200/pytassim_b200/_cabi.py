@@ -34,6 +34,7 @@ SIGNATURES = {
     "b200da_block_offset": (_i64, [_vp, _i64]),
     "b200da_grid_order": (_i, [_vp, _vp, _vp]),
     "b200da_letkf": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "b200da_letkf_gram": (_i, [_vp, _vp, _i64, _i64, _vp]),
     "b200da_letkf_host": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "b200da_neighbour_count": (_i, [_vp, _vp, _vp, _vp]),
     "b200da_neighbour_fill": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -126,6 +126,15 @@ class LETKFEngine(object):
             res.append(int(amb.item()))
         return res[0] if len(res) == 1 else tuple(res)
 
+    def local_gram(self, blocks=None):
+        """(N, k+1, k+1) FP64: the localization-weighted augmented Gram matrix of every grid point (lower triangle),
+        i.e. the output of the Gram kernel alone (parity hook; core/etkf.py:68,72 after interface/wrapper.py:91-97)."""
+        out = torch.zeros((self.n_grid, self.k + 1, self.k + 1), dtype=torch.float64, device=self.device)
+        b0, b1 = (0, self.n_blocks) if blocks is None else blocks
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_letkf_gram(self._plan, _ptr(out), b0, b1, _stream()))
+        return out
+
     def analyse_host(self, state, obs_coords, normed_perts, normed_obs, out=None):
         """End-to-end call with HOST arrays (numpy or pinned CPU tensors): upload, bin, analyse, download."""
         nd = self._np_dtype
