@@ -33,10 +33,15 @@ namespace b200da {
 
 constexpr int kTcM = 128;          // grid points per CTA (rows of D)
 constexpr int kTcObs = 32;         // observations per staged tile (two K = 16 MMA steps)
-constexpr int kTcThreads = 512;
+constexpr int kTcGenWarps = 16;    // operand-generating warps (also the epilogue warps)
+constexpr int kTcGenThreads = kTcGenWarps * 32;
+constexpr int kTcMmaWarp = kTcGenWarps;        // issues the tcgen05.mma stream, owns the tensor-memory allocation
+constexpr int kTcLoadWarp = kTcGenWarps + 1;   // first of the loader warps: candidate filter + observation-tile loads
+constexpr int kTcYStages = 4;      // loader warps = observation-tile buffers (one each) between loaders and generators
+constexpr int kTcThreads = (kTcGenWarps + 1 + kTcYStages) * 32;
 constexpr int kTcYLd = 36;         // row length of the member-major observation tile: 32 obs + 4 (conflict-free LDS.128)
 constexpr int kTcMaxCols = 512;    // tensor-memory columns = accumulator columns per CTA
-constexpr int kTcMaxYItems = 3;    // 16-byte chunks of the observation tile per thread (k + 1 <= 136)
+constexpr int kTcFilterUnroll = 8; // candidates per lane and filter pass (independent loads in flight)
 
 struct TcParams {
     LetkfParams L;
@@ -44,6 +49,8 @@ struct TcParams {
     int n_chunks;      // column chunks = CTAs per grid-point block
     int nc;            // columns per chunk, multiple of 32, <= 512
     int kp;            // row length of the staging copy ys (floats)
+    int n_load;        // active loader warps = observation-tile buffers (2..kTcYStages, limited by shared memory)
+    int asin_poly;     // haversine: chord / 2 stays below 0.3, asin by its series
     float r_scale;     // distance -> r:  1 / radius  (haversine: 2 R / radius, applied to asin(chord / 2))
     float eps;
     float period;
@@ -54,6 +61,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {     // release at CTA scope
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -95,14 +105,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
 }
 // x[0..7] -> eight bf16 "hi" terms and eight bf16 "lo" terms (x = hi + lo to 16 significant bits)
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-    float h[8], l[8];
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        h[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
-        l[i] = x[i] - h[i];
+    for (int i = 0; i < 4; ++i) {
+        h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+        const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xffff0000u);
+        l[i] = pack_bf16x2(x[2 * i] - h0, x[2 * i + 1] - h1);
     }
-    hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // ---- FP32 tapers ---------------------------------------------------------------------------------------------------------
@@ -139,16 +150,26 @@ __device__ __forceinline__ float taper_gcinf_f32(float r) {       // gaspari_coh
     return 0.0f;
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // localization weight of a pair from positions relative to the block centre (bin space)
-__device__ __forceinline__ float pair_weight_f32(int metric, int taper, float r_scale, float eps, float period,
+__device__ __forceinline__ float pair_weight_f32(int metric, int taper, int asin_poly, float r_scale, float eps, float period,
                                                  float gx, float gy, float gz, float ox, float oy, float oz) {
     const float dx = ox - gx, dy = oy - gy, dz = oz - gz;
     float r;
     if (metric == B200DA_METRIC_HAVERSINE) {
-        const float h = fminf(0.5f * sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz))), 1.0f);
-        r = r_scale * asinf(h);
+        const float h2 = 0.25f * fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        const float h = sqrt_approx(h2);
+        if (asin_poly)     // asin(h) = h (1 + h^2/6 + 3 h^4/40 + 15 h^6/336 + 35 h^8/1152 + ...), |h| <= 0.3
+            r = r_scale * h * fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 35.0f / 1152.0f, 15.0f / 336.0f), 3.0f / 40.0f), 1.0f / 6.0f), 1.0f);
+        else
+            r = r_scale * asinf(fminf(h, 1.0f));
     } else if (metric == B200DA_METRIC_EUCLID) {
-        r = r_scale * sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+        r = r_scale * sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
     } else {
         float d = fabsf(dz);
         if (metric == B200DA_METRIC_PERIODIC1D) d = fminf(d, period - d);
@@ -159,39 +180,44 @@ __device__ __forceinline__ float pair_weight_f32(int metric, int taper, float r_
 }
 
 // ---- shared-memory carve-up ------------------------------------------------------------------------------------------------
+// barriers: [0..1] operand stage full (16 generator warps), [2..3] operand stage free (tcgen05.commit),
+//           [4..7] observation tile full (loader), [8..11] observation tile free (16 generator warps), [12] all MMAs done
 struct TcSmem {
     BlockHeader<kTcM>* H;
-    uint64_t* bars;          // [0], [1]: operand stage free; [2]: all MMAs done
+    uint64_t* bars;
     uint32_t* tmem_slot;
-    float4* otile;           // [2][kTcObs] observation positions relative to the block centre, .w = 1 valid / 0 padding
-    float* ytile;            // [2][kp][kTcYLd] member-major [Yn; d] of the tile
+    int* ymeta;              // [kTcYStages] valid observations of the tile, 0 = end of the candidate stream
+    int* op_last;            // [2] set by the generators when the operand stage carries the end marker instead of a tile
+    float4* otile;           // [kTcYStages][kTcObs] observation positions relative to the block centre, .w = 1 valid / 0 padding
+    float* ytile;            // [kTcYStages][kp][kTcYLd] member-major [Yn; d] of the tile
     unsigned char* a_hi;     // [2][kTcM * 64]
     unsigned char* a_lo;
     unsigned char* b_hi;     // [2][nc * 64]
     unsigned char* b_lo;
 };
-__host__ __device__ inline size_t tc_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
-__host__ __device__ inline size_t tc_smem_bytes(int kp, int nc) {
+__host__ __device__ constexpr size_t tc_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline size_t tc_smem_bytes(int kp, int nc, int n_load) {
     size_t o = tc_align(sizeof(BlockHeader<kTcM>), 128);
-    o += 128;                                             // barriers + tensor-memory address
-    o += sizeof(float4) * 2 * kTcObs;
-    o = tc_align(o + sizeof(float) * 2 * (size_t)kp * kTcYLd, 128);
+    o += 256;                                             // barriers, tensor-memory address, tile meta data
+    o += sizeof(float4) * kTcYStages * kTcObs;
+    o = tc_align(o + sizeof(float) * n_load * (size_t)kp * kTcYLd, 128);
     o += 2 * 2 * (size_t)kTcM * 64;
     o += 2 * 2 * (size_t)nc * 64;
-    return o + 128;                                       // slack for the manual 128-byte alignment of the base
+    return o;
 }
-__device__ inline TcSmem tc_carve(unsigned char* base, int kp, int nc) {
+__device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int kp, int nc, int n_load) {
     TcSmem S;
-    size_t o = 0;
+    size_t o = tc_align(sizeof(BlockHeader<kTcM>), 128);
     S.H = reinterpret_cast<BlockHeader<kTcM>*>(base);
-    o = tc_align(sizeof(BlockHeader<kTcM>), 128);
     S.bars = reinterpret_cast<uint64_t*>(base + o);
-    S.tmem_slot = reinterpret_cast<uint32_t*>(base + o + 64);
-    o += 128;
+    S.tmem_slot = reinterpret_cast<uint32_t*>(base + o + 128);
+    S.ymeta = reinterpret_cast<int*>(base + o + 144);
+    S.op_last = reinterpret_cast<int*>(base + o + 176);
+    o += 256;
     S.otile = reinterpret_cast<float4*>(base + o);
-    o += sizeof(float4) * 2 * kTcObs;
+    o += sizeof(float4) * kTcYStages * kTcObs;
     S.ytile = reinterpret_cast<float*>(base + o);
-    o = tc_align(o + sizeof(float) * 2 * (size_t)kp * kTcYLd, 128);
+    o = tc_align(o + sizeof(float) * n_load * (size_t)kp * kTcYLd, 128);
     S.a_hi = base + o; o += 2 * (size_t)kTcM * 64;
     S.a_lo = base + o; o += 2 * (size_t)kTcM * 64;
     S.b_hi = base + o; o += 2 * (size_t)nc * 64;
@@ -207,11 +233,16 @@ __device__ __forceinline__ void col_to_pair(int c, int& a, int& b) {
     b = c - a * (a + 1) / 2;
 }
 
+// Warp roles.  16 generator warps turn observation tiles into operand tiles (W: taper weights of 128 grid points x 32
+// observations, Z: the pair products of this CTA's columns x 32 observations; bf16 hi / lo); one warp issues the MMAs; four
+// loader warps each filter an interleaved quarter of the candidate observations of the block (the sum over observations
+// does not depend on their order) and load the surviving rows into their own tile buffer.  The pipelines are coupled by
+// mbarriers only: there is no CTA-wide barrier between set-up and the epilogue.
 __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
     const int kp = P.kp, nc = P.nc;
-    const TcSmem S = tc_carve(base, kp, nc);
+    const int n_load = P.n_load;
+    const TcSmem S = tc_carve(smem_dyn, kp, nc, n_load);
     BlockHeader<kTcM>& H = *S.H;
     const LetkfParams& L = P.L;
     const Geometry& g = L.g;
@@ -219,15 +250,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
     const int blk = L.block_begin + (int)(blockIdx.x / P.n_chunks);
     const int chunk = (int)(blockIdx.x % P.n_chunks);
     const int k1 = L.k + 1;                                       // rows of the augmented [Yn; d]
-    const float* __restrict__ ys = reinterpret_cast<const float*>(L.ys);
+    uint64_t* op_full = S.bars;
+    uint64_t* op_free = S.bars + 2;
+    uint64_t* y_full = S.bars + 4;
+    uint64_t* y_free = S.bars + 4 + kTcYStages;
+    uint64_t* all_done = S.bars + 4 + 2 * kTcYStages;
 
     // ---- one-time set-up: candidate runs of the block, barriers, tensor memory ----------------------------------------
     setup_block<kTcM>(H, g, L.gpos, L.block_off, L.cell_start, L.n_obs, L.cut_pad, blk);
     if (tid == 0) {
-        mbar_init(&S.bars[0], 1); mbar_init(&S.bars[1], 1); mbar_init(&S.bars[2], 1);
+        mbar_init(&op_full[0], kTcGenWarps); mbar_init(&op_full[1], kTcGenWarps);
+        mbar_init(&op_free[0], 1); mbar_init(&op_free[1], 1);
+        for (int i = 0; i < kTcYStages; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_free[i], kTcGenWarps); }
+        mbar_init(all_done, 1);
+        S.op_last[0] = 0; S.op_last[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(smem_u32(S.tmem_slot)), "r"((uint32_t)kTcMaxCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -237,190 +276,203 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
     tc_fence_after();
     const uint32_t tmem = *S.tmem_slot;
     const int ng = H.ng;
-    const int slot0 = L.block_off[blk];
-
-    // this thread's grid point (W generation) and pair column (Z generation)
-    const int my_g = tid & (kTcM - 1), my_kc = tid >> 7;          // 128 grid points x 4 chunks of 8 observations
-    float gxr = 0.f, gyr = 0.f, gzr = 0.f;
-    const bool g_ok = my_g < ng;
-    if (g_ok) {
-        gxr = (float)(H.gp[my_g].x - H.cx); gyr = (float)(H.gp[my_g].y - H.cy); gzr = (float)(H.gp[my_g].z - H.cz);
-    }
-    const int my_col = chunk * nc + tid;
-    const bool c_ok = tid < nc && my_col < P.n_cols;
-    int ca = 0, cb = 0;
-    if (c_ok) col_to_pair(my_col, ca, cb);
-
-    const int cand_total = H.cand_total, n_runs = H.n_runs;
-    const double bcx = H.cx, bcy = H.cy, bcz = H.cz;
-    const double reach = (L.cut_pad + H.rb) * (1.0 + 1e-12);
-    int cand_pos = 0, ring_head = 0, ring_tail = 0;
-
-    auto refill = [&]() {                 // keep at least one tile of surviving candidates in the ring; CTA-uniform
-        while (ring_tail - ring_head < kTcObs && cand_pos < cand_total) {
-            const int c = cand_pos + tid;
-            bool keep = false;
-            int s = 0;
-            if (c < cand_total) {
-                int lo_ = 0, hi_ = n_runs;
-                while (hi_ - lo_ > 1) {
-                    const int mid = (lo_ + hi_) >> 1;
-                    if (H.run_pref[mid] <= c) lo_ = mid; else hi_ = mid;
-                }
-                s = H.run_start[lo_] + (c - H.run_pref[lo_]);
-                const Pos4 po = L.opos[s];
-                keep = bin_distance(g, bcx, bcy, bcz, po.x, po.y, po.z) <= reach;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) H.warp_counts[warp] = __popc(bal);
-            __syncthreads();
-            int before = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < kTcThreads / 32; ++w) {
-                const int cnt = H.warp_counts[w];
-                if (w < warp) before += cnt;
-                total += cnt;
-            }
-            if (keep) H.ring[(ring_tail + before + __popc(bal & ((1u << lane) - 1u))) & (kRing - 1)] = s;
-            __syncthreads();
-            ring_tail += total;
-            cand_pos += kTcThreads;
-        }
-    };
-
-    // global -> registers of one tile (positions by the first 32 threads, observation rows by everybody)
-    const int chr = kp >> 2;                                      // 16-byte chunks per staged row
-    const int y_items = kTcObs * chr;
-    float4 pre_y[kTcMaxYItems];
-    float4 pre_o = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto fetch = [&](int head, int n_tile) {
-#pragma unroll
-        for (int i = 0; i < kTcMaxYItems; ++i) {
-            const int item = tid + i * kTcThreads;
-            if (item < y_items) {
-                const int j = item & (kTcObs - 1), q = item >> 5;
-                const int s = H.ring[(head + (j < n_tile ? j : 0)) & (kRing - 1)];
-                pre_y[i] = *reinterpret_cast<const float4*>(ys + (size_t)s * kp + q * 4);
-            }
-        }
-        if (tid < kTcObs) {
-            pre_o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tid < n_tile) {
-                const Pos4 po = L.opos[H.ring[(head + tid) & (kRing - 1)]];
-                pre_o = make_float4((float)(po.x - bcx), (float)(po.y - bcy), (float)(po.z - bcz), 1.0f);
-            }
-        }
-    };
-    auto stash = [&](int buf) {           // registers -> shared memory, observation rows transposed to member-major
-        float* yt = S.ytile + (size_t)buf * kp * kTcYLd;
-#pragma unroll
-        for (int i = 0; i < kTcMaxYItems; ++i) {
-            const int item = tid + i * kTcThreads;
-            if (item < y_items) {
-                const int j = item & (kTcObs - 1), q = item >> 5;
-                yt[(q * 4 + 0) * kTcYLd + j] = pre_y[i].x; yt[(q * 4 + 1) * kTcYLd + j] = pre_y[i].y;
-                yt[(q * 4 + 2) * kTcYLd + j] = pre_y[i].z; yt[(q * 4 + 3) * kTcYLd + j] = pre_y[i].w;
-            }
-        }
-        if (tid < kTcObs) S.otile[buf * kTcObs + tid] = pre_o;
-    };
-
-    const uint32_t idesc = tc_idesc_bf16(nc >> 1);                // two MMAs of N = nc / 2 per K step
     const uint32_t a_lbo = kTcM * 16, b_lbo = (uint32_t)nc * 16;
     int n_tiles = 0;
 
-    refill();
-    int n_tile = min(kTcObs, ring_tail - ring_head);
-    if (n_tile > 0) {
-        fetch(ring_head, n_tile);
-        ring_head += n_tile;
-        stash(0);
-    }
-    __syncthreads();
-
-    while (n_tile > 0) {
-        const int t = n_tiles, st = t & 1;
-        // ---- prefetch the next tile into registers -------------------------------------------------------------------
-        refill();
-        const int n_next = min(kTcObs, ring_tail - ring_head);
-        if (n_next > 0) { fetch(ring_head, n_next); ring_head += n_next; }
-        // ---- operand stage free?  (MMAs of tile t - 2 have finished reading it) ----------------------------------------
-        if (t >= 2) mbar_wait(&S.bars[st], (uint32_t)(((t >> 1) - 1) & 1));
-        // ---- W tile: taper weights of 128 grid points x 32 observations ------------------------------------------------
-        {
-            float w[8];
-            const float4* ot = S.otile + st * kTcObs + my_kc * 8;
+    if (warp >= kTcLoadWarp + n_load) {
+        // spare loader warp (fewer tile buffers than loader warps fit in shared memory): nothing to do
+    } else if (warp >= kTcLoadWarp) {
+        // =================================================================================================================
+        // loaders: candidate filter (bounding sphere of the block) -> private ring of surviving observation slots -> tiles
+        // =================================================================================================================
+        const int lw = warp - kTcLoadWarp;                        // loader index = tile buffer
+        const float* __restrict__ ys = reinterpret_cast<const float*>(L.ys);
+        const int cand_total = H.cand_total, n_runs = H.n_runs;
+        const double bcx = H.cx, bcy = H.cy, bcz = H.cz;
+        const double reach = (L.cut_pad + H.rb) * (1.0 + 1e-12);
+        const int chr = kp >> 2;                                  // 16-byte chunks per staged row
+        constexpr int kPass = kTcFilterUnroll * 32, kRingW = kRing / kTcYStages;
+        int* ring = H.ring + lw * kRingW;
+        int cand_pos = lw * kPass, head = 0, tail = 0;
+        for (int u = 0;; ++u) {
+            while (tail - head < kTcObs && cand_pos < cand_total) {
+                int s[kTcFilterUnroll];
+                Pos4 po[kTcFilterUnroll];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const float4 o = ot[jj];
-                float v = 0.0f;
-                if (g_ok && o.w != 0.0f)
-                    v = pair_weight_f32(g.metric, g.taper, P.r_scale, P.eps, P.period, gxr, gyr, gzr, o.x, o.y, o.z);
-                w[jj] = v;
-            }
-            uint4 hi, lo;
-            split8(w, hi, lo);
-            const size_t off = (size_t)st * kTcM * 64 + (size_t)my_kc * a_lbo + (size_t)my_g * 16;
-            *reinterpret_cast<uint4*>(S.a_hi + off) = hi;
-            *reinterpret_cast<uint4*>(S.a_lo + off) = lo;
-        }
-        // ---- Z tile: products y_a y_b of this thread's pair column -------------------------------------------------------
-        if (c_ok) {
-            const float* yt = S.ytile + (size_t)st * kp * kTcYLd;
-            const float* ya = yt + ca * kTcYLd;
-            const float* yb = yt + cb * kTcYLd;
+                for (int q = 0; q < kTcFilterUnroll; ++q) {
+                    const int c = cand_pos + q * 32 + lane;
+                    s[q] = -1;
+                    if (c < cand_total) {
+                        int lo_ = 0, hi_ = n_runs;
+                        while (hi_ - lo_ > 1) {
+                            const int mid = (lo_ + hi_) >> 1;
+                            if (H.run_pref[mid] <= c) lo_ = mid; else hi_ = mid;
+                        }
+                        s[q] = H.run_start[lo_] + (c - H.run_pref[lo_]);
+                    }
+                }
 #pragma unroll
-            for (int kc = 0; kc < kTcObs / 8; ++kc) {
-                const float4 a0 = *reinterpret_cast<const float4*>(ya + kc * 8), a1 = *reinterpret_cast<const float4*>(ya + kc * 8 + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(yb + kc * 8), b1 = *reinterpret_cast<const float4*>(yb + kc * 8 + 4);
-                const float z[8] = {a0.x * b0.x, a0.y * b0.y, a0.z * b0.z, a0.w * b0.w, a1.x * b1.x, a1.y * b1.y, a1.z * b1.z, a1.w * b1.w};
-                uint4 hi, lo;
-                split8(z, hi, lo);
-                const size_t off = (size_t)st * nc * 64 + (size_t)kc * b_lbo + (size_t)tid * 16;
-                *reinterpret_cast<uint4*>(S.b_hi + off) = hi;
-                *reinterpret_cast<uint4*>(S.b_lo + off) = lo;
+                for (int q = 0; q < kTcFilterUnroll; ++q) po[q] = L.opos[max(s[q], 0)];
+#pragma unroll
+                for (int q = 0; q < kTcFilterUnroll; ++q) {
+                    const bool keep = s[q] >= 0 && bin_distance(g, bcx, bcy, bcz, po[q].x, po[q].y, po[q].z) <= reach;
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) ring[(tail + __popc(bal & ((1u << lane) - 1u))) & (kRingW - 1)] = s[q];
+                    tail += __popc(bal);
+                }
+                cand_pos += n_load * kPass;
+                __syncwarp();
             }
+            const int n = min(kTcObs, tail - head);
+            if (u >= 1) mbar_wait(&y_free[lw], (uint32_t)((u - 1) & 1));
+            if (n == 0) {
+                if (lane == 0) { S.ymeta[lw] = 0; mbar_arrive(&y_full[lw]); }
+                break;
+            }
+            const int slot = ring[(head + (lane < n ? lane : 0)) & (kRingW - 1)];
+            const float* row = ys + (size_t)slot * kp;
+            float* yt = S.ytile + (size_t)lw * kp * kTcYLd + lane;
+            const Pos4 p = L.opos[slot];
+            for (int q0 = 0; q0 < chr; q0 += 12) {                 // 12 independent 16-byte loads in flight per lane
+                float4 v[12];
+#pragma unroll
+                for (int q = 0; q < 12; ++q)
+                    if (q0 + q < chr) v[q] = *reinterpret_cast<const float4*>(row + (q0 + q) * 4);
+#pragma unroll
+                for (int q = 0; q < 12; ++q)
+                    if (q0 + q < chr) {
+                        float* dst = yt + (size_t)(q0 + q) * 4 * kTcYLd;
+                        dst[0] = v[q].x; dst[kTcYLd] = v[q].y; dst[2 * kTcYLd] = v[q].z; dst[3 * kTcYLd] = v[q].w;
+                    }
+            }
+            {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < n) o = make_float4((float)(p.x - bcx), (float)(p.y - bcy), (float)(p.z - bcz), 1.0f);
+                S.otile[lw * kTcObs + lane] = o;
+            }
+            head += n;
+            __syncwarp();
+            if (lane == 0) { S.ymeta[lw] = n; mbar_arrive(&y_full[lw]); }
         }
-        // ---- hand the prefetched tile to the other buffer, publish the operands to the tensor core -----------------------
-        if (n_next > 0) stash(st ^ 1);
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
+    } else if (warp == kTcMmaWarp) {
+        // =================================================================================================================
+        // MMA issuer: per tile 2 K steps x 2 column halves x (hi hi + hi lo + lo hi)
+        // =================================================================================================================
+        const uint32_t idesc = tc_idesc_bf16(nc >> 1);
+        const uint64_t da_hi0 = tc_smem_desc(smem_u32(S.a_hi), a_lbo, 128), da_lo0 = tc_smem_desc(smem_u32(S.a_lo), a_lbo, 128);
+        const uint64_t db_hi0 = tc_smem_desc(smem_u32(S.b_hi), b_lbo, 128), db_lo0 = tc_smem_desc(smem_u32(S.b_lo), b_lbo, 128);
+        int t = 0;
+        for (;; ++t) {
+            const int st = t & 1;
+            mbar_wait(&op_full[st], (uint32_t)((t >> 1) & 1));
+            if (S.op_last[st]) break;
             tc_fence_after();
-            const uint32_t ahi = smem_u32(S.a_hi + (size_t)st * kTcM * 64), alo = smem_u32(S.a_lo + (size_t)st * kTcM * 64);
-            const uint32_t bhi = smem_u32(S.b_hi + (size_t)st * nc * 64), blo = smem_u32(S.b_lo + (size_t)st * nc * 64);
+            if (lane == 0) {
 #pragma unroll
-            for (int ks = 0; ks < kTcObs / 16; ++ks) {
+                for (int ks = 0; ks < kTcObs / 16; ++ks) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t boff = (uint32_t)ks * 2 * b_lbo + (uint32_t)h * (uint32_t)(nc >> 1) * 16;
-                    const uint64_t da_hi = tc_smem_desc(ahi + ks * 2 * a_lbo, a_lbo, 128), da_lo = tc_smem_desc(alo + ks * 2 * a_lbo, a_lbo, 128);
-                    const uint64_t db_hi = tc_smem_desc(bhi + boff, b_lbo, 128), db_lo = tc_smem_desc(blo + boff, b_lbo, 128);
-                    const uint32_t d = tmem + (uint32_t)h * (uint32_t)(nc >> 1);
-                    tc_mma_bf16(d, da_hi, db_hi, idesc, (t > 0 || ks > 0) ? 1u : 0u);
-                    tc_mma_bf16(d, da_hi, db_lo, idesc, 1u);
-                    tc_mma_bf16(d, da_lo, db_hi, idesc, 1u);
+                    for (int h = 0; h < 2; ++h) {
+                        // descriptor start addresses advance in 16-byte units inside the 14-bit address field
+                        const uint32_t aoff = ((uint32_t)st * kTcM * 64 + (uint32_t)ks * 2 * a_lbo) >> 4;
+                        const uint32_t boff = ((uint32_t)st * (uint32_t)nc * 64 + (uint32_t)ks * 2 * b_lbo + (uint32_t)h * (uint32_t)(nc >> 1) * 16) >> 4;
+                        const uint32_t d = tmem + (uint32_t)h * (uint32_t)(nc >> 1);
+                        tc_mma_bf16(d, da_hi0 + aoff, db_hi0 + boff, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+                        tc_mma_bf16(d, da_hi0 + aoff, db_lo0 + boff, idesc, 1u);
+                        tc_mma_bf16(d, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
+                    }
+                }
+                tc_commit(&op_free[st]);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (t > 0) tc_commit(all_done); else mbar_arrive(all_done);
+        }
+    } else {
+        // =================================================================================================================
+        // generators
+        // =================================================================================================================
+        const int my_g = tid & (kTcM - 1), my_kc = tid >> 7;      // 128 grid points x 4 chunks of 8 observations
+        float gxr = 0.f, gyr = 0.f, gzr = 0.f;
+        const bool g_ok = my_g < ng;
+        if (g_ok) {
+            gxr = (float)(H.gp[my_g].x - H.cx); gyr = (float)(H.gp[my_g].y - H.cy); gzr = (float)(H.gp[my_g].z - H.cz);
+        }
+        const int my_col = chunk * nc + tid;
+        const bool c_ok = tid < nc && my_col < P.n_cols;
+        int ca = 0, cb = 0;
+        if (c_ok) col_to_pair(my_col, ca, cb);
+        const int metric = g.metric, taper = g.taper, asin_poly = P.asin_poly;
+        const float r_scale = P.r_scale, eps = P.eps, period = P.period;
+        unsigned alive = (1u << n_load) - 1u, par = 0u;       // loaders still producing; phase parity of their buffers
+        int t = 0;                                                  // operand tiles produced so far
+        for (int turn = 0; alive != 0u; ++turn) {
+            const int yst = turn % n_load;
+            if (!((alive >> yst) & 1u)) continue;
+            mbar_wait(&y_full[yst], (par >> yst) & 1u);
+            if (S.ymeta[yst] == 0) { alive &= ~(1u << yst); continue; }      // this loader has run out of candidates
+            par ^= 1u << yst;
+            const int st = t & 1;
+            if (t >= 2) mbar_wait(&op_free[st], (uint32_t)(((t >> 1) - 1) & 1));
+            // ---- W tile: taper weights of this thread's grid point for 8 observations -----------------------------------
+            {
+                float w[8];
+                const float4* ot = S.otile + yst * kTcObs + my_kc * 8;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const float4 o = ot[jj];
+                    float v = 0.0f;
+                    if (g_ok && o.w != 0.0f)
+                        v = pair_weight_f32(metric, taper, asin_poly, r_scale, eps, period, gxr, gyr, gzr, o.x, o.y, o.z);
+                    w[jj] = v;
+                }
+                uint4 hi, lo;
+                split8(w, hi, lo);
+                const size_t off = (size_t)st * kTcM * 64 + (size_t)my_kc * a_lbo + (size_t)my_g * 16;
+                *reinterpret_cast<uint4*>(S.a_hi + off) = hi;
+                *reinterpret_cast<uint4*>(S.a_lo + off) = lo;
+            }
+            // ---- Z tile: products y_a y_b of this thread's pair column ----------------------------------------------------
+            if (c_ok) {
+                const float* yt = S.ytile + (size_t)yst * kp * kTcYLd;
+                const float* ya = yt + ca * kTcYLd;
+                const float* yb = yt + cb * kTcYLd;
+#pragma unroll
+                for (int kc = 0; kc < kTcObs / 8; ++kc) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(ya + kc * 8), a1 = *reinterpret_cast<const float4*>(ya + kc * 8 + 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(yb + kc * 8), b1 = *reinterpret_cast<const float4*>(yb + kc * 8 + 4);
+                    const float z[8] = {a0.x * b0.x, a0.y * b0.y, a0.z * b0.z, a0.w * b0.w, a1.x * b1.x, a1.y * b1.y, a1.z * b1.z, a1.w * b1.w};
+                    uint4 hi, lo;
+                    split8(z, hi, lo);
+                    const size_t off = (size_t)st * nc * 64 + (size_t)kc * b_lbo + (size_t)tid * 16;
+                    *reinterpret_cast<uint4*>(S.b_hi + off) = hi;
+                    *reinterpret_cast<uint4*>(S.b_lo + off) = lo;
                 }
             }
-            tc_commit(&S.bars[st]);
+            // ---- publish the operand stage to the tensor core, release the observation tile -----------------------------------
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&op_full[st]); mbar_arrive(&y_free[yst]); }
+            ++t;
         }
-        ++n_tiles;
-        n_tile = n_next;
-    }
+        {   // end marker for the MMA warp in the next operand stage
+            const int st = t & 1;
+            if (t >= 2) mbar_wait(&op_free[st], (uint32_t)(((t >> 1) - 1) & 1));
+            if (tid == 0) S.op_last[st] = 1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&op_full[st]);
+            n_tiles = t;
+        }
 
-    // ---- epilogue: tensor memory -> FP64 tile-packed Gram scratch of the solve kernel ----------------------------------------
-    if (n_tiles > 0) {
-        if (tid == 0) tc_commit(&S.bars[2]);
-        mbar_wait(&S.bars[2], 0);
+        // ---- epilogue: tensor memory -> FP64 tile-packed Gram scratch of the solve kernel ------------------------------------
+        mbar_wait(all_done, 0);
         tc_fence_after();
-    }
-    {
         const int lq = warp & 3, cw = warp >> 2;                  // TMEM lane quarter of this warp, column group
         const int gi = lq * 32 + lane;
-        const int64_t slot = (int64_t)slot0 + gi - L.slot_base;
+        const int64_t slot = (int64_t)L.block_off[blk] + gi - L.slot_base;
         const int kt = (k1 + 7) >> 3;
         double* C = L.cmat + (size_t)(gi < ng ? slot : 0) * (size_t)(tri_tiles(kt) * 64);
-        for (int cb16 = cw; cb16 < (nc >> 4); cb16 += kTcThreads / 128) {
+        for (int cb16 = cw; cb16 < (nc >> 4); cb16 += kTcGenThreads / 128) {
             uint32_t v[16];
             if (n_tiles > 0) {
                 const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(cb16 * 16);
@@ -433,7 +485,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0u;
             }
-            int col = chunk * nc + cb16 * 16;
+            const int col = chunk * nc + cb16 * 16;
             if (gi < ng && col < P.n_cols) {
                 int a, b;
                 col_to_pair(col, a, b);
@@ -447,7 +499,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kTcMaxCols) : "memory");
     }
 }

@@ -19,10 +19,13 @@ int launch_tc_gram(b200da_plan* pl, const LetkfParams& L, int nblocks, cudaStrea
     P.kp = pl->kp;
     const Geometry& g = pl->geom;
     P.r_scale = (float)(g.metric == B200DA_METRIC_HAVERSINE ? 2.0 * g.sphere_r / g.radius : 1.0 / g.radius);
+    P.asin_poly = (g.metric == B200DA_METRIC_HAVERSINE && g.cut_bin <= 0.4) ? 1 : 0;
     P.eps = (float)g.eps;
     P.period = (float)g.period;
-    const size_t smem = tc_smem_bytes(P.kp, P.nc);
-    if (smem > kMaxSmem || (pl->kp >> 2) * kTcObs > kTcMaxYItems * kTcThreads) return B200DA_ERR_UNSUPPORTED;
+    P.n_load = kTcYStages;
+    while (P.n_load > 2 && tc_smem_bytes(P.kp, P.nc, P.n_load) > kMaxSmem) --P.n_load;
+    const size_t smem = tc_smem_bytes(P.kp, P.nc, P.n_load);
+    if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
     B200DA_CUDA(cudaFuncSetAttribute(k_tc_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_tc_gram<<<nblocks * P.n_chunks, kTcThreads, smem, st>>>(P);
     B200DA_LAUNCH_CHECK();
