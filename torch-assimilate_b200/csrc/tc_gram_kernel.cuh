@@ -116,67 +116,75 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// ---- FP32 tapers ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float taper_gc_f32(float r) {          // gaspari_cohn.py:78-95, outer branch in s = 2 - r
-    if (r < 1.0f) {
-        const float r2 = r * r;
-        return fmaf(r2, fmaf(r, fmaf(r, fmaf(r, -0.25f, 0.5f), 0.625f), -5.0f / 3.0f), 1.0f);
-    }
-    if (r < 2.0f) {
-        const float s = 2.0f - r, s2 = s * s;
-        return __fdividef(s2 * s2 * fmaf(s, fmaf(s, 1.0f / 12.0f, -0.5f), 0.625f), r);
-    }
-    return 0.0f;
+// ---- FP32 tapers, branch-free (straight-line code lets the eight pairs of a thread interleave) -----------------------------
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-__device__ __forceinline__ float taper_gcinf_f32(float r) {       // gaspari_cohn.py:172-210, last branch in s = 2 - r
-    if (r < 0.5f) {
-        const float r2 = r * r;
-        return fmaf(r2, fmaf(r, fmaf(r, fmaf(r, -28.0f / 33.0f, 8.0f / 11.0f), 20.0f / 11.0f), -80.0f / 33.0f), 1.0f);
-    }
-    if (r < 1.0f) {
-        const float poly = fmaf(r, fmaf(r, fmaf(r, fmaf(r, fmaf(r, 20.0f / 33.0f, -16.0f / 11.0f), 0.0f), 100.0f / 33.0f),
-                                        -45.0f / 11.0f), 51.0f / 22.0f);
-        return poly - __fdividef(7.0f / 44.0f, r);
-    }
-    if (r < 1.5f) {
-        const float poly = fmaf(r, fmaf(r, fmaf(r, fmaf(r, fmaf(r, -4.0f / 11.0f, 16.0f / 11.0f), -10.0f / 11.0f),
-                                               -100.0f / 33.0f), 5.0f), -61.0f / 22.0f);
-        return poly + __fdividef(115.0f / 132.0f, r);
-    }
-    if (r < 2.0f) {
-        const float s = 2.0f - r, s2 = s * s;
-        return __fdividef(s2 * s2 * fmaf(s, fmaf(s, 4.0f / 33.0f, -8.0f / 11.0f), 10.0f / 11.0f), r);
-    }
-    return 0.0f;
-}
-
 __device__ __forceinline__ float sqrt_approx(float x) {
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// gaspari_cohn.py:78-95; the outer branch in s = 2 - r:  f2(r) = s^4 (5/8 - s/2 + s^2/12) / r  (no cancellation)
+__device__ __forceinline__ float taper_gc_f32(float r) {
+    const float r2 = r * r;
+    const float inner = fmaf(r2, fmaf(r, fmaf(r, fmaf(r, -0.25f, 0.5f), 0.625f), -5.0f / 3.0f), 1.0f);
+    const float s = fmaxf(2.0f - r, 0.0f), s2 = s * s;
+    const float outer = s2 * s2 * fmaf(s, fmaf(s, 1.0f / 12.0f, -0.5f), 0.625f) * rcp_approx(r);
+    return r < 1.0f ? inner : outer;
+}
+// gaspari_cohn.py:172-210; the last branch in s = 2 - r:  f4(r) = s^4 (10/11 - 8 s/11 + 4 s^2/33) / r
+__device__ __forceinline__ float taper_gcinf_f32(float r) {
+    const float r2 = r * r, ri = rcp_approx(r);
+    const float p1 = fmaf(r2, fmaf(r, fmaf(r, fmaf(r, -28.0f / 33.0f, 8.0f / 11.0f), 20.0f / 11.0f), -80.0f / 33.0f), 1.0f);
+    const float p2 = fmaf(r, fmaf(r, fmaf(r, fmaf(r, fmaf(r, 20.0f / 33.0f, -16.0f / 11.0f), 0.0f), 100.0f / 33.0f),
+                                  -45.0f / 11.0f), 51.0f / 22.0f) - (7.0f / 44.0f) * ri;
+    const float p3 = fmaf(r, fmaf(r, fmaf(r, fmaf(r, fmaf(r, -4.0f / 11.0f, 16.0f / 11.0f), -10.0f / 11.0f),
+                                         -100.0f / 33.0f), 5.0f), -61.0f / 22.0f) + (115.0f / 132.0f) * ri;
+    const float s = fmaxf(2.0f - r, 0.0f), s2 = s * s;
+    const float p4 = s2 * s2 * fmaf(s, fmaf(s, 4.0f / 33.0f, -8.0f / 11.0f), 10.0f / 11.0f) * ri;
+    return r < 0.5f ? p1 : (r < 1.0f ? p2 : (r < 1.5f ? p3 : p4));
+}
 
-// localization weight of a pair from positions relative to the block centre (bin space)
-__device__ __forceinline__ float pair_weight_f32(int metric, int taper, int asin_poly, float r_scale, float eps, float period,
-                                                 float gx, float gy, float gz, float ox, float oy, float oz) {
-    const float dx = ox - gx, dy = oy - gy, dz = oz - gz;
+// distance kinds of the FP32 weight evaluation (uniform per launch)
+enum { kTcHavPoly = 0, kTcHavAsin = 1, kTcEuclid = 2, kTcAbs = 3, kTcPeriodic = 4 };
+
+// localization weight of a pair from positions relative to the block centre (bin space); `valid` is 0 for padding
+template <int DIST, int TAPER>
+__device__ __forceinline__ float pair_weight_f32(float r_scale, float eps, float period, float gx, float gy, float gz,
+                                                 float4 o, float valid) {
+    const float dx = o.x - gx, dy = o.y - gy, dz = o.z - gz;
     float r;
-    if (metric == B200DA_METRIC_HAVERSINE) {
+    if (DIST == kTcHavPoly) {          // asin(h) = h (1 + h^2/6 + 3 h^4/40 + 15 h^6/336 + 35 h^8/1152 + ...), h <= 0.3
         const float h2 = 0.25f * fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        const float h = sqrt_approx(h2);
-        if (asin_poly)     // asin(h) = h (1 + h^2/6 + 3 h^4/40 + 15 h^6/336 + 35 h^8/1152 + ...), |h| <= 0.3
-            r = r_scale * h * fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 35.0f / 1152.0f, 15.0f / 336.0f), 3.0f / 40.0f), 1.0f / 6.0f), 1.0f);
-        else
-            r = r_scale * asinf(fminf(h, 1.0f));
-    } else if (metric == B200DA_METRIC_EUCLID) {
+        r = (r_scale * sqrt_approx(h2)) *
+            fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 35.0f / 1152.0f, 15.0f / 336.0f), 3.0f / 40.0f), 1.0f / 6.0f), 1.0f);
+    } else if (DIST == kTcHavAsin) {
+        r = r_scale * asinf(fminf(0.5f * sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz))), 1.0f));
+    } else if (DIST == kTcEuclid) {
         r = r_scale * sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
     } else {
         float d = fabsf(dz);
-        if (metric == B200DA_METRIC_PERIODIC1D) d = fminf(d, period - d);
+        if (DIST == kTcPeriodic) d = fminf(d, period - d);
         r = r_scale * d;
     }
-    const float w = taper == B200DA_TAPER_GCINF ? taper_gcinf_f32(r) : taper_gc_f32(r);
-    return w > eps ? w : 0.0f;                                     // gaspari_cohn.py:135
+    const float w = TAPER == B200DA_TAPER_GCINF ? taper_gcinf_f32(r) : taper_gc_f32(r);
+    return (w > eps ? w : 0.0f) * valid;                           // gaspari_cohn.py:135
+}
+
+// taper weights of one grid point for the 8 observations ot[0..7] -> bf16 hi / lo
+template <int DIST, int TAPER>
+__device__ __forceinline__ void w_chunk(const float4* __restrict__ ot, float r_scale, float eps, float period, float gx, float gy,
+                                        float gz, float g_valid, uint4& hi, uint4& lo) {
+    float w[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+        const float4 o = ot[jj];
+        w[jj] = pair_weight_f32<DIST, TAPER>(r_scale, eps, period, gx, gy, gz, o, o.w * g_valid);
+    }
+    split8(w, hi, lo);
 }
 
 // ---- shared-memory carve-up ------------------------------------------------------------------------------------------------
@@ -402,12 +410,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
         const bool c_ok = tid < nc && my_col < P.n_cols;
         int ca = 0, cb = 0;
         if (c_ok) col_to_pair(my_col, ca, cb);
-        const int metric = g.metric, taper = g.taper, asin_poly = P.asin_poly;
+        const int dist_kind = g.metric == B200DA_METRIC_HAVERSINE ? (P.asin_poly ? kTcHavPoly : kTcHavAsin)
+                            : g.metric == B200DA_METRIC_EUCLID ? kTcEuclid
+                            : g.metric == B200DA_METRIC_PERIODIC1D ? kTcPeriodic : kTcAbs;
+        const int wmode = dist_kind * 2 + (g.taper == B200DA_TAPER_GCINF ? 1 : 0);
         const float r_scale = P.r_scale, eps = P.eps, period = P.period;
+        const float g_valid = g_ok ? 1.0f : 0.0f;
         unsigned alive = (1u << n_load) - 1u, par = 0u;       // loaders still producing; phase parity of their buffers
         int t = 0;                                                  // operand tiles produced so far
-        for (int turn = 0; alive != 0u; ++turn) {
-            const int yst = turn % n_load;
+        for (int yst = -1; alive != 0u;) {
+            if (++yst == n_load) yst = 0;
             if (!((alive >> yst) & 1u)) continue;
             mbar_wait(&y_full[yst], (par >> yst) & 1u);
             if (S.ymeta[yst] == 0) { alive &= ~(1u << yst); continue; }      // this loader has run out of candidates
@@ -416,18 +428,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
             if (t >= 2) mbar_wait(&op_free[st], (uint32_t)(((t >> 1) - 1) & 1));
             // ---- W tile: taper weights of this thread's grid point for 8 observations -----------------------------------
             {
-                float w[8];
                 const float4* ot = S.otile + yst * kTcObs + my_kc * 8;
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const float4 o = ot[jj];
-                    float v = 0.0f;
-                    if (g_ok && o.w != 0.0f)
-                        v = pair_weight_f32(metric, taper, asin_poly, r_scale, eps, period, gxr, gyr, gzr, o.x, o.y, o.z);
-                    w[jj] = v;
-                }
                 uint4 hi, lo;
-                split8(w, hi, lo);
+                switch (wmode) {                                   // uniform over the launch
+#define B200DA_TC_W(D, T) case (D) * 2 + (T): w_chunk<D, T>(ot, r_scale, eps, period, gxr, gyr, gzr, g_valid, hi, lo); break;
+                    B200DA_TC_W(kTcHavPoly, 0) B200DA_TC_W(kTcHavPoly, 1) B200DA_TC_W(kTcHavAsin, 0) B200DA_TC_W(kTcHavAsin, 1)
+                    B200DA_TC_W(kTcEuclid, 0) B200DA_TC_W(kTcEuclid, 1) B200DA_TC_W(kTcAbs, 0) B200DA_TC_W(kTcAbs, 1)
+                    B200DA_TC_W(kTcPeriodic, 0)
+                    default: w_chunk<kTcPeriodic, 1>(ot, r_scale, eps, period, gxr, gyr, gzr, g_valid, hi, lo); break;
+#undef B200DA_TC_W
+                }
                 const size_t off = (size_t)st * kTcM * 64 + (size_t)my_kc * a_lbo + (size_t)my_g * 16;
                 *reinterpret_cast<uint4*>(S.a_hi + off) = hi;
                 *reinterpret_cast<uint4*>(S.a_lo + off) = lo;
