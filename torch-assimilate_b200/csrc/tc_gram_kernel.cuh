@@ -37,11 +37,12 @@ constexpr int kTcGenWarps = 16;    // operand-generating warps (also the epilogu
 constexpr int kTcGenThreads = kTcGenWarps * 32;
 constexpr int kTcMmaWarp = kTcGenWarps;        // issues the tcgen05.mma stream, owns the tensor-memory allocation
 constexpr int kTcLoadWarp = kTcGenWarps + 1;   // first of the loader warps: candidate filter + observation-tile loads
-constexpr int kTcYStages = 4;      // loader warps = observation-tile buffers (one each) between loaders and generators
+constexpr int kTcYStages = 6;      // loader warps = observation-tile buffers (one each) between loaders and generators
 constexpr int kTcThreads = (kTcGenWarps + 1 + kTcYStages) * 32;
 constexpr int kTcYLd = 36;         // row length of the member-major observation tile: 32 obs + 4 (conflict-free LDS.128)
 constexpr int kTcMaxCols = 512;    // tensor-memory columns = accumulator columns per CTA
-constexpr int kTcFilterUnroll = 8; // candidates per lane and filter pass (independent loads in flight)
+constexpr float kTcFar = 1.0e18f;  // coordinate of padding observations (+) and padding grid points (-)
+constexpr int kTcFilterUnroll = 4; // candidates per lane and filter pass (independent loads in flight)
 
 struct TcParams {
     LetkfParams L;
@@ -151,10 +152,13 @@ __device__ __forceinline__ float taper_gcinf_f32(float r) {
 // distance kinds of the FP32 weight evaluation (uniform per launch)
 enum { kTcHavPoly = 0, kTcHavAsin = 1, kTcEuclid = 2, kTcAbs = 3, kTcPeriodic = 4 };
 
-// localization weight of a pair from positions relative to the block centre (bin space); `valid` is 0 for padding
+// localization weight of a pair from positions relative to the block centre (bin space).  Padding observations and
+// the unused grid-point rows of a partial block sit at +kTcFar / -kTcFar in all three coordinates: their distance to
+// every real partner is huge (or inf), so s = max(2 - r, 0) = 0 and the weight is exactly 0.  The 1-D metrics, whose
+// x coordinate is otherwise 0, add |dx| to the distance for that purpose.
 template <int DIST, int TAPER>
 __device__ __forceinline__ float pair_weight_f32(float r_scale, float eps, float period, float gx, float gy, float gz,
-                                                 float4 o, float valid) {
+                                                 float4 o) {
     const float dx = o.x - gx, dy = o.y - gy, dz = o.z - gz;
     float r;
     if (DIST == kTcHavPoly) {          // asin(h) = h (1 + h^2/6 + 3 h^4/40 + 15 h^6/336 + 35 h^8/1152 + ...), h <= 0.3
@@ -162,27 +166,28 @@ __device__ __forceinline__ float pair_weight_f32(float r_scale, float eps, float
         r = (r_scale * sqrt_approx(h2)) *
             fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 35.0f / 1152.0f, 15.0f / 336.0f), 3.0f / 40.0f), 1.0f / 6.0f), 1.0f);
     } else if (DIST == kTcHavAsin) {
-        r = r_scale * asinf(fminf(0.5f * sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz))), 1.0f));
+        const float h = 0.5f * sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+        r = fmaf(fmaxf(h - 1.0f, 0.0f), kTcFar, r_scale * asinf(fminf(h, 1.0f)));      // h > 1 only for padding
     } else if (DIST == kTcEuclid) {
         r = r_scale * sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
     } else {
         float d = fabsf(dz);
-        if (DIST == kTcPeriodic) d = fminf(d, period - d);
-        r = r_scale * d;
+        if (DIST == kTcPeriodic) d = fminf(d, fabsf(period - d));
+        r = r_scale * (d + fabsf(dx));
     }
     const float w = TAPER == B200DA_TAPER_GCINF ? taper_gcinf_f32(r) : taper_gc_f32(r);
-    return (w > eps ? w : 0.0f) * valid;                           // gaspari_cohn.py:135
+    return w > eps ? w : 0.0f;                                     // gaspari_cohn.py:135
 }
 
 // taper weights of one grid point for the 8 observations ot[0..7] -> bf16 hi / lo
 template <int DIST, int TAPER>
 __device__ __forceinline__ void w_chunk(const float4* __restrict__ ot, float r_scale, float eps, float period, float gx, float gy,
-                                        float gz, float g_valid, uint4& hi, uint4& lo) {
+                                        float gz, uint4& hi, uint4& lo) {
     float w[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
         const float4 o = ot[jj];
-        w[jj] = pair_weight_f32<DIST, TAPER>(r_scale, eps, period, gx, gy, gz, o, o.w * g_valid);
+        w[jj] = pair_weight_f32<DIST, TAPER>(r_scale, eps, period, gx, gy, gz, o);
     }
     split8(w, hi, lo);
 }
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
     const uint32_t tmem = *S.tmem_slot;
     const int ng = H.ng;
     const uint32_t a_lbo = kTcM * 16, b_lbo = (uint32_t)nc * 16;
+    const float far_rel = kTcFar;                                   // padding coordinate, see pair_weight_f32
     int n_tiles = 0;
 
     if (warp >= kTcLoadWarp + n_load) {
@@ -299,7 +305,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
         const double bcx = H.cx, bcy = H.cy, bcz = H.cz;
         const double reach = (L.cut_pad + H.rb) * (1.0 + 1e-12);
         const int chr = kp >> 2;                                  // 16-byte chunks per staged row
-        constexpr int kPass = kTcFilterUnroll * 32, kRingW = kRing / kTcYStages;
+        constexpr int kPass = kTcFilterUnroll * 32, kRingW = 256;  // private ring: power of two >= kTcObs - 1 + kPass
+        static_assert(kRingW * kTcYStages <= kRing && kTcObs - 1 + kPass <= kRingW, "loader rings do not fit");
         int* ring = H.ring + lw * kRingW;
         int cand_pos = lw * kPass, head = 0, tail = 0;
         for (int u = 0;; ++u) {
@@ -341,20 +348,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
             const float* row = ys + (size_t)slot * kp;
             float* yt = S.ytile + (size_t)lw * kp * kTcYLd + lane;
             const Pos4 p = L.opos[slot];
-            for (int q0 = 0; q0 < chr; q0 += 12) {                 // 12 independent 16-byte loads in flight per lane
-                float4 v[12];
+            for (int q0 = 0; q0 < chr; q0 += 16) {                 // 16 independent 16-byte loads in flight per lane
+                float4 v[16];
 #pragma unroll
-                for (int q = 0; q < 12; ++q)
+                for (int q = 0; q < 16; ++q)
                     if (q0 + q < chr) v[q] = *reinterpret_cast<const float4*>(row + (q0 + q) * 4);
 #pragma unroll
-                for (int q = 0; q < 12; ++q)
+                for (int q = 0; q < 16; ++q)
                     if (q0 + q < chr) {
                         float* dst = yt + (size_t)(q0 + q) * 4 * kTcYLd;
                         dst[0] = v[q].x; dst[kTcYLd] = v[q].y; dst[2 * kTcYLd] = v[q].z; dst[3 * kTcYLd] = v[q].w;
                     }
             }
             {
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 o = make_float4(far_rel, far_rel, far_rel, 0.f);   // padding: out of reach of every grid point -> weight 0
                 if (lane < n) o = make_float4((float)(p.x - bcx), (float)(p.y - bcy), (float)(p.z - bcz), 1.0f);
                 S.otile[lw * kTcObs + lane] = o;
             }
@@ -401,7 +408,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
         // generators
         // =================================================================================================================
         const int my_g = tid & (kTcM - 1), my_kc = tid >> 7;      // 128 grid points x 4 chunks of 8 observations
-        float gxr = 0.f, gyr = 0.f, gzr = 0.f;
+        float gxr = -far_rel, gyr = -far_rel, gzr = -far_rel;
         const bool g_ok = my_g < ng;
         if (g_ok) {
             gxr = (float)(H.gp[my_g].x - H.cx); gyr = (float)(H.gp[my_g].y - H.cy); gzr = (float)(H.gp[my_g].z - H.cz);
@@ -415,7 +422,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
                             : g.metric == B200DA_METRIC_PERIODIC1D ? kTcPeriodic : kTcAbs;
         const int wmode = dist_kind * 2 + (g.taper == B200DA_TAPER_GCINF ? 1 : 0);
         const float r_scale = P.r_scale, eps = P.eps, period = P.period;
-        const float g_valid = g_ok ? 1.0f : 0.0f;
         unsigned alive = (1u << n_load) - 1u, par = 0u;       // loaders still producing; phase parity of their buffers
         int t = 0;                                                  // operand tiles produced so far
         for (int yst = -1; alive != 0u;) {
@@ -431,32 +437,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
                 const float4* ot = S.otile + yst * kTcObs + my_kc * 8;
                 uint4 hi, lo;
                 switch (wmode) {                                   // uniform over the launch
-#define B200DA_TC_W(D, T) case (D) * 2 + (T): w_chunk<D, T>(ot, r_scale, eps, period, gxr, gyr, gzr, g_valid, hi, lo); break;
+#define B200DA_TC_W(D, T) case (D) * 2 + (T): w_chunk<D, T>(ot, r_scale, eps, period, gxr, gyr, gzr, hi, lo); break;
                     B200DA_TC_W(kTcHavPoly, 0) B200DA_TC_W(kTcHavPoly, 1) B200DA_TC_W(kTcHavAsin, 0) B200DA_TC_W(kTcHavAsin, 1)
                     B200DA_TC_W(kTcEuclid, 0) B200DA_TC_W(kTcEuclid, 1) B200DA_TC_W(kTcAbs, 0) B200DA_TC_W(kTcAbs, 1)
                     B200DA_TC_W(kTcPeriodic, 0)
-                    default: w_chunk<kTcPeriodic, 1>(ot, r_scale, eps, period, gxr, gyr, gzr, g_valid, hi, lo); break;
+                    default: w_chunk<kTcPeriodic, 1>(ot, r_scale, eps, period, gxr, gyr, gzr, hi, lo); break;
 #undef B200DA_TC_W
                 }
                 const size_t off = (size_t)st * kTcM * 64 + (size_t)my_kc * a_lbo + (size_t)my_g * 16;
                 *reinterpret_cast<uint4*>(S.a_hi + off) = hi;
                 *reinterpret_cast<uint4*>(S.a_lo + off) = lo;
             }
-            // ---- Z tile: products y_a y_b of this thread's pair column ----------------------------------------------------
+            // ---- Z tile: products y_a y_b of this thread's pair column (loads of chunk kc + 1 ahead of the stores of kc) --------
             if (c_ok) {
                 const float* yt = S.ytile + (size_t)yst * kp * kTcYLd;
-                const float* ya = yt + ca * kTcYLd;
-                const float* yb = yt + cb * kTcYLd;
+                const float4* ya = reinterpret_cast<const float4*>(yt + ca * kTcYLd);
+                const float4* yb = reinterpret_cast<const float4*>(yt + cb * kTcYLd);
+                unsigned char* zh = S.b_hi + (size_t)st * nc * 64 + (size_t)tid * 16;
+                unsigned char* zl = S.b_lo + (size_t)st * nc * 64 + (size_t)tid * 16;
+                float4 a0 = ya[0], a1 = ya[1], b0 = yb[0], b1 = yb[1];
 #pragma unroll
                 for (int kc = 0; kc < kTcObs / 8; ++kc) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(ya + kc * 8), a1 = *reinterpret_cast<const float4*>(ya + kc * 8 + 4);
-                    const float4 b0 = *reinterpret_cast<const float4*>(yb + kc * 8), b1 = *reinterpret_cast<const float4*>(yb + kc * 8 + 4);
                     const float z[8] = {a0.x * b0.x, a0.y * b0.y, a0.z * b0.z, a0.w * b0.w, a1.x * b1.x, a1.y * b1.y, a1.z * b1.z, a1.w * b1.w};
+                    if (kc + 1 < kTcObs / 8) { a0 = ya[2 * kc + 2]; a1 = ya[2 * kc + 3]; b0 = yb[2 * kc + 2]; b1 = yb[2 * kc + 3]; }
                     uint4 hi, lo;
                     split8(z, hi, lo);
-                    const size_t off = (size_t)st * nc * 64 + (size_t)kc * b_lbo + (size_t)tid * 16;
-                    *reinterpret_cast<uint4*>(S.b_hi + off) = hi;
-                    *reinterpret_cast<uint4*>(S.b_lo + off) = lo;
+                    *reinterpret_cast<uint4*>(zh + (size_t)kc * b_lbo) = hi;
+                    *reinterpret_cast<uint4*>(zl + (size_t)kc * b_lbo) = lo;
                 }
             }
             // ---- publish the operand stage to the tensor core, release the observation tile -----------------------------------
