@@ -399,9 +399,29 @@ def main():
         achieved = flops_gram / (g_ms * 1e-3) * 1e-12            # dominant kernel: the DMMA Gram kernel
         kt = (k + 1 + 7) // 8
         exec_ratio = (kt * (kt + 1) // 2) * 128.0 / (2.0 * k * k + 2.0 * k)
+        tc_path = "tcgen05" in eng.kernel_name
+        peak_used, peak_src = peak_sus, ("measured live: cuBLAS DGEMM 8192^3 via torch.matmul, sustained {0:.2f} / burst {1:.2f} "
+                                         "TFLOP/s (FP64 DMMA pipe; MEASURED_PEAKS.json has no FP64 entry)".format(peak_sus, peak_burst))
+        exec_note = ("executed DMMA FLOPs (lower-triangle 8x8 tiles of the padded [Yn; d] Gram) / algorithmic "
+                     "FLOPs = {0:.3f}".format(exec_ratio))
+        if tc_path:
+            # FP32 plan: bf16 hi/lo split operands on the tcgen05 tensor cores -> the bf16 dense peak of MEASURED_PEAKS.json
+            try:
+                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                peak_used = float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops"))
+                peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3, seconds-long loop), of measured"
+            except Exception:
+                peak_used, peak_src = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md), of fallback"
+            n_cols = (k + 1) * (k + 2) // 2
+            n_chunks = -(-n_cols // 512)
+            nc = -(-(-(-n_cols // n_chunks)) // 32) * 32
+            exec_ratio = 3.0 * 2.0 * nc * n_chunks / (2.0 * k * k + 2.0 * k)
+            exec_note = ("executed tensor FLOPs per accepted (grid point, obs) pair = 3 bf16 MMAs (hi*hi + hi*lo + lo*hi) x 2 x {0} "
+                         "pair columns; / algorithmic FLOPs = {1:.3f} (candidates rejected per grid point but kept for the "
+                         "128-point block add to the executed side)".format(nc * n_chunks, exec_ratio))
         path_tflops = flops_local / (kern_ms * 1e-3) * 1e-12      # Gram + solve kernels together
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_{0}.json".format(args.workload))
+        tpath = os.path.join(ROOT, "profiles", "traffic_{0}{1}.json".format(args.workload, "" if args.dtype == "f64" else "_f32"))
         if os.path.exists(tpath):
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
@@ -418,25 +438,25 @@ def main():
                            n_obs * eng.k * esz * 1.12 / 1e6, n_grid * k * esz / 1e6) if n_obs * k * esz > 2e8 else
                              "inputs fit in L2; no flush (workload is latency/compute bound, not DRAM bound)",
                        "kernel": eng.kernel_name},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s",
-                         "frac": achieved / peak_sus if peak_sus else None, "traffic": traffic,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_used, "unit": "TFLOP/s",
+                         "frac": achieved / peak_used if peak_used else None, "traffic": traffic,
                          "kernel": eng.kernel_name, "kernel_ms": g_ms,
                          "algorithmic_flops_per_launch": flops_gram,
                          "flop_model": "Gram kernel: sum_g 2k^2 p_g + 2k p_g (SURVEY.md 8d; full k x k Gram counted, the kernel "
                                        "computes the lower triangle), p_g from the neighbour-count kernel, rank 0's share",
-                         "peak_source": "measured live: cuBLAS DGEMM 8192^3 via torch.matmul, sustained {0:.2f} / burst {1:.2f} "
-                                        "TFLOP/s (FP64 DMMA pipe; MEASURED_PEAKS.json has no FP64 entry)".format(peak_sus, peak_burst),
+                         "fp64_dgemm_peak_tflops": peak_sus,
+                         "peak_source": peak_src,
                          "kernel_share_of_step": g_ms / ms_per_step,
-                         "executed_frac": (achieved * exec_ratio / peak_sus) if peak_sus else None,
-                         "executed_note": "executed DMMA FLOPs (lower-triangle 8x8 tiles of the padded [Yn; d] Gram) / algorithmic "
-                                          "FLOPs = {0:.3f}".format(exec_ratio),
+                         "executed_frac": (achieved * exec_ratio / peak_used) if peak_used else None,
+                         "executed_note": exec_note,
                          "solve_kernel": {"name": "k_letkf_solve_ns (Newton-Schulz inverse square root + transform + update)", "kernel_ms": s_ms,
                                           "algorithmic_flops_per_launch": flops_solve,
                                           "achieved_tflops": flops_solve / (s_ms * 1e-3) * 1e-12 if s_ms > 0 else None,
                                           "share_of_step": s_ms / ms_per_step},
-                         "path": {"achieved_tflops": path_tflops, "frac": path_tflops / peak_sus if peak_sus else None,
+                         "path": {"achieved_tflops": path_tflops, "frac": path_tflops / peak_used if peak_used else None,
                                   "kernel_ms": kern_ms,
                                   "flop_model": "sum_g 2k^2 p_g + 2k p_g + 13k^3 + 2k^2 n_s (SURVEY.md 8d)"}},
+            "solver": "FP64 Newton-Schulz (k x k solve and update in FP64 for both plan dtypes)",
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         if cpu_info is not None:

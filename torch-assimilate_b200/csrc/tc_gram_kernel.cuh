@@ -18,9 +18,11 @@
 //
 // Precision.  Operands are split into two bfloat16 terms (x = hi + lo, 16 significant bits) and the product is
 // accumulated as hi*hi + hi*lo + lo*hi in FP32 (3 kind::f16 MMAs per 16 observations; the dropped lo*lo term is 2^-18
-// relative).  The taper is evaluated in FP32 on positions relative to the block centre, with the outer Gaspari-Cohn
-// branch rewritten in s = 2 - r, w = s^4 (5/8 - s/2 + s^2/12) / r, which has no cancellation (the reference form sums
-// terms of magnitude 10 to get 1e-5).  The k x k solve and the update stay in FP64 (ns_solve_kernel.cuh).
+// relative).  The taper is read from a per-CTA table of the weight as a function of the SQUARED bin-space distance
+// (2048 intervals, linear interpolation, error < 1e-6; built in FP64 from the same taper code as the FP64 path, mask
+// w > eps included), evaluated on FP32 positions relative to the block centre: a pair costs 3 subtractions, 3 FMAs, one
+// table read and one FMA instead of a square root, an arc sine and two polynomials.  The k x k solve and the update stay
+// in FP64 (ns_solve_kernel.cuh).
 //
 // Shared-memory operand tiles use the no-swizzle K-major canonical layout of the UMMA shared-memory descriptor: core
 // matrices of 8 rows x 16 bytes, element (row, kk) at  (kk / 8) * ROWS * 16 + row * 16 + (kk % 8) * 2  bytes, i.e.
@@ -51,9 +53,7 @@ struct TcParams {
     int nc;            // columns per chunk, multiple of 32, <= 512
     int kp;            // row length of the staging copy ys (floats)
     int n_load;        // active loader warps = observation-tile buffers (2..kTcYStages, limited by shared memory)
-    int asin_poly;     // haversine: chord / 2 stays below 0.3, asin by its series
-    float r_scale;     // distance -> r:  1 / radius  (haversine: 2 R / radius, applied to asin(chord / 2))
-    float eps;
+    float q_max;       // table domain: squared bin-space distance beyond which the weight is 0
     float period;
 };
 
@@ -117,79 +117,54 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// ---- FP32 tapers, branch-free (straight-line code lets the eight pairs of a thread interleave) -----------------------------
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// gaspari_cohn.py:78-95; the outer branch in s = 2 - r:  f2(r) = s^4 (5/8 - s/2 + s^2/12) / r  (no cancellation)
-__device__ __forceinline__ float taper_gc_f32(float r) {
-    const float r2 = r * r;
-    const float inner = fmaf(r2, fmaf(r, fmaf(r, fmaf(r, -0.25f, 0.5f), 0.625f), -5.0f / 3.0f), 1.0f);
-    const float s = fmaxf(2.0f - r, 0.0f), s2 = s * s;
-    const float outer = s2 * s2 * fmaf(s, fmaf(s, 1.0f / 12.0f, -0.5f), 0.625f) * rcp_approx(r);
-    return r < 1.0f ? inner : outer;
-}
-// gaspari_cohn.py:172-210; the last branch in s = 2 - r:  f4(r) = s^4 (10/11 - 8 s/11 + 4 s^2/33) / r
-__device__ __forceinline__ float taper_gcinf_f32(float r) {
-    const float r2 = r * r, ri = rcp_approx(r);
-    const float p1 = fmaf(r2, fmaf(r, fmaf(r, fmaf(r, -28.0f / 33.0f, 8.0f / 11.0f), 20.0f / 11.0f), -80.0f / 33.0f), 1.0f);
-    const float p2 = fmaf(r, fmaf(r, fmaf(r, fmaf(r, fmaf(r, 20.0f / 33.0f, -16.0f / 11.0f), 0.0f), 100.0f / 33.0f),
-                                  -45.0f / 11.0f), 51.0f / 22.0f) - (7.0f / 44.0f) * ri;
-    const float p3 = fmaf(r, fmaf(r, fmaf(r, fmaf(r, fmaf(r, -4.0f / 11.0f, 16.0f / 11.0f), -10.0f / 11.0f),
-                                         -100.0f / 33.0f), 5.0f), -61.0f / 22.0f) + (115.0f / 132.0f) * ri;
-    const float s = fmaxf(2.0f - r, 0.0f), s2 = s * s;
-    const float p4 = s2 * s2 * fmaf(s, fmaf(s, 4.0f / 33.0f, -8.0f / 11.0f), 10.0f / 11.0f) * ri;
-    return r < 0.5f ? p1 : (r < 1.0f ? p2 : (r < 1.5f ? p3 : p4));
-}
+// ---- localization weights from the table ---------------------------------------------------------------------------------
+constexpr int kTcTab = 2048;       // intervals of the weight table over [0, q_max]; entry kTcTab is the zero beyond
 
-// distance kinds of the FP32 weight evaluation (uniform per launch)
-enum { kTcHavPoly = 0, kTcHavAsin = 1, kTcEuclid = 2, kTcAbs = 3, kTcPeriodic = 4 };
+// distance kinds (uniform per launch): squared distance in three coordinates (haversine through the chord, Euclidean),
+// |dz|, periodic |dz|
+enum { kTcSq3 = 0, kTcAbs = 1, kTcPeriodic = 2 };
 
-// localization weight of a pair from positions relative to the block centre (bin space).  Padding observations and
-// the unused grid-point rows of a partial block sit at +kTcFar / -kTcFar in all three coordinates: their distance to
-// every real partner is huge (or inf), so s = max(2 - r, 0) = 0 and the weight is exactly 0.  The 1-D metrics, whose
-// x coordinate is otherwise 0, add |dx| to the distance for that purpose.
-template <int DIST, int TAPER>
-__device__ __forceinline__ float pair_weight_f32(float r_scale, float eps, float period, float gx, float gy, float gz,
-                                                 float4 o) {
+// Weight of a pair from positions relative to the block centre (bin space).  Padding observations and the unused
+// grid-point rows of a partial block sit at +kTcFar / -kTcFar in all three coordinates: their squared distance to every
+// real partner is huge, the table index saturates at the zero entry.  The 1-D metrics, whose x coordinate is otherwise 0,
+// add |dx| to the distance for that purpose.
+template <int DIST>
+__device__ __forceinline__ float pair_weight_f32(const float2* __restrict__ tab, float xs, float period, float gx, float gy,
+                                                 float gz, float4 o) {
     const float dx = o.x - gx, dy = o.y - gy, dz = o.z - gz;
-    float r;
-    if (DIST == kTcHavPoly) {          // asin(h) = h (1 + h^2/6 + 3 h^4/40 + 15 h^6/336 + 35 h^8/1152 + ...), h <= 0.3
-        const float h2 = 0.25f * fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        r = (r_scale * sqrt_approx(h2)) *
-            fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 35.0f / 1152.0f, 15.0f / 336.0f), 3.0f / 40.0f), 1.0f / 6.0f), 1.0f);
-    } else if (DIST == kTcHavAsin) {
-        const float h = 0.5f * sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-        r = fmaf(fmaxf(h - 1.0f, 0.0f), kTcFar, r_scale * asinf(fminf(h, 1.0f)));      // h > 1 only for padding
-    } else if (DIST == kTcEuclid) {
-        r = r_scale * sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+    float q;
+    if (DIST == kTcSq3) {
+        q = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
     } else {
         float d = fabsf(dz);
         if (DIST == kTcPeriodic) d = fminf(d, fabsf(period - d));
-        r = r_scale * (d + fabsf(dx));
+        d += fabsf(dx);
+        q = d * d;
     }
-    const float w = TAPER == B200DA_TAPER_GCINF ? taper_gcinf_f32(r) : taper_gc_f32(r);
-    return w > eps ? w : 0.0f;                                     // gaspari_cohn.py:135
+    const float x = fminf(q * xs, (float)kTcTab);                 // table coordinate, saturated at the zero entry
+    const int i = __float2int_rz(x);
+    const float2 e = tab[i];
+    return fmaf(x - (float)i, e.y, e.x);                           // linear interpolation: e = (w_i, w_{i+1} - w_i)
 }
 
 // taper weights of one grid point for the 8 observations ot[0..7] -> bf16 hi / lo
-template <int DIST, int TAPER>
-__device__ __forceinline__ void w_chunk(const float4* __restrict__ ot, float r_scale, float eps, float period, float gx, float gy,
-                                        float gz, uint4& hi, uint4& lo) {
+template <int DIST>
+__device__ __forceinline__ void w_chunk(const float4* __restrict__ ot, const float2* __restrict__ tab, float xs, float period,
+                                        float gx, float gy, float gz, uint4& hi, uint4& lo) {
     float w[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-        const float4 o = ot[jj];
-        w[jj] = pair_weight_f32<DIST, TAPER>(r_scale, eps, period, gx, gy, gz, o);
-    }
+    for (int jj = 0; jj < 8; ++jj) w[jj] = pair_weight_f32<DIST>(tab, xs, period, gx, gy, gz, ot[jj]);
     split8(w, hi, lo);
+}
+
+// table entry i: weight at squared bin-space distance q_i = i q_max / kTcTab, evaluated in FP64 with the reference's
+// selection logic and mask (gaspari_cohn.py:126-135)
+__device__ inline double tab_weight(const Geometry& g, double q) {
+    double dist;
+    if (g.metric == B200DA_METRIC_HAVERSINE) dist = 2.0 * g.sphere_r * asin(fmin(0.5 * sqrt(q), 1.0));
+    else dist = sqrt(q);
+    const double w = taper_eval(g.taper, dist / g.radius);
+    return w > g.eps ? w : 0.0;
 }
 
 // ---- shared-memory carve-up ------------------------------------------------------------------------------------------------
@@ -201,6 +176,7 @@ struct TcSmem {
     uint32_t* tmem_slot;
     int* ymeta;              // [kTcYStages] valid observations of the tile, 0 = end of the candidate stream
     int* op_last;            // [2] set by the generators when the operand stage carries the end marker instead of a tile
+    float2* wtab;            // [kTcTab + 1] weight table (w_i, w_{i+1} - w_i)
     float4* otile;           // [kTcYStages][kTcObs] observation positions relative to the block centre, .w = 1 valid / 0 padding
     float* ytile;            // [kTcYStages][kp][kTcYLd] member-major [Yn; d] of the tile
     unsigned char* a_hi;     // [2][kTcM * 64]
@@ -212,6 +188,7 @@ __host__ __device__ constexpr size_t tc_align(size_t x, size_t a) { return (x + 
 __host__ __device__ inline size_t tc_smem_bytes(int kp, int nc, int n_load) {
     size_t o = tc_align(sizeof(BlockHeader<kTcM>), 128);
     o += 256;                                             // barriers, tensor-memory address, tile meta data
+    o += tc_align(sizeof(float2) * (kTcTab + 1), 128);
     o += sizeof(float4) * kTcYStages * kTcObs;
     o = tc_align(o + sizeof(float) * n_load * (size_t)kp * kTcYLd, 128);
     o += 2 * 2 * (size_t)kTcM * 64;
@@ -227,6 +204,8 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int kp, int nc, 
     S.ymeta = reinterpret_cast<int*>(base + o + 144);
     S.op_last = reinterpret_cast<int*>(base + o + 176);
     o += 256;
+    S.wtab = reinterpret_cast<float2*>(base + o);
+    o += tc_align(sizeof(float2) * (kTcTab + 1), 128);
     S.otile = reinterpret_cast<float4*>(base + o);
     o += sizeof(float4) * kTcYStages * kTcObs;
     S.ytile = reinterpret_cast<float*>(base + o);
@@ -278,6 +257,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
         mbar_init(all_done, 1);
         S.op_last[0] = 0; S.op_last[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i <= kTcTab; i += kTcThreads) {          // weight table (FP64 evaluation, once per CTA)
+        const double dq = (double)P.q_max / kTcTab;
+        const double w0 = i < kTcTab ? tab_weight(g, i * dq) : 0.0;
+        const double w1 = i + 1 < kTcTab ? tab_weight(g, (i + 1) * dq) : 0.0;
+        S.wtab[i] = make_float2((float)w0, (float)(w1 - w0));
     }
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -417,11 +402,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
         const bool c_ok = tid < nc && my_col < P.n_cols;
         int ca = 0, cb = 0;
         if (c_ok) col_to_pair(my_col, ca, cb);
-        const int dist_kind = g.metric == B200DA_METRIC_HAVERSINE ? (P.asin_poly ? kTcHavPoly : kTcHavAsin)
-                            : g.metric == B200DA_METRIC_EUCLID ? kTcEuclid
-                            : g.metric == B200DA_METRIC_PERIODIC1D ? kTcPeriodic : kTcAbs;
-        const int wmode = dist_kind * 2 + (g.taper == B200DA_TAPER_GCINF ? 1 : 0);
-        const float r_scale = P.r_scale, eps = P.eps, period = P.period;
+        const int dist_kind = g.metric == B200DA_METRIC_PERIODIC1D ? kTcPeriodic
+                            : g.metric == B200DA_METRIC_ABS1D ? kTcAbs : kTcSq3;
+        const float xs = (float)kTcTab / P.q_max, period = P.period;
+        const float2* wtab = S.wtab;
         unsigned alive = (1u << n_load) - 1u, par = 0u;       // loaders still producing; phase parity of their buffers
         int t = 0;                                                  // operand tiles produced so far
         for (int yst = -1; alive != 0u;) {
@@ -436,14 +420,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
             {
                 const float4* ot = S.otile + yst * kTcObs + my_kc * 8;
                 uint4 hi, lo;
-                switch (wmode) {                                   // uniform over the launch
-#define B200DA_TC_W(D, T) case (D) * 2 + (T): w_chunk<D, T>(ot, r_scale, eps, period, gxr, gyr, gzr, hi, lo); break;
-                    B200DA_TC_W(kTcHavPoly, 0) B200DA_TC_W(kTcHavPoly, 1) B200DA_TC_W(kTcHavAsin, 0) B200DA_TC_W(kTcHavAsin, 1)
-                    B200DA_TC_W(kTcEuclid, 0) B200DA_TC_W(kTcEuclid, 1) B200DA_TC_W(kTcAbs, 0) B200DA_TC_W(kTcAbs, 1)
-                    B200DA_TC_W(kTcPeriodic, 0)
-                    default: w_chunk<kTcPeriodic, 1>(ot, r_scale, eps, period, gxr, gyr, gzr, hi, lo); break;
-#undef B200DA_TC_W
-                }
+                if (dist_kind == kTcSq3) w_chunk<kTcSq3>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo);        // uniform over the launch
+                else if (dist_kind == kTcAbs) w_chunk<kTcAbs>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo);
+                else w_chunk<kTcPeriodic>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo);
                 const size_t off = (size_t)st * kTcM * 64 + (size_t)my_kc * a_lbo + (size_t)my_g * 16;
                 *reinterpret_cast<uint4*>(S.a_hi + off) = hi;
                 *reinterpret_cast<uint4*>(S.a_lo + off) = lo;

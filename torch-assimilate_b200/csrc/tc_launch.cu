@@ -18,9 +18,9 @@ int launch_tc_gram(b200da_plan* pl, const LetkfParams& L, int nblocks, cudaStrea
     tc_chunking(pl->k, &P.n_cols, &P.n_chunks, &P.nc);
     P.kp = pl->kp;
     const Geometry& g = pl->geom;
-    P.r_scale = (float)(g.metric == B200DA_METRIC_HAVERSINE ? 2.0 * g.sphere_r / g.radius : 1.0 / g.radius);
-    P.asin_poly = (g.metric == B200DA_METRIC_HAVERSINE && g.cut_bin <= 0.4) ? 1 : 0;
-    P.eps = (float)g.eps;
+    // the weight vanishes beyond the padded cutoff (bin space: chord length for haversine)
+    const double cut = g.cut_bin * (1.0 + 1e-6);
+    P.q_max = (float)(cut * cut);
     P.period = (float)g.period;
     P.n_load = kTcYStages;
     while (P.n_load > 2 && tc_smem_bytes(P.kp, P.nc, P.n_load) > kMaxSmem) --P.n_load;
