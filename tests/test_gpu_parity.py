@@ -264,3 +264,26 @@ def test_analysis_is_deterministic():
     ref, _ = orc.letkf_analysis(data["state"], data["normed_perts"], data["normed_obs"], data["grid_rows"],
                                 data["obs_rows"], orc.make_dist_haversine(6371.0), 1000.0, inf_factor=1.1, grid_subset=sel)
     np.testing.assert_allclose(xa1[..., sel], ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-4)])
+def test_global_etkf_cfg4_shape_against_oracle(dtype, tol):
+    """BASELINE cfg4 shape, scaled: global ETKF with k = 100 members, many observations, a long state (the split-M Gram,
+    the single ensemble-space solve and the streaming update) against the oracle (interface/etkf.py:99-120, base.py:257-278)."""
+    from pytassim_b200.engine import LETKFEngine
+    m = _metrics()
+    rng = np.random.RandomState(4)
+    k, n, nobs = 100, 40_000, 3_000
+    st = rng.normal(size=(1, 1, k, n))
+    hx = st[0, 0][:, ::13][:, :nobs]
+    yn = np.ascontiguousarray(hx - hx.mean(axis=0, keepdims=True))
+    d = rng.normal(size=nobs) * 0.5
+    npd = np.float64 if dtype == torch.float64 else np.float32
+    ref, wref = orc.etkf_analysis(st.astype(npd).astype(np.float64), yn.astype(npd).astype(np.float64),
+                                  d.astype(npd).astype(np.float64), inf_factor=1.1)
+    eng = LETKFEngine(k, 1, m.AbsDistance1D(), 1.0, inf_factor=1.1, dtype=dtype)
+    w = eng.etkf_weights(yn, d)
+    xa = eng.apply_weights(torch.as_tensor(st.reshape(1, k, n), dtype=dtype).cuda(), w).cpu().numpy().reshape(st.shape)
+    scale = np.abs(ref).max()
+    assert np.abs(w.cpu().numpy() - wref).max() <= tol * max(1.0, np.abs(wref).max())
+    assert np.abs(xa - ref).max() <= tol * scale
