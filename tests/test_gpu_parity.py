@@ -287,3 +287,16 @@ def test_global_etkf_cfg4_shape_against_oracle(dtype, tol):
     scale = np.abs(ref).max()
     assert np.abs(w.cpu().numpy() - wref).max() <= tol * max(1.0, np.abs(wref).max())
     assert np.abs(xa - ref).max() <= tol * scale
+
+
+@pytest.mark.parametrize("k,n_grid,radius", [(112, 80, 7.0), (120, 72, 6.0), (128, 64, 9.0)])
+def test_large_ensembles_newton_against_oracle(k, n_grid, radius):
+    """Ensemble sizes beyond the shared-memory Jacobi limit (k > 111) run on the tensor-core Newton-Schulz solver only
+    (BASELINE cfg5 goes up to k = 128)."""
+    m = _metrics()
+    data = syn.lorenz96_1d(n_grid, k, 1, seed=300 + k)
+    eng, xa, w, namb = _run(data, m.PeriodicDistance1D(float(n_grid)), radius, 1.05, weights=True, solver="newton")
+    ref, wref = orc.letkf_analysis(data["state"], data["normed_perts"], data["normed_obs"], data["grid_rows"],
+                                   data["obs_rows"], orc.make_dist_periodic1d(float(n_grid)), radius, inf_factor=1.05)
+    np.testing.assert_allclose(xa, ref, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(w, wref, rtol=RTOL, atol=ATOL)

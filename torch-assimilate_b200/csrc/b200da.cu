@@ -58,7 +58,7 @@ static KernelConfig config_for_kt(int kt) {
     if (kt <= 10) return {4, 4};
     return {2, 8};
 }
-constexpr int kMaxKt = 14;
+constexpr int kMaxKt = 17;
 
 template <int KT>
 static int launch_etkf_gram(int f32, const void* yn, const void* d, int64_t m, int k, int ncta, int64_t chunk, double* partial,
@@ -74,7 +74,33 @@ static int dispatch_etkf_gram(int kt, int f32, const void* yn, const void* d, in
     switch (kt) {
         B200DA_EG_CASE(1) B200DA_EG_CASE(2) B200DA_EG_CASE(3) B200DA_EG_CASE(4) B200DA_EG_CASE(5) B200DA_EG_CASE(6)
         B200DA_EG_CASE(7) B200DA_EG_CASE(8) B200DA_EG_CASE(9) B200DA_EG_CASE(10) B200DA_EG_CASE(11) B200DA_EG_CASE(12)
-        B200DA_EG_CASE(13) B200DA_EG_CASE(14)
+        B200DA_EG_CASE(13) B200DA_EG_CASE(14) B200DA_EG_CASE(15) B200DA_EG_CASE(16) B200DA_EG_CASE(17)
+        default: return B200DA_ERR_UNSUPPORTED;
+    }
+}
+
+template <int MT>
+static int launch_apply_global(int f32, const void* x, const void* w, int k, int n_rows, int64_t n_grid, void* xa, cudaStream_t st) {
+    const size_t smem = sizeof(double) * (size_t)MT * 8 * apply_lda(k);
+    if (smem > kMaxSmem - 2048) return B200DA_ERR_UNSUPPORTED;
+    const int64_t n_chunks = (n_grid + kApplyNTW * 8 - 1) / (kApplyNTW * 8);
+    const int grid = (int)std::min<int64_t>((n_chunks + kApplyWarps - 1) / kApplyWarps, 148 * 2);
+    if (f32) {
+        B200DA_CUDA(cudaFuncSetAttribute(k_apply_global<float, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_apply_global<float, MT><<<grid, kApplyWarps * 32, smem, st>>>((const float*)x, (const float*)w, k, n_rows, n_grid, (float*)xa);
+    } else {
+        B200DA_CUDA(cudaFuncSetAttribute(k_apply_global<double, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_apply_global<double, MT><<<grid, kApplyWarps * 32, smem, st>>>((const double*)x, (const double*)w, k, n_rows, n_grid, (double*)xa);
+    }
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+#define B200DA_AG_CASE(MT) case MT: return launch_apply_global<MT>(f32, x, w, k, n_rows, n_grid, xa, st);
+static int dispatch_apply_global(int f32, const void* x, const void* w, int k, int n_rows, int64_t n_grid, void* xa, cudaStream_t st) {
+    switch ((k + 7) / 8) {
+        B200DA_AG_CASE(1) B200DA_AG_CASE(2) B200DA_AG_CASE(3) B200DA_AG_CASE(4) B200DA_AG_CASE(5) B200DA_AG_CASE(6)
+        B200DA_AG_CASE(7) B200DA_AG_CASE(8) B200DA_AG_CASE(9) B200DA_AG_CASE(10) B200DA_AG_CASE(11) B200DA_AG_CASE(12)
+        B200DA_AG_CASE(13) B200DA_AG_CASE(14) B200DA_AG_CASE(15) B200DA_AG_CASE(16)
         default: return B200DA_ERR_UNSUPPORTED;
     }
 }
@@ -156,8 +182,9 @@ int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int
     pl->kt = kt; pl->kp = kt * 8;
     const KernelConfig cfg = config_for_kt(kt);
     pl->gpb = cfg.g;
-    pl->use_tc = (dtype == B200DA_F32 && k >= 32);
-    pl->kernel_name = std::string("letkf_gram_") + (dtype == B200DA_F32 ? "f32in_f64dmma" : "f64") + "_kt" + std::to_string(kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
+    pl->use_tc = (dtype == B200DA_F32 && k >= 8);
+    pl->kernel_name = std::string("letkf_gram_") + (dtype == B200DA_F32 ? "f32in_f64dmma" : "f64") + (k % 8 == 0 ? "_brow" : "") +
+                      "_kt" + std::to_string(k % 8 == 0 ? kt - 1 : kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
     if (pl->use_tc) {
         int n_cols, n_chunks, nc;
         tc_chunking(k, &n_cols, &n_chunks, &nc);
@@ -441,8 +468,8 @@ int b200da_apply_weights(b200da_plan* pl, const void* X, const void* W, int per_
     if (!pl || !X || !W || !Xa || n_grid <= 0) return B200DA_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     const int k = pl->k;
-    const size_t smem = per_grid ? 0 : sizeof(double) * (size_t)k * k;
-    if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
+    if (!per_grid) return dispatch_apply_global(pl->dtype == B200DA_F32, X, W, k, pl->n_slices, n_grid, Xa, st);
+    const size_t smem = 0;
     if (pl->dtype == B200DA_F32) {
         B200DA_CUDA(cudaFuncSetAttribute(k_apply_weights<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
         k_apply_weights<float, 8><<<grid1d(n_grid, 128), 128, smem, st>>>((const float*)X, (const float*)W, per_grid, k,

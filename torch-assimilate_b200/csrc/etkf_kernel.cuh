@@ -128,6 +128,99 @@ __global__ void __launch_bounds__(128) k_apply_weights(const T* __restrict__ x, 
     }
 }
 
+// Xa = mean + (X - mean) W with ONE global W (k x k): a streaming GEMM on the FP64 tensor pipe.
+//   x_a[j, g] = sum_i x[i, g] W'[i][j],   W'[i][j] = W[i][j] + (1 - sum_i' W[i'][j]) / k
+// (the ensemble mean folds into the weights: mean (1 - colsum_j) = sum_i x_i (1 - colsum_j) / k), i.e.
+// Xa (k x N) = W'^T (k x k) X (k x N) for every state slice.  DMMA m8n8k4: A = W'^T fragments from shared memory (rows j,
+// columns i), B = x fragments read straight from global memory in the reference layout (4 members x 8 consecutive grid
+// points = four 64-byte segments), C = 8 members x 8 grid points.  One warp owns NTW * 8 consecutive grid points and all MT
+// row tiles; every x element is read once and every x_a element written once (algorithmic HBM traffic), the FP64 work is
+// 2 k^2 per state element.
+constexpr int kApplyWarps = 8;
+constexpr int kApplyNTW = 2;            // 8-point column tiles per warp
+__host__ __device__ inline int apply_lda(int k) {          // leading dimension of W'^T in shared memory: == 4 (mod 16) doubles
+    int lda = (k + 3) & ~3;
+    while ((lda & 15) != 4) lda += 4;
+    return lda;
+}
+template <typename T, int MT>
+__global__ void __launch_bounds__(kApplyWarps * 32) k_apply_global(const T* __restrict__ x, const T* __restrict__ w, int k, int n_rows,
+                                                                 int64_t n_grid, T* __restrict__ xa) {
+    extern __shared__ double wsm_raw[];
+    double* At = wsm_raw;                                   // [MT * 8][lda]: At[j][i] = W'[i][j]
+    __shared__ double colsum[MT * 8];
+    const int lda = apply_lda(k);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < MT * 8 * lda; e += blockDim.x) At[e] = 0.0;
+    __syncthreads();
+    for (int e = tid; e < k * k; e += blockDim.x) {
+        const int i = e / k, j = e - i * k;
+        At[j * lda + i] = (double)w[e];
+    }
+    __syncthreads();
+    for (int j = tid; j < k; j += blockDim.x) {
+        double s = 0.0;
+        for (int i = 0; i < k; ++i) s += At[j * lda + i];
+        colsum[j] = (1.0 - s) / (double)k;
+    }
+    __syncthreads();
+    for (int e = tid; e < k * k; e += blockDim.x) {
+        const int j = e / k, i = e - j * k;
+        At[j * lda + i] += colsum[j];
+    }
+    __syncthreads();
+    const int ksteps = (k + 3) >> 2;
+    const int r = lane >> 2, q = lane & 3;
+    const int64_t n_chunks = (n_grid + kApplyNTW * 8 - 1) / (kApplyNTW * 8);
+    for (int srow = 0; srow < n_rows; ++srow) {
+        const T* xs = x + (int64_t)srow * k * n_grid;
+        T* xo = xa + (int64_t)srow * k * n_grid;
+        for (int64_t ch = (int64_t)blockIdx.x * kApplyWarps + warp; ch < n_chunks; ch += (int64_t)gridDim.x * kApplyWarps) {
+            const int64_t g0 = ch * (kApplyNTW * 8);
+            double acc[MT][kApplyNTW][2];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < kApplyNTW; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+#pragma unroll 4
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int i = ks * 4 + q;
+                double b[kApplyNTW];
+#pragma unroll
+                for (int nt = 0; nt < kApplyNTW; ++nt) {
+                    const int64_t g = g0 + nt * 8 + r;
+                    b[nt] = (i < k && g < n_grid) ? (double)xs[(int64_t)i * n_grid + g] : 0.0;
+                }
+                const double* ap = At + r * lda + i;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const double a = ap[mt * 8 * lda];
+#pragma unroll
+                    for (int nt = 0; nt < kApplyNTW; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a, b[nt]);
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int j = mt * 8 + r;
+#pragma unroll
+                for (int nt = 0; nt < kApplyNTW; ++nt) {
+                    const int64_t g = g0 + nt * 8 + q * 2;
+                    if (j < k) {
+                        T* dst = xo + (int64_t)j * n_grid + g;
+                        if (g + 1 < n_grid && ((n_grid & 1) == 0)) {
+                            if constexpr (sizeof(T) == 8) *reinterpret_cast<double2*>(dst) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                            else *reinterpret_cast<float2*>(dst) = make_float2((float)acc[mt][nt][0], (float)acc[mt][nt][1]);
+                        } else {
+                            if (g < n_grid) dst[0] = (T)acc[mt][nt][0];
+                            if (g + 1 < n_grid) dst[1] = (T)acc[mt][nt][1];
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // (n_rows, N) <-> dense (n_rows, n_cols) in block-sorted order: the all-gather payload of the grid-sharded run
 template <typename T>
 __global__ void k_pack_columns(const T* __restrict__ xa, const int* __restrict__ order, int64_t slot0, int64_t n_cols,

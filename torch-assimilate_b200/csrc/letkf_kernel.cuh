@@ -22,7 +22,8 @@
 namespace b200da {
 
 constexpr int kTileObs = 64;      // observations per staged tile
-constexpr int kStages = 3;
+// ring depth of the staged tiles: 3, or 2 when three FP64 tiles of a large ensemble would not fit in shared memory
+template <typename T, int KPT> __host__ __device__ constexpr int gram_stages() { return (sizeof(T) == 8 && KPT > 14) ? 2 : 3; }
 constexpr int kRing = 2048;       // survivor ring (sorted obs slots), power of two
 
 struct LetkfParams {
@@ -67,10 +68,13 @@ __host__ __device__ constexpr int tile_ld() {
     return sizeof(T) == 8 ? KT * 8 + 4 : KT * 8 + ((8 - (KT * 8) % 32 + 32) % 32);
 }
 
-template <typename T, int KT, int WPG, int SUB>
+// BROW: the ensemble size is a multiple of 8, so the innovation row d (row k of the augmented matrix) would cost a whole
+// extra row of tiles; instead b = sum_j w_j d_j y_j is accumulated with plain FMAs next to the DMMA tiles of C.
+template <typename T, int KT, int WPG, int SUB, bool BROW>
 __device__ __forceinline__ void gram_tile(const T* __restrict__ ytile, const double* __restrict__ wrow,
-                                          double (&acc)[(KT * (KT + 1) / 2 + WPG - 1) / WPG][2], int lane) {
-    constexpr int LDY = tile_ld<T, KT>();
+                                          double (&acc)[(KT * (KT + 1) / 2 + WPG - 1) / WPG][2],
+                                          double (&bacc)[(KT + WPG - 1) / WPG], int lane) {
+    constexpr int LDY = tile_ld<T, KT + (BROW ? 1 : 0)>();
 #pragma unroll 2
     for (int ks = 0; ks < kTileObs / 4; ++ks) {
         const int j = ks * 4 + (lane & 3);
@@ -80,6 +84,13 @@ __device__ __forceinline__ void gram_tile(const T* __restrict__ ytile, const dou
         double f[KT];
 #pragma unroll
         for (int t = 0; t < KT; ++t) f[t] = (double)yr[t * 8];
+        if constexpr (BROW) {
+            const double wd = w * (double)ytile[j * LDY + KT * 8];
+            int nb = 0;
+#pragma unroll
+            for (int t = 0; t < KT; ++t)
+                if (t % WPG == SUB) { bacc[nb] = fma(f[t], wd, bacc[nb]); ++nb; }
+        }
         int idx = 0, n = 0;
 #pragma unroll
         for (int mt = 0; mt < KT; ++mt) {
@@ -120,10 +131,23 @@ __device__ __forceinline__ void dump_tiles(const double (&acc)[(KT * (KT + 1) / 
 
 // accumulators -> global scratch in the tile-packed layout (common.cuh): one 512-byte tile per accumulator pair set,
 // rows 0..k-1 = C (diagonal tiles hold the full 8x8 product), row k = b
-template <int KT, int WPG, int SUB>
+template <int KT, int WPG, int SUB, bool BROW>
 __device__ __forceinline__ void dump_tiles_global(const double (&acc)[(KT * (KT + 1) / 2 + WPG - 1) / WPG][2],
-                                                  double* __restrict__ C, int lane) {
+                                                  double (&bacc)[(KT + WPG - 1) / WPG], double* __restrict__ C, int lane) {
     const int r = lane >> 2, c = (lane & 3) * 2;
+    if constexpr (BROW) {                       // row k = KT * 8 of the augmented matrix: first row of tile row KT
+        int nb = 0;
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            if (t % WPG == SUB) {
+                double v = bacc[nb];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if ((lane & 3) == 0) C[tile_off(KT, t) + tile_elem(0, r)] = v;
+                ++nb;
+            }
+        }
+    }
     int idx = 0, n = 0;
 #pragma unroll
     for (int mt = 0; mt < KT; ++mt) {
@@ -220,15 +244,18 @@ __device__ void setup_block(BlockHeader<G>& H, const Geometry& g, const Pos4* __
 
 }
 
-template <typename T, int KT, int G, int WPG>
+template <typename T, int KT, int G, int WPG, bool BROW>
 __host__ __device__ constexpr size_t gram_smem_bytes() {
-    return sizeof(double) * ((size_t)kStages * G * kTileObs) + sizeof(T) * ((size_t)kStages * kTileObs * tile_ld<T, KT>());
+    constexpr int KPT = KT + (BROW ? 1 : 0), S = gram_stages<T, KPT>();
+    return sizeof(double) * ((size_t)S * G * kTileObs) + sizeof(T) * ((size_t)S * kTileObs * tile_ld<T, KPT>());
 }
 
-template <typename T, int KT, int G, int WPG>
+template <typename T, int KT, int G, int WPG, bool BROW>
 __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParams P) {
     constexpr int NT = G * WPG * 32;
-    constexpr int KP = KT * 8, LDY = tile_ld<T, KT>();
+    constexpr int KPT = KT + (BROW ? 1 : 0);                  // 8-row tiles of the staged [Yn; d] rows
+    constexpr int kStages = gram_stages<T, KPT>();
+    constexpr int KP = KPT * 8, LDY = tile_ld<T, KPT>();
     constexpr int NTILES = KT * (KT + 1) / 2;
     constexpr int ACC = (NTILES + WPG - 1) / WPG;
     extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -250,6 +277,9 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
     double acc[ACC][2];
 #pragma unroll
     for (int i = 0; i < ACC; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+    double bacc[(KT + WPG - 1) / WPG];
+#pragma unroll
+    for (int i = 0; i < (KT + WPG - 1) / WPG; ++i) bacc[i] = 0.0;
 
     // ------------------------------------------------------------------------------------------------------------
     // Gram phase
@@ -323,10 +353,10 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
     };
 
     if (cand_total > 0) {
-        if (produce()) { cp_async_commit(); if (produce()) {} cp_async_commit(); }
-        else { cp_async_commit(); cp_async_commit(); }
+#pragma unroll
+        for (int i = 0; i < kStages - 1; ++i) { produce(); cp_async_commit(); }      // one group per tile, possibly empty
         while (consumed < produced) {
-            cp_async_wait<1>();
+            cp_async_wait<kStages - 2>();
             __syncthreads();
             produce();
             cp_async_commit();                        // one group per iteration, possibly empty
@@ -334,27 +364,27 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
                 const int stage = consumed % kStages;
                 const T* yst = ybuf + (size_t)stage * kTileObs * LDY;
                 const double* wrow = wbuf + ((size_t)stage * G + my_g) * kTileObs;
-                if constexpr (WPG == 1) gram_tile<T, KT, WPG, 0>(yst, wrow, acc, lane);
+                if constexpr (WPG == 1) gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane);
                 else if constexpr (WPG == 2) {
-                    if (my_sub == 0) gram_tile<T, KT, WPG, 0>(yst, wrow, acc, lane);
-                    else gram_tile<T, KT, WPG, 1>(yst, wrow, acc, lane);
+                    if (my_sub == 0) gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane);
+                    else gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane);
                 } else if constexpr (WPG == 4) {
                     switch (my_sub) {
-                        case 0: gram_tile<T, KT, WPG, 0>(yst, wrow, acc, lane); break;
-                        case 1: gram_tile<T, KT, WPG, 1>(yst, wrow, acc, lane); break;
-                        case 2: gram_tile<T, KT, WPG, 2>(yst, wrow, acc, lane); break;
-                        default: gram_tile<T, KT, WPG, 3>(yst, wrow, acc, lane); break;
+                        case 0: gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane); break;
+                        case 1: gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane); break;
+                        case 2: gram_tile<T, KT, WPG, 2, BROW>(yst, wrow, acc, bacc, lane); break;
+                        default: gram_tile<T, KT, WPG, 3, BROW>(yst, wrow, acc, bacc, lane); break;
                     }
                 } else {
                     switch (my_sub) {
-                        case 0: gram_tile<T, KT, WPG, 0>(yst, wrow, acc, lane); break;
-                        case 1: gram_tile<T, KT, WPG, 1>(yst, wrow, acc, lane); break;
-                        case 2: gram_tile<T, KT, WPG, 2>(yst, wrow, acc, lane); break;
-                        case 3: gram_tile<T, KT, WPG, 3>(yst, wrow, acc, lane); break;
-                        case 4: gram_tile<T, KT, WPG, 4>(yst, wrow, acc, lane); break;
-                        case 5: gram_tile<T, KT, WPG, 5>(yst, wrow, acc, lane); break;
-                        case 6: gram_tile<T, KT, WPG, 6>(yst, wrow, acc, lane); break;
-                        default: gram_tile<T, KT, WPG, 7>(yst, wrow, acc, lane); break;
+                        case 0: gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane); break;
+                        case 1: gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane); break;
+                        case 2: gram_tile<T, KT, WPG, 2, BROW>(yst, wrow, acc, bacc, lane); break;
+                        case 3: gram_tile<T, KT, WPG, 3, BROW>(yst, wrow, acc, bacc, lane); break;
+                        case 4: gram_tile<T, KT, WPG, 4, BROW>(yst, wrow, acc, bacc, lane); break;
+                        case 5: gram_tile<T, KT, WPG, 5, BROW>(yst, wrow, acc, bacc, lane); break;
+                        case 6: gram_tile<T, KT, WPG, 6, BROW>(yst, wrow, acc, bacc, lane); break;
+                        default: gram_tile<T, KT, WPG, 7, BROW>(yst, wrow, acc, bacc, lane); break;
                     }
                 }
             }
@@ -370,28 +400,28 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
     // hand the augmented Gram matrices to the solve kernel through the (L2-resident) scratch
     // ------------------------------------------------------------------------------------------------------------
     if (my_g < ng) {
-        double* C = P.cmat + (size_t)((int64_t)P.block_off[blk] + my_g - P.slot_base) * (size_t)(NTILES * 64);
-        if constexpr (WPG == 1) dump_tiles_global<KT, WPG, 0>(acc, C, lane);
+        double* C = P.cmat + (size_t)((int64_t)P.block_off[blk] + my_g - P.slot_base) * (size_t)(tri_tiles(KPT) * 64);
+        if constexpr (WPG == 1) dump_tiles_global<KT, WPG, 0, BROW>(acc, bacc, C, lane);
         else if constexpr (WPG == 2) {
-            if (my_sub == 0) dump_tiles_global<KT, WPG, 0>(acc, C, lane);
-            else dump_tiles_global<KT, WPG, 1>(acc, C, lane);
+            if (my_sub == 0) dump_tiles_global<KT, WPG, 0, BROW>(acc, bacc, C, lane);
+            else dump_tiles_global<KT, WPG, 1, BROW>(acc, bacc, C, lane);
         } else if constexpr (WPG == 4) {
             switch (my_sub) {
-                case 0: dump_tiles_global<KT, WPG, 0>(acc, C, lane); break;
-                case 1: dump_tiles_global<KT, WPG, 1>(acc, C, lane); break;
-                case 2: dump_tiles_global<KT, WPG, 2>(acc, C, lane); break;
-                default: dump_tiles_global<KT, WPG, 3>(acc, C, lane); break;
+                case 0: dump_tiles_global<KT, WPG, 0, BROW>(acc, bacc, C, lane); break;
+                case 1: dump_tiles_global<KT, WPG, 1, BROW>(acc, bacc, C, lane); break;
+                case 2: dump_tiles_global<KT, WPG, 2, BROW>(acc, bacc, C, lane); break;
+                default: dump_tiles_global<KT, WPG, 3, BROW>(acc, bacc, C, lane); break;
             }
         } else {
             switch (my_sub) {
-                case 0: dump_tiles_global<KT, WPG, 0>(acc, C, lane); break;
-                case 1: dump_tiles_global<KT, WPG, 1>(acc, C, lane); break;
-                case 2: dump_tiles_global<KT, WPG, 2>(acc, C, lane); break;
-                case 3: dump_tiles_global<KT, WPG, 3>(acc, C, lane); break;
-                case 4: dump_tiles_global<KT, WPG, 4>(acc, C, lane); break;
-                case 5: dump_tiles_global<KT, WPG, 5>(acc, C, lane); break;
-                case 6: dump_tiles_global<KT, WPG, 6>(acc, C, lane); break;
-                default: dump_tiles_global<KT, WPG, 7>(acc, C, lane); break;
+                case 0: dump_tiles_global<KT, WPG, 0, BROW>(acc, bacc, C, lane); break;
+                case 1: dump_tiles_global<KT, WPG, 1, BROW>(acc, bacc, C, lane); break;
+                case 2: dump_tiles_global<KT, WPG, 2, BROW>(acc, bacc, C, lane); break;
+                case 3: dump_tiles_global<KT, WPG, 3, BROW>(acc, bacc, C, lane); break;
+                case 4: dump_tiles_global<KT, WPG, 4, BROW>(acc, bacc, C, lane); break;
+                case 5: dump_tiles_global<KT, WPG, 5, BROW>(acc, bacc, C, lane); break;
+                case 6: dump_tiles_global<KT, WPG, 6, BROW>(acc, bacc, C, lane); break;
+                default: dump_tiles_global<KT, WPG, 7, BROW>(acc, bacc, C, lane); break;
             }
         }
     }

@@ -31,7 +31,7 @@ int dispatch_ns(int kts, const NsParams& P, cudaStream_t st) {
     switch (kts) {
         B200DA_NS_CASE(1) B200DA_NS_CASE(2) B200DA_NS_CASE(3) B200DA_NS_CASE(4) B200DA_NS_CASE(5) B200DA_NS_CASE(6)
         B200DA_NS_CASE(7) B200DA_NS_CASE(8) B200DA_NS_CASE(9) B200DA_NS_CASE(10) B200DA_NS_CASE(11) B200DA_NS_CASE(12)
-        B200DA_NS_CASE(13) B200DA_NS_CASE(14)
+        B200DA_NS_CASE(13) B200DA_NS_CASE(14) B200DA_NS_CASE(15) B200DA_NS_CASE(16)
         default: return B200DA_ERR_UNSUPPORTED;
     }
 }

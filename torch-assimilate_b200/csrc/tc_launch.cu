@@ -4,12 +4,16 @@
 
 namespace b200da {
 
-// column chunking of the (k + 1)(k + 2) / 2 pair columns: as few chunks as fit 512 tensor-memory columns each
+// column chunking of the (k + 1)(k + 2) / 2 pair columns: as few chunks as fit 512 tensor-memory columns each and, with at
+// least two loader warps, the shared memory of one SM
 void tc_chunking(int k, int* n_cols, int* n_chunks, int* nc) {
+    const int kp = (k + 1 + 7) / 8 * 8;
     *n_cols = (k + 1) * (k + 2) / 2;
-    *n_chunks = (*n_cols + kTcMaxCols - 1) / kTcMaxCols;
-    const int per = (*n_cols + *n_chunks - 1) / *n_chunks;
-    *nc = (per + 31) / 32 * 32;
+    for (*n_chunks = (*n_cols + kTcMaxCols - 1) / kTcMaxCols;; ++*n_chunks) {
+        const int per = (*n_cols + *n_chunks - 1) / *n_chunks;
+        *nc = (per + 31) / 32 * 32;
+        if (tc_smem_bytes(kp, *nc, 2) <= kMaxSmem || *nc <= 64) break;
+    }
 }
 
 int launch_tc_gram(b200da_plan* pl, const LetkfParams& L, int nblocks, cudaStream_t st) {
