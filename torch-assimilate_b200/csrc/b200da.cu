@@ -455,11 +455,27 @@ int b200da_etkf_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t 
         if ((rc = dispatch_etkf_gram(pl->kt, pl->dtype == B200DA_F32, Yn, d, m, k, ncta, chunk,
                                      pl->etkf_partial.as<double>(), st))) return rc;
     }
+    const int f32 = pl->dtype == B200DA_F32 ? 1 : 0;
+    if (m > 0 && pl->solver == B200DA_SOLVER_NEWTON_SCHULZ) {
+        // partial Grams -> one tile-packed slot -> the tensor-core Newton-Schulz solve (one matrix, no state update)
+        const size_t slot_doubles = (size_t)tri_tiles(pl->kt) * 64;
+        if ((rc = pl->etkf_w.ensure(sizeof(Pos4) + sizeof(double) * slot_doubles))) return rc;
+        if ((rc = pl->counter.ensure(sizeof(unsigned int) * 4))) return rc;
+        B200DA_CUDA(cudaMemsetAsync(pl->etkf_w.p, 0, sizeof(Pos4) + sizeof(double) * slot_doubles, st));   // Pos4.id = 0
+        B200DA_CUDA(cudaMemsetAsync(pl->counter.p, 0, sizeof(unsigned int) * 4, st));
+        double* slot = reinterpret_cast<double*>(pl->etkf_w.as<unsigned char>() + sizeof(Pos4));
+        k_etkf_reduce<<<grid1d((int64_t)(k + 1) * kp, 128), 128, 0, st>>>(pl->etkf_partial.as<double>(), ncta, kp, k, slot);
+        B200DA_LAUNCH_CHECK();
+        NsParams S{};
+        S.cmat = slot; S.slot_stride = (int64_t)slot_doubles; S.gpos = pl->etkf_w.as<Pos4>(); S.x = nullptr; S.xa = nullptr;
+        S.w_out = W; S.io_f32 = f32; S.stats = nullptr; S.counter = pl->counter.as<unsigned int>();
+        S.slot_base = 0; S.n_slots = 1; S.n_grid = 0; S.k = k; S.n_slices = 0; S.rho = pl->rho;
+        return dispatch_ns((k + 7) / 8, S, st);
+    }
     const size_t smem = solve_smem_bytes(k);
     if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
     B200DA_CUDA(cudaFuncSetAttribute(k_etkf_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_etkf_solve<<<1, 512, smem, st>>>(pl->etkf_partial.as<double>(), m > 0 ? ncta : 0, kp, k, pl->rho, W,
-                                       pl->dtype == B200DA_F32 ? 1 : 0);
+    k_etkf_solve<<<1, 512, smem, st>>>(pl->etkf_partial.as<double>(), m > 0 ? ncta : 0, kp, k, pl->rho, W, f32);
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }

@@ -66,6 +66,18 @@ __global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const T* __restri
     }
 }
 
+// Sum the partial Grams in a fixed order into one tile-packed augmented Gram slot (common.cuh): the input format of the
+// ensemble-space solve kernels.  One thread per entry (r, c), c <= r <= k; the slot is zeroed beforehand.
+__global__ void k_etkf_reduce(const double* __restrict__ partial, int n_partial, int kp, int k, double* __restrict__ slot) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (k + 1) * kp) return;
+    const int r = e / kp, c = e - r * kp;
+    if (c > r || c >= k) return;
+    double s = 0.0;
+    for (int p = 0; p < n_partial; ++p) s += partial[(size_t)p * kp * kp + e];
+    slot[sym_off(r, c)] = s;
+}
+
 // Sum the partial Grams in a fixed order, eigendecompose, transform; W (k x k) row-major to global memory.
 __global__ void __launch_bounds__(512, 1) k_etkf_solve(const double* __restrict__ partial, int n_partial, int kp, int k,
                                                     double rho, void* __restrict__ w_out, int io_f32) {
