@@ -94,6 +94,15 @@ int b200da_set_grid(b200da_plan* plan, const double* grid_coord, int64_t n_grid,
 int b200da_bin_obs(b200da_plan* plan, const double* obs_coord, const void* Yn, const void* d, int64_t n_obs,
                    void* stream);
 
+/* Replaces BaseAssimilation._get_obs_space_variables for observations with a diagonal R (interface/base.py:359-379,
+ * observation.py:241-245,277-279; the step right before the hot path): from the ensemble of observation
+ * equivalents HX (k, M) (dataset-, time-, obs_grid_1-stacked as _stack_obs does, interface/base.py:223-241), the
+ * observations y (M) and their error variances (M):  Yn = (HX - mean_k HX) / sqrt(var),  d = (y - mean_k HX) / sqrt(var).
+ * The ensemble mean is summed in member order, so FP64 results are bit-identical to the reference's numpy arithmetic.
+ * Correlated R (Cholesky of an M x M matrix, observation.py:247-275) stays on the host. */
+int b200da_obs_prep(b200da_plan* plan, const void* HX, const void* y, const void* variance, int64_t n_obs, void* Yn, void* d,
+                    void* stream);
+
 int64_t b200da_num_blocks(const b200da_plan* plan);      /* grid-point blocks (unit of multi-GPU sharding)     */
 int64_t b200da_num_grid(const b200da_plan* plan);
 int64_t b200da_num_obs(const b200da_plan* plan);

@@ -86,3 +86,30 @@ def test_localize_obs_signature(golden):
     np.testing.assert_allclose(w[use], rw[ruse], rtol=1e-12, atol=5e-15)
     use, _ = loc.localize_obs(np.array([0.0, 9999999.0]), grid)
     assert not use.any()
+
+
+def test_device_obs_prep_bit_exact_against_oracle():
+    """b200da_obs_prep == BaseAssimilation._get_obs_space_variables with a diagonal R
+    (interface/base.py:359-379, observation.py:241-245): FP64 bit-exact, FP32 to rounding."""
+    import numpy as np
+    import torch
+    import letkf_oracle as orc
+    from pytassim_b200.engine import LETKFEngine
+    from pytassim_b200.localization.metrics import AbsDistance1D
+    rng = np.random.RandomState(3)
+    k, n_t, n_o = 23, 3, 1777
+    hx = rng.normal(size=(k, n_t, n_o)) * 3.0 + 1.5
+    y = rng.normal(size=(n_t, n_o))
+    var = rng.uniform(0.1, 4.0, size=n_o)
+    innov_ref, perts_ref = orc.obs_space_variables([hx], [y], [var])
+    eng = LETKFEngine(k, 1, AbsDistance1D(), 1.0, dtype=torch.float64)
+    yn, d = eng.obs_prep(hx.reshape(k, -1), y.reshape(-1), np.tile(var, n_t))
+    np.testing.assert_array_equal(yn.cpu().numpy(), perts_ref)
+    np.testing.assert_array_equal(d.cpu().numpy(), innov_ref)
+    eng32 = LETKFEngine(k, 1, AbsDistance1D(), 1.0, dtype=torch.float32)
+    yn32, d32 = eng32.obs_prep(hx.reshape(k, -1), y.reshape(-1), np.tile(var, n_t))
+    assert yn32.dtype == torch.float32
+    np.testing.assert_allclose(yn32.cpu().numpy(), perts_ref, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(d32.cpu().numpy(), innov_ref, rtol=2e-5, atol=2e-5)
+    with pytest.raises(ValueError):
+        eng.obs_prep(hx.reshape(k, -1), y.reshape(-1)[:-1], np.tile(var, n_t))

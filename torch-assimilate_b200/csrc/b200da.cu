@@ -245,6 +245,21 @@ int b200da_bin_obs(b200da_plan* plan, const double* obs_coord, const void* Yn, c
     return bin_obs_impl<double>(plan, obs_coord, (const double*)Yn, (const double*)d, n_obs, (cudaStream_t)stream);
 }
 
+int b200da_obs_prep(b200da_plan* pl, const void* HX, const void* y, const void* variance, int64_t m, void* Yn, void* d,
+                    void* stream) {
+    if (!pl || m < 0 || (m > 0 && (!HX || !y || !variance || !Yn || !d))) return B200DA_ERR_INVALID;
+    if (m == 0) return B200DA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl->dtype == B200DA_F32)
+        k_obs_prep<float><<<grid1d(m, 256), 256, 0, st>>>((const float*)HX, (const float*)y, (const float*)variance, pl->k, m,
+                                                          (float*)Yn, (float*)d);
+    else
+        k_obs_prep<double><<<grid1d(m, 256), 256, 0, st>>>((const double*)HX, (const double*)y, (const double*)variance, pl->k, m,
+                                                           (double*)Yn, (double*)d);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
 int64_t b200da_num_blocks(const b200da_plan* plan) { return plan ? plan->n_blocks : 0; }
 int64_t b200da_num_grid(const b200da_plan* plan) { return plan ? plan->n_grid : 0; }
 int64_t b200da_num_obs(const b200da_plan* plan) { return plan ? plan->n_obs : 0; }

@@ -163,6 +163,23 @@ __global__ void k_gather_obs(const unsigned long long* __restrict__ sorted, cons
     }
 }
 
+// Observation-space variables of one stacked observation vector (interface/base.py:359-379 with a diagonal R,
+// observation.py:241-245,277-279): mean_j = (sum_i hx[i][j]) / k summed in member order (bit-identical to numpy's
+// mean over the leading axis), Yn[i][j] = (hx[i][j] - mean_j) * rc_j, d[j] = (y[j] - mean_j) * rc_j, rc_j = 1 / sqrt(var_j).
+// One thread per observation: member rows are read coalesced, the second pass over the column hits L1 / L2.
+template <typename T>
+__global__ void __launch_bounds__(256) k_obs_prep(const T* __restrict__ hx, const T* __restrict__ y, const T* __restrict__ var,
+                                                  int k, int64_t m, T* __restrict__ yn, T* __restrict__ d) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    T sum = (T)0;
+    for (int i = 0; i < k; ++i) sum += hx[(int64_t)i * m + j];
+    const T mean = sum / (T)k;
+    const T rc = (T)1 / sqrt(var[j]);
+    for (int i = 0; i < k; ++i) yn[(int64_t)i * m + j] = (hx[(int64_t)i * m + j] - mean) * rc;
+    d[j] = (y[j] - mean) * rc;
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------
 
 inline int grid1d(int64_t n, int block) { return (int)std::max<int64_t>(1, (n + block - 1) / block); }

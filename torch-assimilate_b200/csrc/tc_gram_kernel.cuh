@@ -42,7 +42,10 @@ constexpr int kTcLoadWarp = kTcGenWarps + 1;   // first of the loader warps: can
 constexpr int kTcYStages = 6;      // loader warps = observation-tile buffers (one each) between loaders and generators
 constexpr int kTcThreads = (kTcGenWarps + 1 + kTcYStages) * 32;
 constexpr int kTcYLd = 36;         // row length of the member-major observation tile: 32 obs + 4 (conflict-free LDS.128)
-constexpr int kTcMaxCols = 512;    // tensor-memory columns = accumulator columns per CTA
+constexpr bool kTcATmem = true;    // W operand (A) in tensor memory (written with tcgen05.st) instead of shared memory
+constexpr int kTcTmemCols = 512;   // tensor-memory allocation
+constexpr int kTcACols = 64;       // A operand in tensor memory: 2 stages x (hi, lo) x 2 K steps x 8 columns (16 bf16 each)
+constexpr int kTcMaxCols = kTcATmem ? kTcTmemCols - kTcACols : kTcTmemCols;   // accumulator columns per CTA
 constexpr float kTcFar = 1.0e18f;  // coordinate of padding observations (+) and padding grid points (-)
 constexpr int kTcFilterUnroll = 4; // candidates per lane and filter pass (independent loads in flight)
 
@@ -89,6 +92,13 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
                  "setp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// the same with the A operand in tensor memory (lane = row, one 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // shared-memory matrix descriptor, K-major, no swizzle (SM100 descriptor version 1)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -191,7 +201,7 @@ __host__ __device__ inline size_t tc_smem_bytes(int kp, int nc, int n_load) {
     o += tc_align(sizeof(float2) * (kTcTab + 1), 128);
     o += sizeof(float4) * kTcYStages * kTcObs;
     o = tc_align(o + sizeof(float) * n_load * (size_t)kp * kTcYLd, 128);
-    o += 2 * 2 * (size_t)kTcM * 64;
+    o += kTcATmem ? 0 : 2 * 2 * (size_t)kTcM * 64;
     o += 2 * 2 * (size_t)nc * 64;
     return o;
 }
@@ -210,8 +220,8 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int kp, int nc, 
     o += sizeof(float4) * kTcYStages * kTcObs;
     S.ytile = reinterpret_cast<float*>(base + o);
     o = tc_align(o + sizeof(float) * n_load * (size_t)kp * kTcYLd, 128);
-    S.a_hi = base + o; o += 2 * (size_t)kTcM * 64;
-    S.a_lo = base + o; o += 2 * (size_t)kTcM * 64;
+    S.a_hi = base + o; o += kTcATmem ? 0 : 2 * (size_t)kTcM * 64;
+    S.a_lo = base + o; o += kTcATmem ? 0 : 2 * (size_t)kTcM * 64;
     S.b_hi = base + o; o += 2 * (size_t)nc * 64;
     S.b_lo = base + o;
     return S;
@@ -266,7 +276,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
     }
     if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(S.tmem_slot)), "r"((uint32_t)kTcMaxCols) : "memory");
+                     :: "r"(smem_u32(S.tmem_slot)), "r"((uint32_t)kTcTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -376,9 +386,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
                         const uint32_t aoff = ((uint32_t)st * kTcM * 64 + (uint32_t)ks * 2 * a_lbo) >> 4;
                         const uint32_t boff = ((uint32_t)st * (uint32_t)nc * 64 + (uint32_t)ks * 2 * b_lbo + (uint32_t)h * (uint32_t)(nc >> 1) * 16) >> 4;
                         const uint32_t d = tmem + (uint32_t)h * (uint32_t)(nc >> 1);
-                        tc_mma_bf16(d, da_hi0 + aoff, db_hi0 + boff, idesc, (t > 0 || ks > 0) ? 1u : 0u);
-                        tc_mma_bf16(d, da_hi0 + aoff, db_lo0 + boff, idesc, 1u);
-                        tc_mma_bf16(d, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
+                        if constexpr (kTcATmem) {
+                            // A columns: stage * 32 + {hi: 0, lo: 16} + K step * 8 behind the accumulator columns
+                            const uint32_t a_hi = tmem + (uint32_t)kTcMaxCols + (uint32_t)st * 32 + (uint32_t)ks * 8;
+                            tc_mma_bf16_ts(d, a_hi, db_hi0 + boff, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+                            tc_mma_bf16_ts(d, a_hi, db_lo0 + boff, idesc, 1u);
+                            tc_mma_bf16_ts(d, a_hi + 16, db_hi0 + boff, idesc, 1u);
+                        } else {
+                            tc_mma_bf16(d, da_hi0 + aoff, db_hi0 + boff, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+                            tc_mma_bf16(d, da_hi0 + aoff, db_lo0 + boff, idesc, 1u);
+                            tc_mma_bf16(d, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
+                        }
                     }
                 }
                 tc_commit(&op_free[st]);
@@ -423,9 +441,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
                 if (dist_kind == kTcSq3) w_chunk<kTcSq3>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo);        // uniform over the launch
                 else if (dist_kind == kTcAbs) w_chunk<kTcAbs>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo);
                 else w_chunk<kTcPeriodic>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo);
-                const size_t off = (size_t)st * kTcM * 64 + (size_t)my_kc * a_lbo + (size_t)my_g * 16;
-                *reinterpret_cast<uint4*>(S.a_hi + off) = hi;
-                *reinterpret_cast<uint4*>(S.a_lo + off) = lo;
+                if constexpr (kTcATmem) {
+                    // this thread's row (grid point) = its tensor-memory lane; 8 bf16 = 4 columns at K offset my_kc * 8
+                    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)kTcMaxCols + (uint32_t)st * 32 +
+                                           (uint32_t)(my_kc >> 1) * 8 + (uint32_t)(my_kc & 1) * 4;
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                                 :: "r"(taddr), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                                 :: "r"(taddr + 16), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+                } else {
+                    const size_t off = (size_t)st * kTcM * 64 + (size_t)my_kc * a_lbo + (size_t)my_g * 16;
+                    *reinterpret_cast<uint4*>(S.a_hi + off) = hi;
+                    *reinterpret_cast<uint4*>(S.a_lo + off) = lo;
+                }
             }
             // ---- Z tile: products y_a y_b of this thread's pair column (loads of chunk kc + 1 ahead of the stores of kc) --------
             if (c_ok) {
@@ -447,6 +475,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
             }
             // ---- publish the operand stage to the tensor core, release the observation tile -----------------------------------
             fence_async_smem();
+            if constexpr (kTcATmem) {
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+            }
             __syncwarp();
             if (lane == 0) { mbar_arrive(&op_full[st]); mbar_arrive(&y_free[yst]); }
             ++t;
@@ -496,7 +528,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
     tc_fence_before();
     __syncthreads();
     if (warp == kTcMmaWarp) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kTcMaxCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kTcTmemCols) : "memory");
     }
 }
 

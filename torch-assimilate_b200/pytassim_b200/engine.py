@@ -107,6 +107,23 @@ class LETKFEngine(object):
         self.n_obs = int(d.shape[0])
         return self
 
+    def obs_prep(self, ens_obs, observations, variance):
+        """Observation-space variables on the device for a diagonal R (interface/base.py:359-379, observation.py:241-245):
+        ens_obs (k, M), observations (M,), variance (M,) -> (normed_perts (k, M), normed_obs (M,)) device tensors."""
+        hx = _dev(ens_obs, dtype=self.dtype, device=self.device)
+        y = _dev(observations, dtype=self.dtype, device=self.device).reshape(-1)
+        var = _dev(variance, dtype=self.dtype, device=self.device).reshape(-1)
+        if hx.dim() != 2 or hx.shape[0] != self.k:
+            raise ValueError("ens_obs must be (ens_size, n_obs)")
+        if hx.shape[1] != y.shape[0] or var.shape[0] != y.shape[0]:
+            raise ValueError('Observational size between ensemble ({0:d}) and observations '
+                             '({1:d}) do not match!'.format(hx.shape[1], y.shape[0]))
+        yn = torch.empty_like(hx)
+        d = torch.empty_like(y)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_obs_prep(self._plan, _ptr(hx), _ptr(y), _ptr(var), y.shape[0], _ptr(yn), _ptr(d), _stream()))
+        return yn, d
+
     # -- hot path ----------------------------------------------------------------------------------------------
     def analyse(self, state, out=None, return_weights=False, blocks=None, count_ambiguous=False):
         """state (n_slices, k, N) on the device -> analysis of the same shape (interface/base.py:257-278)."""

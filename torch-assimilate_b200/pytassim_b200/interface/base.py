@@ -178,6 +178,28 @@ class BaseAssimilation(object):
             infos.append(info)
         return np.concatenate(innovations), np.concatenate(perts, axis=1), np.concatenate(infos, axis=0)
 
+    @staticmethod
+    def _stack_obs_space_inputs(ens_obs, observations):
+        """The raw inputs of ``_get_obs_space_variables`` stacked like ``_stack_obs`` (base.py:223-241) for the device
+        prep kernel: (hx (k, M), y (M,), variance (M,), obs_info (M, 1+nc)), or None when a dataset carries a correlated
+        covariance (obs_grid_2): that case is normalised on the host (observation.py:247-275)."""
+        hxs, ys, vars_, infos = [], [], [], []
+        for hx, obs in zip(ens_obs, observations):
+            cov = obs['covariance']
+            if 'obs_grid_2' in cov.dims:
+                return None
+            hxv = hx.transpose('ensemble', 'time', 'obs_grid_1').values \
+                if tuple(hx.dims) != ('ensemble', 'time', 'obs_grid_1') else hx.values
+            hxv = np.asarray(hxv, dtype=np.float64)
+            y = np.asarray(obs['observations'].values, dtype=np.float64)
+            n_t, n_o = y.shape
+            covv = np.broadcast_to(np.asarray(cov.values, dtype=np.float64), (n_t, n_o))
+            t_unix = dtindex_to_total_seconds(_time_coord(obs['observations']))
+            coords = index_to_array(obs['observations'].indexes['obs_grid_1'])
+            infos.append(np.concatenate([np.repeat(t_unix, n_o)[:, None], np.tile(coords, (n_t, 1))], axis=1))
+            hxs.append(hxv.reshape(hxv.shape[0], -1)); ys.append(y.reshape(-1)); vars_.append(covv.reshape(-1))
+        return np.concatenate(hxs, axis=1), np.concatenate(ys), np.concatenate(vars_), np.concatenate(infos, axis=0)
+
     @abc.abstractmethod
     def update_state(self, state, observations, pseudo_state, analysis_time):
         pass
@@ -229,7 +251,12 @@ class FilterAssimilation(BaseAssimilation):
 
     @abc.abstractmethod
     def _analyse_arrays(self, state, x, innov, perts, obs_info):
-        """x (n_slices, k, N) host array -> analysed (n_slices, k, N) host array."""
+        """x (n_slices, k, N) host array, innov (M,) / perts (k, M) host arrays or device tensors ->
+        analysed (n_slices, k, N) host array."""
+
+    @abc.abstractmethod
+    def _prep_engine(self, k, n_slices):
+        """An engine of the right ensemble size / dtype whose ``obs_prep`` runs the device prep kernel."""
 
     def update_state(self, state, observations, pseudo_state, analysis_time):
         pseudo_state = self.get_pseudo_state(pseudo_state, state)
@@ -240,8 +267,13 @@ class FilterAssimilation(BaseAssimilation):
         if not filtered_obs:
             warnings.warn('No observation is given, I will return the background state!', UserWarning)
             return state
-        innov, perts, obs_info = self._get_obs_space_variables(ens_obs, filtered_obs)
         values = np.ascontiguousarray(state.values, dtype=np.float64)
         n_var, n_t, k, n_grid = values.shape
+        stacked = self._stack_obs_space_inputs(ens_obs, filtered_obs)
+        if stacked is not None:                     # diagonal R: mean / perturbations / innovations / R^-1/2 on the device
+            hx, y, var, obs_info = stacked
+            perts, innov = self._prep_engine(k, n_var * n_t).obs_prep(hx, y, var)
+        else:
+            innov, perts, obs_info = self._get_obs_space_variables(ens_obs, filtered_obs)
         xa = self._analyse_arrays(state, values.reshape(n_var * n_t, k, n_grid), innov, perts, obs_info)
         return state.copy(data=np.asarray(xa).reshape(values.shape).astype(state.values.dtype, copy=False))

@@ -40,6 +40,9 @@ class ETKF(FilterAssimilation):
                                              dtype=self.dtype)
         return self._engines[key]
 
+    def _prep_engine(self, k, n_slices):
+        return self._global_engine(k, n_slices)
+
     def _analyse_arrays(self, state, x, innov, perts, obs_info):
         eng = self._global_engine(x.shape[1], x.shape[0])
         weights = eng.etkf_weights(perts, innov)                            # etkf.py:99-120
