@@ -58,6 +58,10 @@ struct TcParams {
     int n_load;        // active loader warps = observation-tile buffers (2..kTcYStages, limited by shared memory)
     float q_max;       // table domain: squared bin-space distance beyond which the weight is 0
     float period;
+    int w_closed;      // 1: closed-form FP32 weights (no table reads), 0: table in squared distance
+    int asin_poly;     // closed form, haversine: chord / 2 stays below 0.3, asin by its series
+    float r_scale;     // closed form, distance -> r: 1 / radius (haversine: 2 R / radius, applied to asin(chord / 2))
+    float eps;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
@@ -164,6 +168,70 @@ __device__ __forceinline__ void w_chunk(const float4* __restrict__ ot, const flo
     float w[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) w[jj] = pair_weight_f32<DIST>(tab, xs, period, gx, gy, gz, ot[jj]);
+    split8(w, hi, lo);
+}
+
+// ---- the same weights by closed forms in FP32 (no shared-memory traffic, more instructions) ---------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// gaspari_cohn.py:78-95, branch-free; the outer branch in s = 2 - r:  f2(r) = s^4 (5/8 - s/2 + s^2/12) / r  (no cancellation,
+// the reference form sums terms of magnitude 10 to get 1e-5)
+__device__ __forceinline__ float taper_gc_f32(float r) {
+    const float r2 = r * r;
+    const float inner = fmaf(r2, fmaf(r, fmaf(r, fmaf(r, -0.25f, 0.5f), 0.625f), -5.0f / 3.0f), 1.0f);
+    const float s = fmaxf(2.0f - r, 0.0f), s2 = s * s;
+    const float outer = s2 * s2 * fmaf(s, fmaf(s, 1.0f / 12.0f, -0.5f), 0.625f) * rcp_approx(r);
+    return r < 1.0f ? inner : outer;
+}
+// gaspari_cohn.py:172-210; the last branch in s = 2 - r:  f4(r) = s^4 (10/11 - 8 s/11 + 4 s^2/33) / r
+__device__ __forceinline__ float taper_gcinf_f32(float r) {
+    const float r2 = r * r, ri = rcp_approx(r);
+    const float p1 = fmaf(r2, fmaf(r, fmaf(r, fmaf(r, -28.0f / 33.0f, 8.0f / 11.0f), 20.0f / 11.0f), -80.0f / 33.0f), 1.0f);
+    const float p2 = fmaf(r, fmaf(r, fmaf(r, fmaf(r, fmaf(r, 20.0f / 33.0f, -16.0f / 11.0f), 0.0f), 100.0f / 33.0f),
+                                  -45.0f / 11.0f), 51.0f / 22.0f) - (7.0f / 44.0f) * ri;
+    const float p3 = fmaf(r, fmaf(r, fmaf(r, fmaf(r, fmaf(r, -4.0f / 11.0f, 16.0f / 11.0f), -10.0f / 11.0f),
+                                         -100.0f / 33.0f), 5.0f), -61.0f / 22.0f) + (115.0f / 132.0f) * ri;
+    const float s = fmaxf(2.0f - r, 0.0f), s2 = s * s;
+    const float p4 = s2 * s2 * fmaf(s, fmaf(s, 4.0f / 33.0f, -8.0f / 11.0f), 10.0f / 11.0f) * ri;
+    return r < 0.5f ? p1 : (r < 1.0f ? p2 : (r < 1.5f ? p3 : p4));
+}
+// closed-form kinds: haversine with asin by its series (chord / 2 <= 0.3), haversine with asinf, Euclidean, |dz|, periodic
+enum { kTcHavPoly = 0, kTcHavAsin = 1, kTcEuclid = 2, kTcAbsF = 3, kTcPeriodicF = 4 };
+template <int DIST, int TAPER>
+__device__ __forceinline__ float pair_weight_closed(float r_scale, float eps, float period, float gx, float gy, float gz, float4 o) {
+    const float dx = o.x - gx, dy = o.y - gy, dz = o.z - gz;
+    float r;
+    if (DIST == kTcHavPoly) {          // asin(h) = h (1 + h^2/6 + 3 h^4/40 + 15 h^6/336 + 35 h^8/1152 + ...)
+        const float h2 = 0.25f * fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        r = (r_scale * sqrt_approx(h2)) *
+            fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 35.0f / 1152.0f, 15.0f / 336.0f), 3.0f / 40.0f), 1.0f / 6.0f), 1.0f);
+    } else if (DIST == kTcHavAsin) {
+        const float h = 0.5f * sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+        r = fmaf(fmaxf(h - 1.0f, 0.0f), kTcFar, r_scale * asinf(fminf(h, 1.0f)));      // h > 1 only for padding
+    } else if (DIST == kTcEuclid) {
+        r = r_scale * sqrt_approx(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+    } else {
+        float d = fabsf(dz);
+        if (DIST == kTcPeriodicF) d = fminf(d, fabsf(period - d));
+        r = r_scale * (d + fabsf(dx));
+    }
+    const float w = TAPER == B200DA_TAPER_GCINF ? taper_gcinf_f32(r) : taper_gc_f32(r);
+    return w > eps ? w : 0.0f;                                     // gaspari_cohn.py:135
+}
+template <int DIST, int TAPER>
+__device__ __forceinline__ void w_chunk_closed(const float4* __restrict__ ot, float r_scale, float eps, float period, float gx,
+                                               float gy, float gz, uint4& hi, uint4& lo) {
+    float w[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) w[jj] = pair_weight_closed<DIST, TAPER>(r_scale, eps, period, gx, gy, gz, ot[jj]);
     split8(w, hi, lo);
 }
 
@@ -422,8 +490,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
         if (c_ok) col_to_pair(my_col, ca, cb);
         const int dist_kind = g.metric == B200DA_METRIC_PERIODIC1D ? kTcPeriodic
                             : g.metric == B200DA_METRIC_ABS1D ? kTcAbs : kTcSq3;
-        const float xs = (float)kTcTab / P.q_max, period = P.period;
+        const float xs = (float)kTcTab / P.q_max, period = P.period, r_scale = P.r_scale, eps = P.eps;
         const float2* wtab = S.wtab;
+        int wmode = dist_kind;
+        if (P.w_closed) {
+            const int ck = g.metric == B200DA_METRIC_HAVERSINE ? (P.asin_poly ? kTcHavPoly : kTcHavAsin)
+                         : g.metric == B200DA_METRIC_EUCLID ? kTcEuclid
+                         : g.metric == B200DA_METRIC_PERIODIC1D ? kTcPeriodicF : kTcAbsF;
+            wmode = 8 + ck * 2 + (g.taper == B200DA_TAPER_GCINF ? 1 : 0);
+        }
         unsigned alive = (1u << n_load) - 1u, par = 0u;       // loaders still producing; phase parity of their buffers
         int t = 0;                                                  // operand tiles produced so far
         for (int yst = -1; alive != 0u;) {
@@ -438,9 +513,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
             {
                 const float4* ot = S.otile + yst * kTcObs + my_kc * 8;
                 uint4 hi, lo;
-                if (dist_kind == kTcSq3) w_chunk<kTcSq3>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo);        // uniform over the launch
-                else if (dist_kind == kTcAbs) w_chunk<kTcAbs>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo);
-                else w_chunk<kTcPeriodic>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo);
+                switch (wmode) {                                   // uniform over the launch
+                    case 0: w_chunk<kTcSq3>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo); break;
+                    case 1: w_chunk<kTcAbs>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo); break;
+                    case 2: w_chunk<kTcPeriodic>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo); break;
+#define B200DA_TC_W(D, T) case 8 + (D) * 2 + (T): w_chunk_closed<D, T>(ot, r_scale, eps, period, gxr, gyr, gzr, hi, lo); break;
+                    B200DA_TC_W(kTcHavPoly, 0) B200DA_TC_W(kTcHavPoly, 1) B200DA_TC_W(kTcHavAsin, 0) B200DA_TC_W(kTcHavAsin, 1)
+                    B200DA_TC_W(kTcEuclid, 0) B200DA_TC_W(kTcEuclid, 1) B200DA_TC_W(kTcAbsF, 0) B200DA_TC_W(kTcAbsF, 1)
+                    B200DA_TC_W(kTcPeriodicF, 0)
+                    default: w_chunk_closed<kTcPeriodicF, 1>(ot, r_scale, eps, period, gxr, gyr, gzr, hi, lo); break;
+#undef B200DA_TC_W
+                }
                 if constexpr (kTcATmem) {
                     // this thread's row (grid point) = its tensor-memory lane; 8 bf16 = 4 columns at K offset my_kc * 8
                     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)kTcMaxCols + (uint32_t)st * 32 +
