@@ -1,8 +1,7 @@
 """ctypes binding of libb200da.so — the C ABI declared in include/b200da.h.
 
 There is no CPU fallback: if the shared library is missing or no sm_100 device is present every entry
-point raises.  Build the library with ``python -c "import __graft_entry__ as g; g.build()"`` (or
-``make -C torch-assimilate_b200``).
+point raises.  Build the library with ``python -c "import __graft_entry__ as g; g.build()"``.
 """
 import ctypes
 import os
