@@ -397,8 +397,8 @@ def main():
 
     if rank == 0:
         achieved = flops_gram / (g_ms * 1e-3) * 1e-12            # dominant kernel: the DMMA Gram kernel
-        kt = (k + 1 + 7) // 8
-        exec_ratio = (kt * (kt + 1) // 2) * 128.0 / (2.0 * k * k + 2.0 * k)
+        kt = k // 8 if k % 8 == 0 else (k + 1 + 7) // 8        # multiples of 8: the innovation row is accumulated by FMAs
+        exec_ratio = ((kt * (kt + 1) // 2) * 128.0 + (2.0 * k if k % 8 == 0 else 0.0)) / (2.0 * k * k + 2.0 * k)
         tc_path = "tcgen05" in eng.kernel_name
         peak_used, peak_src = peak_sus, ("measured live: cuBLAS DGEMM 8192^3 via torch.matmul, sustained {0:.2f} / burst {1:.2f} "
                                          "TFLOP/s (FP64 DMMA pipe; MEASURED_PEAKS.json has no FP64 entry)".format(peak_sus, peak_burst))

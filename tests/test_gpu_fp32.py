@@ -108,3 +108,28 @@ def test_fp32_global_etkf_and_host_path(golden):
                             data["normed_perts"].astype(np.float32), data["normed_obs"].astype(np.float32))
     assert out.dtype == np.float32
     np.testing.assert_array_equal(out.reshape(s2.shape), xa2)
+
+
+def test_fp32_edge_cases_no_obs_tiny_grid_slices():
+    """tcgen05 path corner cases: no observations at all, a grid smaller than one 128-point block, the smallest
+    tensor-core ensemble size (k = 8)."""
+    m = _metrics()
+    from pytassim_b200.engine import LETKFEngine
+    data = syn.lorenz96_1d(37, 8, 1, seed=31)
+    st = data["state"]
+    n_slices, k = st.shape[0] * st.shape[1], st.shape[2]
+    eng = LETKFEngine(k, n_slices, m.PeriodicDistance1D(37.0), 4.0, inf_factor=1.21, dtype=torch.float32)
+    assert "tcgen05" in eng.kernel_name
+    eng.set_grid(data["grid_rows"][:, 1:])
+    x = torch.as_tensor(st.reshape(n_slices, k, -1), dtype=torch.float32).cuda()
+    # (i) no observations: inflated prior  (core/etkf.py:91-95)
+    eng.bin_obs(np.zeros((0, 1)), np.zeros((k, 0)), np.zeros((0,)))
+    xa0 = eng.analyse(x).cpu().numpy().reshape(st.shape)
+    mean = st.mean(axis=2, keepdims=True)
+    _close(xa0, mean + 1.1 * (st - mean))
+    # (ii) with observations, against the oracle
+    eng.bin_obs(data["obs_rows"][:, 1:], data["normed_perts"], data["normed_obs"])
+    xa = eng.analyse(x).cpu().numpy().reshape(st.shape)
+    ref, _ = orc.letkf_analysis(st, data["normed_perts"], data["normed_obs"], data["grid_rows"], data["obs_rows"],
+                                orc.make_dist_periodic1d(37.0), 4.0, inf_factor=1.21)
+    _close(xa, ref)
