@@ -158,6 +158,23 @@ int b200da_etkf_weights(b200da_plan* plan, const void* Yn, const void* d, int64_
 int b200da_apply_weights(b200da_plan* plan, const void* X, const void* W, int per_grid, int64_t n_grid, void* Xa,
                          void* stream);
 
+/* Observation- and state-sharded form of the two calls above (the reference hands the whole observation
+ * vector to one torch call, interface/etkf.py:99-120; on G GPUs each rank owns a column range of Yn / d and of the state):
+ *   b200da_etkf_gram              the augmented Gram  [Yn; d][Yn; d]^T  of an observation range (core/etkf.py:68,72 =
+ *                                 core/utils.py:153-173 on that range): Yn points at the first column of the range inside a
+ *                                 (k, ld_obs) array, d at its first element; gram_out: dense (k+1) x (k+1) FP64 row-major,
+ *                                 lower triangle filled (row k = b), element (k, k) and the upper triangle zero.  The Grams of
+ *                                 disjoint ranges add up (one all-reduce of (k+1)^2 doubles);
+ *   b200da_etkf_weights_from_gram evd -> rev_evd x2 -> W = w_mean + w_perts (core/utils.py:26-93, core/etkf.py:57-77,102) from
+ *                                 the summed Gram; n_obs_total = 0 gives sqrt(inf_factor) * I (core/etkf.py:91-95);
+ *   b200da_apply_weights_cols     _apply_weights (interface/base.py:257-278) on grid columns [col_begin, col_end) of the
+ *                                 (n_slices, k, n_grid) arrays X / Xa (other columns untouched); per_grid W is (n_grid, k, k). */
+int b200da_etkf_gram(b200da_plan* plan, const void* Yn, const void* d, int64_t n_obs, int64_t ld_obs, double* gram_out,
+                     void* stream);
+int b200da_etkf_weights_from_gram(b200da_plan* plan, const double* gram, int64_t n_obs_total, void* W, void* stream);
+int b200da_apply_weights_cols(b200da_plan* plan, const void* X, const void* W, int per_grid, int64_t col_begin,
+                              int64_t col_end, int64_t n_grid, void* Xa, void* stream);
+
 /* ---- multi-GPU helpers ------------------------------------------------------------------------------------ */
 
 /* Pack / unpack the analysed columns of blocks [block_begin, block_end) between the (n_slices, k, N) layout and

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import letkf_oracle as orc
-from pytassim_b200.parallel import ShardedAnalysis, block_range
+from pytassim_b200.parallel import ShardedAnalysis, ShardedETKF, block_range
 from pytassim_b200.testing import synthetic as syn
 
 
@@ -87,3 +87,91 @@ def test_sharded_analysis_two_ranks_gloo():
                                 data["obs_rows"], orc.make_dist_periodic1d(float(n_grid)), 4.0, inf_factor=1.1)
     for rank in (0, 1):
         np.testing.assert_allclose(ret[rank], ref[0], rtol=1e-12, atol=1e-12)
+
+
+class OracleEtkfEngine(object):
+    """CPU stand-in with the engine's sharded-ETKF interface (numpy restatement of core/etkf.py on the summed Gram)."""
+
+    def __init__(self, k, rho):
+        self.k, self.rho = k, rho
+
+    def etkf_gram(self, yn, d, obs_range=None):
+        j0, j1 = obs_range
+        a = np.concatenate([yn.numpy()[:, j0:j1], d.numpy()[None, j0:j1]], axis=0)
+        g = np.tril(a @ a.T)
+        g[self.k, self.k] = 0.0
+        return torch.as_tensor(g)
+
+    def etkf_weights_from_gram(self, gram, n_obs_total):
+        k = self.k
+        if n_obs_total == 0:
+            return torch.as_tensor(np.sqrt(self.rho) * np.eye(k))
+        g = gram.numpy()
+        c = np.tril(g[:k, :k]) + np.tril(g[:k, :k], -1).T
+        b = g[k, :k]
+        evals, evects = np.linalg.eigh(c)                                   # core/utils.py:26-61
+        evals = np.clip(evals, 0.0, None) + (k - 1) / self.rho
+        cov = (evects / evals) @ evects.T                                   # core/etkf.py:70
+        w_mean = cov @ b                                                    # core/etkf.py:72
+        w_perts = (evects * np.sqrt((k - 1) / evals)) @ evects.T            # core/etkf.py:74-76
+        return torch.as_tensor(w_mean[:, None] + w_perts)                   # core/etkf.py:102
+
+    def apply_weights_cols(self, x, w, c0, c1, out):
+        xs = x.numpy()[:, :, c0:c1]
+        mean = xs.mean(axis=1, keepdims=True)
+        out[:, :, c0:c1] = torch.as_tensor(mean + np.einsum('sig,ij->sjg', xs - mean, w.numpy()))
+        return out
+
+
+def _etkf_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(9)
+    k, n, m = 7, 53, 37                                                    # ragged against the 16-column alignment
+    x = torch.as_tensor(rng.normal(size=(2, k, n)))
+    hx = rng.normal(size=(k, m))
+    yn = torch.as_tensor(hx - hx.mean(axis=0, keepdims=True))
+    d = torch.as_tensor(rng.normal(size=m))
+    sh = ShardedETKF(OracleEtkfEngine(k, 1.1))
+    out = torch.full_like(x, float("nan"))
+    sh.run(x, yn, d, out, gather=True)
+    own = torch.full_like(x, float("nan"))
+    sh.run(x, yn, d, own, gather=False)
+    ret[rank] = (out.numpy(), own.numpy(), sh.ranges(n))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_etkf_two_ranks_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_etkf_worker, args=(2, port, ret), nprocs=2, join=True)
+    rng = np.random.RandomState(9)
+    k, n, m = 7, 53, 37
+    x = rng.normal(size=(2, k, n)); hx = rng.normal(size=(k, m)); d = rng.normal(size=m)
+    yn = hx - hx.mean(axis=0, keepdims=True)
+    ref, _ = orc.etkf_analysis(x[:, None], yn, d, inf_factor=1.1)           # (n_var, n_time, k, N)
+    ref = ref[:, 0]
+    for rank in (0, 1):
+        out, own, cols = ret[rank]
+        np.testing.assert_allclose(out, ref, rtol=1e-11, atol=1e-11)
+        c0, c1 = cols[rank]
+        np.testing.assert_allclose(own[:, :, c0:c1], ref[:, :, c0:c1], rtol=1e-11, atol=1e-11)
+        mask = np.ones(n, bool); mask[c0:c1] = False
+        assert np.isnan(own[:, :, mask]).all()                             # other ranks' columns untouched without gather
+    assert ret[0][2] == [(0, 32), (32, 53)]
+
+
+def test_sharded_etkf_ranges_cover_and_align():
+    class _E(object):
+        pass
+    sh = ShardedETKF(_E())
+    for world in (1, 2, 3, 8):
+        sh.world = world
+        for n in (0, 1, 15, 16, 17, 1000, 10_000_000):
+            rs = sh.ranges(n)
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            assert all(a % 16 == 0 for a, _ in rs if a < n)

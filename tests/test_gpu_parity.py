@@ -289,6 +289,62 @@ def test_global_etkf_cfg4_shape_against_oracle(dtype, tol):
     assert np.abs(xa - ref).max() <= tol * scale
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-4)])
+def test_sharded_etkf_entry_points(dtype, tol):
+    """Observation- and state-sharded global ETKF on one GPU playing three ranks in turn: Grams of ragged
+    observation ranges add up to the whole Gram, weights from the summed Gram equal b200da_etkf_weights, column-range
+    updates tile the whole update bit-exactly, and everything agrees with the oracle."""
+    from pytassim_b200.engine import LETKFEngine
+    from pytassim_b200.parallel import ShardedETKF
+    m = _metrics()
+    rng = np.random.RandomState(14)
+    k, n, nobs, n_sl = 50, 10_007, 2_501, 2
+    npd = np.float64 if dtype == torch.float64 else np.float32
+    st = rng.normal(size=(n_sl, 1, k, n)).astype(npd)
+    hx = rng.normal(size=(k, nobs))
+    yn = np.ascontiguousarray(hx - hx.mean(axis=0, keepdims=True)).astype(npd)
+    d = (rng.normal(size=nobs) * 0.5).astype(npd)
+    ref, wref = orc.etkf_analysis(st.astype(np.float64), yn.astype(np.float64), d.astype(np.float64), inf_factor=1.1)
+    eng = LETKFEngine(k, n_sl, m.AbsDistance1D(), 1.0, inf_factor=1.1, dtype=dtype)
+    ynd, dd = torch.as_tensor(yn).cuda(), torch.as_tensor(d).cuda()
+    x = torch.as_tensor(st.reshape(n_sl, k, n)).cuda()
+    w_whole = eng.etkf_weights(ynd, dd)
+    xa_whole = eng.apply_weights(x, w_whole)
+    sh = ShardedETKF(eng)
+    sh.world = 3
+    gram = torch.zeros((k + 1, k + 1), dtype=torch.float64, device="cuda")
+    for j0, j1 in sh.ranges(nobs):
+        gram += eng.etkf_gram(ynd, dd, obs_range=(j0, j1))
+    aug = np.concatenate([yn.astype(np.float64), d.astype(np.float64)[None]], axis=0)
+    gref = np.tril(aug @ aug.T); gref[k, k] = 0.0
+    assert np.abs(gram.cpu().numpy() - gref).max() <= 1e-12 * np.abs(gref).max()
+    assert np.array_equal(np.triu(gram.cpu().numpy(), 1), np.zeros((k + 1, k + 1)))
+    w = eng.etkf_weights_from_gram(gram, nobs)
+    assert np.abs(w.cpu().numpy() - wref).max() <= tol * max(1.0, np.abs(wref).max())
+    assert np.abs((w - w_whole).cpu().numpy()).max() <= tol * 0.1 * max(1.0, np.abs(wref).max())
+    # one "rank": the whole range through the sharded entry points is bit-identical to the unsharded call
+    g1 = eng.etkf_gram(ynd, dd)
+    assert torch.equal(eng.etkf_weights_from_gram(g1, nobs), w_whole)
+    out = torch.full_like(x, float("nan"))
+    for c0, c1 in sh.ranges(n):
+        eng.apply_weights_cols(x, w_whole, c0, c1, out)
+    assert torch.equal(out, xa_whole)
+    assert np.abs(out.cpu().numpy().reshape(st.shape) - ref).max() <= tol * np.abs(ref).max()
+    # odd column boundaries (unaligned rows take the scalar stores) and per-grid weights
+    out2 = torch.full_like(x, float("nan"))
+    for c0, c1 in ((0, 333), (333, 4001), (4001, n)):
+        eng.apply_weights_cols(x, w_whole, c0, c1, out2)
+    assert torch.equal(out2, xa_whole)
+    wg = w_whole[None].repeat(n, 1, 1).contiguous()
+    out3 = torch.full_like(x, float("nan"))
+    for c0, c1 in ((0, 5000), (5000, n)):
+        eng.apply_weights_cols(x, wg, c0, c1, out3)
+    assert torch.equal(out3, eng.apply_weights(x, wg))
+    # no observations: the inflated prior (core/etkf.py:91-95)
+    w0 = eng.etkf_weights_from_gram(torch.zeros_like(gram), 0).cpu().numpy()
+    np.testing.assert_allclose(w0, np.sqrt(1.1) * np.eye(k), rtol=0, atol=1e-6 if dtype == torch.float32 else 1e-14)
+
+
 @pytest.mark.parametrize("k,n_grid,radius", [(112, 80, 7.0), (120, 72, 6.0), (128, 64, 9.0)])
 def test_large_ensembles_newton_against_oracle(k, n_grid, radius):
     """Ensemble sizes beyond the shared-memory Jacobi limit (k > 111) run on the tensor-core Newton-Schulz solver only

@@ -61,16 +61,16 @@ static KernelConfig config_for_kt(int kt) {
 constexpr int kMaxKt = 17;
 
 template <int KT>
-static int launch_etkf_gram(int f32, const void* yn, const void* d, int64_t m, int k, int ncta, int64_t chunk, double* partial,
-                            cudaStream_t st) {
-    if (f32) k_etkf_gram<float, KT><<<ncta, kEtkfWarps * 32, 0, st>>>((const float*)yn, (const float*)d, m, k, chunk, partial);
-    else k_etkf_gram<double, KT><<<ncta, kEtkfWarps * 32, 0, st>>>((const double*)yn, (const double*)d, m, k, chunk, partial);
+static int launch_etkf_gram(int f32, const void* yn, const void* d, int64_t m, int64_t ld, int k, int ncta, int64_t chunk,
+                            double* partial, cudaStream_t st) {
+    if (f32) k_etkf_gram<float, KT><<<ncta, kEtkfWarps * 32, 0, st>>>((const float*)yn, (const float*)d, m, ld, k, chunk, partial);
+    else k_etkf_gram<double, KT><<<ncta, kEtkfWarps * 32, 0, st>>>((const double*)yn, (const double*)d, m, ld, k, chunk, partial);
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
-#define B200DA_EG_CASE(KT) case KT: return launch_etkf_gram<KT>(f32, yn, d, m, k, ncta, chunk, partial, st);
-static int dispatch_etkf_gram(int kt, int f32, const void* yn, const void* d, int64_t m, int k, int ncta, int64_t chunk,
-                              double* partial, cudaStream_t st) {
+#define B200DA_EG_CASE(KT) case KT: return launch_etkf_gram<KT>(f32, yn, d, m, ld, k, ncta, chunk, partial, st);
+static int dispatch_etkf_gram(int kt, int f32, const void* yn, const void* d, int64_t m, int64_t ld, int k, int ncta,
+                              int64_t chunk, double* partial, cudaStream_t st) {
     switch (kt) {
         B200DA_EG_CASE(1) B200DA_EG_CASE(2) B200DA_EG_CASE(3) B200DA_EG_CASE(4) B200DA_EG_CASE(5) B200DA_EG_CASE(6)
         B200DA_EG_CASE(7) B200DA_EG_CASE(8) B200DA_EG_CASE(9) B200DA_EG_CASE(10) B200DA_EG_CASE(11) B200DA_EG_CASE(12)
@@ -80,23 +80,27 @@ static int dispatch_etkf_gram(int kt, int f32, const void* yn, const void* d, in
 }
 
 template <int MT>
-static int launch_apply_global(int f32, const void* x, const void* w, int k, int n_rows, int64_t n_grid, void* xa, cudaStream_t st) {
+static int launch_apply_global(int f32, const void* x, const void* w, int k, int n_rows, int64_t n_grid, int64_t ld, void* xa,
+                               cudaStream_t st) {
+    const size_t esz = f32 ? 4 : 8;
+    const int vec_ok = ((ld * (int64_t)esz) % (2 * esz) == 0 && (reinterpret_cast<uintptr_t>(xa) % (2 * esz)) == 0) ? 1 : 0;
     const size_t smem = sizeof(double) * (size_t)MT * 8 * apply_lda(k);
     if (smem > kMaxSmem - 2048) return B200DA_ERR_UNSUPPORTED;
     const int64_t n_chunks = (n_grid + kApplyNTW * 8 - 1) / (kApplyNTW * 8);
     const int grid = (int)std::min<int64_t>((n_chunks + kApplyWarps - 1) / kApplyWarps, 148 * 2);
     if (f32) {
         B200DA_CUDA(cudaFuncSetAttribute(k_apply_global<float, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_apply_global<float, MT><<<grid, kApplyWarps * 32, smem, st>>>((const float*)x, (const float*)w, k, n_rows, n_grid, (float*)xa);
+        k_apply_global<float, MT><<<grid, kApplyWarps * 32, smem, st>>>((const float*)x, (const float*)w, k, n_rows, n_grid, ld, vec_ok, (float*)xa);
     } else {
         B200DA_CUDA(cudaFuncSetAttribute(k_apply_global<double, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_apply_global<double, MT><<<grid, kApplyWarps * 32, smem, st>>>((const double*)x, (const double*)w, k, n_rows, n_grid, (double*)xa);
+        k_apply_global<double, MT><<<grid, kApplyWarps * 32, smem, st>>>((const double*)x, (const double*)w, k, n_rows, n_grid, ld, vec_ok, (double*)xa);
     }
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
-#define B200DA_AG_CASE(MT) case MT: return launch_apply_global<MT>(f32, x, w, k, n_rows, n_grid, xa, st);
-static int dispatch_apply_global(int f32, const void* x, const void* w, int k, int n_rows, int64_t n_grid, void* xa, cudaStream_t st) {
+#define B200DA_AG_CASE(MT) case MT: return launch_apply_global<MT>(f32, x, w, k, n_rows, n_grid, ld, xa, st);
+static int dispatch_apply_global(int f32, const void* x, const void* w, int k, int n_rows, int64_t n_grid, int64_t ld, void* xa,
+                                 cudaStream_t st) {
     switch ((k + 7) / 8) {
         B200DA_AG_CASE(1) B200DA_AG_CASE(2) B200DA_AG_CASE(3) B200DA_AG_CASE(4) B200DA_AG_CASE(5) B200DA_AG_CASE(6)
         B200DA_AG_CASE(7) B200DA_AG_CASE(8) B200DA_AG_CASE(9) B200DA_AG_CASE(10) B200DA_AG_CASE(11) B200DA_AG_CASE(12)
@@ -453,9 +457,8 @@ int b200da_neighbour_ambiguous(b200da_plan* pl, int64_t capacity, int64_t* grid_
     return launch_neighbours<2>(pl, P, st);
 }
 
-int b200da_etkf_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t m, void* W, void* stream) {
-    if (!pl || !W || m < 0 || (m > 0 && (!Yn || !d))) return B200DA_ERR_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
+// stage 1 of the global ETKF: per-CTA partial Grams of an observation range into pl->etkf_partial; returns the number of partials
+static int etkf_partial_grams(b200da_plan* pl, const void* Yn, const void* d, int64_t m, int64_t ld, int* ncta_out, cudaStream_t st) {
     const int k = pl->k, kp = pl->kp;
     int ncta = 1;
     int64_t chunk = 4;
@@ -467,11 +470,19 @@ int b200da_etkf_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t 
     int rc;
     if ((rc = pl->etkf_partial.ensure(sizeof(double) * (size_t)ncta * kp * kp))) return rc;
     if (m > 0) {
-        if ((rc = dispatch_etkf_gram(pl->kt, pl->dtype == B200DA_F32, Yn, d, m, k, ncta, chunk,
+        if ((rc = dispatch_etkf_gram(pl->kt, pl->dtype == B200DA_F32, Yn, d, m, ld, k, ncta, chunk,
                                      pl->etkf_partial.as<double>(), st))) return rc;
     }
+    *ncta_out = m > 0 ? ncta : 0;
+    return B200DA_OK;
+}
+
+// stage 2: n_partial partial Grams in pl->etkf_partial -> W (k, k); n_partial = 0 gives sqrt(rho) I
+static int etkf_solve_partials(b200da_plan* pl, int n_partial, void* W, cudaStream_t st) {
+    const int k = pl->k, kp = pl->kp;
     const int f32 = pl->dtype == B200DA_F32 ? 1 : 0;
-    if (m > 0 && pl->solver == B200DA_SOLVER_NEWTON_SCHULZ) {
+    int rc;
+    if (n_partial > 0 && pl->solver == B200DA_SOLVER_NEWTON_SCHULZ) {
         // partial Grams -> one tile-packed slot -> the tensor-core Newton-Schulz solve (one matrix, no state update)
         const size_t slot_doubles = (size_t)tri_tiles(pl->kt) * 64;
         if ((rc = pl->etkf_w.ensure(sizeof(Pos4) + sizeof(double) * slot_doubles))) return rc;
@@ -479,7 +490,7 @@ int b200da_etkf_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t 
         B200DA_CUDA(cudaMemsetAsync(pl->etkf_w.p, 0, sizeof(Pos4) + sizeof(double) * slot_doubles, st));   // Pos4.id = 0
         B200DA_CUDA(cudaMemsetAsync(pl->counter.p, 0, sizeof(unsigned int) * 4, st));
         double* slot = reinterpret_cast<double*>(pl->etkf_w.as<unsigned char>() + sizeof(Pos4));
-        k_etkf_reduce<<<grid1d((int64_t)(k + 1) * kp, 128), 128, 0, st>>>(pl->etkf_partial.as<double>(), ncta, kp, k, slot);
+        k_etkf_reduce<<<grid1d((int64_t)(k + 1) * kp, 128), 128, 0, st>>>(pl->etkf_partial.as<double>(), n_partial, kp, k, slot);
         B200DA_LAUNCH_CHECK();
         NsParams S{};
         S.cmat = slot; S.slot_stride = (int64_t)slot_doubles; S.gpos = pl->etkf_w.as<Pos4>(); S.x = nullptr; S.xa = nullptr;
@@ -490,28 +501,75 @@ int b200da_etkf_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t 
     const size_t smem = solve_smem_bytes(k);
     if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
     B200DA_CUDA(cudaFuncSetAttribute(k_etkf_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_etkf_solve<<<1, 512, smem, st>>>(pl->etkf_partial.as<double>(), m > 0 ? ncta : 0, kp, k, pl->rho, W, f32);
+    k_etkf_solve<<<1, 512, smem, st>>>(pl->etkf_partial.as<double>(), n_partial, kp, k, pl->rho, W, f32);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
+int b200da_etkf_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t m, void* W, void* stream) {
+    if (!pl || !W || m < 0 || (m > 0 && (!Yn || !d))) return B200DA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc, n_partial = 0;
+    if ((rc = etkf_partial_grams(pl, Yn, d, m, m, &n_partial, st))) return rc;
+    return etkf_solve_partials(pl, n_partial, W, st);
+}
+
+int b200da_etkf_gram(b200da_plan* pl, const void* Yn, const void* d, int64_t m, int64_t ld_obs, double* gram_out, void* stream) {
+    if (!pl || !gram_out || m < 0 || ld_obs < m || (m > 0 && (!Yn || !d))) return B200DA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc, n_partial = 0;
+    if ((rc = etkf_partial_grams(pl, Yn, d, m, ld_obs, &n_partial, st))) return rc;
+    const int k = pl->k;
+    k_etkf_reduce_dense<<<grid1d((int64_t)(k + 1) * (k + 1), 128), 128, 0, st>>>(pl->etkf_partial.as<double>(), n_partial, pl->kp, k, gram_out);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
+int b200da_etkf_weights_from_gram(b200da_plan* pl, const double* gram, int64_t n_obs_total, void* W, void* stream) {
+    if (!pl || !gram || !W || n_obs_total < 0) return B200DA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kp = pl->kp;
+    int rc;
+    if ((rc = pl->etkf_partial.ensure(sizeof(double) * (size_t)kp * kp))) return rc;
+    if (n_obs_total > 0) {
+        k_etkf_dense_to_partial<<<grid1d((int64_t)kp * kp, 128), 128, 0, st>>>(gram, kp, pl->k, pl->etkf_partial.as<double>());
+        B200DA_LAUNCH_CHECK();
+    }
+    return etkf_solve_partials(pl, n_obs_total > 0 ? 1 : 0, W, st);
+}
+
+static int apply_weights_impl(b200da_plan* pl, const void* X, const void* W, int per_grid, int64_t n_grid, int64_t ld, void* Xa,
+                              cudaStream_t st) {
+    const int k = pl->k;
+    if (!per_grid) return dispatch_apply_global(pl->dtype == B200DA_F32, X, W, k, pl->n_slices, n_grid, ld, Xa, st);
+    const size_t smem = 0;
+    if (pl->dtype == B200DA_F32) {
+        B200DA_CUDA(cudaFuncSetAttribute(k_apply_weights<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        k_apply_weights<float, 8><<<grid1d(n_grid, 128), 128, smem, st>>>((const float*)X, (const float*)W, per_grid, k,
+                                                                        pl->n_slices, n_grid, ld, (float*)Xa);
+    } else {
+        B200DA_CUDA(cudaFuncSetAttribute(k_apply_weights<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        k_apply_weights<double, 8><<<grid1d(n_grid, 128), 128, smem, st>>>((const double*)X, (const double*)W, per_grid, k,
+                                                                         pl->n_slices, n_grid, ld, (double*)Xa);
+    }
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
 
 int b200da_apply_weights(b200da_plan* pl, const void* X, const void* W, int per_grid, int64_t n_grid, void* Xa, void* stream) {
     if (!pl || !X || !W || !Xa || n_grid <= 0) return B200DA_ERR_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int k = pl->k;
-    if (!per_grid) return dispatch_apply_global(pl->dtype == B200DA_F32, X, W, k, pl->n_slices, n_grid, Xa, st);
-    const size_t smem = 0;
-    if (pl->dtype == B200DA_F32) {
-        B200DA_CUDA(cudaFuncSetAttribute(k_apply_weights<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-        k_apply_weights<float, 8><<<grid1d(n_grid, 128), 128, smem, st>>>((const float*)X, (const float*)W, per_grid, k,
-                                                                        pl->n_slices, n_grid, (float*)Xa);
-    } else {
-        B200DA_CUDA(cudaFuncSetAttribute(k_apply_weights<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-        k_apply_weights<double, 8><<<grid1d(n_grid, 128), 128, smem, st>>>((const double*)X, (const double*)W, per_grid, k,
-                                                                         pl->n_slices, n_grid, (double*)Xa);
-    }
-    B200DA_LAUNCH_CHECK();
-    return B200DA_OK;
+    return apply_weights_impl(pl, X, W, per_grid, n_grid, n_grid, Xa, (cudaStream_t)stream);
+}
+
+int b200da_apply_weights_cols(b200da_plan* pl, const void* X, const void* W, int per_grid, int64_t col_begin, int64_t col_end,
+                              int64_t n_grid, void* Xa, void* stream) {
+    if (!pl || !X || !W || !Xa || n_grid <= 0 || col_begin < 0 || col_end > n_grid || col_begin > col_end) return B200DA_ERR_INVALID;
+    if (col_begin == col_end) return B200DA_OK;
+    const size_t esz = pl->dtype == B200DA_F32 ? 4 : 8;
+    const unsigned char* x = static_cast<const unsigned char*>(X) + (size_t)col_begin * esz;
+    unsigned char* xa = static_cast<unsigned char*>(Xa) + (size_t)col_begin * esz;
+    const unsigned char* w = static_cast<const unsigned char*>(W) + (per_grid ? (size_t)col_begin * pl->k * pl->k * esz : 0);
+    return apply_weights_impl(pl, x, w, per_grid, col_end - col_begin, n_grid, xa, (cudaStream_t)stream);
 }
 
 static int pack_impl(b200da_plan* pl, const void* xa, int64_t b0, int64_t b1, void* packed, int unpack, cudaStream_t st) {

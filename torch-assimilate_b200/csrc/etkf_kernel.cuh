@@ -10,11 +10,11 @@ namespace b200da {
 constexpr int kEtkfWarps = 8;
 
 // Partial Gram of [Yn; d] over a chunk of observations per CTA; the lower-triangle tiles are split over the
-// CTA's warps.  Yn is read in the reference layout (k, M) directly: a DMMA fragment is 4 consecutive
+// CTA's warps.  ld = row stride of Yn (== m_obs for a whole array, the global M for a column shard of it).  Yn is read in the reference layout (k, M) directly: a DMMA fragment is 4 consecutive
 // observations of 8 members = eight 32-byte sectors.
 template <typename T, int KT>
 __global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const T* __restrict__ yn, const T* __restrict__ d,
-                                                               int64_t m_obs, int k, int64_t chunk,
+                                                               int64_t m_obs, int64_t ld, int k, int64_t chunk,
                                                                double* __restrict__ partial) {
     constexpr int NTILES = KT * (KT + 1) / 2;
     constexpr int ACC = (NTILES + kEtkfWarps - 1) / kEtkfWarps;
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const T* __restri
             const int mem = t * 8 + (lane >> 2);
             double v = 0.0;
             if (j < j1) {
-                if (mem < k) v = (double)yn[(int64_t)mem * m_obs + j];
+                if (mem < k) v = (double)yn[(int64_t)mem * ld + j];
                 else if (mem == k) v = (double)d[j];
             }
             f[t] = v;
@@ -78,6 +78,26 @@ __global__ void k_etkf_reduce(const double* __restrict__ partial, int n_partial,
     slot[sym_off(r, c)] = s;
 }
 
+// Sum the partial Grams in a fixed order into a dense (k+1) x (k+1) row-major lower triangle (row k = b, element (k, k) and
+// the upper triangle zero): the all-reduce payload of the observation-sharded global ETKF.
+__global__ void k_etkf_reduce_dense(const double* __restrict__ partial, int n_partial, int kp, int k, double* __restrict__ gram) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (k + 1) * (k + 1)) return;
+    const int r = e / (k + 1), c = e - r * (k + 1);
+    double s = 0.0;
+    if (c <= r && c < k)
+        for (int p = 0; p < n_partial; ++p) s += partial[(size_t)p * kp * kp + r * kp + c];
+    gram[e] = s;
+}
+
+// dense (k+1) x (k+1) lower triangle -> one kp x kp "partial" (the input format of the solve stage)
+__global__ void k_etkf_dense_to_partial(const double* __restrict__ gram, int kp, int k, double* __restrict__ partial) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= kp * kp) return;
+    const int r = e / kp, c = e - r * kp;
+    partial[e] = (r <= k && c <= r && c < k) ? gram[r * (k + 1) + c] : 0.0;
+}
+
 // Sum the partial Grams in a fixed order, eigendecompose, transform; W (k x k) row-major to global memory.
 __global__ void __launch_bounds__(512, 1) k_etkf_solve(const double* __restrict__ partial, int n_partial, int kp, int k,
                                                     double rho, void* __restrict__ w_out, int io_f32) {
@@ -105,7 +125,7 @@ __global__ void __launch_bounds__(512, 1) k_etkf_solve(const double* __restrict_
 // pass; W is staged in shared memory when it is global (per_grid = 0).
 template <typename T, int JB>
 __global__ void __launch_bounds__(128) k_apply_weights(const T* __restrict__ x, const T* __restrict__ w,
-                                                       int per_grid, int k, int n_rows, int64_t n_grid,
+                                                       int per_grid, int k, int n_rows, int64_t n_grid, int64_t ld,
                                                        T* __restrict__ xa) {
     extern __shared__ double wsm_raw[];
     T* wsm = reinterpret_cast<T*>(wsm_raw);
@@ -117,17 +137,17 @@ __global__ void __launch_bounds__(128) k_apply_weights(const T* __restrict__ x, 
     if (gi >= n_grid) return;
     const T* wg = per_grid ? (w + gi * (int64_t)k * k) : wsm;
     for (int s = 0; s < n_rows; ++s) {
-        const T* xs = x + (int64_t)s * k * n_grid + gi;
-        T* xo = xa + (int64_t)s * k * n_grid + gi;
+        const T* xs = x + (int64_t)s * k * ld + gi;
+        T* xo = xa + (int64_t)s * k * ld + gi;
         double mean = 0.0;
-        for (int i = 0; i < k; ++i) mean += (double)xs[(int64_t)i * n_grid];
+        for (int i = 0; i < k; ++i) mean += (double)xs[(int64_t)i * ld];
         mean /= (double)k;
         for (int j0 = 0; j0 < k; j0 += JB) {
             double acc[JB];
 #pragma unroll
             for (int j = 0; j < JB; ++j) acc[j] = 0.0;
             for (int i = 0; i < k; ++i) {
-                const double p = (double)xs[(int64_t)i * n_grid] - mean;
+                const double p = (double)xs[(int64_t)i * ld] - mean;
                 const T* wr = wg + i * k + j0;
 #pragma unroll
                 for (int j = 0; j < JB; ++j)
@@ -135,7 +155,7 @@ __global__ void __launch_bounds__(128) k_apply_weights(const T* __restrict__ x, 
             }
 #pragma unroll
             for (int j = 0; j < JB; ++j)
-                if (j0 + j < k) xo[(int64_t)(j0 + j) * n_grid] = (T)(mean + acc[j]);
+                if (j0 + j < k) xo[(int64_t)(j0 + j) * ld] = (T)(mean + acc[j]);
         }
     }
 }
@@ -147,7 +167,8 @@ __global__ void __launch_bounds__(128) k_apply_weights(const T* __restrict__ x, 
 // columns i), B = x fragments read straight from global memory in the reference layout (4 members x 8 consecutive grid
 // points = four 64-byte segments), C = 8 members x 8 grid points.  One warp owns NTW * 8 consecutive grid points and all MT
 // row tiles; every x element is read once and every x_a element written once (algorithmic HBM traffic), the FP64 work is
-// 2 k^2 per state element.
+// 2 k^2 per state element.  n_grid columns are processed; ld is the row stride of x / xa (== n_grid for a whole state,
+// the global N for a column shard of it); vec_ok: rows are 16-byte aligned, so the 2-element stores may be vectorised.
 constexpr int kApplyWarps = 8;
 constexpr int kApplyNTW = 2;            // 8-point column tiles per warp
 __host__ __device__ inline int apply_lda(int k) {          // leading dimension of W'^T in shared memory: == 4 (mod 16) doubles
@@ -157,7 +178,7 @@ __host__ __device__ inline int apply_lda(int k) {          // leading dimension 
 }
 template <typename T, int MT>
 __global__ void __launch_bounds__(kApplyWarps * 32) k_apply_global(const T* __restrict__ x, const T* __restrict__ w, int k, int n_rows,
-                                                                 int64_t n_grid, T* __restrict__ xa) {
+                                                                 int64_t n_grid, int64_t ld, int vec_ok, T* __restrict__ xa) {
     extern __shared__ double wsm_raw[];
     double* At = wsm_raw;                                   // [MT * 8][lda]: At[j][i] = W'[i][j]
     __shared__ double colsum[MT * 8];
@@ -185,8 +206,8 @@ __global__ void __launch_bounds__(kApplyWarps * 32) k_apply_global(const T* __re
     const int r = lane >> 2, q = lane & 3;
     const int64_t n_chunks = (n_grid + kApplyNTW * 8 - 1) / (kApplyNTW * 8);
     for (int srow = 0; srow < n_rows; ++srow) {
-        const T* xs = x + (int64_t)srow * k * n_grid;
-        T* xo = xa + (int64_t)srow * k * n_grid;
+        const T* xs = x + (int64_t)srow * k * ld;
+        T* xo = xa + (int64_t)srow * k * ld;
         for (int64_t ch = (int64_t)blockIdx.x * kApplyWarps + warp; ch < n_chunks; ch += (int64_t)gridDim.x * kApplyWarps) {
             const int64_t g0 = ch * (kApplyNTW * 8);
             double acc[MT][kApplyNTW][2];
@@ -201,7 +222,7 @@ __global__ void __launch_bounds__(kApplyWarps * 32) k_apply_global(const T* __re
 #pragma unroll
                 for (int nt = 0; nt < kApplyNTW; ++nt) {
                     const int64_t g = g0 + nt * 8 + r;
-                    b[nt] = (i < k && g < n_grid) ? (double)xs[(int64_t)i * n_grid + g] : 0.0;
+                    b[nt] = (i < k && g < n_grid) ? (double)xs[(int64_t)i * ld + g] : 0.0;
                 }
                 const double* ap = At + r * lda + i;
 #pragma unroll
@@ -218,8 +239,8 @@ __global__ void __launch_bounds__(kApplyWarps * 32) k_apply_global(const T* __re
                 for (int nt = 0; nt < kApplyNTW; ++nt) {
                     const int64_t g = g0 + nt * 8 + q * 2;
                     if (j < k) {
-                        T* dst = xo + (int64_t)j * n_grid + g;
-                        if (g + 1 < n_grid && ((n_grid & 1) == 0)) {
+                        T* dst = xo + (int64_t)j * ld + g;
+                        if (g + 1 < n_grid && vec_ok) {
                             if constexpr (sizeof(T) == 8) *reinterpret_cast<double2*>(dst) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
                             else *reinterpret_cast<float2*>(dst) = make_float2((float)acc[mt][nt][0], (float)acc[mt][nt][1]);
                         } else {

@@ -41,6 +41,9 @@ SIGNATURES = {
     "b200da_neighbour_ambiguous": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "b200da_etkf_weights": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "b200da_apply_weights": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp]),
+    "b200da_etkf_gram": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "b200da_etkf_weights_from_gram": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "b200da_apply_weights_cols": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i64, _vp, _vp]),
     "b200da_pack_columns": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "b200da_unpack_columns": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "b200da_strerror": (_c.c_char_p, [_i]),

@@ -237,6 +237,54 @@ class LETKFEngine(object):
             _cabi.check(self.lib.b200da_apply_weights(self._plan, _ptr(x), _ptr(w), per_grid, n_grid, _ptr(xa), _stream()))
         return xa
 
+    # -- global ETKF, observation- / state-sharded ------------------------------------------------------
+    def etkf_gram(self, normed_perts, normed_obs, obs_range=None):
+        """Augmented Gram ``[Yn; d][Yn; d]^T`` (core/etkf.py:68,72) of the observation columns ``obs_range = (j0, j1)`` of
+        (k, M) / (M,) device arrays (default: all) -> dense (k+1, k+1) FP64, lower triangle filled.  Grams of disjoint
+        ranges add up: this is the all-reduce payload of the observation-sharded ETKF."""
+        yn = _dev(normed_perts, dtype=self.dtype, device=self.device)
+        d = _dev(normed_obs, dtype=self.dtype, device=self.device).reshape(-1)
+        if yn.dim() != 2 or yn.shape[0] != self.k:
+            raise ValueError("normed_perts must be (ens_size, n_obs)")
+        if yn.shape[-1] != d.shape[-1]:
+            raise ValueError('Observational size between ensemble ({0:d}) and observations '
+                             '({1:d}) do not match!'.format(yn.shape[-1], d.shape[-1]))
+        m = int(d.shape[0])
+        j0, j1 = (0, m) if obs_range is None else (int(obs_range[0]), int(obs_range[1]))
+        if not 0 <= j0 <= j1 <= m:
+            raise ValueError("obs_range outside [0, n_obs]")
+        gram = torch.empty((self.k + 1, self.k + 1), dtype=torch.float64, device=self.device)
+        esz = yn.element_size()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_etkf_gram(self._plan, ctypes.c_void_p(yn.data_ptr() + j0 * esz),
+                                                  ctypes.c_void_p(d.data_ptr() + j0 * esz), j1 - j0, m, _ptr(gram), _stream()))
+        self._keep["etkf_gram"] = (yn, d)
+        return gram
+
+    def etkf_weights_from_gram(self, gram, n_obs_total):
+        """W (k, k) from the (summed) augmented Gram: evd -> rev_evd x2 -> w_mean + w_perts (core/etkf.py:57-77,102)."""
+        g = _dev(gram, dtype=torch.float64, device=self.device)
+        if tuple(g.shape) != (self.k + 1, self.k + 1):
+            raise ValueError("gram must be (ens_size + 1, ens_size + 1)")
+        w = torch.empty((self.k, self.k), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_etkf_weights_from_gram(self._plan, _ptr(g), int(n_obs_total), _ptr(w), _stream()))
+        return w
+
+    def apply_weights_cols(self, state, weights, col_begin, col_end, out):
+        """``_apply_weights`` (interface/base.py:257-278) on grid columns [col_begin, col_end) of ``state`` (n_slices, k, N)
+        into the same columns of ``out``; the other columns of ``out`` are left untouched."""
+        x = _dev(state, dtype=self.dtype, device=self.device)
+        n_grid = x.shape[-1]
+        w = _dev(weights, dtype=self.dtype, device=self.device)
+        per_grid = 1 if w.dim() == 3 else 0
+        if out.dtype != self.dtype or not out.is_contiguous() or out.numel() != x.numel():
+            raise ValueError("out must be a contiguous {0} tensor of the state's shape".format(self.dtype))
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_apply_weights_cols(self._plan, _ptr(x), _ptr(w), per_grid, int(col_begin), int(col_end),
+                                                           n_grid, _ptr(out), _stream()))
+        return out
+
     # -- multi-GPU helpers --------------------------------------------------------------------------------------
     def block_offset(self, block):
         return int(self.lib.b200da_block_offset(self._plan, int(block)))

@@ -13,7 +13,7 @@ data-path collective.
 import torch
 import torch.distributed as dist
 
-__all__ = ["block_range", "ShardedAnalysis"]
+__all__ = ["block_range", "ShardedAnalysis", "ShardedETKF"]
 
 
 def block_range(n_blocks, world_size, rank):
@@ -58,4 +58,65 @@ class ShardedAnalysis(object):
         for r, (rb0, rb1) in enumerate(self.ranges):
             if r != self.rank and self.ncols[r] > 0:
                 self.engine.unpack_columns(recv[r, :, :self.ncols[r]].contiguous(), rb0, rb1, out)
+        return out
+
+
+class ShardedETKF(object):
+    """Global ETKF (no localization; pytassim/interface/etkf.py:99-120) over the GPUs of one node.
+
+    The reference makes one torch call on the whole observation vector and one einsum over the whole state.  Both shard:
+    the augmented Gram ``[Yn; d][Yn; d]^T`` is a sum over observations, the update is independent per grid column.  Rank r
+    computes the Gram of its observation range, ONE all-reduce of (k+1)^2 doubles gives every rank the full Gram, every rank
+    solves the same k x k problem redundantly (cheaper than broadcasting W from one rank) and updates its own range of state
+    columns; ``gather=True`` all-gathers the analysed columns so every rank ends with the whole analysis.
+
+    ``engine`` is duck-typed: ``etkf_gram(yn, d, obs_range=(j0, j1)) -> (k+1, k+1)``,
+    ``etkf_weights_from_gram(gram, n_obs_total) -> (k, k)`` and ``apply_weights_cols(x, w, c0, c1, out)``.
+    """
+
+    def __init__(self, engine, group=None, align=16):
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.align = int(align)
+
+    def ranges(self, n):
+        """Contiguous split of n columns into world ranges whose boundaries are multiples of ``align`` (16-byte aligned rows
+        for the vectorised stores of the update kernel and whole DMMA fragments for the Gram kernel)."""
+        units = (n + self.align - 1) // self.align
+        out = []
+        for r in range(self.world):
+            u0, u1 = block_range(units, self.world, r)
+            out.append((min(u0 * self.align, n), min(u1 * self.align, n)))
+        return out
+
+    def weights(self, normed_perts, normed_obs):
+        """W (k, k), identical on every rank.  normed_perts (k, M) / normed_obs (M,) are the full arrays (every rank reads
+        only its own column range)."""
+        m = int(normed_obs.shape[-1])
+        j0, j1 = self.ranges(m)[self.rank]
+        gram = self.engine.etkf_gram(normed_perts, normed_obs, obs_range=(j0, j1))
+        if self.world > 1:
+            dist.all_reduce(gram, op=dist.ReduceOp.SUM, group=self.group)
+        return self.engine.etkf_weights_from_gram(gram, m)
+
+    def run(self, x, normed_perts, normed_obs, out, gather=True):
+        """x, out: (n_slices, k, N).  Updates this rank's column range of ``out`` (all columns when ``gather``)."""
+        w = self.weights(normed_perts, normed_obs)
+        n = int(x.shape[-1])
+        cols = self.ranges(n)
+        c0, c1 = cols[self.rank]
+        self.engine.apply_weights_cols(x, w, c0, c1, out)
+        if gather and self.world > 1:
+            rows = out.shape[0] * out.shape[1]
+            maxc = max(b - a for a, b in cols)
+            send = torch.zeros((rows, maxc), dtype=out.dtype, device=out.device)
+            send[:, :c1 - c0] = out.view(rows, n)[:, c0:c1]
+            recv = torch.empty((self.world * rows, maxc), dtype=out.dtype, device=out.device)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+            recv = recv.view(self.world, rows, maxc)
+            for r, (a, b) in enumerate(cols):
+                if r != self.rank and b > a:
+                    out.view(rows, n)[:, a:b] = recv[r, :, :b - a]
         return out
