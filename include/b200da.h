@@ -103,6 +103,16 @@ int b200da_bin_obs(b200da_plan* plan, const double* obs_coord, const void* Yn, c
 int b200da_obs_prep(b200da_plan* plan, const void* HX, const void* y, const void* variance, int64_t n_obs, void* Yn, void* d,
                     void* stream);
 
+/* b200da_obs_prep with the observation operator fused in front, for operators that select grid columns of one state variable
+ * (obs_ops/lorenz_96/identity.py:88-92 `sel(var_name='x').sel(grid=points)`, examples/benchmark_letkf.py:100-104
+ * `sel(grid=obs_grid, method='nearest')`, time selection of obs_ops/base_ops.py:63-75):
+ *   HX[i][j] = Xp[src_offset[j] + i * member_stride]
+ * Xp: the pseudo state (n_var, n_time, k, N) on the device (member_stride = N); src_offset[j] (device int64) = element offset
+ * of member 0 of observation j's (variable, time, grid column).  Gathered values are exact copies, the arithmetic is
+ * b200da_obs_prep's: FP64 results are bit-identical to operator -> _get_obs_space_variables. */
+int b200da_obs_gather_prep(b200da_plan* plan, const void* Xp, const int64_t* src_offset, int64_t member_stride, const void* y,
+                           const void* variance, int64_t n_obs, void* Yn, void* d, void* stream);
+
 int64_t b200da_num_blocks(const b200da_plan* plan);      /* grid-point blocks (unit of multi-GPU sharding)     */
 int64_t b200da_num_grid(const b200da_plan* plan);
 int64_t b200da_num_obs(const b200da_plan* plan);

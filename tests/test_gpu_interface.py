@@ -113,3 +113,58 @@ def test_device_obs_prep_bit_exact_against_oracle():
     np.testing.assert_allclose(d32.cpu().numpy(), innov_ref, rtol=2e-5, atol=2e-5)
     with pytest.raises(ValueError):
         eng.obs_prep(hx.reshape(k, -1), y.reshape(-1)[:-1], np.tile(var, n_t))
+
+
+def _wrap_host_only(op):
+    """The same operator without ``device_index``: forces the host operator path (base.py:181-220)."""
+    return lambda obs_ds, st: op(obs_ds, st)
+
+
+@pytest.mark.parametrize("smoother", [False, True])
+def test_device_obs_operator_gather_equals_host_operator(smoother):
+    """column-selecting operators (obs_ops/lorenz_96/identity.py, examples/benchmark_letkf.py:90-104) are
+    gathered from the device-resident state and fused with the prep; the analysis is bit-identical to calling the operators on
+    the host and uploading HX (FP64), for a localized LETKF and the global ETKF, filter and smoother mode, two datasets."""
+    from pytassim_b200.obs_ops import IdentityOperator, NearestGridOperator
+    from test_host_logic import _operator_objects, _obs_for
+    rng, t, state = _operator_objects(n_grid=200, k=12, n_time=3, seed=8)
+    pts = np.sort(np.random.RandomState(2).choice(200, size=90, replace=False))
+    op1 = IdentityOperator(obs_points=pts, len_grid=200)
+    op2 = NearestGridOperator(len_grid=200, nr_obs=37)
+    times = t if smoother else t[[2]]
+
+    def datasets(device):
+        r = np.random.RandomState(77)
+        ds1 = _obs_for(r, times, pts); ds1.obs.operator = op1 if device else _wrap_host_only(op1)
+        ds2 = _obs_for(r, times[-1:], op2.obs_grid); ds2.obs.operator = op2 if device else _wrap_host_only(op2)
+        return ds1, ds2
+    for alg in (LETKF(localization=GaspariCohn(6., AbsDistance1D()), inf_factor=1.05, smoother=smoother),
+                ETKF(inf_factor=1.05, smoother=smoother)):
+        ana_dev = alg.assimilate(state, datasets(True))
+        ana_host = alg.assimilate(state, datasets(False))
+        assert ana_dev.shape == ((2, 3, 12, 200) if smoother else (2, 1, 12, 200))
+        np.testing.assert_array_equal(ana_dev.values, ana_host.values)
+        assert np.abs(ana_dev.values - state.values[:, -ana_dev.shape[1]:]).max() > 1e-3      # something was assimilated
+    # a separate pseudo state (assimilate(..., pseudo_state=)) is what the operators read (base.py:342-357)
+    pseudo = state.copy(data=state.values + 0.1 * rng.normal(size=state.values.shape))
+    alg = LETKF(localization=GaspariCohn(6., AbsDistance1D()), smoother=smoother)
+    np.testing.assert_array_equal(alg.assimilate(state, datasets(True), pseudo).values,
+                                  alg.assimilate(state, datasets(False), pseudo).values)
+
+
+def test_device_obs_gather_prep_fp32_and_bounds():
+    from pytassim_b200.engine import LETKFEngine
+    import torch
+    rng = np.random.RandomState(6)
+    k, n, m = 9, 1000, 333
+    xp = rng.normal(size=(2, 2, k, n)).astype(np.float32)
+    g_pos = rng.randint(0, n, size=m)
+    src = ((1 * 2 + 1) * k * n + g_pos).astype(np.int64)
+    y = rng.normal(size=m).astype(np.float32); var = (0.5 + rng.rand(m)).astype(np.float32)
+    eng = LETKFEngine(k, 4, AbsDistance1D(), 1.0, dtype=torch.float32)
+    yn, d = eng.obs_gather_prep(xp, src, n, y, var)
+    hx = xp[1, 1][:, g_pos]
+    yn_ref, d_ref = eng.obs_prep(hx, y, var)
+    assert torch.equal(yn, yn_ref) and torch.equal(d, d_ref)
+    with pytest.raises(IndexError):
+        eng.obs_gather_prep(xp, src + 2 * k * n, n, y, var)

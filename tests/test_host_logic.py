@@ -187,3 +187,86 @@ def test_datasets_without_operator_are_dropped(golden):
     no_op = xrlite.Dataset(obs.data_vars)
     hx, kept = BaseAssimilation._apply_obs_operator(state, [no_op, obs])
     assert len(hx) == 1 and kept == [obs]
+
+
+# ---- observation operators that select grid columns ---------------------------------------------------------
+def _operator_objects(n_grid=40, k=6, n_time=3, seed=3, grid=None):
+    rng = np.random.RandomState(seed)
+    t = pd.to_datetime("1992-12-25") + pd.to_timedelta(np.arange(n_time), unit="h")
+    grid = np.arange(n_grid) if grid is None else grid
+    state = xrlite.DataArray(rng.normal(size=(2, n_time, k, n_grid)),
+                             dict(var_name=["y", "x"], time=t, ensemble=np.arange(k), grid=grid),
+                             ("var_name", "time", "ensemble", "grid"))
+    return rng, t, state
+
+
+def _obs_for(rng, times, obs_grid, var=0.25):
+    n_o = len(obs_grid)
+    return xrlite.Dataset({
+        "observations": xrlite.DataArray(rng.normal(size=(len(times), n_o)), dict(time=times, obs_grid_1=obs_grid), ("time", "obs_grid_1")),
+        "covariance": xrlite.DataArray(np.full(n_o, var) + 0.01 * np.arange(n_o), dict(obs_grid_1=obs_grid), ("obs_grid_1",))})
+
+
+def test_identity_operator_semantics():
+    """obs_ops/lorenz_96/identity.py:74-92 and obs_ops/base_ops.py:63-75."""
+    from pytassim_b200.obs_ops import IdentityOperator
+    rng, t, state = _operator_objects()
+    op_all = IdentityOperator(len_grid=40)                                     # None -> every grid point
+    obs = _obs_for(rng, t[[2, 0]], np.arange(40))                              # observation times in a different order
+    hx = op_all(obs, state)
+    assert hx.dims == ("time", "ensemble", "obs_grid_1") and hx.shape == (2, 6, 40)
+    np.testing.assert_array_equal(hx.values, state.values[1][[2, 0]])         # var 'x' is position 1
+    assert list(hx.indexes["time"]) == list(t[[2, 0]])
+    op_list = IdentityOperator(obs_points=[7, 3, 39], len_grid=40)
+    obs3 = _obs_for(rng, t[:1], [7, 3, 39])
+    np.testing.assert_array_equal(op_list(obs3, state).values, state.values[1][:1][:, :, [7, 3, 39]])
+    op_rand = IdentityOperator(obs_points=5, len_grid=40, random_state=np.random.RandomState(0))
+    expect = np.random.RandomState(0).choice(40, size=5, replace=False)
+    np.testing.assert_array_equal(op_rand.device_index(_obs_for(rng, t[:1], expect), state)[2], expect)
+    # labels, not positions: a grid index with shuffled labels
+    perm = np.random.RandomState(1).permutation(40)
+    _, _, shuffled = _operator_objects(grid=perm)
+    pos = op_list.device_index(obs3, shuffled)[2]
+    np.testing.assert_array_equal(perm[pos], [7, 3, 39])
+    with pytest.raises(KeyError):                                              # a grid label the state does not have
+        IdentityOperator(obs_points=[41], len_grid=40).device_index(_obs_for(rng, t[:1], [41]), state)
+    with pytest.raises(KeyError):                                              # an observation time the state does not have
+        op_all(_obs_for(rng, t[:1] + pd.Timedelta("30min"), np.arange(40)), state)
+    with pytest.raises(ValueError):                                            # obs_grid_1 of the wrong length
+        op_all(_obs_for(rng, t[:1], np.arange(39)), state)
+
+
+def test_nearest_grid_operator_semantics():
+    """examples/benchmark_letkf.py:90-104: linspace positions, nearest label, ties to the larger label (pandas)."""
+    from pytassim_b200.obs_ops import NearestGridOperator
+    rng, t, state = _operator_objects(n_grid=40)
+    op = NearestGridOperator(len_grid=40, nr_obs=7)
+    np.testing.assert_allclose(op.obs_grid, np.linspace(0, 40, 7, endpoint=False))
+    pos = op.device_index(_obs_for(rng, t[:1], op.obs_grid), state)[2]
+    np.testing.assert_array_equal(pos, [0, 6, 11, 17, 23, 29, 34])
+    ties = NearestGridOperator(len_grid=40, obs_grid=[0.5, 1.5, 2.49, 2.51, -3.0, 99.0])
+    np.testing.assert_array_equal(ties.grid_positions(state.indexes["grid"]), [1, 2, 2, 3, 0, 39])
+    op1k = NearestGridOperator(len_grid=10_000, nr_obs=1_000)                  # the benchmark script's default shape
+    np.testing.assert_array_equal(op1k.grid_positions(pd.Index(np.arange(10_000))), np.arange(0, 10_000, 10))
+
+
+def test_gather_offsets_equal_host_operator_stack():
+    """The device gather plan (src offsets into the flattened pseudo state) reproduces operator -> _stack_obs: same HX,
+    observations, variances and obs_info, dataset-major / time-major / obs_grid_1-minor (base.py:223-241)."""
+    from pytassim_b200.obs_ops import IdentityOperator, NearestGridOperator
+    rng, t, state = _operator_objects(n_grid=40, k=6, n_time=3)
+    ds1 = _obs_for(rng, t[[0, 2]], [5, 9, 33]); ds1.obs.operator = IdentityOperator(obs_points=[5, 9, 33], len_grid=40)
+    op2 = NearestGridOperator(len_grid=40, nr_obs=7)
+    ds2 = _obs_for(rng, t[[1]], op2.obs_grid); ds2.obs.operator = op2
+    obs = (ds1, ds2)
+    src, stride, y, var, info = BaseAssimilation._stack_gather_inputs(state, obs)
+    ens_obs, filtered = BaseAssimilation._apply_obs_operator(state, obs)
+    hx_ref, y_ref, var_ref, info_ref = BaseAssimilation._stack_obs_space_inputs(ens_obs, filtered)
+    flat = state.values.reshape(-1)
+    hx = np.stack([flat[src + i * stride] for i in range(6)])
+    np.testing.assert_array_equal(hx, hx_ref)
+    np.testing.assert_array_equal(y, y_ref); np.testing.assert_array_equal(var, var_ref); np.testing.assert_array_equal(info, info_ref)
+    assert stride == 40 and src.dtype == np.int64 and src.shape == (2 * 3 + 7,)
+    # a dataset with a plain callable operator or a correlated R switches the whole call to the host operators
+    ds3 = _obs_for(rng, t[[1]], np.arange(40)); ds3.obs.operator = lambda o, s: IdentityOperator(len_grid=40)(o, s)
+    assert BaseAssimilation._stack_gather_inputs(state, (ds1, ds3)) is None

@@ -264,6 +264,21 @@ int b200da_obs_prep(b200da_plan* pl, const void* HX, const void* y, const void* 
     return B200DA_OK;
 }
 
+int b200da_obs_gather_prep(b200da_plan* pl, const void* Xp, const int64_t* src_offset, int64_t member_stride, const void* y,
+                           const void* variance, int64_t m, void* Yn, void* d, void* stream) {
+    if (!pl || m < 0 || member_stride <= 0 || (m > 0 && (!Xp || !src_offset || !y || !variance || !Yn || !d))) return B200DA_ERR_INVALID;
+    if (m == 0) return B200DA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl->dtype == B200DA_F32)
+        k_obs_gather_prep<float><<<grid1d(m, 256), 256, 0, st>>>((const float*)Xp, (const long long*)src_offset, member_stride,
+                                                                 (const float*)y, (const float*)variance, pl->k, m, (float*)Yn, (float*)d);
+    else
+        k_obs_gather_prep<double><<<grid1d(m, 256), 256, 0, st>>>((const double*)Xp, (const long long*)src_offset, member_stride,
+                                                                  (const double*)y, (const double*)variance, pl->k, m, (double*)Yn, (double*)d);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
 int64_t b200da_num_blocks(const b200da_plan* plan) { return plan ? plan->n_blocks : 0; }
 int64_t b200da_num_grid(const b200da_plan* plan) { return plan ? plan->n_grid : 0; }
 int64_t b200da_num_obs(const b200da_plan* plan) { return plan ? plan->n_obs : 0; }

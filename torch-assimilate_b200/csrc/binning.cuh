@@ -180,6 +180,28 @@ __global__ void __launch_bounds__(256) k_obs_prep(const T* __restrict__ hx, cons
     d[j] = (y[j] - mean) * rc;
 }
 
+// The same with the observation operator fused in front: for operators that SELECT grid columns of one
+// state variable (obs_ops/lorenz_96/identity.py:88-92: `sel(var_name='x').sel(grid=points)`; examples/benchmark_letkf.py:
+// 100-104: `sel(grid=obs_grid, method='nearest')`; obs_ops/base_ops.py:63-75 picks the observation times) the ensemble of
+// observation equivalents is a gather from the pseudo state:  hx[i][j] = xp[src[j] + i * member_stride],  src[j] = offset of
+// member 0 of (variable, time, grid column) of observation j in the (n_var, n_time, k, N) array.  The gathered values are
+// exact copies and the arithmetic is that of k_obs_prep, so FP64 results are bit-identical to operator -> prep.
+template <typename T>
+__global__ void __launch_bounds__(256) k_obs_gather_prep(const T* __restrict__ xp, const long long* __restrict__ src,
+                                                         int64_t member_stride, const T* __restrict__ y,
+                                                         const T* __restrict__ var, int k, int64_t m, T* __restrict__ yn,
+                                                         T* __restrict__ d) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const T* col = xp + src[j];
+    T sum = (T)0;
+    for (int i = 0; i < k; ++i) sum += col[(int64_t)i * member_stride];
+    const T mean = sum / (T)k;
+    const T rc = (T)1 / sqrt(var[j]);
+    for (int i = 0; i < k; ++i) yn[(int64_t)i * m + j] = (col[(int64_t)i * member_stride] - mean) * rc;
+    d[j] = (y[j] - mean) * rc;
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------
 
 inline int grid1d(int64_t n, int block) { return (int)std::max<int64_t>(1, (n + block - 1) / block); }

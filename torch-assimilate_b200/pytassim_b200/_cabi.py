@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200da_set_grid": (_i, [_vp, _vp, _i64, _vp]),
     "b200da_bin_obs": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "b200da_obs_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "b200da_obs_gather_prep": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
     "b200da_num_blocks": (_i64, [_vp]),
     "b200da_num_grid": (_i64, [_vp]),
     "b200da_num_obs": (_i64, [_vp]),

@@ -124,6 +124,26 @@ class LETKFEngine(object):
             _cabi.check(self.lib.b200da_obs_prep(self._plan, _ptr(hx), _ptr(y), _ptr(var), y.shape[0], _ptr(yn), _ptr(d), _stream()))
         return yn, d
 
+    def obs_gather_prep(self, pseudo_state, src_offset, member_stride, observations, variance):
+        """``obs_prep`` with a column-selecting observation operator fused in front (obs_ops/lorenz_96/identity.py:88-92,
+        obs_ops/base_ops.py:63-75): HX[i, j] = pseudo_state.flat[src_offset[j] + i * member_stride]."""
+        xp = _dev(pseudo_state, dtype=self.dtype, device=self.device)
+        src = _dev(src_offset, dtype=torch.int64, device=self.device).reshape(-1)
+        y = _dev(observations, dtype=self.dtype, device=self.device).reshape(-1)
+        var = _dev(variance, dtype=self.dtype, device=self.device).reshape(-1)
+        m = int(y.shape[0])
+        if src.shape[0] != m or var.shape[0] != m:
+            raise ValueError('Observational size between ensemble ({0:d}) and observations '
+                             '({1:d}) do not match!'.format(int(src.shape[0]), m))
+        if m and (int(src.min()) < 0 or int(src.max()) + (self.k - 1) * int(member_stride) >= xp.numel()):
+            raise IndexError("src_offset points outside the pseudo state")
+        yn = torch.empty((self.k, m), dtype=self.dtype, device=self.device)
+        d = torch.empty_like(y)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_obs_gather_prep(self._plan, _ptr(xp), _ptr(src), int(member_stride), _ptr(y), _ptr(var), m,
+                                                        _ptr(yn), _ptr(d), _stream()))
+        return yn, d
+
     # -- hot path ----------------------------------------------------------------------------------------------
     def analyse(self, state, out=None, return_weights=False, blocks=None, count_ambiguous=False):
         """state (n_slices, k, N) on the device -> analysis of the same shape (interface/base.py:257-278)."""

@@ -200,6 +200,33 @@ class BaseAssimilation(object):
             hxs.append(hxv.reshape(hxv.shape[0], -1)); ys.append(y.reshape(-1)); vars_.append(covv.reshape(-1))
         return np.concatenate(hxs, axis=1), np.concatenate(ys), np.concatenate(vars_), np.concatenate(infos, axis=0)
 
+    @staticmethod
+    def _stack_gather_inputs(pseudo_state, observations):
+        """The inputs of ``b200da_obs_gather_prep`` when EVERY dataset's operator selects grid columns (it has
+        ``device_index``, see :mod:`pytassim_b200.obs_ops`) and carries a diagonal R: (src_offset (M,) int64 into the
+        flattened (n_var, n_time, k, N) pseudo state, member stride, y (M,), variance (M,), obs_info (M, 1+nc)) stacked like
+        ``_stack_obs`` (base.py:223-241); None otherwise (the operators are then called on the host, base.py:181-220)."""
+        if not observations or tuple(pseudo_state.dims) != ('var_name', 'time', 'ensemble', 'grid'):
+            return None
+        for obs in observations:
+            if not callable(getattr(obs.obs.operator, 'device_index', None)) or 'obs_grid_2' in obs['covariance'].dims:
+                return None
+        _, n_time, k, n_grid = pseudo_state.values.shape
+        srcs, ys, vars_, infos = [], [], [], []
+        for obs in observations:
+            var_pos, t_pos, g_pos = obs.obs.operator.device_index(obs, pseudo_state)
+            y = np.asarray(obs['observations'].values, dtype=np.float64)
+            n_t, n_o = y.shape
+            covv = np.broadcast_to(np.asarray(obs['covariance'].values, dtype=np.float64), (n_t, n_o))
+            base = (var_pos * n_time + t_pos) * (k * n_grid)                                # member 0 of (variable, time)
+            srcs.append((base[:, None] + g_pos[None, :]).reshape(-1))
+            t_unix = dtindex_to_total_seconds(_time_coord(obs['observations']))
+            coords = index_to_array(obs['observations'].indexes['obs_grid_1'])
+            infos.append(np.concatenate([np.repeat(t_unix, n_o)[:, None], np.tile(coords, (n_t, 1))], axis=1))
+            ys.append(y.reshape(-1)); vars_.append(covv.reshape(-1))
+        return (np.concatenate(srcs).astype(np.int64), int(n_grid), np.concatenate(ys), np.concatenate(vars_),
+                np.concatenate(infos, axis=0))
+
     @abc.abstractmethod
     def update_state(self, state, observations, pseudo_state, analysis_time):
         pass
@@ -263,17 +290,25 @@ class FilterAssimilation(BaseAssimilation):
         self._validate_state(pseudo_state)
         if not self.smoother:
             state, observations, pseudo_state = self._slice_analysis(analysis_time, state, observations, pseudo_state)
-        ens_obs, filtered_obs = self._apply_obs_operator(pseudo_state, observations)
-        if not filtered_obs:
-            warnings.warn('No observation is given, I will return the background state!', UserWarning)
-            return state
         values = np.ascontiguousarray(state.values, dtype=np.float64)
         n_var, n_t, k, n_grid = values.shape
-        stacked = self._stack_obs_space_inputs(ens_obs, filtered_obs)
-        if stacked is not None:                     # diagonal R: mean / perturbations / innovations / R^-1/2 on the device
-            hx, y, var, obs_info = stacked
-            perts, innov = self._prep_engine(k, n_var * n_t).obs_prep(hx, y, var)
+        gathered = self._stack_gather_inputs(pseudo_state, observations)
+        if gathered is not None:                    # column-selecting operators + diagonal R: operator and prep on the device
+            src, member_stride, y, var, obs_info = gathered
+            same = pseudo_state.values.shape == values.shape and np.array_equal(pseudo_state.values, values)
+            values = torch.as_tensor(values).cuda()  # one upload serves the operator gather and the analysis
+            xp = values if same else np.ascontiguousarray(pseudo_state.values, dtype=np.float64)
+            perts, innov = self._prep_engine(k, n_var * n_t).obs_gather_prep(xp, src, member_stride, y, var)
         else:
-            innov, perts, obs_info = self._get_obs_space_variables(ens_obs, filtered_obs)
+            ens_obs, filtered_obs = self._apply_obs_operator(pseudo_state, observations)
+            if not filtered_obs:
+                warnings.warn('No observation is given, I will return the background state!', UserWarning)
+                return state
+            stacked = self._stack_obs_space_inputs(ens_obs, filtered_obs)
+            if stacked is not None:                 # diagonal R: mean / perturbations / innovations / R^-1/2 on the device
+                hx, y, var, obs_info = stacked
+                perts, innov = self._prep_engine(k, n_var * n_t).obs_prep(hx, y, var)
+            else:
+                innov, perts, obs_info = self._get_obs_space_variables(ens_obs, filtered_obs)
         xa = self._analyse_arrays(state, values.reshape(n_var * n_t, k, n_grid), innov, perts, obs_info)
-        return state.copy(data=np.asarray(xa).reshape(values.shape).astype(state.values.dtype, copy=False))
+        return state.copy(data=np.asarray(xa).reshape(state.values.shape).astype(state.values.dtype, copy=False))
