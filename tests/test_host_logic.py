@@ -270,3 +270,27 @@ def test_gather_offsets_equal_host_operator_stack():
     # a dataset with a plain callable operator or a correlated R switches the whole call to the host operators
     ds3 = _obs_for(rng, t[[1]], np.arange(40)); ds3.obs.operator = lambda o, s: IdentityOperator(len_grid=40)(o, s)
     assert BaseAssimilation._stack_gather_inputs(state, (ds1, ds3)) is None
+
+
+def test_forward_model_builds_the_pseudo_state(golden):
+    """base.py:327-357 / filter.py:139-146: without an explicit pseudo state a given forward model is run on
+    mean + perturbations (identity prior weights) and its second return value is the pseudo state."""
+    _, state, _ = _fixture_objects(golden)
+    seen = {}
+
+    def model(model_state, iter_num):
+        seen["state"], seen["iter"] = model_state, iter_num
+        return model_state, model_state.copy(data=model_state.values * 2.0)
+    alg = ETKF(forward_model=model)
+    pseudo = alg.get_pseudo_state(None, state)
+    mean = state.values.mean(axis=2, keepdims=True)
+    np.testing.assert_array_equal(seen["state"].values, mean + (state.values - mean))
+    np.testing.assert_array_equal(pseudo.values, seen["state"].values * 2.0)
+    assert seen["iter"] == 0 and pseudo.dims == state.dims
+    assert alg.get_pseudo_state(state, state) is state                     # an explicit pseudo state wins
+    assert ETKF().get_pseudo_state(None, state) is state                   # no model: the state itself
+
+    def bad_model(model_state, iter_num):
+        return model_state, xrlite.DataArray(model_state.values, {}, ("v", "time", "ensemble", "grid"))
+    with pytest.raises(StateError):
+        ETKF(forward_model=bad_model).get_pseudo_state(None, state)

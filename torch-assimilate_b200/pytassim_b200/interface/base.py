@@ -135,10 +135,20 @@ class BaseAssimilation(object):
                 pass
         return obs_equivalent, filtered
 
-    def get_pseudo_state(self, pseudo_state, state):
-        """base.py:342-357 without the forward-model propagation (outside the hot path)."""
+    def propagate_model(self, state, iter_num=0):
+        """base.py:327-340 with the filter's prior weights (identity, filter.py:139-141): the model state handed to
+        ``forward_model`` is ``mean + perturbations`` exactly as ``_apply_weights`` forms it (base.py:257-278)."""
+        values = np.asarray(state.values)
+        mean = values.mean(axis=2, keepdims=True)                       # state.py:160-161
+        model_state = state.copy(data=mean + (values - mean))
+        _, pseudo_state = self.forward_model(model_state, iter_num)
+        self._validate_state(pseudo_state)
+        return pseudo_state
+
+    def get_pseudo_state(self, pseudo_state, state, iter_num=0):
+        """base.py:342-357."""
         if pseudo_state is None and self.forward_model is not None:
-            raise NotImplementedError("forward_model propagation is outside the B200 hot path")
+            return self.propagate_model(state, iter_num)
         return state if pseudo_state is None else pseudo_state
 
     # -- obs-space variables (base.py:359-379, 223-241; observation.py:241-295) ---------------------------------------
