@@ -345,6 +345,49 @@ def test_sharded_etkf_entry_points(dtype, tol):
     np.testing.assert_allclose(w0, np.sqrt(1.1) * np.eye(k), rtol=0, atol=1e-6 if dtype == torch.float32 else 1e-14)
 
 
+@pytest.mark.parametrize("k,scale,tol", [(40, 1.0, 1e-10), (40, 10.0, 1e-10), (40, 30.0, 1e-10), (40, 100.0, 1e-10),
+                                         (50, 300.0, 1e-10), (100, 200.0, 1e-10), (40, 1000.0, 2e-9), (24, 3000.0, 2e-8)])
+def test_stiff_ensemble_space_problems_letkf(k, scale, tol):
+    """Accurate / dense observations make C + (k-1)/rho I stiff (largest over smallest eigenvalue 1e3 ... 2e7 here).  The
+    symmetric-storage Newton-Schulz iteration alone loses all accuracy beyond a ratio of a few thousand (measured: 1e-7 at
+    1e4); the solve kernel must switch to its two-level form and stay within the FP64 tolerance of the north star.  For the
+    last two cases (ratio 2e6 and 2e7) the eigendecomposition route of the reference is itself only reproducible to
+    ~ratio * 1e-16 (the Jacobi solver and LAPACK differ by 6e-10 there), so the tolerance is widened accordingly."""
+    m = _metrics()
+    n_grid = 96
+    data = syn.lorenz96_1d(n_grid, k, 1, seed=900 + k)
+    data["normed_perts"] = data["normed_perts"] * scale                # observation error std 1 / scale
+    data["normed_obs"] = data["normed_obs"] * scale
+    eng, xa, w, namb = _run(data, m.PeriodicDistance1D(float(n_grid)), 6.0, 1.05, weights=True, solver="newton")
+    ref, wref = orc.letkf_analysis(data["state"], data["normed_perts"], data["normed_obs"], data["grid_rows"],
+                                   data["obs_rows"], orc.make_dist_periodic1d(float(n_grid)), 6.0, inf_factor=1.05)
+    assert np.abs(w - wref).max() <= tol * max(1.0, np.abs(wref).max())
+    assert np.abs(xa - ref).max() <= tol * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-4)])
+@pytest.mark.parametrize("k,nobs", [(100, 400_000), (50, 1_000_000), (128, 100_000)])
+def test_stiff_global_etkf_weights(k, nobs, dtype, tol):
+    """BASELINE cfg4 has 1e6 observations against a prior precision of (k-1)/rho: eigenvalue ratio ~1e4.  Weights against a
+    numpy eigh solve of the device Gram (same arithmetic as core/etkf.py:57-77 on that Gram)."""
+    from pytassim_b200.engine import LETKFEngine
+    m = _metrics()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    hx = torch.randn((k, nobs), dtype=torch.float64, device="cuda", generator=g)
+    yn = (hx - hx.mean(dim=0, keepdim=True)).to(dtype).contiguous()
+    d = (torch.randn(nobs, dtype=torch.float64, device="cuda", generator=g) * 0.5).to(dtype)
+    rho = 1.1
+    eng = LETKFEngine(k, 1, m.AbsDistance1D(), 1.0, inf_factor=rho, dtype=dtype)
+    gram = eng.etkf_gram(yn, d).cpu().numpy()
+    c = np.tril(gram[:k, :k]) + np.tril(gram[:k, :k], -1).T
+    ev, u = np.linalg.eigh(c)
+    ev = np.clip(ev, 0.0, None) + (k - 1) / rho
+    assert ev.max() / ev.min() > 5e2
+    wref = ((u / ev) @ u.T @ gram[k, :k])[:, None] + (u * np.sqrt((k - 1) / ev)) @ u.T
+    w = eng.etkf_weights(yn, d).cpu().numpy().astype(np.float64)
+    assert np.abs(w - wref).max() <= tol * np.abs(wref).max()
+
+
 @pytest.mark.parametrize("k,n_grid,radius", [(112, 80, 7.0), (120, 72, 6.0), (128, 64, 9.0)])
 def test_large_ensembles_newton_against_oracle(k, n_grid, radius):
     """Ensemble sizes beyond the shared-memory Jacobi limit (k > 111) run on the tensor-core Newton-Schulz solver only

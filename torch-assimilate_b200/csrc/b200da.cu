@@ -109,6 +109,13 @@ static int dispatch_apply_global(int f32, const void* x, const void* w, int k, i
     }
 }
 
+// spectral-bound ratio s / a above which the solve kernel switches to its two-level path (ns_solve_kernel.cuh): the
+// single-level error is ~1e-12 at 2e3 (FP64 tolerance 1e-10) and ~1e-8 at 2e4 (FP32 tolerance 1e-4)
+static double ns_stiff_ratio(const b200da_plan* pl) {
+    if (pl->ns_stiff > 0.0) return pl->ns_stiff;
+    return pl->dtype == B200DA_F32 ? 2.0e4 : 2.0e3;
+}
+
 static int check_device() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return B200DA_ERR_NO_DEVICE; }
@@ -230,7 +237,7 @@ void b200da_plan_destroy(b200da_plan* pl) {
     DevBuf* bufs[] = {&pl->gpos, &pl->gorder, &pl->block_off, &pl->opos, &pl->cell_start, &pl->ys, &pl->tmp_keys,
                       &pl->tmp_cell, &pl->tmp_count, &pl->tmp_a, &pl->tmp_b, &pl->tmp_pos, &pl->host_stage_obs,
                       &pl->host_stage_y, &pl->host_stage_d, &pl->host_stage_x, &pl->host_stage_xa, &pl->etkf_partial,
-                      &pl->etkf_w, &pl->stats, &pl->cmat, &pl->counter};
+                      &pl->etkf_w, &pl->stats, &pl->cmat, &pl->counter, &pl->ns_scratch};
     for (cudaEvent_t ev : pl->ev_pool) cudaEventDestroy(ev);
     for (DevBuf* b : bufs) b->release();
     if (pl->ev0) cudaEventDestroy(pl->ev0);
@@ -378,6 +385,8 @@ static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int
             S.counter = pl->counter.as<unsigned int>();
             S.io_f32 = f32;
             S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = pl->rho;
+            if ((rc = pl->ns_scratch.ensure(ns_scratch_bytes((k + 7) / 8)))) return rc;
+            S.scratch = pl->ns_scratch.as<double>(); S.stiff = ns_stiff_ratio(pl);
             if ((rc = dispatch_ns((k + 7) / 8, S, st))) return rc;
         }
         if (pl->timing) B200DA_CUDA(cudaEventRecord(ec, st));
@@ -511,6 +520,8 @@ static int etkf_solve_partials(b200da_plan* pl, int n_partial, void* W, cudaStre
         S.cmat = slot; S.slot_stride = (int64_t)slot_doubles; S.gpos = pl->etkf_w.as<Pos4>(); S.x = nullptr; S.xa = nullptr;
         S.w_out = W; S.io_f32 = f32; S.stats = nullptr; S.counter = pl->counter.as<unsigned int>();
         S.slot_base = 0; S.n_slots = 1; S.n_grid = 0; S.k = k; S.n_slices = 0; S.rho = pl->rho;
+        if ((rc = pl->ns_scratch.ensure(ns_scratch_bytes((k + 7) / 8)))) return rc;
+        S.scratch = pl->ns_scratch.as<double>(); S.stiff = ns_stiff_ratio(pl);
         return dispatch_ns((k + 7) / 8, S, st);
     }
     const size_t smem = solve_smem_bytes(k);

@@ -291,8 +291,8 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
     int produced = 0, consumed = 0;
     unsigned long long my_amb = 0;
 
-    auto produce = [&]() -> bool {      // stage one more tile if any observation is left; uniform across the CTA
-        // 1. refill the survivor ring
+    // 1. refill the survivor ring (CTA-collective: two barriers per pass of NT candidates; needed once every few tiles)
+    auto refill = [&]() {
         while (ring_tail - ring_head < kTileObs && cand_pos < cand_total) {
             const int c = cand_pos + tid;
             bool keep = false;
@@ -322,10 +322,11 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
             ring_tail += total;
             cand_pos += NT;
         }
-        const int n_tile = min(kTileObs, ring_tail - ring_head);
-        if (n_tile <= 0) return false;
+    };
+    // 2. + 3. this thread's share of the next tile (no barrier inside): localization weights, one (slot, grid point) pair per
+    // thread and pass, and the asynchronous copy of the observation rows; padded slots re-read the first row with weight 0
+    auto stage_tile = [&](int n_tile) {
         const int stage = produced % kStages;
-        // 2. localization weights of the tile: one (slot, grid point) pair per thread and pass
         double* wst = wbuf + (size_t)stage * G * kTileObs;
         for (int q = tid; q < G * kTileObs; q += NT) {
             const int slot = q % kTileObs, gi = q / kTileObs;
@@ -338,7 +339,6 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
             }
             wst[q] = w;
         }
-        // 3. asynchronous copy of the observation rows; padded slots re-read the first row with weight 0
         T* yst = ybuf + (size_t)stage * kTileObs * LDY;
         constexpr int EPC = 16 / sizeof(T);          // elements per 16-byte chunk
         constexpr int CH = KP / EPC;                 // 16-byte chunks per row
@@ -349,44 +349,63 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
         }
         ring_head += n_tile;
         ++produced;
-        return true;
     };
+    auto consume_tile = [&]() {
+        if (my_g < ng) {
+            const int stage = consumed % kStages;
+            const T* yst = ybuf + (size_t)stage * kTileObs * LDY;
+            const double* wrow = wbuf + ((size_t)stage * G + my_g) * kTileObs;
+            if constexpr (WPG == 1) gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane);
+            else if constexpr (WPG == 2) {
+                if (my_sub == 0) gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane);
+                else gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane);
+            } else if constexpr (WPG == 4) {
+                switch (my_sub) {
+                    case 0: gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane); break;
+                    case 1: gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane); break;
+                    case 2: gram_tile<T, KT, WPG, 2, BROW>(yst, wrow, acc, bacc, lane); break;
+                    default: gram_tile<T, KT, WPG, 3, BROW>(yst, wrow, acc, bacc, lane); break;
+                }
+            } else {
+                switch (my_sub) {
+                    case 0: gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane); break;
+                    case 1: gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane); break;
+                    case 2: gram_tile<T, KT, WPG, 2, BROW>(yst, wrow, acc, bacc, lane); break;
+                    case 3: gram_tile<T, KT, WPG, 3, BROW>(yst, wrow, acc, bacc, lane); break;
+                    case 4: gram_tile<T, KT, WPG, 4, BROW>(yst, wrow, acc, bacc, lane); break;
+                    case 5: gram_tile<T, KT, WPG, 5, BROW>(yst, wrow, acc, bacc, lane); break;
+                    case 6: gram_tile<T, KT, WPG, 6, BROW>(yst, wrow, acc, bacc, lane); break;
+                    default: gram_tile<T, KT, WPG, 7, BROW>(yst, wrow, acc, bacc, lane); break;
+                }
+            }
+        }
+    };
+    // Half of the warps of every scheduler (warp id bit 2) stage the tile after next BEFORE their share of the tensor work
+    // on the current tile, the other half AFTER it: right behind the per-tile barrier there is always a warp with DMMA work on
+    // every scheduler while the others sit in the latency chain of the FP64 taper (global load -> asin -> polynomial).
+    const bool stage_first = ((warp >> 2) & 1) == 0;
 
     if (cand_total > 0) {
 #pragma unroll
-        for (int i = 0; i < kStages - 1; ++i) { produce(); cp_async_commit(); }      // one group per tile, possibly empty
+        for (int i = 0; i < kStages - 1; ++i) {          // prologue: one cp.async group per tile, possibly empty
+            refill();
+            const int n_tile = min(kTileObs, ring_tail - ring_head);
+            if (n_tile > 0) stage_tile(n_tile);
+            cp_async_commit();
+        }
         while (consumed < produced) {
             cp_async_wait<kStages - 2>();
             __syncthreads();
-            produce();
-            cp_async_commit();                        // one group per iteration, possibly empty
-            if (my_g < ng) {
-                const int stage = consumed % kStages;
-                const T* yst = ybuf + (size_t)stage * kTileObs * LDY;
-                const double* wrow = wbuf + ((size_t)stage * G + my_g) * kTileObs;
-                if constexpr (WPG == 1) gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane);
-                else if constexpr (WPG == 2) {
-                    if (my_sub == 0) gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane);
-                    else gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane);
-                } else if constexpr (WPG == 4) {
-                    switch (my_sub) {
-                        case 0: gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane); break;
-                        case 1: gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane); break;
-                        case 2: gram_tile<T, KT, WPG, 2, BROW>(yst, wrow, acc, bacc, lane); break;
-                        default: gram_tile<T, KT, WPG, 3, BROW>(yst, wrow, acc, bacc, lane); break;
-                    }
-                } else {
-                    switch (my_sub) {
-                        case 0: gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane); break;
-                        case 1: gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane); break;
-                        case 2: gram_tile<T, KT, WPG, 2, BROW>(yst, wrow, acc, bacc, lane); break;
-                        case 3: gram_tile<T, KT, WPG, 3, BROW>(yst, wrow, acc, bacc, lane); break;
-                        case 4: gram_tile<T, KT, WPG, 4, BROW>(yst, wrow, acc, bacc, lane); break;
-                        case 5: gram_tile<T, KT, WPG, 5, BROW>(yst, wrow, acc, bacc, lane); break;
-                        case 6: gram_tile<T, KT, WPG, 6, BROW>(yst, wrow, acc, bacc, lane); break;
-                        default: gram_tile<T, KT, WPG, 7, BROW>(yst, wrow, acc, bacc, lane); break;
-                    }
-                }
+            refill();
+            const int n_tile = min(kTileObs, ring_tail - ring_head);
+            if (stage_first) {
+                if (n_tile > 0) stage_tile(n_tile);
+                cp_async_commit();                        // one group per iteration, possibly empty
+                consume_tile();
+            } else {
+                consume_tile();
+                if (n_tile > 0) stage_tile(n_tile);
+                cp_async_commit();
             }
             ++consumed;
         }

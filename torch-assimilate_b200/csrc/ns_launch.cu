@@ -26,6 +26,16 @@ static int launch_ns(const NsParams& P, cudaStream_t st) {
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
+template <int KT> static size_t scratch_bytes() { return sizeof(double) * ns_scratch_doubles(KT) * (size_t)NsPick<KT>::GROUPS * 148; }
+#define B200DA_NSS_CASE(KT) case KT: return scratch_bytes<KT>();
+size_t ns_scratch_bytes(int kts) {
+    switch (kts) {
+        B200DA_NSS_CASE(1) B200DA_NSS_CASE(2) B200DA_NSS_CASE(3) B200DA_NSS_CASE(4) B200DA_NSS_CASE(5) B200DA_NSS_CASE(6)
+        B200DA_NSS_CASE(7) B200DA_NSS_CASE(8) B200DA_NSS_CASE(9) B200DA_NSS_CASE(10) B200DA_NSS_CASE(11) B200DA_NSS_CASE(12)
+        B200DA_NSS_CASE(13) B200DA_NSS_CASE(14) B200DA_NSS_CASE(15) B200DA_NSS_CASE(16)
+        default: return 0;
+    }
+}
 #define B200DA_NS_CASE(KT) case KT: return launch_ns<KT>(P, st);
 int dispatch_ns(int kts, const NsParams& P, cudaStream_t st) {
     switch (kts) {

@@ -75,14 +75,32 @@ __device__ __forceinline__ double sym_frag(const double* __restrict__ S, int t, 
     return S[off];
 }
 
-template <int KT, int WPM, int SUB, int KS>
-__device__ __forceinline__ void gemm_kstep(const double* __restrict__ L, const double* __restrict__ R, int kt,
+// Operand storage of the products below:
+//   kOpSym    symmetric, tile-packed lower triangle, in shared memory (every matrix of the iteration itself)
+//   kOpSymG   the same in the per-group global scratch (written earlier by this group: read through L2, never the
+//             non-coherent path)
+//   kOpFullG  general matrix as a full KT x KT grid of 8x8 tiles (tile (mt, nt) at (mt * KT + nt) * 64) in the global
+//             scratch, used as RIGHT operand: fragment = rows [kt*8 + ks*4, +4) x columns [t*8, +8)
+enum { kOpSym = 0, kOpSymG = 1, kOpFullG = 2 };
+template <int MODE, int KS, int KT>
+__device__ __forceinline__ double op_frag(const double* S, int t, int kt, const FragOff& fo) {
+    if constexpr (MODE == kOpSym) return sym_frag<KS>(S, t, kt, fo);
+    else if constexpr (MODE == kOpSymG) {
+        const int off = kt <= t ? tile_off(t, kt) + (KS ? fo.d1 : fo.d0) : tile_off(kt, t) + (KS ? fo.t1 : fo.t0);
+        return __ldcg(S + off);
+    } else {
+        return __ldcg(S + (kt * KT + t) * 64 + (KS ? fo.t1 : fo.t0));
+    }
+}
+
+template <int KT, int WPM, int SUB, int KS, int LM = kOpSym, int RM = kOpSym>
+__device__ __forceinline__ void gemm_kstep(const double* L, const double* R, int kt,
                                            const FragOff& fo, double (&acc)[NsCfg<KT, WPM>::OWN][2]) {
     double fl[KT], fr[KT];
 #pragma unroll
     for (int t = 0; t < KT; ++t) {            // fragments of rows / columns this warp does not own are dead code
-        fl[t] = sym_frag<KS>(L, t, kt, fo);
-        fr[t] = sym_frag<KS>(R, t, kt, fo);
+        fl[t] = op_frag<LM, KS, KT>(L, t, kt, fo);
+        fr[t] = op_frag<RM, KS, KT>(R, t, kt, fo);
     }
     int idx = 0, n = 0;
 #pragma unroll
@@ -95,31 +113,71 @@ __device__ __forceinline__ void gemm_kstep(const double* __restrict__ L, const d
     }
 }
 
-// acc = lower-triangle tiles (owned by warp SUB of the group) of L R for symmetric, commuting L and R
-template <int KT, int WPM, int SUB>
-__device__ __forceinline__ void sym_gemm_sub(const double* __restrict__ L, const double* __restrict__ R, const FragOff& fo,
+// acc = lower-triangle tiles (owned by warp SUB of the group, diagonal tiles complete) of L R
+template <int KT, int WPM, int SUB, int LM = kOpSym, int RM = kOpSym>
+__device__ __forceinline__ void sym_gemm_sub(const double* L, const double* R, const FragOff& fo,
                                              double (&acc)[NsCfg<KT, WPM>::OWN][2]) {
 #pragma unroll
     for (int i = 0; i < NsCfg<KT, WPM>::OWN; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
 #pragma unroll 1
     for (int kt = 0; kt < KT; ++kt) {
-        gemm_kstep<KT, WPM, SUB, 0>(L, R, kt, fo, acc);
-        gemm_kstep<KT, WPM, SUB, 1>(L, R, kt, fo, acc);
+        gemm_kstep<KT, WPM, SUB, 0, LM, RM>(L, R, kt, fo, acc);
+        gemm_kstep<KT, WPM, SUB, 1, LM, RM>(L, R, kt, fo, acc);
     }
 }
 
-template <int KT, int WPM>
-__device__ __forceinline__ void sym_gemm(int sub, const double* __restrict__ L, const double* __restrict__ R,
+template <int KT, int WPM, int LM = kOpSym, int RM = kOpSym>
+__device__ __forceinline__ void sym_gemm(int sub, const double* L, const double* R,
                                          const FragOff& fo, double (&acc)[NsCfg<KT, WPM>::OWN][2]) {
-    if constexpr (WPM == 1) sym_gemm_sub<KT, 1, 0>(L, R, fo, acc);
+    if constexpr (WPM == 1) sym_gemm_sub<KT, 1, 0, LM, RM>(L, R, fo, acc);
     else if constexpr (WPM == 2) {
-        if (sub == 0) sym_gemm_sub<KT, 2, 0>(L, R, fo, acc); else sym_gemm_sub<KT, 2, 1>(L, R, fo, acc);
+        if (sub == 0) sym_gemm_sub<KT, 2, 0, LM, RM>(L, R, fo, acc); else sym_gemm_sub<KT, 2, 1, LM, RM>(L, R, fo, acc);
     } else {
         switch (sub) {
-            case 0: sym_gemm_sub<KT, 4, 0>(L, R, fo, acc); break;
-            case 1: sym_gemm_sub<KT, 4, 1>(L, R, fo, acc); break;
-            case 2: sym_gemm_sub<KT, 4, 2>(L, R, fo, acc); break;
-            default: sym_gemm_sub<KT, 4, 3>(L, R, fo, acc); break;
+            case 0: sym_gemm_sub<KT, 4, 0, LM, RM>(L, R, fo, acc); break;
+            case 1: sym_gemm_sub<KT, 4, 1, LM, RM>(L, R, fo, acc); break;
+            case 2: sym_gemm_sub<KT, 4, 2, LM, RM>(L, R, fo, acc); break;
+            default: sym_gemm_sub<KT, 4, 3, LM, RM>(L, R, fo, acc); break;
+        }
+    }
+}
+
+// The warp's lower-triangle accumulator tiles into a FULL tile grid in global memory: directly (tile (mt, nt), nt <= mt), or
+// transposed into the strictly upper tiles (element (r, c) of tile (mt, nt) -> element (c, r) of tile (nt, mt), nt < mt).
+// lower(L R) stored directly plus lower(R L) stored transposed is the complete product L R of two symmetric matrices.
+template <int KT, int WPM, int SUB, bool TRANSPOSED>
+__device__ __forceinline__ void store_full_sub(double* F, const double (&acc)[NsCfg<KT, WPM>::OWN][2], int lane) {
+    const int r = lane >> 2, c = (lane & 3) * 2;
+    int idx = 0, n = 0;
+#pragma unroll
+    for (int mt = 0; mt < KT; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt <= mt; ++nt) {
+            if (tile_owned<KT, WPM, SUB>(idx)) {
+                if constexpr (!TRANSPOSED) {
+                    *reinterpret_cast<double2*>(F + (mt * KT + nt) * 64 + tile_elem(r, c)) = make_double2(acc[n][0], acc[n][1]);
+                } else if (mt != nt) {
+                    double* tp = F + (nt * KT + mt) * 64;
+                    tp[tile_elem(c, r)] = acc[n][0];
+                    tp[tile_elem(c + 1, r)] = acc[n][1];
+                }
+                ++n;
+            }
+            ++idx;
+        }
+    }
+}
+template <int KT, int WPM, bool TRANSPOSED>
+__device__ __forceinline__ void store_full(int sub, double* F, const double (&acc)[NsCfg<KT, WPM>::OWN][2], int lane) {
+    if constexpr (WPM == 1) store_full_sub<KT, 1, 0, TRANSPOSED>(F, acc, lane);
+    else if constexpr (WPM == 2) {
+        if (sub == 0) store_full_sub<KT, 2, 0, TRANSPOSED>(F, acc, lane); else store_full_sub<KT, 2, 1, TRANSPOSED>(F, acc, lane);
+    } else {
+        switch (sub) {
+            case 0: store_full_sub<KT, 4, 0, TRANSPOSED>(F, acc, lane); break;
+            case 1: store_full_sub<KT, 4, 1, TRANSPOSED>(F, acc, lane); break;
+            case 2: store_full_sub<KT, 4, 2, TRANSPOSED>(F, acc, lane); break;
+            default: store_full_sub<KT, 4, 3, TRANSPOSED>(F, acc, lane); break;
         }
     }
 }
@@ -184,7 +242,12 @@ struct NsParams {
     int k;
     int n_slices;
     double rho;
+    double* scratch;           // per group (blockIdx.x * GROUPS + group) ns_scratch_doubles(KT) doubles: stiff matrices only
+    double stiff;              // spectral-bound ratio s / a above which the two-level solve is used
 };
+
+// doubles of global scratch per group: fixed-up A and B (tile-packed symmetric) + one full tile grid
+__host__ __device__ constexpr size_t ns_scratch_doubles(int kt) { return 2 * (size_t)tri_tiles(kt) * 64 + (size_t)kt * kt * 64; }
 
 template <int WPM>
 __device__ __forceinline__ void ns_sync(int bar_id) {
@@ -195,7 +258,8 @@ __device__ __forceinline__ void ns_sync(int bar_id) {
 // One matrix: everything between "augmented Gram in global memory" and "analysis columns written".
 template <int KT, int WPM>
 __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict__ Z, double* __restrict__ Y,
-                             double* __restrict__ T, double* __restrict__ vec, int gtid, int sub, int lane, int bar_id) {
+                             double* __restrict__ T, double* __restrict__ vec, double* scratch, int gtid, int sub, int lane,
+                             int bar_id) {
     using Cfg = NsCfg<KT, WPM>;
     constexpr int GT = WPM * 32, KP = Cfg::KP, MAT = Cfg::MAT, LDW = Cfg::LDW;
     const int k = P.k;
@@ -249,63 +313,117 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         for (int w = 1; w < WPM; ++w) { rs_max = fmax(rs_max, red[w]); sq += red[4 + w]; }
     }
     const double s = fmin(sqrt(sq), rs_max) * (1.0 + 1e-12);
-    const double inv_s = 1.0 / s;
-    // ---- iteration 0 (Z0 = I): T = (3 I - g Y0) / 2, Z1 = sqrt(g) T, Y1 = sqrt(g) Y0 T ---------------------------------
-    double lo = fmin(alpha * inv_s, 1.0);
-    double g = 3.0 / (1.0 + sqrt(lo) + lo);
-    double sg = sqrt(g);
-    for (int e = gtid; e < MAT; e += GT) {
-        const int tile = e >> 6, r = (e >> 3) & 7, c = (e & 7) ^ ((r & 2) << 1);   // e = tile*64 + tile_elem(r, c)
-        // tile -> (mt, nt): diagonal tiles sit at mt (mt + 3) / 2
-        int mt = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
-        while (mt * (mt + 1) / 2 > tile) --mt;
-        while ((mt + 1) * (mt + 2) / 2 <= tile) ++mt;
-        const int nt = tile - mt * (mt + 1) / 2;
-        const bool on_diag = (mt == nt) && (r == c);
-        double y = Y[e] * inv_s;
-        if (on_diag && mt * 8 + r >= k) y = 1.0;                 // padding: decoupled unit eigenvalues
-        const double t = fma(-0.5 * g, y, on_diag ? 1.5 : 0.0);
-        Y[e] = y; T[e] = t; Z[e] = sg * t;
-    }
-    ns_sync<WPM>(bar_id);
     double acc[Cfg::OWN][2];
-    int iters = 1;
-    {
-        sym_gemm<KT, WPM>(sub, Y, T, fo, acc);
+    // ---- Z <- ((Y + shift I) / sc)^(-1/2) for a symmetric Y whose shifted spectrum lies in [lo_abs, sc]; Y, T destroyed -------
+    auto inv_sqrt = [&](const double shift, const double sc, const double lo_abs) -> int {
+        const double inv_sc = 1.0 / sc;
+        // iteration 0 (Z0 = I): T = (3 I - g Y0) / 2, Z1 = sqrt(g) T, Y1 = sqrt(g) Y0 T
+        double lo = fmin(lo_abs * inv_sc, 1.0);
+        double g = 3.0 / (1.0 + sqrt(lo) + lo);
+        double sg = sqrt(g);
+        for (int e = gtid; e < MAT; e += GT) {
+            const int tile = e >> 6, r = (e >> 3) & 7, c = (e & 7) ^ ((r & 2) << 1);   // e = tile*64 + tile_elem(r, c)
+            // tile -> (mt, nt): diagonal tiles sit at mt (mt + 3) / 2
+            int mt = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
+            while (mt * (mt + 1) / 2 > tile) --mt;
+            while ((mt + 1) * (mt + 2) / 2 <= tile) ++mt;
+            const int nt = tile - mt * (mt + 1) / 2;
+            const bool on_diag = (mt == nt) && (r == c);
+            double y = (Y[e] + (on_diag ? shift : 0.0)) * inv_sc;
+            if (on_diag && mt * 8 + r >= k) y = 1.0;                 // padding: decoupled unit eigenvalues
+            const double t = fma(-0.5 * g, y, on_diag ? 1.5 : 0.0);
+            Y[e] = y; T[e] = t; Z[e] = sg * t;
+        }
         ns_sync<WPM>(bar_id);
-        store_tiles<KT, WPM>(sub, Y, acc, sg, 0.0, lane);
+        int iters = 1;
+        {
+            sym_gemm<KT, WPM>(sub, Y, T, fo, acc);
+            ns_sync<WPM>(bar_id);
+            store_tiles<KT, WPM>(sub, Y, acc, sg, 0.0, lane);
+            ns_sync<WPM>(bar_id);
+            const double m = g * lo;
+            lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
+        }
+        for (; iters < 64; ++iters) {
+            const bool last = (1.0 - lo) < 2e-8;
+            g = 3.0 / (1.0 + sqrt(lo) + lo);
+            sg = sqrt(g);
+            sym_gemm<KT, WPM>(sub, Z, Y, fo, acc);                    // M = Z Y
+            store_tiles<KT, WPM>(sub, T, acc, -0.5 * g, 1.5, lane);   // T = (3 I - g M) / 2
+            ns_sync<WPM>(bar_id);
+            sym_gemm<KT, WPM>(sub, T, Z, fo, acc);                    // Z' = sqrt(g) T Z
+            ns_sync<WPM>(bar_id);
+            store_tiles<KT, WPM>(sub, Z, acc, sg, 0.0, lane);
+            if (last) break;
+            sym_gemm<KT, WPM>(sub, Y, T, fo, acc);                    // Y' = sqrt(g) Y T
+            ns_sync<WPM>(bar_id);
+            store_tiles<KT, WPM>(sub, Y, acc, sg, 0.0, lane);
+            ns_sync<WPM>(bar_id);
+            const double m = g * lo;
+            lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
+        }
         ns_sync<WPM>(bar_id);
-        const double m = g * lo;
-        lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
+        return iters + 1;
+    };
+    double* D = Y;                      // dense A^(-1/2), over the Y | T buffers
+    int iters;
+    const bool stiff_path = !(scratch == nullptr || s <= P.stiff * alpha);
+    if (!stiff_path) {
+        // ---- one level: D = A^(-1/2) = Z / sqrt(s) ---------------------------------------------------------------------
+        iters = inv_sqrt(0.0, s, alpha);
+        const double zs = sqrt(1.0 / s);
+        for (int e = gtid; e < k * k; e += GT) {
+            const int i = e / k, j = e - i * k;
+            D[i * LDW + j] = sym_get(Z, i, j) * zs;
+        }
+    } else {
+        // ---- stiff matrix (s / a above P.stiff): two levels.  Every product of the iteration is stored as a symmetric matrix
+        // (lower-triangle tiles); the rounding-level commutators this discards are amplified from one iteration to the next,
+        // which is harmless up to ~8 iterations (s / a of a few thousand: error ~1e-12) and ruinous beyond (1e-7 at 1e4, no
+        // correct digit at 1e5).  So the spectrum is split with an intermediate shift a1, a < a1 < s:
+        //     B = (C + a1 I)^(-1/2)              spectrum ratio s / a1
+        //     E = B A B                          a congruence: symmetric, the error of B enters multiplicatively, spectrum
+        //                                        (l + a) / (l + a1) in [a / a1, 1)
+        //     A^(-1/2) = sym(E^(-1/2) B)         B and E are functions of C, so the product is symmetric up to rounding
+        // The error of B enters E relative to B's own conditioning, sqrt(s / a1), so the first level gets the smaller share of the
+        // ratio: s / a1 = max(30, sqrt(s / a) / 2), a1 / a = the rest.  Measured error of A^(-1/2): < 1e-11 up to s / a = 1e5,
+        // ~1e-10 at 5e6 (where the eigendecomposition route itself is no better).  A, B and one full-grid temporary live in
+        // global scratch.
+        double* gA = scratch;
+        double* gB = gA + MAT;
+        double* gF = gB + MAT;
+        for (int e = gtid; e < MAT; e += GT) gA[e] = Y[e];
+        const double a1 = s / fmax(30.0, 0.5 * sqrt(s / alpha));
+        const double shift = a1 - alpha;
+        const double s1 = (s + shift) * (1.0 + 1e-12);
+        iters = inv_sqrt(shift, s1, a1);
+        const double zs1 = sqrt(1.0 / s1);
+        for (int e = gtid; e < MAT; e += GT) gB[e] = Z[e] * zs1;
+        ns_sync<WPM>(bar_id);
+        sym_gemm<KT, WPM, kOpSymG, kOpSymG>(sub, gA, gB, fo, acc);    // W = A B: lower tiles, then the upper ones as lower(B A)^T
+        store_full<KT, WPM, false>(sub, gF, acc, lane);
+        sym_gemm<KT, WPM, kOpSymG, kOpSymG>(sub, gB, gA, fo, acc);
+        store_full<KT, WPM, true>(sub, gF, acc, lane);
+        ns_sync<WPM>(bar_id);
+        sym_gemm<KT, WPM, kOpSymG, kOpFullG>(sub, gB, gF, fo, acc);   // E = B W (padding rows and columns are exactly 0)
+        store_tiles<KT, WPM>(sub, Y, acc, 1.0, 0.0, lane);
+        ns_sync<WPM>(bar_id);
+        const double s2 = 1.0 + 1e-9;
+        iters += inv_sqrt(0.0, s2, (alpha / a1) * (1.0 - 1e-9));
+        sym_gemm<KT, WPM, kOpSym, kOpSymG>(sub, Z, gB, fo, acc);      // F = E^(-1/2) B, full, over W
+        store_full<KT, WPM, false>(sub, gF, acc, lane);
+        sym_gemm<KT, WPM, kOpSymG, kOpSym>(sub, gB, Z, fo, acc);
+        store_full<KT, WPM, true>(sub, gF, acc, lane);
+        ns_sync<WPM>(bar_id);
+        const double zs = 0.5 * sqrt(1.0 / s2);
+        for (int e = gtid; e < k * k; e += GT) {
+            const int i = e / k, j = e - i * k;
+            const double fij = __ldcg(gF + ((i >> 3) * KT + (j >> 3)) * 64 + tile_elem(i & 7, j & 7));
+            const double fji = __ldcg(gF + ((j >> 3) * KT + (i >> 3)) * 64 + tile_elem(j & 7, i & 7));
+            D[i * LDW + j] = (fij + fji) * zs;
+        }
     }
-    // ---- iterations 1.. ----------------------------------------------------------------------------------------------
-    for (; iters < 64; ++iters) {
-        const bool last = (1.0 - lo) < 2e-8;
-        g = 3.0 / (1.0 + sqrt(lo) + lo);
-        sg = sqrt(g);
-        sym_gemm<KT, WPM>(sub, Z, Y, fo, acc);                    // M = Z Y
-        store_tiles<KT, WPM>(sub, T, acc, -0.5 * g, 1.5, lane);   // T = (3 I - g M) / 2
-        ns_sync<WPM>(bar_id);
-        sym_gemm<KT, WPM>(sub, T, Z, fo, acc);                    // Z' = sqrt(g) T Z
-        ns_sync<WPM>(bar_id);
-        store_tiles<KT, WPM>(sub, Z, acc, sg, 0.0, lane);
-        if (last) break;
-        sym_gemm<KT, WPM>(sub, Y, T, fo, acc);                    // Y' = sqrt(g) Y T
-        ns_sync<WPM>(bar_id);
-        store_tiles<KT, WPM>(sub, Y, acc, sg, 0.0, lane);
-        ns_sync<WPM>(bar_id);
-        const double m = g * lo;
-        lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
-    }
-    ns_sync<WPM>(bar_id);
-    if (P.stats && gtid == 0) { atomicAdd(P.stats + 2, (unsigned long long)(iters + 1)); atomicAdd(P.stats + 3, 1ull); }
-    // ---- D = A^(-1/2) = Z / sqrt(s), dense, over the Y | T buffers -------------------------------------------------------
-    double* D = Y;
-    const double zs = sqrt(inv_s);
-    for (int e = gtid; e < k * k; e += GT) {
-        const int i = e / k, j = e - i * k;
-        D[i * LDW + j] = sym_get(Z, i, j) * zs;
-    }
+    if (P.stats && gtid == 0) { atomicAdd(P.stats + 2, (unsigned long long)iters); atomicAdd(P.stats + 3, 1ull); }
     ns_sync<WPM>(bar_id);
     for (int i = gtid; i < k; i += GT) {                          // u = D b
         double a = 0.0;
@@ -319,6 +437,30 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         wbar[i] = a;
     }
     ns_sync<WPM>(bar_id);
+    // ---- iterative refinement of w_mean against the Gram in global memory.  D carries an unstructured error e |D|; through
+    // w_mean = D D b with |b| ~ lambda_max it becomes e * (lambda_max / a) in w_mean.  One residual step with the exact A
+    // removes it (contraction e * s / a per step); two steps on the two-level path, none when s / a is small anyway.
+    const int n_refine = stiff_path ? 2 : (s > 64.0 * alpha ? 1 : 0);
+    for (int it = 0; it < n_refine; ++it) {
+        for (int i = gtid; i < k; i += GT) {                      // r = b - A w_mean
+            double a = fma(-alpha, wbar[i], bvec[i]);
+            for (int j = 0; j < k; ++j) a = fma(-sym_get(gC, i, j), wbar[j], a);
+            xbuf[i] = a;
+        }
+        ns_sync<WPM>(bar_id);
+        for (int i = gtid; i < k; i += GT) {
+            double a = 0.0;
+            for (int j = 0; j < k; ++j) a = fma(D[i * LDW + j], xbuf[j], a);
+            uvec[i] = a;
+        }
+        ns_sync<WPM>(bar_id);
+        for (int i = gtid; i < k; i += GT) {
+            double a = 0.0;
+            for (int j = 0; j < k; ++j) a = fma(D[i * LDW + j], uvec[j], a);
+            wbar[i] += a;
+        }
+        ns_sync<WPM>(bar_id);
+    }
     const double sk = sqrt((double)(k - 1));
     const int64_t gi = P.gpos[P.slot_base + slot].id;
     const int f32 = P.io_f32;
@@ -359,6 +501,7 @@ __global__ void __launch_bounds__(GROUPS * WPM * 32, 1) k_letkf_solve_ns(const N
     double* T = base + 2 * Cfg::MAT;
     double* vec = base + 3 * Cfg::MAT;
     const int bar_id = 1 + group;
+    double* scratch = P.scratch ? P.scratch + ((size_t)blockIdx.x * GROUPS + group) * ns_scratch_doubles(KT) : nullptr;
     const long long t0 = clock64();
     while (true) {
         long long slot;
@@ -373,7 +516,7 @@ __global__ void __launch_bounds__(GROUPS * WPM * 32, 1) k_letkf_solve_ns(const N
             ns_sync<WPM>(bar_id);
         }
         if (slot >= P.n_slots) break;
-        ns_solve_one<KT, WPM>(P, slot, Z, Y, T, vec, gtid, sub, lane, bar_id);
+        ns_solve_one<KT, WPM>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id);
     }
     if (P.stats && tid == 0) atomicAdd(P.stats + 1, (unsigned long long)(clock64() - t0));
 }
