@@ -1,0 +1,10 @@
+set -x
+mkdir -p gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r22_launches_etkf.csv python tools/bench_etkf.py --steps 1 --warmup 1 > gpurun_out/r22_ncu.log 2>&1
+python - <<'PY'
+import csv
+rows=[r for r in csv.reader(open("gpurun_out/r22_launches_etkf.csv")) if len(r)>10]
+hdr=rows[0]; ki=hdr.index("Kernel Name"); vi=hdr.index("Metric Value"); ui=hdr.index("Metric Unit")
+for r in rows[1:]:
+    print(r[ki][:70], r[vi], r[ui])
+PY

@@ -63,8 +63,14 @@ constexpr int kMaxKt = 17;
 template <int KT>
 static int launch_etkf_gram(int f32, const void* yn, const void* d, int64_t m, int64_t ld, int k, int ncta, int64_t chunk,
                             double* partial, cudaStream_t st) {
-    if (f32) k_etkf_gram<float, KT><<<ncta, kEtkfWarps * 32, 0, st>>>((const float*)yn, (const float*)d, m, ld, k, chunk, partial);
-    else k_etkf_gram<double, KT><<<ncta, kEtkfWarps * 32, 0, st>>>((const double*)yn, (const double*)d, m, ld, k, chunk, partial);
+    const size_t smem = sizeof(double) * (size_t)KT * 8 * kEtkfLd;
+    if (f32) {
+        B200DA_CUDA(cudaFuncSetAttribute(k_etkf_gram<float, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_etkf_gram<float, KT><<<ncta, kEtkfWarps * 32, smem, st>>>((const float*)yn, (const float*)d, m, ld, k, chunk, partial);
+    } else {
+        B200DA_CUDA(cudaFuncSetAttribute(k_etkf_gram<double, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_etkf_gram<double, KT><<<ncta, kEtkfWarps * 32, smem, st>>>((const double*)yn, (const double*)d, m, ld, k, chunk, partial);
+    }
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
@@ -488,7 +494,7 @@ static int etkf_partial_grams(b200da_plan* pl, const void* Yn, const void* d, in
     int64_t chunk = 4;
     if (m > 0) {
         ncta = (int)std::min<int64_t>(148 * 2, (m + 255) / 256);
-        chunk = ((m + ncta - 1) / ncta + 3) / 4 * 4;
+        chunk = ((m + ncta - 1) / ncta + kEtkfTileObs - 1) / kEtkfTileObs * kEtkfTileObs;
         ncta = (int)((m + chunk - 1) / chunk);
     }
     int rc;

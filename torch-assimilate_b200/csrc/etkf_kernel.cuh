@@ -9,9 +9,36 @@ namespace b200da {
 
 constexpr int kEtkfWarps = 8;
 
-// Partial Gram of [Yn; d] over a chunk of observations per CTA; the lower-triangle tiles are split over the
-// CTA's warps.  ld = row stride of Yn (== m_obs for a whole array, the global M for a column shard of it).  Yn is read in the reference layout (k, M) directly: a DMMA fragment is 4 consecutive
-// observations of 8 members = eight 32-byte sectors.
+// Partial Gram of [Yn; d] over a chunk of observations per CTA; the lower-triangle tiles are split over the CTA's warps.
+// ld = row stride of Yn (== m_obs for a whole array, the global M for a column shard of it).
+// Yn is read in the reference layout (k, M) with coalesced row segments: a tile of kEtkfTileObs observations x (k + 1) rows
+// goes through registers into shared memory once (the next tile's loads are in flight while the tensor work on the current
+// one runs), and the eight warps take their DMMA fragments from there; every element is read from HBM exactly once.
+constexpr int kEtkfTileObs = 64;
+constexpr int kEtkfLd = kEtkfTileObs + 4;      // row stride of the staged tile in doubles: conflict-free fragment reads
+
+// the tensor work of warp SUB on one staged tile: tile t of the lower triangle is owned by warp t % kEtkfWarps and is that
+// warp's (t / kEtkfWarps)-th accumulator.  SUB is a template parameter so that only the warp's own DMMAs are in its
+// instruction stream (a run-time ownership test turns the other 7/8 into predicated-off tensor instructions).
+template <int KT, int SUB>
+__device__ __forceinline__ void etkf_gram_tile(const double* __restrict__ tile, int nks, int lane,
+                                               double (&acc)[(KT * (KT + 1) / 2 + kEtkfWarps - 1) / kEtkfWarps][2]) {
+    for (int ks = 0; ks < nks; ++ks) {
+        const double* fr = tile + (lane >> 2) * kEtkfLd + ks * 4 + (lane & 3);
+        double f[KT];
+#pragma unroll
+        for (int t = 0; t < KT; ++t) f[t] = fr[t * 8 * kEtkfLd];
+        int idx = 0;
+#pragma unroll
+        for (int mt = 0; mt < KT; ++mt) {
+#pragma unroll
+            for (int nt = 0; nt <= mt; ++nt) {
+                if (idx % kEtkfWarps == SUB) dmma884(acc[idx / kEtkfWarps][0], acc[idx / kEtkfWarps][1], f[mt], f[nt]);
+                ++idx;
+            }
+        }
+    }
+}
 template <typename T, int KT>
 __global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const T* __restrict__ yn, const T* __restrict__ d,
                                                                int64_t m_obs, int64_t ld, int k, int64_t chunk,
@@ -19,34 +46,54 @@ __global__ void __launch_bounds__(kEtkfWarps * 32) k_etkf_gram(const T* __restri
     constexpr int NTILES = KT * (KT + 1) / 2;
     constexpr int ACC = (NTILES + kEtkfWarps - 1) / kEtkfWarps;
     constexpr int KP = KT * 8;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NT = kEtkfWarps * 32;
+    constexpr int PRE = (KP * kEtkfTileObs + NT - 1) / NT;      // staged elements per thread and tile
+    extern __shared__ double etkf_tile[];                       // [KP][kEtkfLd]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double acc[ACC][2];
 #pragma unroll
     for (int i = 0; i < ACC; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
     const int64_t j0 = (int64_t)blockIdx.x * chunk;
     const int64_t j1 = min(j0 + chunk, m_obs);
-    for (int64_t jb = j0; jb < j1; jb += 4) {
-        const int64_t j = jb + (lane & 3);
-        double f[KT];
+    T pre[PRE];
+    auto fetch = [&](int64_t jb) {          // element e = row * 64 + obs: consecutive threads read consecutive observations
 #pragma unroll
-        for (int t = 0; t < KT; ++t) {
-            const int mem = t * 8 + (lane >> 2);
-            double v = 0.0;
-            if (j < j1) {
-                if (mem < k) v = (double)yn[(int64_t)mem * ld + j];
-                else if (mem == k) v = (double)d[j];
+        for (int i = 0; i < PRE; ++i) {
+            const int e = tid + i * NT;
+            const int row = e / kEtkfTileObs, o = e - row * kEtkfTileObs;
+            const int64_t j = jb + o;
+            T v = (T)0;
+            if (e < KP * kEtkfTileObs && j < j1) {
+                if (row < k) v = yn[(int64_t)row * ld + j];
+                else if (row == k) v = d[j];
             }
-            f[t] = v;
+            pre[i] = v;
         }
-        // runtime ownership: tile t is owned by warp t % kEtkfWarps and is that warp's (t / kEtkfWarps)-th accumulator
-        int idx = 0;
+    };
+    auto stash = [&]() {
 #pragma unroll
-        for (int mt = 0; mt < KT; ++mt) {
-#pragma unroll
-            for (int nt = 0; nt <= mt; ++nt) {
-                if (idx % kEtkfWarps == warp) dmma884(acc[idx / kEtkfWarps][0], acc[idx / kEtkfWarps][1], f[mt], f[nt]);
-                ++idx;
-            }
+        for (int i = 0; i < PRE; ++i) {
+            const int e = tid + i * NT;
+            const int row = e / kEtkfTileObs, o = e - row * kEtkfTileObs;
+            if (e < KP * kEtkfTileObs) etkf_tile[row * kEtkfLd + o] = (double)pre[i];
+        }
+    };
+    if (j0 < j1) fetch(j0);
+    for (int64_t jb = j0; jb < j1; jb += kEtkfTileObs) {
+        __syncthreads();                    // the previous tile has been consumed
+        stash();
+        __syncthreads();
+        if (jb + kEtkfTileObs < j1) fetch(jb + kEtkfTileObs);
+        const int nks = (int)min((int64_t)kEtkfTileObs, j1 - jb + 3) / 4;
+        switch (warp) {
+            case 0: etkf_gram_tile<KT, 0>(etkf_tile, nks, lane, acc); break;
+            case 1: etkf_gram_tile<KT, 1>(etkf_tile, nks, lane, acc); break;
+            case 2: etkf_gram_tile<KT, 2>(etkf_tile, nks, lane, acc); break;
+            case 3: etkf_gram_tile<KT, 3>(etkf_tile, nks, lane, acc); break;
+            case 4: etkf_gram_tile<KT, 4>(etkf_tile, nks, lane, acc); break;
+            case 5: etkf_gram_tile<KT, 5>(etkf_tile, nks, lane, acc); break;
+            case 6: etkf_gram_tile<KT, 6>(etkf_tile, nks, lane, acc); break;
+            default: etkf_gram_tile<KT, 7>(etkf_tile, nks, lane, acc); break;
         }
     }
     double* out = partial + (size_t)blockIdx.x * KP * KP;
