@@ -174,7 +174,29 @@ def measure_fp64_peak(torch, seconds=1.5):
     return flops / best * 1e-9, flops * reps / e0.elapsed_time(e1) * 1e-9
 
 
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """Keep the real stdout for the ONE JSON line and send everything else that writes to fd 1 (the NCCL version banner,
+    library chatter of child processes) to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    payload = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(payload.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, payload)
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -214,7 +236,7 @@ def main():
                 "cpu_baseline": info,
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        _emit(line)
         return
 
     # ------------------------------------------------------------------------------------------------------------
@@ -235,6 +257,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL writes its version banner to STDOUT when NCCL_DEBUG is VERSION: keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     k = w["k"]
@@ -461,7 +486,7 @@ def main():
         }
         if cpu_info is not None:
             line["cpu_baseline"] = cpu_info
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -93,6 +93,9 @@ def main_sharded(args, world):
     from pytassim_b200.parallel import ShardedETKF
     rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # NCCL writes its version banner to STDOUT when NCCL_DEBUG is VERSION: keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     tdt = torch.float64 if args.dtype == "f64" else torch.float32
     k, n, m = args.k, args.n_grid, args.n_obs

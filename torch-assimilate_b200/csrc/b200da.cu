@@ -92,13 +92,20 @@ static int launch_apply_global(int f32, const void* x, const void* w, int k, int
     const int vec_ok = ((ld * (int64_t)esz) % (2 * esz) == 0 && (reinterpret_cast<uintptr_t>(xa) % (2 * esz)) == 0) ? 1 : 0;
     const size_t smem = sizeof(double) * (size_t)MT * 8 * apply_lda(k);
     if (smem > kMaxSmem - 2048) return B200DA_ERR_UNSUPPORTED;
-    const int64_t n_chunks = (n_grid + kApplyNTW * 8 - 1) / (kApplyNTW * 8);
-    const int grid = (int)std::min<int64_t>((n_chunks + kApplyWarps - 1) / kApplyWarps, 148 * 2);
+    const int ntw = f32 ? apply_ntw<float>(MT) : apply_ntw<double>(MT);
+    const int64_t n_chunks = (n_grid + ntw * 8 - 1) / (ntw * 8);
+    int occ = 1;
     if (f32) {
         B200DA_CUDA(cudaFuncSetAttribute(k_apply_global<float, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_apply_global<float, MT><<<grid, kApplyWarps * 32, smem, st>>>((const float*)x, (const float*)w, k, n_rows, n_grid, ld, vec_ok, (float*)xa);
+        B200DA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_apply_global<float, MT>, kApplyWarps * 32, smem));
     } else {
         B200DA_CUDA(cudaFuncSetAttribute(k_apply_global<double, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200DA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_apply_global<double, MT>, kApplyWarps * 32, smem));
+    }
+    const int grid = (int)std::min<int64_t>((n_chunks + kApplyWarps - 1) / kApplyWarps, 148 * (int64_t)std::max(occ, 1));
+    if (f32) {
+        k_apply_global<float, MT><<<grid, kApplyWarps * 32, smem, st>>>((const float*)x, (const float*)w, k, n_rows, n_grid, ld, vec_ok, (float*)xa);
+    } else {
         k_apply_global<double, MT><<<grid, kApplyWarps * 32, smem, st>>>((const double*)x, (const double*)w, k, n_rows, n_grid, ld, vec_ok, (double*)xa);
     }
     B200DA_LAUNCH_CHECK();

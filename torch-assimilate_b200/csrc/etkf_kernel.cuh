@@ -217,15 +217,21 @@ __global__ void __launch_bounds__(128) k_apply_weights(const T* __restrict__ x, 
 // 2 k^2 per state element.  n_grid columns are processed; ld is the row stride of x / xa (== n_grid for a whole state,
 // the global N for a column shard of it); vec_ok: rows are 16-byte aligned, so the 2-element stores may be vectorised.
 constexpr int kApplyWarps = 8;
-constexpr int kApplyNTW = 2;            // 8-point column tiles per warp
+// 8-point column tiles per warp: two while the accumulators (MT x NTW x 2 doubles) leave room for >= 2 CTAs per SM, one for
+// large ensembles (k > 64: with two tiles the kernel needs 165 registers, one 256-thread CTA per SM, and the loads of X are
+// not hidden: ncu long-scoreboard 4.1 per issue, DMMA pipe 67 %)
+// (measured at cfg4: FP64 8.42 -> 8.26 ms with one tile and 2 CTAs per SM; FP32 plans keep two tiles: 8.6 vs 9.4 ms)
+template <typename T> __host__ __device__ constexpr int apply_ntw(int mt) { return (sizeof(T) == 8 && mt > 8) ? 1 : 2; }
+template <typename T> __host__ __device__ constexpr int apply_min_ctas(int mt) { return (apply_ntw<T>(mt) == 2 && mt > 8) ? 0 : 2; }   // 0: no occupancy request
 __host__ __device__ inline int apply_lda(int k) {          // leading dimension of W'^T in shared memory: == 4 (mod 16) doubles
     int lda = (k + 3) & ~3;
     while ((lda & 15) != 4) lda += 4;
     return lda;
 }
 template <typename T, int MT>
-__global__ void __launch_bounds__(kApplyWarps * 32) k_apply_global(const T* __restrict__ x, const T* __restrict__ w, int k, int n_rows,
+__global__ void __launch_bounds__(kApplyWarps * 32, apply_min_ctas<T>(MT)) k_apply_global(const T* __restrict__ x, const T* __restrict__ w, int k, int n_rows,
                                                                  int64_t n_grid, int64_t ld, int vec_ok, T* __restrict__ xa) {
+    constexpr int kApplyNTW = apply_ntw<T>(MT);
     extern __shared__ double wsm_raw[];
     double* At = wsm_raw;                                   // [MT * 8][lda]: At[j][i] = W'[i][j]
     __shared__ double colsum[MT * 8];
