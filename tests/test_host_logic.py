@@ -294,3 +294,13 @@ def test_forward_model_builds_the_pseudo_state(golden):
         return model_state, xrlite.DataArray(model_state.values, {}, ("v", "time", "ensemble", "grid"))
     with pytest.raises(StateError):
         ETKF(forward_model=bad_model).get_pseudo_state(None, state)
+
+
+def test_position_operator():
+    from pytassim_b200.obs_ops import PositionOperator
+    rng, t, state = _operator_objects()
+    op = PositionOperator([3, 3, 39])
+    obs = _obs_for(rng, t[:1], [0., 1., 2.])
+    np.testing.assert_array_equal(op(obs, state).values, state.values[1][:1][:, :, [3, 3, 39]])
+    with pytest.raises(IndexError):
+        PositionOperator([40])(_obs_for(rng, t[:1], [0.]), state)

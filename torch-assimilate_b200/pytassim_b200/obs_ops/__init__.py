@@ -16,7 +16,7 @@ import pandas as pd
 
 from ..xrlite import DataArray
 
-__all__ = ["GridSelectOperator", "IdentityOperator", "NearestGridOperator"]
+__all__ = ["GridSelectOperator", "IdentityOperator", "NearestGridOperator", "PositionOperator"]
 
 
 class GridSelectOperator(object):
@@ -115,3 +115,18 @@ class NearestGridOperator(GridSelectOperator):
 
     def grid_positions(self, grid_index):
         return pd.Index(grid_index).get_indexer(self.obs_grid, method='nearest')
+
+
+class PositionOperator(GridSelectOperator):
+    """Selection by precomputed integer grid POSITIONS (not labels), e.g. the nearest-neighbour indices a KD-tree lookup
+    returns (the pattern of obs_ops/terrsysmp/cos_t2m.py:137-143 without its lapse-rate correction)."""
+
+    def __init__(self, positions, var_name='x'):
+        positions = np.asarray(positions, dtype=np.int64)
+        super().__init__(len_grid=None, var_name=var_name)
+        self.positions = positions
+
+    def grid_positions(self, grid_index):
+        if self.positions.size and (self.positions.min() < 0 or self.positions.max() >= len(grid_index)):
+            raise IndexError("grid position outside the state grid")
+        return self.positions
