@@ -41,11 +41,11 @@ def main():
     ogrid = pd.MultiIndex.from_arrays([data["obs_rows"][:, 1], data["obs_rows"][:, 2]], names=["lat", "lon"])
     state = xrlite.DataArray(data["state"], dict(var_name=["x"], time=t, ensemble=np.arange(args.k), grid=grid),
                              ("var_name", "time", "ensemble", "grid"))
-    rnd = np.random.RandomState(7)
+    y = np.random.RandomState(7).normal(size=(1, m))
 
     def observations(device):
         ds = xrlite.Dataset({
-            "observations": xrlite.DataArray(rnd.normal(size=(1, m)), dict(time=t, obs_grid_1=ogrid), ("time", "obs_grid_1")),
+            "observations": xrlite.DataArray(y, dict(time=t, obs_grid_1=ogrid), ("time", "obs_grid_1")),
             "covariance": xrlite.DataArray(np.ones(m), dict(obs_grid_1=ogrid), ("obs_grid_1",))})
         op = PositionOperator(data["h_index"])
         ds.obs.operator = op if device else (lambda o, s: op(o, s))

@@ -8,10 +8,19 @@ namespace b200da {
 
 // ---- tensor-core solve (ns_solve_kernel.cuh): warps per matrix and matrices per CTA by ensemble size ----------------
 template <int KT> struct NsPick {
+#ifdef B200DA_NS_WPM1
     static constexpr int WPM = KT <= 7 ? 1 : (KT <= 10 ? 2 : 4);
+    static constexpr int MAXW = 8;
+#else
+    // two warps per matrix from k > 40 on: with one warp per matrix only 5 (k = 50) warps fit next to their matrices in shared
+    // memory and the DMMA pipe idles half of the time (ncu: 53 %); splitting the tiles of a matrix over two warps doubles the
+    // warps per scheduler at the same shared-memory footprint (cfg3 solve 225 -> 192 ms; k = 40: 6.0 -> 6.3 ms, so not there)
+    static constexpr int WPM = KT <= 5 ? 1 : (KT <= 10 ? 2 : 4);
+    static constexpr int MAXW = WPM == 1 ? 8 : 16;
+#endif
     static constexpr size_t GB = NsCfg<KT, WPM>::GROUP_BYTES;
     static constexpr int FIT = (int)((kMaxSmem - 1024) / GB);
-    static constexpr int GROUPS = FIT * WPM >= 8 ? 8 / WPM : (FIT < 1 ? 1 : FIT);
+    static constexpr int GROUPS = FIT * WPM >= MAXW ? MAXW / WPM : (FIT < 1 ? 1 : FIT);
 };
 
 template <int KT>
@@ -26,6 +35,7 @@ static int launch_ns(const NsParams& P, cudaStream_t st) {
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
+#ifndef B200DA_NS_LARGE
 template <int KT> static size_t scratch_bytes() { return sizeof(double) * ns_scratch_doubles(KT) * (size_t)NsPick<KT>::GROUPS * 148; }
 #define B200DA_NSS_CASE(KT) case KT: return scratch_bytes<KT>();
 size_t ns_scratch_bytes(int kts) {
@@ -36,14 +46,32 @@ size_t ns_scratch_bytes(int kts) {
         default: return 0;
     }
 }
+#endif
 #define B200DA_NS_CASE(KT) case KT: return launch_ns<KT>(P, st);
+#ifndef B200DA_NS_LARGE
+int dispatch_ns_large(int kts, const NsParams& P, cudaStream_t st);      // ns_launch_b.cu: 11 <= kts <= 16
 int dispatch_ns(int kts, const NsParams& P, cudaStream_t st) {
     switch (kts) {
         B200DA_NS_CASE(1) B200DA_NS_CASE(2) B200DA_NS_CASE(3) B200DA_NS_CASE(4) B200DA_NS_CASE(5) B200DA_NS_CASE(6)
-        B200DA_NS_CASE(7) B200DA_NS_CASE(8) B200DA_NS_CASE(9) B200DA_NS_CASE(10) B200DA_NS_CASE(11) B200DA_NS_CASE(12)
-        B200DA_NS_CASE(13) B200DA_NS_CASE(14) B200DA_NS_CASE(15) B200DA_NS_CASE(16)
+        B200DA_NS_CASE(7) B200DA_NS_CASE(8) B200DA_NS_CASE(9) B200DA_NS_CASE(10)
+        default: return dispatch_ns_large(kts, P, st);
+    }
+}
+#elif B200DA_NS_LARGE == 1
+int dispatch_ns_large2(int kts, const NsParams& P, cudaStream_t st);     // ns_launch_c.cu: 14 <= kts <= 16
+int dispatch_ns_large(int kts, const NsParams& P, cudaStream_t st) {
+    switch (kts) {
+        B200DA_NS_CASE(11) B200DA_NS_CASE(12) B200DA_NS_CASE(13)
+        default: return dispatch_ns_large2(kts, P, st);
+    }
+}
+#else
+int dispatch_ns_large2(int kts, const NsParams& P, cudaStream_t st) {
+    switch (kts) {
+        B200DA_NS_CASE(14) B200DA_NS_CASE(15) B200DA_NS_CASE(16)
         default: return B200DA_ERR_UNSUPPORTED;
     }
 }
+#endif
 
 }  // namespace b200da

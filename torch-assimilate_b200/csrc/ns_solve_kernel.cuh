@@ -255,8 +255,11 @@ __device__ __forceinline__ void ns_sync(int bar_id) {
     else asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(WPM * 32) : "memory");
 }
 
+// SUB (the warp's index inside its group) is a template parameter: with a run-time index every product call is a branch over
+// WPM instantiations that all write the accumulator array, which the compiler then keeps in local memory (measured: ~700
+// LDL/STL.128 in the two-warp kernel).
 // One matrix: everything between "augmented Gram in global memory" and "analysis columns written".
-template <int KT, int WPM>
+template <int KT, int WPM, int SUB>
 __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict__ Z, double* __restrict__ Y,
                              double* __restrict__ T, double* __restrict__ vec, double* scratch, int gtid, int sub, int lane,
                              int bar_id) {
@@ -337,9 +340,9 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         ns_sync<WPM>(bar_id);
         int iters = 1;
         {
-            sym_gemm<KT, WPM>(sub, Y, T, fo, acc);
+            sym_gemm_sub<KT, WPM, SUB>(Y, T, fo, acc);
             ns_sync<WPM>(bar_id);
-            store_tiles<KT, WPM>(sub, Y, acc, sg, 0.0, lane);
+            store_tiles_sub<KT, WPM, SUB>(Y, acc, sg, 0.0, lane);
             ns_sync<WPM>(bar_id);
             const double m = g * lo;
             lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
@@ -348,16 +351,16 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
             const bool last = (1.0 - lo) < 2e-8;
             g = 3.0 / (1.0 + sqrt(lo) + lo);
             sg = sqrt(g);
-            sym_gemm<KT, WPM>(sub, Z, Y, fo, acc);                    // M = Z Y
-            store_tiles<KT, WPM>(sub, T, acc, -0.5 * g, 1.5, lane);   // T = (3 I - g M) / 2
+            sym_gemm_sub<KT, WPM, SUB>(Z, Y, fo, acc);                    // M = Z Y
+            store_tiles_sub<KT, WPM, SUB>(T, acc, -0.5 * g, 1.5, lane);   // T = (3 I - g M) / 2
             ns_sync<WPM>(bar_id);
-            sym_gemm<KT, WPM>(sub, T, Z, fo, acc);                    // Z' = sqrt(g) T Z
+            sym_gemm_sub<KT, WPM, SUB>(T, Z, fo, acc);                    // Z' = sqrt(g) T Z
             ns_sync<WPM>(bar_id);
-            store_tiles<KT, WPM>(sub, Z, acc, sg, 0.0, lane);
+            store_tiles_sub<KT, WPM, SUB>(Z, acc, sg, 0.0, lane);
             if (last) break;
-            sym_gemm<KT, WPM>(sub, Y, T, fo, acc);                    // Y' = sqrt(g) Y T
+            sym_gemm_sub<KT, WPM, SUB>(Y, T, fo, acc);                    // Y' = sqrt(g) Y T
             ns_sync<WPM>(bar_id);
-            store_tiles<KT, WPM>(sub, Y, acc, sg, 0.0, lane);
+            store_tiles_sub<KT, WPM, SUB>(Y, acc, sg, 0.0, lane);
             ns_sync<WPM>(bar_id);
             const double m = g * lo;
             lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
@@ -400,20 +403,20 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         const double zs1 = sqrt(1.0 / s1);
         for (int e = gtid; e < MAT; e += GT) gB[e] = Z[e] * zs1;
         ns_sync<WPM>(bar_id);
-        sym_gemm<KT, WPM, kOpSymG, kOpSymG>(sub, gA, gB, fo, acc);    // W = A B: lower tiles, then the upper ones as lower(B A)^T
-        store_full<KT, WPM, false>(sub, gF, acc, lane);
-        sym_gemm<KT, WPM, kOpSymG, kOpSymG>(sub, gB, gA, fo, acc);
-        store_full<KT, WPM, true>(sub, gF, acc, lane);
+        sym_gemm_sub<KT, WPM, SUB, kOpSymG, kOpSymG>(gA, gB, fo, acc);    // W = A B: lower tiles, then the upper ones as lower(B A)^T
+        store_full_sub<KT, WPM, SUB, false>(gF, acc, lane);
+        sym_gemm_sub<KT, WPM, SUB, kOpSymG, kOpSymG>(gB, gA, fo, acc);
+        store_full_sub<KT, WPM, SUB, true>(gF, acc, lane);
         ns_sync<WPM>(bar_id);
-        sym_gemm<KT, WPM, kOpSymG, kOpFullG>(sub, gB, gF, fo, acc);   // E = B W (padding rows and columns are exactly 0)
-        store_tiles<KT, WPM>(sub, Y, acc, 1.0, 0.0, lane);
+        sym_gemm_sub<KT, WPM, SUB, kOpSymG, kOpFullG>(gB, gF, fo, acc);   // E = B W (padding rows and columns are exactly 0)
+        store_tiles_sub<KT, WPM, SUB>(Y, acc, 1.0, 0.0, lane);
         ns_sync<WPM>(bar_id);
         const double s2 = 1.0 + 1e-9;
         iters += inv_sqrt(0.0, s2, (alpha / a1) * (1.0 - 1e-9));
-        sym_gemm<KT, WPM, kOpSym, kOpSymG>(sub, Z, gB, fo, acc);      // F = E^(-1/2) B, full, over W
-        store_full<KT, WPM, false>(sub, gF, acc, lane);
-        sym_gemm<KT, WPM, kOpSymG, kOpSym>(sub, gB, Z, fo, acc);
-        store_full<KT, WPM, true>(sub, gF, acc, lane);
+        sym_gemm_sub<KT, WPM, SUB, kOpSym, kOpSymG>(Z, gB, fo, acc);      // F = E^(-1/2) B, full, over W
+        store_full_sub<KT, WPM, SUB, false>(gF, acc, lane);
+        sym_gemm_sub<KT, WPM, SUB, kOpSymG, kOpSym>(gB, Z, fo, acc);
+        store_full_sub<KT, WPM, SUB, true>(gF, acc, lane);
         ns_sync<WPM>(bar_id);
         const double zs = 0.5 * sqrt(1.0 / s2);
         for (int e = gtid; e < k * k; e += GT) {
@@ -516,7 +519,18 @@ __global__ void __launch_bounds__(GROUPS * WPM * 32, 1) k_letkf_solve_ns(const N
             ns_sync<WPM>(bar_id);
         }
         if (slot >= P.n_slots) break;
-        ns_solve_one<KT, WPM>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id);
+        if constexpr (WPM == 1) ns_solve_one<KT, 1, 0>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id);
+        else if constexpr (WPM == 2) {
+            if (sub == 0) ns_solve_one<KT, 2, 0>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id);
+            else ns_solve_one<KT, 2, 1>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id);
+        } else {
+            switch (sub) {
+                case 0: ns_solve_one<KT, 4, 0>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id); break;
+                case 1: ns_solve_one<KT, 4, 1>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id); break;
+                case 2: ns_solve_one<KT, 4, 2>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id); break;
+                default: ns_solve_one<KT, 4, 3>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id); break;
+            }
+        }
     }
     if (P.stats && tid == 0) atomicAdd(P.stats + 1, (unsigned long long)(clock64() - t0));
 }
