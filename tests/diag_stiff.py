@@ -1,4 +1,5 @@
-"""Diagnostic: LETKF weights on stiff ensemble-space problems, Newton-Schulz (two-level) and Jacobi against the oracle."""
+"""Diagnostic (test infrastructure, run by hand on the GPU box: python tests/diag_stiff.py): LETKF weights on stiff
+ensemble-space problems, Newton-Schulz (two-level) and Jacobi solver against the oracle."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
