@@ -168,3 +168,20 @@ def test_device_obs_gather_prep_fp32_and_bounds():
     assert torch.equal(yn, yn_ref) and torch.equal(d, d_ref)
     with pytest.raises(IndexError):
         eng.obs_gather_prep(xp, src + 2 * k * n, n, y, var)
+
+
+def test_letkf_with_all_ones_localization_equals_etkf(golden):
+    """test_letkf.py:79-104: ``GaspariCohn((1., 1.), dist_func=zeros)`` (two radii, one distance row: only the first radius is
+    used, gaspari_cohn.py:126-127) makes every observation local with weight 1, so the LETKF equals the global ETKF at every
+    grid point (rtol = atol = 1e-10), with a plain and with a MultiIndex grid, two observation datasets."""
+    from pytassim_b200.localization import ZeroDistance
+    g, state, obs = _fixture_objects(golden)
+    etkf_ana = ETKF().assimilate(state, (obs, obs))
+    alg = LETKF(localization=GaspariCohn((1., 1.), dist_func=ZeroDistance()), chunksize=10)
+    np.testing.assert_allclose(alg.assimilate(state, (obs, obs)).values, etkf_ana.values, **TOL)
+    mi = pd.MultiIndex.from_product((np.arange(40), [0, ]), names=['grid_point', 'height'])
+    state_mi = xrlite.DataArray(state.values, dict(var_name=state.indexes["var_name"], time=state.indexes["time"],
+                                                   ensemble=state.indexes["ensemble"], grid=mi), state.dims)
+    np.testing.assert_allclose(alg.assimilate(state_mi, (obs, obs)).values, etkf_ana.values, **TOL)
+    use, w = alg.localization.localize_obs(np.array([0., 3.]), np.column_stack([np.zeros(5), np.arange(5.)]))
+    assert use.all() and np.array_equal(w, np.ones(5))

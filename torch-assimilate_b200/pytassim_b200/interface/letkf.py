@@ -51,9 +51,14 @@ class LETKF(ETKF):
         if self.localization is None:                      # letkf.py / wrapper.py:87: plain ETKF for every grid point
             return super()._analyse_arrays(state, x, innov, perts, obs_info)
         nc = self.localization.dist_func.n_coord
-        grid_coords = index_to_array(state.indexes['grid'])             # mixin_local.py:50-69
-        if grid_coords.shape[1] < nc or obs_info.shape[1] - 1 < nc:
-            raise ValueError("the metric needs {0} coordinate column(s)".format(nc))
+        if getattr(self.localization.dist_func, 'zero_coords', False):      # ZeroDistance: every pair at distance 0
+            grid_coords = np.zeros((len(state.indexes['grid']), nc))
+            obs_coords = np.zeros((obs_info.shape[0], nc))
+        else:
+            grid_coords = index_to_array(state.indexes['grid'])             # mixin_local.py:50-69
+            if grid_coords.shape[1] < nc or obs_info.shape[1] - 1 < nc:
+                raise ValueError("the metric needs {0} coordinate column(s)".format(nc))
+            obs_coords = obs_info[:, 1:1 + nc]
         eng = self._local_engine(x.shape[1], x.shape[0], np.ascontiguousarray(grid_coords[:, :nc]))
-        eng.bin_obs(obs_info[:, 1:1 + nc], perts, innov)
+        eng.bin_obs(obs_coords, perts, innov)
         return eng.analyse(torch.as_tensor(x)).cpu().numpy()

@@ -27,6 +27,8 @@ class BaseLocalization(object):
         obs = np.asarray(getattr(obs_grid, "values", obs_grid), dtype=np.float64)
         grid = np.asarray(grid_ind, dtype=np.float64).reshape(1, -1)
         nc = self.dist_func.n_coord
+        if getattr(self.dist_func, 'zero_coords', False):
+            obs = np.zeros_like(obs[:, :1 + nc]); grid = np.zeros_like(grid[:, :1 + nc])
         eng = self._engine_for()
         eng.set_grid(grid[:, 1:1 + nc])
         m = obs.shape[0]

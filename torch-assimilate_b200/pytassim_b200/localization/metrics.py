@@ -12,7 +12,7 @@ import numpy as np
 
 from .. import _cabi
 
-__all__ = ["AbsDistance1D", "PeriodicDistance1D", "EuclideanDistance", "HaversineDistance"]
+__all__ = ["AbsDistance1D", "PeriodicDistance1D", "EuclideanDistance", "HaversineDistance", "ZeroDistance"]
 
 
 def _rows(obs_grid):
@@ -36,6 +36,18 @@ class AbsDistance1D(_Metric):
     def __call__(self, grid_ind, obs_grid):
         obs = _rows(obs_grid)
         return np.abs(np.asarray(grid_ind, dtype=np.float64)[1] - obs[:, 1])
+
+
+class ZeroDistance(_Metric):
+    """Distance 0 between every grid point and every observation: every observation is local with weight 1, the LETKF
+    degenerates to the global ETKF at every grid point.  This is the ``dist_func=lambda x, y: np.zeros(y.shape[0])`` of the
+    reference's own tests (tests/unit_tests/interface/test_letkf.py:79-104); on the device it is |x_g - x_o| with every
+    coordinate replaced by 0 (``zero_coords``)."""
+    metric_id = _cabi.METRIC_ABS1D
+    zero_coords = True
+
+    def __call__(self, grid_ind, obs_grid):
+        return np.zeros(_rows(obs_grid).shape[0])
 
 
 class PeriodicDistance1D(_Metric):
