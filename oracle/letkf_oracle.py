@@ -250,6 +250,42 @@ def etkf_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_factor: f
     return w_mean + w_perts                                       # etkf.py:102
 
 
+def ketkf_linear_estimate_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_factor: float):
+    """Reference: core/ketkf.py:69-100 with ``LinearKernel`` (kernels/linear.py:62-63: K(x, y) = x y^T).
+    normed_perts (k, p), normed_obs (1, p) -> (w_mean (k,1), w_perts (k,k), cov_analysed (k,k))."""
+    ens_size = normed_perts.shape[0]
+    reg_value = (ens_size - 1) / inf_factor                                           # ketkf.py:78
+    k_perts = normed_perts @ normed_perts.T                                           # :80
+    k_partial_mean = k_perts.mean(axis=-1, keepdims=True)                             # :81
+    k_partial_mean = k_partial_mean - k_partial_mean.mean(axis=-2, keepdims=True)     # :82-83
+    k_perts_centered = k_perts - k_perts.mean(axis=-2, keepdims=True) - k_partial_mean   # :84-85
+    evals, evects, evals_inv = evd(k_perts_centered, reg_value)                       # :87
+    cov_analysed = rev_evd(evals_inv, evects)                                         # :88
+    k_obs = normed_perts @ normed_obs.T                                               # :90
+    k_obs_centered = k_obs - k_obs.mean(axis=-2, keepdims=True)                       # :91
+    k_obs_centered = k_obs_centered - k_partial_mean                                  # :92
+    w_mean = cov_analysed @ k_obs_centered                                            # :93
+    square_root_einv = np.sqrt((ens_size - 1) * evals_inv)                            # :95
+    w_perts = rev_evd(square_root_einv, evects)                                       # :96
+    return w_mean, w_perts, cov_analysed
+
+
+def ketkf_linear_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_factor: float = 1.0) -> np.ndarray:
+    """``KETKFModule(LinearKernel).forward`` = ``ETKFModule.forward`` (core/etkf.py:79-103) with the kernelised
+    ``_estimate_weights``."""
+    normed_perts = np.asarray(normed_perts, dtype=float)
+    normed_obs = np.asarray(normed_obs, dtype=float)
+    if normed_perts.shape[-1] != normed_obs.shape[-1]:
+        raise ValueError('Observational size between ensemble ({0:d}) and observations '
+                         '({1:d}) do not match!'.format(normed_perts.shape[-1], normed_obs.shape[-1]))
+    ens_size = normed_perts.shape[-2]
+    if normed_perts.shape[-1] == 0:
+        return np.eye(ens_size) * np.sqrt(inf_factor)
+    w_mean, w_perts, _ = ketkf_linear_estimate_weights(normed_perts.reshape(-1, normed_perts.shape[-1]),
+                                                       normed_obs.reshape(1, -1), inf_factor)
+    return w_mean + w_perts
+
+
 # ----------------------------------------------------------------------------------------------
 # Per-grid-point glue  (pytassim/interface/wrapper.py)
 # ----------------------------------------------------------------------------------------------

@@ -101,6 +101,67 @@ def reference_letkf(ref, state, normed_perts, normed_obs, grid_rows, obs_rows, l
     return analysis, weights, lists, lws
 
 
+def load_reference_ketkf(ref=REF):
+    """core/ketkf.py + kernels/{utils,base_kernels,linear}.py, unchanged, by file path (after load_reference_leaves)."""
+    if "pytassim.kernels" not in sys.modules:
+        mod = types.ModuleType("pytassim.kernels"); mod.__path__ = []; sys.modules["pytassim.kernels"] = mod
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ref, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    load("pytassim.kernels.utils", "pytassim/kernels/utils.py")
+    load("pytassim.kernels.base_kernels", "pytassim/kernels/base_kernels.py")
+    linear = load("pytassim.kernels.linear", "pytassim/kernels/linear.py")
+    core = load("pytassim.core.ketkf", "pytassim/core/ketkf.py")
+    return core, linear
+
+
+def make_ketkf_golden():
+    """tests/golden/ketkf_linear.npz: KETKFModule(LinearKernel) of the reference on seeded inputs (centred and uncentred
+    perturbations, empty observations) and the localized KETKF on the reference fixtures (interface/lketkf.py path:
+    wrapper_localization(wrapper_bridge(KETKFModule)) per grid point, GaspariCohn((10.,), |grid - obs|))."""
+    ref = load_reference_leaves()
+    core, linear = load_reference_ketkf()
+    out = {}
+    rng = np.random.RandomState(1234)
+    for i, (k, p, rho) in enumerate([(2, 1, 1.0), (5, 3, 1.0), (10, 40, 1.1), (40, 38, 1.2), (50, 200, 1.05)]):
+        hx = rng.normal(size=(k, p))
+        perts = hx - hx.mean(axis=0, keepdims=True)
+        obs = rng.normal(size=(1, p))
+        module = core.KETKFModule(kernel=linear.LinearKernel(), inf_factor=torch.tensor(rho, dtype=torch.float64))
+        out["c{0}_perts".format(i)] = perts; out["c{0}_raw".format(i)] = hx; out["c{0}_obs".format(i)] = obs
+        out["c{0}_rho".format(i)] = np.float64(rho)
+        out["c{0}_w".format(i)] = module(torch.as_tensor(perts), torch.as_tensor(obs)).numpy()
+        out["c{0}_w_raw".format(i)] = module(torch.as_tensor(hx), torch.as_tensor(obs)).numpy()
+    out["n_cases"] = np.int64(5)
+    module = core.KETKFModule(kernel=linear.LinearKernel(), inf_factor=torch.tensor(1.3, dtype=torch.float64))
+    out["empty_w"] = module(torch.zeros((6, 0), dtype=torch.float64), torch.zeros((1, 0), dtype=torch.float64)).numpy()
+    # localized KETKF on the fixtures, first time slice (the setup of interface/test_lketkf.py / test_letkf.py:106-157)
+    fx = read_fixtures()
+    state = fx["state"][:, :1]
+    hx = state[0, 0]                                            # dummy obs operator: variable 'x' (testing/dummy.py:39-66)
+    mean = hx.mean(axis=0)
+    rc = 1.0 / np.sqrt(np.diag(fx["cov"]))
+    perts = (hx - mean) * rc
+    innov = (fx["obs"][0] - mean) * rc
+    grid_rows = np.stack([np.full(40, fx["t_unix"][0]), fx["grid"]], axis=1)
+    obs_rows = np.stack([np.full(40, fx["t_unix"][0]), fx["obs_grid"]], axis=1)
+    loc = ref.loc_gc.GaspariCohn((10.,), lambda g, o: np.abs(g[1] - np.asarray(o)[:, 1]))
+    module = core.KETKFModule(kernel=linear.LinearKernel(), inf_factor=torch.tensor(1.1, dtype=torch.float64))
+    bridged = ref.wrapper.wrapper_bridge(module, torch.device("cpu"), torch.float64)
+    localized = ref.wrapper.wrapper_localization(bridged, loc)
+    weights = np.stack([localized(grid_rows[g], perts, innov[None], obs_info=obs_rows) for g in range(40)])
+    smean = state.mean(axis=2, keepdims=True)
+    analysis = smean + np.einsum('vtig,gij->vtjg', state - smean, weights)          # interface/base.py:257-278
+    out.update(lketkf_state=state, lketkf_perts=perts, lketkf_innov=innov, lketkf_weights=weights, lketkf_analysis=analysis,
+               lketkf_grid=fx["grid"], lketkf_obs_grid=fx["obs_grid"], lketkf_obs=fx["obs"][:1], lketkf_cov=fx["cov"])
+    np.savez(os.path.join(OUT, "ketkf_linear.npz"), **out)
+    print("wrote ketkf_linear.npz")
+
+
 def csr(lists):
     off = np.zeros(len(lists) + 1, dtype=np.int64)
     off[1:] = np.cumsum([len(x) for x in lists])
@@ -248,6 +309,10 @@ def main():
     for f in sorted(os.listdir(OUT)):
         print("  ", f, os.path.getsize(os.path.join(OUT, f)))
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ketkf":
+    make_ketkf_golden()
+    sys.exit(0)
 
 if __name__ == "__main__":
     main()

@@ -185,3 +185,24 @@ def test_letkf_with_all_ones_localization_equals_etkf(golden):
     np.testing.assert_allclose(alg.assimilate(state_mi, (obs, obs)).values, etkf_ana.values, **TOL)
     use, w = alg.localization.localize_obs(np.array([0., 3.]), np.column_stack([np.zeros(5), np.arange(5.)]))
     assert use.all() and np.array_equal(w, np.ones(5))
+
+
+def test_kernelised_etkf_linear_kernel(golden):
+    """interface/ketkf.py, interface/lketkf.py with the default LinearKernel against the reference's KETKFModule
+    (tests/golden/ketkf_linear.npz), same constructor signatures; other kernels raise (no CPU fallback)."""
+    from pytassim_b200.interface import KETKF, LKETKF
+    from pytassim_b200.kernels import LinearKernel
+    g = golden("ketkf_linear.npz")
+    _, state, obs = _fixture_objects(golden)
+    st0, ob0 = state.isel(time=[0]), obs.isel(time=[0])
+    alg = LKETKF(localization=GaspariCohn((10.,), AbsDistance1D()), kernel=LinearKernel(), inf_factor=1.1, smoother=False,
+                 gpu=False, pre_transform=None, post_transform=None, chunksize=10, weight_save_path=None, forward_model=None)
+    ana = alg.assimilate(st0, ob0)
+    np.testing.assert_allclose(ana.values, g["lketkf_analysis"], **TOL)
+    assert str(alg).startswith("Localized KETKF(inf_factor=1.1") and repr(KETKF(inf_factor=2.0)) == "KETKF(2.0,Linear)"
+    glob = KETKF(inf_factor=1.1).assimilate(state, (obs, obs))
+    np.testing.assert_allclose(glob.values, ETKF(inf_factor=1.1).assimilate(state, (obs, obs)).values, rtol=0, atol=0)
+    with pytest.raises(NotImplementedError):
+        KETKF(kernel=object())
+    with pytest.raises(NotImplementedError):
+        alg.kernel = "rbf"

@@ -304,3 +304,16 @@ def test_position_operator():
     np.testing.assert_array_equal(op(obs, state).values, state.values[1][:1][:, :, [3, 3, 39]])
     with pytest.raises(IndexError):
         PositionOperator([40])(_obs_for(rng, t[:1], [0.]), state)
+
+
+def test_kernelised_classes_signatures_and_kernel_check():
+    from pytassim_b200.interface import KETKF, LKETKF
+    from pytassim_b200.kernels import LinearKernel
+    alg = LKETKF(localization=None, kernel=LinearKernel(), inf_factor=1.0, smoother=False, gpu=False, pre_transform=None,
+                 post_transform=None, chunksize=10, weight_save_path=None, forward_model=None)      # lketkf.py:79-91
+    assert isinstance(alg.kernel, LinearKernel) and alg.chunks == {"grid": 10}
+    glob = KETKF(kernel=LinearKernel(), inf_factor=1.5, smoother=True, gpu=False, pre_transform=None, post_transform=None,
+                 weight_save_path=None, forward_model=None)                                          # ketkf.py:69-78
+    assert str(glob) == "Global KETKF(inf_factor=1.5, kernel=LinearKernel)" and glob.smoother
+    with pytest.raises(NotImplementedError):
+        KETKF(kernel=lambda x, y: x @ y.T)

@@ -189,3 +189,25 @@ def test_synthetic_configs_vs_reference(golden, name):
     np.testing.assert_array_equal(idx, g["csr_idx"])
     np.testing.assert_allclose(W[:g["weights"].shape[0]], g["weights"], rtol=RTOL, atol=1e-12)
     np.testing.assert_allclose(ana, g["analysis"], rtol=1e-10, atol=1e-10)
+
+
+def test_ketkf_linear_restatement_against_reference(golden):
+    """core/ketkf.py:69-100 with LinearKernel: the restatement reproduces the reference module on centred and uncentred
+    perturbations; on centred perturbations (what the interface always hands over, base.py:367-372) it equals the ETKF core,
+    which is why KETKF / LKETKF run on the ETKF device path."""
+    g = golden("ketkf_linear.npz")
+    for i in range(int(g["n_cases"])):
+        perts, raw, obs, rho = g["c%d_perts" % i], g["c%d_raw" % i], g["c%d_obs" % i], float(g["c%d_rho" % i])
+        np.testing.assert_allclose(orc.ketkf_linear_weights(perts, obs, rho), g["c%d_w" % i], rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(orc.ketkf_linear_weights(raw, obs, rho), g["c%d_w_raw" % i], rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(orc.etkf_weights(perts, obs, rho), g["c%d_w" % i], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(orc.ketkf_linear_weights(np.zeros((6, 0)), np.zeros((1, 0)), 1.3), g["empty_w"], rtol=0, atol=1e-15)
+    with pytest.raises(ValueError):
+        orc.ketkf_linear_weights(np.zeros((3, 4)), np.zeros((1, 5)))
+    # localized KETKF on the reference fixtures == localized ETKF restatement
+    grid_rows = np.stack([np.zeros(40), g["lketkf_grid"]], axis=1)
+    obs_rows = np.stack([np.zeros(40), g["lketkf_obs_grid"]], axis=1)
+    ana, w = orc.letkf_analysis(g["lketkf_state"], g["lketkf_perts"], g["lketkf_innov"], grid_rows, obs_rows,
+                                orc.dist_abs1d, 10.0, inf_factor=1.1)
+    np.testing.assert_allclose(w, g["lketkf_weights"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(ana, g["lketkf_analysis"], rtol=1e-11, atol=1e-12)

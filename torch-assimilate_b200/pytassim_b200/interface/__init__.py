@@ -1,3 +1,4 @@
 from .etkf import ETKF  # noqa: F401
 from .letkf import LETKF  # noqa: F401
+from .ketkf import KETKF, LKETKF  # noqa: F401
 from .base import StateError, ObservationError  # noqa: F401
