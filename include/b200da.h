@@ -82,6 +82,15 @@ int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int
                        double epsilon, double inf_factor, int dtype, int taper);
 void b200da_plan_destroy(b200da_plan* plan);
 
+/* A `dist_func` that returns SEVERAL distance rows gets one Gaspari-Cohn factor per row, each row divided by its own entry of
+ * `length_scale`, the factors multiplied (localization/gaspari_cohn.py:124-134).  The engine's form of it: the plan's metric
+ * (row 0, radius[0] of b200da_plan_create) times n_extra rows |x_g - x_o| on further coordinate columns (vertical level,
+ * time, ...; 0 <= n_extra <= 2) with radii extra_radius[0..n_extra).  Afterwards every coordinate array (b200da_set_grid,
+ * b200da_bin_obs, b200da_letkf_host) carries n_coord + n_extra rows.  Call before b200da_set_grid.  B200DA_TAPER_GC only
+ * (GaspariCohnInf evaluates a single distance, gaspari_cohn.py:216-254).  The neighbour search uses row 0 (every factor is
+ * <= 1, so this is conservative); FP32 plans with extra rows use the DMMA Gram instead of the tcgen05 one. */
+int b200da_plan_set_extra(b200da_plan* plan, int n_extra, const double* extra_radius);
+
 /* Replaces `_extract_state_information` + the dask chunking of the grid (interface/mixin_local.py:50-69,
  * interface/letkf.py:121): bins the N grid points into cells and forms blocks of neighbouring grid points
  * (one CTA each).  grid_coord: (n_coord, N) float64 device. */

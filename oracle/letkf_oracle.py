@@ -190,6 +190,18 @@ def make_dist_haversine(radius_km: float = EARTH_RADIUS_KM) -> Callable:
     return dist_haversine
 
 
+def make_dist_product(primary: Callable, n_primary: int, n_extra: int) -> Callable:
+    """A dist_func returning SEVERAL rows (gaspari_cohn.py:125 ``np.atleast_2d``): row 0 = ``primary`` on the first
+    ``n_primary`` coordinate columns, rows 1.. = |x_g - x_o| on the following ``n_extra`` columns."""
+    def dist_product(grid_row, obs_rows):
+        obs_rows = np.asarray(obs_rows)
+        rows = [primary(grid_row[:1 + n_primary], obs_rows[:, :1 + n_primary])]
+        for e in range(n_extra):
+            rows.append(np.abs(grid_row[1 + n_primary + e] - obs_rows[:, 1 + n_primary + e]))
+        return np.stack(rows, axis=0)
+    return dist_product
+
+
 # ----------------------------------------------------------------------------------------------
 # Core ETKF weights  (pytassim/core/{base,utils,etkf}.py)
 # ----------------------------------------------------------------------------------------------

@@ -162,6 +162,40 @@ def make_ketkf_golden():
     print("wrote ketkf_linear.npz")
 
 
+def make_product_golden():
+    """tests/golden/product_loc.npz: the reference's GaspariCohn with a dist_func that returns TWO rows (horizontal ring
+    distance x |level difference|) and two length scales: localize_obs for a few grid rows, and the LETKF analysis of the
+    reference's hot loop on seeded inputs (gaspari_cohn.py:124-135, interface/letkf.py:127-143)."""
+    ref = load_reference_leaves()
+    rng = np.random.RandomState(77)
+    n_grid, k, n_lev = 48, 12, 4
+    pos = np.tile(np.arange(n_grid // n_lev, dtype=np.float64), n_lev)
+    lev = np.repeat(np.arange(n_lev, dtype=np.float64), n_grid // n_lev)
+    grid_rows = np.stack([np.zeros(n_grid), pos, lev], axis=1)
+    m = 60
+    obs_rows = np.stack([np.zeros(m), rng.uniform(0, n_grid // n_lev, size=m), rng.randint(0, n_lev, size=m).astype(np.float64)
+                         + rng.uniform(-0.3, 0.3, size=m)], axis=1)
+    period = float(n_grid // n_lev)
+
+    def dist(g, o):
+        o = np.asarray(o)
+        d = np.abs(g[1] - o[:, 1])
+        return np.stack([np.minimum(d, period - d), np.abs(g[2] - o[:, 2])], axis=0)
+    loc = ref.loc_gc.GaspariCohn((3.0, 1.5), dist)
+    use = np.stack([loc.localize_obs(grid_rows[g], obs_rows)[0] for g in range(n_grid)])
+    w = np.stack([loc.localize_obs(grid_rows[g], obs_rows)[1] for g in range(n_grid)])
+    state = rng.normal(size=(1, 1, k, n_grid))
+    hx = rng.normal(size=(k, m))
+    perts = hx - hx.mean(axis=0, keepdims=True)
+    innov = rng.normal(size=m)
+    ana, weights, lists, lws = reference_letkf(ref, state, perts, innov[None], grid_rows, obs_rows, loc, 1.1)
+    off, idx = csr(lists)
+    np.savez(os.path.join(OUT, "product_loc.npz"), grid_rows=grid_rows, obs_rows=obs_rows, period=np.float64(period),
+             radius=np.array([3.0, 1.5]), use=use, w=w, state=state, perts=perts, innov=innov, analysis=ana, weights=weights,
+             csr_off=off, csr_idx=idx, rho=np.float64(1.1))
+    print("wrote product_loc.npz")
+
+
 def csr(lists):
     off = np.zeros(len(lists) + 1, dtype=np.int64)
     off[1:] = np.cumsum([len(x) for x in lists])
@@ -312,6 +346,10 @@ def main():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ketkf":
     make_ketkf_golden()
+    sys.exit(0)
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "product":
+    make_product_golden()
     sys.exit(0)
 
 if __name__ == "__main__":

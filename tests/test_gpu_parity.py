@@ -399,3 +399,62 @@ def test_large_ensembles_newton_against_oracle(k, n_grid, radius):
                                    data["obs_rows"], orc.make_dist_periodic1d(float(n_grid)), radius, inf_factor=1.05)
     np.testing.assert_allclose(xa, ref, rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(w, wref, rtol=RTOL, atol=ATOL)
+
+
+def test_multi_row_localization_against_reference_golden(golden):
+    """A dist_func with two rows (periodic ring distance x |level difference|) and two length scales
+    (localization/gaspari_cohn.py:124-135): local-observation lists bit-exact, weights and analysis within 1e-10 of the
+    reference's own GaspariCohn + hot loop (tests/golden/product_loc.npz)."""
+    from pytassim_b200.engine import LETKFEngine
+    m = _metrics()
+    g = golden("product_loc.npz")
+    k, n = g["state"].shape[2], g["state"].shape[3]
+    metric = m.ProductDistance(m.PeriodicDistance1D(float(g["period"])), n_extra=1)
+    eng = LETKFEngine(k, 1, metric, g["radius"], inf_factor=float(g["rho"]))
+    eng.set_grid(g["grid_rows"][:, 1:])
+    eng.bin_obs(g["obs_rows"][:, 1:], g["perts"], g["innov"])
+    xa, w, namb = eng.analyse(torch.as_tensor(g["state"].reshape(1, k, n)).cuda(), return_weights=True, count_ambiguous=True)
+    assert namb == 0
+    np.testing.assert_allclose(w.cpu().numpy(), g["weights"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(xa.cpu().numpy().reshape(g["state"].shape), g["analysis"], rtol=RTOL, atol=ATOL)
+    off, idx, wl, amb, _ = eng.neighbour_lists()
+    np.testing.assert_array_equal(off.cpu().numpy(), g["csr_off"])
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["csr_idx"])
+    wref = np.concatenate([g["w"][i][g["use"][i]] for i in range(n)])
+    np.testing.assert_allclose(wl.cpu().numpy(), wref, rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-4)])
+def test_product_metric_sphere_with_levels_against_oracle(dtype, tol):
+    """Horizontal haversine x vertical |dz| x time |dt| localization (three rows, three length scales) on the sphere, k = 50:
+    index lists bit-exact, analysis within tolerance; FP32 plans run on the DMMA Gram (the tcgen05 Gram has one distance)."""
+    from pytassim_b200.engine import LETKFEngine
+    m = _metrics()
+    data = syn.sphere_latlon(40, 80, 50, 6000, seed=31)
+    rng = np.random.RandomState(32)
+    n, mo = data["grid_rows"].shape[0], data["obs_rows"].shape[0]
+    grid_rows = np.column_stack([data["grid_rows"], rng.randint(0, 5, n).astype(np.float64), np.zeros(n)])
+    obs_rows = np.column_stack([data["obs_rows"], rng.uniform(0, 4, mo), rng.uniform(-3, 3, mo)])
+    radius = (2500.0, 2.0, 4.0)
+    npd = np.float64 if dtype == torch.float64 else np.float32
+    st, yp, yo = data["state"].astype(npd), data["normed_perts"].astype(npd), data["normed_obs"].astype(npd)
+    metric = m.ProductDistance(m.HaversineDistance(6371.0), n_extra=2)
+    eng = LETKFEngine(50, 1, metric, radius, inf_factor=1.1, dtype=dtype)
+    assert "tcgen05" not in eng.kernel_name
+    eng.set_grid(grid_rows[:, 1:]); eng.bin_obs(obs_rows[:, 1:], yp, yo)
+    xa = eng.analyse(torch.as_tensor(st.reshape(1, 50, n)).cuda()).cpu().numpy().reshape(st.shape)
+    sel = np.arange(0, n, 97)
+    dist = orc.make_dist_product(orc.make_dist_haversine(6371.0), 2, 2)
+    ref, _, lists = orc.letkf_analysis(st.astype(np.float64), yp.astype(np.float64), yo.astype(np.float64), grid_rows, obs_rows,
+                                       dist, radius, inf_factor=1.1, grid_subset=sel, return_lists=True)
+    assert np.abs(xa[..., sel] - ref).max() <= tol * np.abs(ref).max()
+    off, idx, _, _, namb = eng.neighbour_lists(with_weights=False)
+    off, idx = off.cpu().numpy(), idx.cpu().numpy()
+    for gi, l in zip(sel, lists):
+        l = l[0] if isinstance(l, tuple) else l
+        np.testing.assert_array_equal(idx[off[gi]:off[gi + 1]], l)
+    assert len(lists[0][0] if isinstance(lists[0], tuple) else lists[0]) < mo // 4          # the extra rows do localize
+    with pytest.raises(NotImplementedError):                                  # GaspariCohnInf evaluates a single distance
+        LETKFEngine(50, 1, metric, radius, taper="gcinf")
+    with pytest.raises(IndexError):                                           # fewer length scales than distance rows
+        LETKFEngine(50, 1, metric, (2500.0,))

@@ -317,3 +317,20 @@ def test_kernelised_classes_signatures_and_kernel_check():
     assert str(glob) == "Global KETKF(inf_factor=1.5, kernel=LinearKernel)" and glob.smoother
     with pytest.raises(NotImplementedError):
         KETKF(kernel=lambda x, y: x @ y.T)
+
+
+def test_product_distance_equals_oracle_rows():
+    from pytassim_b200.localization import ProductDistance, HaversineDistance
+    rng = np.random.RandomState(3)
+    obs = np.column_stack([np.zeros(50), rng.uniform(-80, 80, 50), rng.uniform(0, 360, 50), rng.uniform(0, 10, 50), rng.uniform(0, 5, 50)])
+    grid = np.array([0.0, 12.0, 200.0, 3.0, 1.0])
+    m = ProductDistance(HaversineDistance(6371.0), n_extra=2)
+    ref = orc.make_dist_product(orc.make_dist_haversine(6371.0), 2, 2)(grid, obs)
+    np.testing.assert_array_equal(m(grid, pd.DataFrame(obs)), ref)
+    assert m.n_coord == 4 and m.n_extra == 2 and m.metric_id == HaversineDistance().metric_id and ref.shape == (3, 50)
+    m1 = ProductDistance(PeriodicDistance1D(12.0))
+    np.testing.assert_array_equal(m1(grid[:3], obs[:, :3]), orc.make_dist_product(orc.make_dist_periodic1d(12.0), 1, 1)(grid[:3], obs[:, :3]))
+    with pytest.raises(ValueError):
+        ProductDistance(m1)
+    with pytest.raises(ValueError):
+        ProductDistance(AbsDistance1D(), n_extra=3)

@@ -211,3 +211,20 @@ def test_ketkf_linear_restatement_against_reference(golden):
                                 orc.dist_abs1d, 10.0, inf_factor=1.1)
     np.testing.assert_allclose(w, g["lketkf_weights"], rtol=1e-11, atol=1e-12)
     np.testing.assert_allclose(ana, g["lketkf_analysis"], rtol=1e-11, atol=1e-12)
+
+
+def test_multi_row_localization_against_reference(golden):
+    """gaspari_cohn.py:124-135 with a dist_func that returns two rows and two length scales: mask, weights, index lists and the
+    LETKF analysis of the restatement against the reference's own GaspariCohn + hot loop (tests/golden/product_loc.npz)."""
+    g = golden("product_loc.npz")
+    dist = orc.make_dist_product(orc.make_dist_periodic1d(float(g["period"])), 1, 1)
+    for gi in range(0, g["grid_rows"].shape[0], 5):
+        use, w = orc.gaspari_cohn_localize(dist(g["grid_rows"][gi], g["obs_rows"]), g["radius"])
+        np.testing.assert_array_equal(use, g["use"][gi])
+        np.testing.assert_array_equal(w, g["w"][gi])
+    ana, w, lists = orc.letkf_analysis(g["state"], g["perts"], g["innov"], g["grid_rows"], g["obs_rows"], dist, g["radius"],
+                                       inf_factor=float(g["rho"]), return_lists=True)
+    np.testing.assert_allclose(ana, g["analysis"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(w, g["weights"], rtol=1e-12, atol=1e-12)
+    idx = np.concatenate([l[0] if isinstance(l, tuple) else l for l in lists])
+    np.testing.assert_array_equal(idx, g["csr_idx"])

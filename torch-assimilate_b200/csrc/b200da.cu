@@ -144,6 +144,7 @@ static NeighbourParams neighbour_params(const b200da_plan* pl) {
     P.gpos = pl->gpos.as<Pos4>();
     P.block_off = pl->block_off.as<int>();
     P.opos = pl->opos.as<Pos4>();
+    P.gext = pl->gext.as<double>(); P.oext = pl->oext.as<double>();
     P.cell_start = pl->cell_start.as<int>();
     P.n_obs = pl->n_obs;
     P.cut_pad = pl->geom.cut_bin * (1.0 + 1e-9) + 1e-300;
@@ -250,12 +251,31 @@ void b200da_plan_destroy(b200da_plan* pl) {
     DevBuf* bufs[] = {&pl->gpos, &pl->gorder, &pl->block_off, &pl->opos, &pl->cell_start, &pl->ys, &pl->tmp_keys,
                       &pl->tmp_cell, &pl->tmp_count, &pl->tmp_a, &pl->tmp_b, &pl->tmp_pos, &pl->host_stage_obs,
                       &pl->host_stage_y, &pl->host_stage_d, &pl->host_stage_x, &pl->host_stage_xa, &pl->etkf_partial,
-                      &pl->etkf_w, &pl->stats, &pl->cmat, &pl->counter, &pl->ns_scratch};
+                      &pl->etkf_w, &pl->stats, &pl->cmat, &pl->counter, &pl->ns_scratch, &pl->gext, &pl->oext};
     for (cudaEvent_t ev : pl->ev_pool) cudaEventDestroy(ev);
     for (DevBuf* b : bufs) b->release();
     if (pl->ev0) cudaEventDestroy(pl->ev0);
     if (pl->ev1) cudaEventDestroy(pl->ev1);
     delete pl;
+}
+
+int b200da_plan_set_extra(b200da_plan* pl, int n_extra, const double* extra_radius) {
+    if (!pl || n_extra < 0 || n_extra > 2 || (n_extra > 0 && !extra_radius)) return B200DA_ERR_INVALID;
+    // GaspariCohnInf.localize_obs evaluates a single distance (localization/gaspari_cohn.py:216-254)
+    if (n_extra > 0 && pl->geom.taper != B200DA_TAPER_GC) return B200DA_ERR_UNSUPPORTED;
+    for (int e = 0; e < n_extra; ++e) if (!(extra_radius[e] > 0.0)) return B200DA_ERR_INVALID;
+    pl->geom.n_ext = n_extra;
+    for (int e = 0; e < 2; ++e) pl->geom.ext_radius[e] = e < n_extra ? extra_radius[e] : 1.0;
+    if (n_extra > 0 && pl->use_tc) {
+        // the tcgen05 Gram evaluates its FP32 weights in closed form for one distance: plans with extra components use the
+        // DMMA Gram (FP32 tiles converted on load)
+        const KernelConfig cfg = config_for_kt(pl->kt);
+        pl->use_tc = false; pl->gpb = cfg.g;
+        pl->kernel_name = std::string("letkf_gram_f32in_f64dmma") + (pl->k % 8 == 0 ? "_brow" : "") + "_kt" +
+                          std::to_string(pl->k % 8 == 0 ? pl->kt - 1 : pl->kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
+    }
+    pl->have_grid = false; pl->have_obs = false;
+    return B200DA_OK;
 }
 
 int b200da_set_grid(b200da_plan* plan, const double* grid_coord, int64_t n_grid, void* stream) {
@@ -325,6 +345,7 @@ static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int
     P.gpos = pl->gpos.as<Pos4>();
     P.block_off = pl->block_off.as<int>();
     P.opos = pl->opos.as<Pos4>();
+    P.gext = pl->gext.as<double>(); P.oext = pl->oext.as<double>();
     P.cell_start = pl->cell_start.as<int>();
     P.ys = pl->ys.p;
     P.x = X; P.xa = Xa; P.w_out = W_opt;
@@ -428,13 +449,14 @@ int b200da_letkf_host(b200da_plan* pl, const double* obs_coord_host, const void*
     const size_t mm = (size_t)std::max<int64_t>(m, 1);
     const size_t es = pl->dtype == B200DA_F32 ? sizeof(float) : sizeof(double);
     const size_t xbytes = es * (size_t)pl->n_slices * pl->k * (size_t)pl->n_grid;
-    if ((rc = pl->host_stage_obs.ensure(sizeof(double) * mm * pl->n_coord))) return rc;
+    const size_t n_rows_coord = (size_t)pl->n_coord + pl->geom.n_ext;
+    if ((rc = pl->host_stage_obs.ensure(sizeof(double) * mm * n_rows_coord))) return rc;
     if ((rc = pl->host_stage_y.ensure(es * mm * pl->k))) return rc;
     if ((rc = pl->host_stage_d.ensure(es * mm))) return rc;
     if ((rc = pl->host_stage_x.ensure(xbytes))) return rc;
     if ((rc = pl->host_stage_xa.ensure(xbytes))) return rc;
     if (m > 0) {
-        B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_obs.p, obs_coord_host, sizeof(double) * (size_t)m * pl->n_coord, cudaMemcpyHostToDevice, st));
+        B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_obs.p, obs_coord_host, sizeof(double) * (size_t)m * n_rows_coord, cudaMemcpyHostToDevice, st));
         B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_y.p, Yn_host, es * (size_t)m * pl->k, cudaMemcpyHostToDevice, st));
         B200DA_CUDA(cudaMemcpyAsync(pl->host_stage_d.p, d_host, es * (size_t)m, cudaMemcpyHostToDevice, st));
     }
@@ -476,7 +498,8 @@ int b200da_neighbour_fill(b200da_plan* pl, const int64_t* offsets, int32_t* idx,
     const int nblk = (int)std::min<int64_t>(pl->n_grid, 148 * 64);
     k_segmented_sort<long long><<<nblk, kSegSortThreads, 0, st>>>(P.keys, (const long long*)offsets, pl->n_grid);
     B200DA_LAUNCH_CHECK();
-    k_neighbour_finalize<<<nblk, 128, 0, st>>>(pl->geom, pl->gpos.as<Pos4>(), pl->opos.as<Pos4>(), (const long long*)offsets,
+    k_neighbour_finalize<<<nblk, 128, 0, st>>>(pl->geom, pl->gpos.as<Pos4>(), pl->opos.as<Pos4>(), pl->gext.as<double>(),
+                                                 pl->oext.as<double>(), (const long long*)offsets,
                                                P.keys, pl->n_grid, idx, w_opt, ambiguous_opt);
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;

@@ -118,6 +118,15 @@ __global__ void k_finalize_points(Geometry g, const unsigned long long* __restri
     if (cell_sorted) cell_sorted[s] = cell_of(g, p.x, p.y, p.z);
 }
 
+// extra coordinate columns (rows n_primary.. of the struct-of-arrays coordinates) in sorted order: out[s][e]
+__global__ void k_gather_ext(const unsigned long long* __restrict__ sorted, const double* __restrict__ coord_ext, int64_t n,
+                             int n_ext, double* __restrict__ out) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const unsigned idx = (unsigned)(sorted[s] & 0xffffffffull);
+    for (int e = 0; e < n_ext; ++e) out[s * n_ext + e] = coord_ext[(int64_t)e * n + idx];
+}
+
 // flag[s] = s + 1 where a new segment of z-adjacent cells starts (0 elsewhere); the +1 keeps slot 0 non-zero
 __global__ void k_segment_flags(Geometry g, const int* __restrict__ cell_sorted, int64_t n, int* __restrict__ flag) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -311,6 +320,11 @@ inline int set_grid_impl(b200da_plan* pl, const double* grid_coord, int64_t n, c
     k_finalize_points<<<grid1d(n, 256), 256, 0, st>>>(g, sorted, pos, n, pl->gpos.as<Pos4>(), pl->gorder.as<int>(),
                                                       cell_sorted);
     B200DA_LAUNCH_CHECK();
+    if (g.n_ext > 0) {
+        if ((rc = pl->gext.ensure(sizeof(double) * (size_t)n * g.n_ext))) return rc;
+        k_gather_ext<<<grid1d(n, 256), 256, 0, st>>>(sorted, grid_coord + (size_t)g.n_coord * n, n, g.n_ext, pl->gext.as<double>());
+        B200DA_LAUNCH_CHECK();
+    }
     int* fa = pl->tmp_a.as<int>();
     int* fb = pl->tmp_b.as<int>();
     k_segment_flags<<<grid1d(n, 256), 256, 0, st>>>(g, cell_sorted, n, fa);
@@ -360,6 +374,11 @@ inline int bin_obs_impl(b200da_plan* pl, const double* obs_coord, const T* yn, c
         k_gather_obs<T><<<grid1d(m, 8), blk, 0, st>>>(sorted, pos, m, yn, d, pl->k, pl->kp, pl->opos.as<Pos4>(),
                                                       pl->ys.as<T>());
         B200DA_LAUNCH_CHECK();
+        if (g.n_ext > 0) {
+            if ((rc = pl->oext.ensure(sizeof(double) * mm * g.n_ext))) return rc;
+            k_gather_ext<<<grid1d(m, 256), 256, 0, st>>>(sorted, obs_coord + (size_t)g.n_coord * m, m, g.n_ext, pl->oext.as<double>());
+            B200DA_LAUNCH_CHECK();
+        }
     }
     pl->have_obs = true;
     return B200DA_OK;

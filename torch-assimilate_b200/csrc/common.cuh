@@ -33,6 +33,8 @@ struct Geometry {
     double h[3];       // cell edge per dimension
     int nc[3];         // cells per dimension
     int ncell;         // nc[0]*nc[1]*nc[2]; cell id ncell is the discard bin (outside the domain)
+    int n_ext;         // extra distance components |x_g - x_o| on further coordinate columns (0..2), one taper factor each
+    double ext_radius[2];
 };
 
 struct __align__(32) Pos4 {     // bin-space position + payload (original index, as raw bits)
@@ -178,11 +180,20 @@ __device__ __forceinline__ double bin_distance(const Geometry& g, double ax, dou
 
 // Localization weight of one (grid point, observation) pair: returns w if w > eps else 0
 // (gaspari_cohn.py:126-135); `ambiguous` is set when |w - eps| is inside the ambiguity band.
+// ge / oe: the extra coordinate values of the grid point / observation (g.n_ext each; may be null when n_ext = 0).  A
+// dist_func that returns several rows gets one taper factor per row, each row divided by its own radius, multiplied in
+// row order starting from 1 (gaspari_cohn.py:124-134); the candidate search only uses the first component, which is
+// conservative because every factor is <= 1.
 __device__ __forceinline__ double pair_weight(const Geometry& g, double gx, double gy, double gz,
-                                              double ox, double oy, double oz, bool& ambiguous) {
+                                              double ox, double oy, double oz, const double* __restrict__ ge,
+                                              const double* __restrict__ oe, bool& ambiguous) {
     const double dist = metric_distance(g, gx, gy, gz, ox, oy, oz);
     const double r = dist / g.radius;                      // gaspari_cohn.py:127
-    const double w = taper_eval(g.taper, r);
+    double w = taper_eval(g.taper, r);
+    for (int e = 0; e < g.n_ext; ++e) {
+        const double re = fabs(ge[e] - oe[e]) / g.ext_radius[e];
+        w = __dmul_rn(w, taper_eval(g.taper, re));          // gaspari_cohn.py:134
+    }
     ambiguous = fabs(w - g.eps) < kAmbiguityBand;
     return (w > g.eps) ? w : 0.0;                          // gaspari_cohn.py:135
 }

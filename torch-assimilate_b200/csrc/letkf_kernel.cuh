@@ -31,6 +31,8 @@ struct LetkfParams {
     const Pos4* gpos;          // block-sorted grid positions (id = original index)
     const int* block_off;
     const Pos4* opos;          // cell-sorted obs positions
+    const double* gext;        // [N][g.n_ext] extra coordinates of the block-sorted grid points (null when n_ext = 0)
+    const double* oext;        // [M][g.n_ext] extra coordinates of the cell-sorted observations
     const int* cell_start;
     const void* ys;            // [M][KP] of the plan dtype
     const void* x;             // (n_slices, k, N) of the plan dtype
@@ -332,9 +334,11 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
             const int slot = q % kTileObs, gi = q / kTileObs;
             double w = 0.0;
             if (slot < n_tile && gi < ng) {
-                const Pos4 po = P.opos[H.ring[(ring_head + slot) & (kRing - 1)]];
+                const int so = H.ring[(ring_head + slot) & (kRing - 1)];
+                const Pos4 po = P.opos[so];
                 bool amb;
-                w = pair_weight(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, amb);
+                w = pair_weight(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z,
+                                P.gext + (size_t)(P.block_off[blk] + gi) * g.n_ext, P.oext + (size_t)so * g.n_ext, amb);
                 if (amb) ++my_amb;
             }
             wst[q] = w;

@@ -13,6 +13,8 @@ struct NeighbourParams {
     const Pos4* gpos;
     const int* block_off;
     const Pos4* opos;
+    const double* gext;                 // extra coordinates, see LetkfParams
+    const double* oext;
     const int* cell_start;
     int64_t n_obs;
     double cut_pad;
@@ -52,7 +54,9 @@ __global__ void __launch_bounds__(256) k_neighbours(const NeighbourParams P) {
         if (!(bin_distance(g, H.cx, H.cy, H.cz, po.x, po.y, po.z) <= reach)) continue;
         for (int gi = 0; gi < ng; ++gi) {
             bool amb;
-            const double w = pair_weight(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, amb);
+            const double* ge = P.gext + (size_t)(P.block_off[blockIdx.x] + gi) * g.n_ext;
+            const double* oe = P.oext + (size_t)s * g.n_ext;
+            const double w = pair_weight(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, ge, oe, amb);
             if (MODE == 0) {
                 if (w > 0.0) atomicAdd(&cnt[gi], 1);
                 if (amb) ++my_amb;
@@ -68,7 +72,9 @@ __global__ void __launch_bounds__(256) k_neighbours(const NeighbourParams P) {
                     if ((long long)at < P.capacity) {
                         const double dist = metric_distance(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z);
                         P.amb_grid[at] = H.gp[gi].id; P.amb_obs[at] = po.id;
-                        P.amb_w[at] = taper_eval(g.taper, dist / g.radius);
+                        double wa = taper_eval(g.taper, dist / g.radius);
+                        for (int e = 0; e < g.n_ext; ++e) wa = __dmul_rn(wa, taper_eval(g.taper, fabs(ge[e] - oe[e]) / g.ext_radius[e]));
+                        P.amb_w[at] = wa;
                     }
                 }
             }
@@ -83,6 +89,7 @@ __global__ void __launch_bounds__(256) k_neighbours(const NeighbourParams P) {
 
 // sorted keys -> obs indices, weights and ambiguity flags; one CTA per block-sorted grid slot
 __global__ void k_neighbour_finalize(Geometry g, const Pos4* __restrict__ gpos, const Pos4* __restrict__ opos,
+                                     const double* __restrict__ gext, const double* __restrict__ oext,
                                      const long long* __restrict__ offsets, const unsigned long long* __restrict__ keys,
                                      int64_t n_grid, int* __restrict__ idx, double* __restrict__ w_out,
                                      unsigned char* __restrict__ amb_out) {
@@ -93,9 +100,11 @@ __global__ void k_neighbour_finalize(Geometry g, const Pos4* __restrict__ gpos, 
             const unsigned long long key = keys[e];
             idx[e] = (int)(key >> 32);
             if (w_out || amb_out) {
-                const Pos4 po = opos[(unsigned)(key & 0xffffffffull)];
+                const unsigned so = (unsigned)(key & 0xffffffffull);
+                const Pos4 po = opos[so];
                 bool amb;
-                const double w = pair_weight(g, gp.x, gp.y, gp.z, po.x, po.y, po.z, amb);
+                const double w = pair_weight(g, gp.x, gp.y, gp.z, po.x, po.y, po.z, gext + (size_t)slot * g.n_ext,
+                                             oext + (size_t)so * g.n_ext, amb);
                 if (w_out) w_out[e] = w;
                 if (amb_out) amb_out[e] = amb ? 1 : 0;
             }

@@ -78,6 +78,7 @@ struct b200da_plan {
     b200da::DevBuf tmp_keys, tmp_cell, tmp_count, tmp_a, tmp_b, tmp_pos;
     b200da::DevBuf host_stage_obs, host_stage_y, host_stage_d, host_stage_x, host_stage_xa;
     b200da::DevBuf etkf_partial, etkf_w, stats, cmat, counter, ns_scratch;
+    b200da::DevBuf gext, oext;  // extra coordinate columns in block- / cell-sorted order (b200da_plan_set_extra)
     double ns_stiff = 0.0;      // 0: default (2e3 for FP64 plans, 2e4 for FP32 plans); see NsParams::stiff
     int solver = B200DA_SOLVER_NEWTON_SCHULZ;
     bool collect_stats = false;

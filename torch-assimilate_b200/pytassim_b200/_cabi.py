@@ -25,6 +25,7 @@ _dp = _c.POINTER(_c.c_double)
 SIGNATURES = {
     "b200da_plan_create": (_i, [_c.POINTER(_vp), _i, _i, _i, _i, _dp, _i, _dp, _i, _dbl, _dbl, _i, _i]),
     "b200da_plan_destroy": (None, [_vp]),
+    "b200da_plan_set_extra": (_i, [_vp, _i, _dp]),
     "b200da_set_grid": (_i, [_vp, _vp, _i64, _vp]),
     "b200da_bin_obs": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "b200da_obs_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),

@@ -51,13 +51,20 @@ class LETKFEngine(object):
         radius = np.atleast_1d(np.asarray(length_scale, dtype=np.float64))
         params = np.asarray(list(metric.params) + [0.0], dtype=np.float64)
         handle = ctypes.c_void_p()
+        n_extra = int(getattr(metric, "n_extra", 0))           # ProductDistance: extra |x_g - x_o| rows, one radius each
+        if radius.size < 1 + n_extra:
+            raise IndexError("the metric returns {0} distance rows but only {1} length scale(s) were given".format(
+                1 + n_extra, radius.size))                     # gaspari_cohn.py:127 raises IndexError on radius[i]
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.b200da_plan_create(
-                ctypes.byref(handle), self.k, self.n_slices, int(metric.n_coord), int(metric.metric_id),
+                ctypes.byref(handle), self.k, self.n_slices, int(metric.n_coord) - n_extra, int(metric.metric_id),
                 params.ctypes.data_as(_cabi._dp), len(metric.params),
                 radius.ctypes.data_as(_cabi._dp), int(radius.size), float(epsilon), float(inf_factor),
                 _cabi.F64 if dtype == torch.float64 else _cabi.F32, _TAPERS[taper]))
         self._plan = handle
+        if n_extra:
+            ext = np.ascontiguousarray(radius[1:1 + n_extra], dtype=np.float64)
+            _cabi.check(self.lib.b200da_plan_set_extra(self._plan, n_extra, ext.ctypes.data_as(_cabi._dp)))
         self.n_grid = 0
         self.n_obs = 0
         self._keep = {}

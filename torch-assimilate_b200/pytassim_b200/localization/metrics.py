@@ -12,7 +12,8 @@ import numpy as np
 
 from .. import _cabi
 
-__all__ = ["AbsDistance1D", "PeriodicDistance1D", "EuclideanDistance", "HaversineDistance", "ZeroDistance"]
+__all__ = ["AbsDistance1D", "PeriodicDistance1D", "EuclideanDistance", "HaversineDistance", "ZeroDistance",
+           "ProductDistance"]
 
 
 def _rows(obs_grid):
@@ -99,3 +100,32 @@ class HaversineDistance(_Metric):
         a = np.sin((phi2 - phi1) / 2) ** 2 + np.cos(phi1) * np.cos(phi2) * np.sin((lam2 - lam1) / 2) ** 2
         a = np.clip(a, 0.0, 1.0)
         return 2.0 * self.radius * np.arcsin(np.sqrt(a))
+
+
+class ProductDistance(_Metric):
+    """Several distance rows: row 0 is ``primary`` on the first ``primary.n_coord`` coordinate columns, rows 1.. are
+    ``|x_g - x_o|`` on the following ``n_extra`` columns (vertical level, time offset, ...; at most 2).  ``GaspariCohn`` takes
+    one ``length_scale`` entry per row and multiplies the tapers (pytassim/localization/gaspari_cohn.py:124-134)."""
+
+    def __init__(self, primary, n_extra=1):
+        if not isinstance(primary, _Metric) or isinstance(primary, ProductDistance) or getattr(primary, "zero_coords", False):
+            raise ValueError("primary must be one of the single-row metric objects")
+        if n_extra not in (1, 2):
+            raise ValueError("ProductDistance supports 1 or 2 extra components")
+        self.primary = primary
+        self.n_extra = int(n_extra)
+        self.metric_id = primary.metric_id
+        self.params = primary.params
+        self.n_coord = primary.n_coord + self.n_extra
+
+    def __repr__(self):
+        return "ProductDistance({0!r}, n_extra={1})".format(self.primary, self.n_extra)
+
+    def __call__(self, grid_ind, obs_grid):
+        obs = _rows(obs_grid)
+        g = np.asarray(grid_ind, dtype=np.float64)
+        np_ = self.primary.n_coord
+        rows = [self.primary(g[:1 + np_], obs[:, :1 + np_])]
+        for e in range(self.n_extra):
+            rows.append(np.abs(g[1 + np_ + e] - obs[:, 1 + np_ + e]))
+        return np.stack(rows, axis=0)
