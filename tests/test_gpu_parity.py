@@ -458,3 +458,32 @@ def test_product_metric_sphere_with_levels_against_oracle(dtype, tol):
         LETKFEngine(50, 1, metric, radius, taper="gcinf")
     with pytest.raises(IndexError):                                           # fewer length scales than distance rows
         LETKFEngine(50, 1, metric, (2500.0,))
+
+
+def test_error_paths_through_the_c_abi():
+    """Status codes -> the reference's exception conventions: unsupported ensemble size, non-finite
+    coordinates, call order, size mismatch (core/base.py:33-38), coordinate-count mismatch."""
+    from pytassim_b200.engine import LETKFEngine
+    from pytassim_b200 import _cabi
+    m = _metrics()
+    with pytest.raises(NotImplementedError):
+        LETKFEngine(200, 1, m.AbsDistance1D(), 1.0)                     # k > 135: beyond the implemented tile counts
+    with pytest.raises(ValueError):
+        LETKFEngine(1, 1, m.AbsDistance1D(), 1.0)                       # an ensemble of one has no perturbations
+    with pytest.raises(ValueError):
+        LETKFEngine(8, 1, m.AbsDistance1D(), -1.0)
+    eng = LETKFEngine(8, 1, m.EuclideanDistance(2), 1.0)
+    with pytest.raises(ValueError):
+        eng.set_grid(np.zeros((5, 3)))                                  # metric expects 2 coordinate columns
+    bad = np.zeros((5, 2)); bad[2, 1] = np.nan
+    with pytest.raises(ValueError):
+        eng.set_grid(bad)                                               # non-finite coordinates
+    with pytest.raises(_cabi.B200DAError):
+        eng.bin_obs(np.zeros((3, 2)), np.zeros((8, 3)), np.zeros(3))    # bin_obs before a valid set_grid
+    eng.set_grid(np.random.RandomState(0).uniform(0, 4, size=(5, 2)))
+    with pytest.raises(ValueError, match="do not match"):
+        eng.bin_obs(np.zeros((3, 2)), np.zeros((8, 3)), np.zeros(4))
+    with pytest.raises(ValueError):
+        eng.bin_obs(np.zeros((3, 2)), np.zeros((7, 3)), np.zeros(3))    # wrong ensemble size
+    with pytest.raises(_cabi.B200DAError):
+        eng.analyse(torch.zeros((1, 8, 5), dtype=torch.float64, device="cuda"))     # analyse before bin_obs
