@@ -72,6 +72,22 @@ typedef enum { B200DA_F64 = 0, B200DA_F32 = 1 } b200da_dtype;
  *   JACOBI         shared-memory parallel cyclic-Jacobi eigendecomposition (k <= 111). */
 typedef enum { B200DA_SOLVER_NEWTON_SCHULZ = 0, B200DA_SOLVER_JACOBI = 1 } b200da_solver;
 
+/* Operations of a kernel program (b200da_plan_set_kernel): the kernels of pytassim/kernels/*.py that are element-wise
+ * functions of x.y, |x|^2, |y|^2, and the three compositions of kernels/base_kernels.py:40-161.  p0 / p1 per operation: */
+typedef enum {
+    B200DA_KOP_LINEAR = 0,    /* x.y                                      kernels/linear.py:62-63        (-, -)          */
+    B200DA_KOP_GAUSS = 1,     /* exp(-|x/l - y/l|^2 / 2)                  kernels/rbf.py GaussKernel     (l, -); RBFKernel: l = sqrt(0.5 / gamma) */
+    B200DA_KOP_POLY = 2,      /* (x.y + c)^p                              kernels/polynomial.py          (p, c)          */
+    B200DA_KOP_TANH = 3,      /* tanh(alpha x.y + c)                      kernels/tanh.py                (alpha, c)      */
+    B200DA_KOP_RATIONAL = 4,  /* (1 + |x/l - y/l|^2 / (2 w))^(-w)         kernels/rational.py            (l, w)          */
+    B200DA_KOP_SCALE = 5,     /* c                                        kernels/scale.py               (c, -)          */
+    B200DA_KOP_DIAG = 6,      /* c I on K(perts, perts), 0 on K(perts, obs)   kernels/diag.py            (c, -)          */
+    B200DA_KOP_ADD = 7,       /* K1 + K2   (pops two)                     base_kernels.py:89-90                          */
+    B200DA_KOP_MUL = 8,       /* K1 * K2                                  base_kernels.py:119-120                        */
+    B200DA_KOP_POW = 9        /* K1 ^ K2                                  base_kernels.py:160-161                        */
+} b200da_kernel_op;
+#define B200DA_MAX_KERNEL_OPS 16
+
 /* ---- plan ------------------------------------------------------------------------------------------------ */
 
 /* Replaces the constructor state of LETKF(localization=GaspariCohn(length_scale, dist_func, epsilon),
@@ -90,6 +106,17 @@ void b200da_plan_destroy(b200da_plan* plan);
  * (GaspariCohnInf evaluates a single distance, gaspari_cohn.py:216-254).  The neighbour search uses row 0 (every factor is
  * <= 1, so this is conservative); FP32 plans with extra rows use the DMMA Gram instead of the tcgen05 one. */
 int b200da_plan_set_extra(b200da_plan* plan, int n_extra, const double* extra_radius);
+
+/* Replaces the `kernel` argument of KETKF / LKETKF (interface/ketkf.py:70-90, interface/lketkf.py:84-110) and
+ * KETKFModule._estimate_weights (core/ketkf.py:69-100): a postfix program of n_ops operations (b200da_kernel_op, parameters
+ * p0[i], p1[i]; leaves push K(x, y), ADD / MUL / POW pop two values; must leave exactly one value).  With a program set,
+ * b200da_letkf and b200da_etkf_weights[_from_gram] turn every augmented Gram into the double-centred kernel matrix and the
+ * centred kernel column of the observations before the ensemble-space solve; the Gram always comes from the FP64 DMMA
+ * kernel with the innovation row inside the tiles (it carries d.d, which the distance-based kernels need).  n_ops = 0
+ * returns to the plain ETKF.  Kernel matrices that are not positive semi-definite (tanh, powers) need
+ * B200DA_SOLVER_JACOBI, which clamps negative eigenvalues as core/utils.py:58 does; the Newton-Schulz solver assumes a
+ * positive semi-definite centred kernel matrix.  Ensemble sizes that are a multiple of 8 are limited to k <= 120. */
+int b200da_plan_set_kernel(b200da_plan* plan, int n_ops, const int* ops, const double* p0, const double* p1);
 
 /* Replaces `_extract_state_information` + the dask chunking of the grid (interface/mixin_local.py:50-69,
  * interface/letkf.py:121): bins the N grid points into cells and forms blocks of neighbouring grid points

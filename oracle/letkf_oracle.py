@@ -262,18 +262,117 @@ def etkf_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_factor: f
     return w_mean + w_perts                                       # etkf.py:102
 
 
-def ketkf_linear_estimate_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_factor: float):
-    """Reference: core/ketkf.py:69-100 with ``LinearKernel`` (kernels/linear.py:62-63: K(x, y) = x y^T).
-    normed_perts (k, p), normed_obs (1, p) -> (w_mean (k,1), w_perts (k,k), cov_analysed (k,k))."""
+class OracleKernel(object):
+    """A kernel of pytassim/kernels as a plain numpy function ``fn(x (n, p), y (m, p)) -> (n, m)`` with the three
+    compositions of kernels/base_kernels.py:40-161 (``+`` :89-90, ``*`` :119-120, ``**`` :160-161)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self, x, y):
+        return self.fn(np.asarray(x, dtype=float), np.asarray(y, dtype=float))
+
+    def __add__(self, other):
+        return OracleKernel(lambda x, y: self(x, y) + other(x, y))
+
+    def __mul__(self, other):
+        return OracleKernel(lambda x, y: self(x, y) * other(x, y))
+
+    def __pow__(self, other):
+        return OracleKernel(lambda x, y: np.power(self(x, y), other(x, y)))
+
+
+def _p(value):
+    """Kernel parameters may be 0-dim torch tensors (the reference's defaults are float32 tensors); torch promotes them to
+    the dtype of the float64 data, i.e. to float(value)."""
+    return float(value)
+
+
+def kernel_distance_matrix(x, y, norm=2.0):
+    """kernels/utils.py:60-86: ``torch.cdist(x, y, p=norm)``."""
+    diff = np.abs(x[:, None, :] - y[None, :, :])
+    if norm == 1.0:
+        return diff.sum(axis=-1)
+    return np.sqrt((diff * diff).sum(axis=-1))
+
+
+def kernel_euclidean_dist(x, y):
+    """kernels/utils.py:89-110: squared 2-norm distance."""
+    return kernel_distance_matrix(x, y, 2.0) ** 2
+
+
+def LinearKernel():
+    """kernels/linear.py:62-63 (dot product, kernels/utils.py:36-57)."""
+    return OracleKernel(lambda x, y: x @ y.T)
+
+
+def GaussKernel(lengthscale=1.):
+    """kernels/rbf.py GaussKernel.forward: exp(-|x/l - y/l|^2 / 2)."""
+    ls = _p(lengthscale)
+    return OracleKernel(lambda x, y: np.exp(-(kernel_euclidean_dist(x / ls, y / ls) / 2.)))
+
+
+def RBFKernel(gamma=0.5):
+    """kernels/rbf.py RBFKernel: GaussKernel with lengthscale (0.5 / gamma) ** 0.5, evaluated in the parameter's own type."""
+    return GaussKernel((0.5 / gamma) ** 0.5)
+
+
+def PolyKernel(degree=2., const=1.):
+    """kernels/polynomial.py forward."""
+    deg, c = _p(degree), _p(const)
+    return OracleKernel(lambda x, y: np.power(x @ y.T + c, deg))
+
+
+def TanhKernel(coeff=1., const=0.):
+    """kernels/tanh.py forward."""
+    a, c = _p(coeff), _p(const)
+    return OracleKernel(lambda x, y: np.tanh(a * (x @ y.T) + c))
+
+
+def RationalKernel(lengthscale=1., weighting=1.):
+    """kernels/rational.py forward."""
+    ls, w = _p(lengthscale), _p(weighting)
+    return OracleKernel(lambda x, y: np.power(1 + kernel_euclidean_dist(x / ls, y / ls) / (2 * w), -w))
+
+
+def _p32(value):
+    """scale.py:70-72 and diag.py:66-71 build their matrix from ``torch.ones`` of the DEFAULT dtype (float32) and multiply by
+    the scaling before anything is cast to the data's dtype: the constant the reference really uses is float32-rounded."""
+    return float(np.float32(float(value)))
+
+
+def ScaleKernel(scaling=0.):
+    """kernels/scale.py forward."""
+    c = _p32(scaling)
+    return OracleKernel(lambda x, y: np.ones((x.shape[0], y.shape[0])) * c)
+
+
+def DiagKernel(scaling=0.):
+    """kernels/diag.py forward: zeros for different sample counts, else scaling * I."""
+    c = _p32(scaling)
+    return OracleKernel(lambda x, y: np.zeros((x.shape[0], y.shape[0])) if x.shape[0] != y.shape[0]
+                        else np.eye(x.shape[0]) * c)
+
+
+def OrnsteinUhlenbeckKernel(lengthscale=1.):
+    """kernels/orn_uhl.py forward (CPU restatement only: the device path rejects L1 kernels)."""
+    ls = _p(lengthscale)
+    return OracleKernel(lambda x, y: np.exp(-kernel_distance_matrix(x, y, 1.0) / ls))
+
+
+def ketkf_estimate_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_factor: float, kernel=None):
+    """Reference: core/ketkf.py:69-100.  normed_perts (k, p), normed_obs (1, p), kernel: an ``OracleKernel`` (default: linear)
+    -> (w_mean (k,1), w_perts (k,k), cov_analysed (k,k))."""
+    kernel = LinearKernel() if kernel is None else kernel
     ens_size = normed_perts.shape[0]
     reg_value = (ens_size - 1) / inf_factor                                           # ketkf.py:78
-    k_perts = normed_perts @ normed_perts.T                                           # :80
+    k_perts = kernel(normed_perts, normed_perts)                                      # :80
     k_partial_mean = k_perts.mean(axis=-1, keepdims=True)                             # :81
     k_partial_mean = k_partial_mean - k_partial_mean.mean(axis=-2, keepdims=True)     # :82-83
     k_perts_centered = k_perts - k_perts.mean(axis=-2, keepdims=True) - k_partial_mean   # :84-85
     evals, evects, evals_inv = evd(k_perts_centered, reg_value)                       # :87
     cov_analysed = rev_evd(evals_inv, evects)                                         # :88
-    k_obs = normed_perts @ normed_obs.T                                               # :90
+    k_obs = kernel(normed_perts, normed_obs)                                          # :90
     k_obs_centered = k_obs - k_obs.mean(axis=-2, keepdims=True)                       # :91
     k_obs_centered = k_obs_centered - k_partial_mean                                  # :92
     w_mean = cov_analysed @ k_obs_centered                                            # :93
@@ -282,8 +381,8 @@ def ketkf_linear_estimate_weights(normed_perts: np.ndarray, normed_obs: np.ndarr
     return w_mean, w_perts, cov_analysed
 
 
-def ketkf_linear_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_factor: float = 1.0) -> np.ndarray:
-    """``KETKFModule(LinearKernel).forward`` = ``ETKFModule.forward`` (core/etkf.py:79-103) with the kernelised
+def ketkf_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_factor: float = 1.0, kernel=None) -> np.ndarray:
+    """``KETKFModule(kernel).forward`` = ``ETKFModule.forward`` (core/etkf.py:79-103) with the kernelised
     ``_estimate_weights``."""
     normed_perts = np.asarray(normed_perts, dtype=float)
     normed_obs = np.asarray(normed_obs, dtype=float)
@@ -293,9 +392,27 @@ def ketkf_linear_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_f
     ens_size = normed_perts.shape[-2]
     if normed_perts.shape[-1] == 0:
         return np.eye(ens_size) * np.sqrt(inf_factor)
-    w_mean, w_perts, _ = ketkf_linear_estimate_weights(normed_perts.reshape(-1, normed_perts.shape[-1]),
-                                                       normed_obs.reshape(1, -1), inf_factor)
+    w_mean, w_perts, _ = ketkf_estimate_weights(normed_perts.reshape(-1, normed_perts.shape[-1]),
+                                                normed_obs.reshape(1, -1), inf_factor, kernel)
     return w_mean + w_perts
+
+
+def ketkf_linear_estimate_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_factor: float):
+    """core/ketkf.py:69-100 with ``LinearKernel`` (kernels/linear.py:62-63: K(x, y) = x y^T)."""
+    return ketkf_estimate_weights(normed_perts, normed_obs, inf_factor, LinearKernel())
+
+
+def ketkf_linear_weights(normed_perts: np.ndarray, normed_obs: np.ndarray, inf_factor: float = 1.0) -> np.ndarray:
+    """``KETKFModule(LinearKernel).forward``."""
+    return ketkf_weights(normed_perts, normed_obs, inf_factor, LinearKernel())
+
+
+def lketkf_weights_point(grid_row, normed_perts, normed_obs, obs_rows, dist_func, radius, kernel,
+                         epsilon=1e-5, inf_factor=1.0):
+    """One grid point of the localized KETKF (interface/lketkf.py:84-110 -> wrapper.py:86-98 around ``KETKFModule``)."""
+    luse, lweights = gaspari_cohn_localize(dist_func(grid_row, obs_rows), radius, epsilon)
+    lw = np.sqrt(lweights[luse])                                  # wrapper.py:91
+    return ketkf_weights(normed_perts[..., luse] * lw, normed_obs[..., luse] * lw, inf_factor, kernel)
 
 
 # ----------------------------------------------------------------------------------------------

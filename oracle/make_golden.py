@@ -162,6 +162,73 @@ def make_ketkf_golden():
     print("wrote ketkf_linear.npz")
 
 
+def load_reference_kernels(ref=REF):
+    """Every module of pytassim/kernels the device path covers, unchanged, by file path -> namespace of the classes."""
+    load_reference_leaves()
+    core, linear = load_reference_ketkf()
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ref, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    ns = types.SimpleNamespace(LinearKernel=linear.LinearKernel)
+    for modname, classes in (("rbf", ("GaussKernel", "RBFKernel")), ("polynomial", ("PolyKernel",)), ("tanh", ("TanhKernel",)),
+                             ("rational", ("RationalKernel",)), ("scale", ("ScaleKernel",)), ("diag", ("DiagKernel",)),
+                             ("orn_uhl", ("OrnsteinUhlenbeckKernel",))):
+        mod = load("pytassim.kernels." + modname, "pytassim/kernels/{0}.py".format(modname))
+        for cls in classes:
+            setattr(ns, cls, getattr(mod, cls))
+    return core, ns
+
+
+def make_kernels_golden():
+    """tests/golden/ketkf_kernels.npz: ``KETKFModule(kernel)`` of the reference (core/ketkf.py + kernels/*.py) for every
+    configuration of pytassim_b200/testing/kernel_cases.py on seeded inputs, and the localized KETKF
+    (wrapper_localization(wrapper_bridge(KETKFModule)), interface/lketkf.py:84-110) on the reference fixtures."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "torch-assimilate_b200", "pytassim_b200", "testing"))
+    import kernel_cases as kc
+    ref = load_reference_leaves()
+    core, ns = load_reference_kernels()
+    out = {}
+    rng = np.random.RandomState(4321)
+    for i, (k, p, rho) in enumerate(kc.PROBLEM_SIZES):
+        hx = rng.normal(size=(k, p))
+        perts = hx - hx.mean(axis=0, keepdims=True)
+        obs = rng.normal(size=(1, p))
+        out["c{0}_perts".format(i)] = perts; out["c{0}_obs".format(i)] = obs; out["c{0}_rho".format(i)] = np.float64(rho)
+        for name, build in kc.KERNEL_CASES:
+            module = core.KETKFModule(kernel=build(ns, p), inf_factor=torch.tensor(rho, dtype=torch.float64))
+            out["c{0}_w_{1}".format(i, name)] = module(torch.as_tensor(perts), torch.as_tensor(obs)).numpy()
+    out["n_cases"] = np.int64(len(kc.PROBLEM_SIZES))
+    # the L1 kernel the device rejects: pins the oracle's restatement only
+    module = core.KETKFModule(kernel=ns.OrnsteinUhlenbeckKernel(lengthscale=30.), inf_factor=torch.tensor(1.1, dtype=torch.float64))
+    out["c0_w_ornuhl"] = module(torch.as_tensor(out["c0_perts"]), torch.as_tensor(out["c0_obs"])).numpy()
+    fx = read_fixtures()
+    state = fx["state"][:, :1]
+    hx = state[0, 0]                                            # dummy obs operator: variable 'x' (testing/dummy.py:39-66)
+    mean = hx.mean(axis=0)
+    rc = 1.0 / np.sqrt(np.diag(fx["cov"]))
+    perts = (hx - mean) * rc
+    innov = (fx["obs"][0] - mean) * rc
+    grid_rows = np.stack([np.full(40, fx["t_unix"][0]), fx["grid"]], axis=1)
+    obs_rows = np.stack([np.full(40, fx["t_unix"][0]), fx["obs_grid"]], axis=1)
+    loc = ref.loc_gc.GaspariCohn((10.,), lambda g, o: np.abs(g[1] - np.asarray(o)[:, 1]))
+    smean = state.mean(axis=2, keepdims=True)
+    for name, build in kc.KERNEL_CASES:
+        module = core.KETKFModule(kernel=build(ns, 20), inf_factor=torch.tensor(1.1, dtype=torch.float64))
+        bridged = ref.wrapper.wrapper_bridge(module, torch.device("cpu"), torch.float64)
+        localized = ref.wrapper.wrapper_localization(bridged, loc)
+        weights = np.stack([localized(grid_rows[g], perts, innov[None], obs_info=obs_rows) for g in range(40)])
+        out["lketkf_weights_" + name] = weights
+        out["lketkf_analysis_" + name] = smean + np.einsum('vtig,gij->vtjg', state - smean, weights)   # interface/base.py:257-278
+    out.update(lketkf_state=state, lketkf_perts=perts, lketkf_innov=innov, lketkf_grid=fx["grid"],
+               lketkf_obs_grid=fx["obs_grid"])
+    np.savez_compressed(os.path.join(OUT, "ketkf_kernels.npz"), **out)
+    print("wrote ketkf_kernels.npz", os.path.getsize(os.path.join(OUT, "ketkf_kernels.npz")))
+
+
 def make_product_golden():
     """tests/golden/product_loc.npz: the reference's GaspariCohn with a dist_func that returns TWO rows (horizontal ring
     distance x |level difference|) and two length scales: localize_obs for a few grid rows, and the LETKF analysis of the
@@ -346,6 +413,10 @@ def main():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ketkf":
     make_ketkf_golden()
+    sys.exit(0)
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "kernels":
+    make_kernels_golden()
     sys.exit(0)
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "product":

@@ -189,7 +189,8 @@ def test_letkf_with_all_ones_localization_equals_etkf(golden):
 
 def test_kernelised_etkf_linear_kernel(golden):
     """interface/ketkf.py, interface/lketkf.py with the default LinearKernel against the reference's KETKFModule
-    (tests/golden/ketkf_linear.npz), same constructor signatures; other kernels raise (no CPU fallback)."""
+    (tests/golden/ketkf_linear.npz), same constructor signatures; objects that are no kernel descriptors raise (no CPU
+    fallback); the non-linear kernels are covered by tests/test_gpu_kernels.py."""
     from pytassim_b200.interface import KETKF, LKETKF
     from pytassim_b200.kernels import LinearKernel
     g = golden("ketkf_linear.npz")
@@ -206,3 +207,31 @@ def test_kernelised_etkf_linear_kernel(golden):
         KETKF(kernel=object())
     with pytest.raises(NotImplementedError):
         alg.kernel = "rbf"
+
+
+def test_weight_save_path_exports_and_applies_stored_weights(golden, tmp_path):
+    """interface/filter.py:159-162: with ``weight_save_path`` the estimated weights are written as netCDF, loaded back and
+    applied; the analysis equals the fused path, and the stored weights equal the reference's (tests/golden)."""
+    from pytassim_b200.utilities import load_netcdf
+    g, state, obs = _fixture_objects(golden)
+    st0, ob0 = state.isel(time=[0]), obs.isel(time=[0])
+    path = str(tmp_path / "letkf_weights.nc")
+    alg = LETKF(localization=GaspariCohn((10.,), AbsDistance1D()), weight_save_path=path)
+    ana = alg.assimilate(st0, ob0)
+    np.testing.assert_allclose(ana.values, g["a_analysis"], **TOL)
+    stored = alg.load_weights()
+    assert stored.dims == ('grid', 'ensemble', 'ensemble_new') and stored.shape == (40, 10, 10)
+    np.testing.assert_allclose(stored.values, g["a_weights"], **TOL)
+    assert list(stored.indexes['grid']) == list(state.indexes['grid'])
+    # MultiIndex grid: levels encoded in the file, decoded on load
+    mi = pd.MultiIndex.from_product((np.arange(40), [0, ]), names=['grid_point', 'height'])
+    state_mi = xrlite.DataArray(st0.values, dict(var_name=state.indexes["var_name"], time=st0.indexes["time"],
+                                                 ensemble=state.indexes["ensemble"], grid=mi), state.dims)
+    ana_mi = LETKF(localization=GaspariCohn((10.,), AbsDistance1D()), weight_save_path=path).assimilate(state_mi, ob0)
+    np.testing.assert_allclose(ana_mi.values, g["a_analysis"], **TOL)
+    assert load_netcdf(path, array=True).indexes['grid'].equals(mi)
+    # global ETKF
+    gpath = str(tmp_path / "etkf_weights.nc")
+    etkf_ana = ETKF(weight_save_path=gpath).assimilate(state, (obs, obs))
+    np.testing.assert_allclose(etkf_ana.values, g["b_analysis"], **TOL)
+    assert load_netcdf(gpath, array=True).dims == ('ensemble', 'ensemble_new')

@@ -316,7 +316,7 @@ def test_sharded_etkf_entry_points(dtype, tol):
     for j0, j1 in sh.ranges(nobs):
         gram += eng.etkf_gram(ynd, dd, obs_range=(j0, j1))
     aug = np.concatenate([yn.astype(np.float64), d.astype(np.float64)[None]], axis=0)
-    gref = np.tril(aug @ aug.T); gref[k, k] = 0.0
+    gref = np.tril(aug @ aug.T)                       # element (k, k) = d d^T rides along for the kernelised ETKF
     assert np.abs(gram.cpu().numpy() - gref).max() <= 1e-12 * np.abs(gref).max()
     assert np.array_equal(np.triu(gram.cpu().numpy(), 1), np.zeros((k + 1, k + 1)))
     w = eng.etkf_weights_from_gram(gram, nobs)

@@ -124,8 +124,42 @@ def test_constructor_signatures_and_properties():
         alg.dtype = float                                  # interface/base.py:115-118
     alg.inf_factor = 1.3
     assert abs(float(alg.inf_factor) - 1.3) < 1e-12
+    assert ETKF(weight_save_path="weights.nc").weight_save_path == "weights.nc"      # interface/base.py:69
+
+
+def test_weight_store_netcdf_roundtrip(tmp_path):
+    """utilities/xarray.py:36-173 on the weight DataArray of interface/letkf.py:143-147: MultiIndex grid encoded as a range +
+    ``multidim_levels`` + one coordinate per level, decoded on load; netCDF-3 layout of an unnamed xarray DataArray."""
+    from scipy.io import netcdf_file
+    from pytassim_b200.utilities import save_netcdf, load_netcdf, DATAARRAY_VARIABLE
+    rng = np.random.RandomState(0)
+    mi = pd.MultiIndex.from_product(([1.5, 2.5, 3.5], [0, 10]), names=['lat', 'lev'])
+    w = xrlite.DataArray(rng.normal(size=(6, 4, 4)), dict(grid=mi, ensemble=np.arange(4), ensemble_new=np.arange(4)),
+                         ('grid', 'ensemble', 'ensemble_new'))
+    path = str(tmp_path / "weights.nc")
+    assert save_netcdf(w, path) is None
+    nc = netcdf_file(path, 'r', mmap=False)
+    assert set(nc.variables) == {DATAARRAY_VARIABLE, 'grid', 'lat', 'lev', 'ensemble', 'ensemble_new'}
+    assert nc.variables['grid']._attributes['multidim_levels'] == b'lat;lev'                     # xarray.py:84-89
+    assert nc.variables[DATAARRAY_VARIABLE].dimensions == ('grid', 'ensemble', 'ensemble_new')
+    assert np.array_equal(nc.variables['grid'][:], np.arange(6))
+    nc.close()
+    back = load_netcdf(path, array=True)
+    assert back.dims == w.dims and np.array_equal(back.values, w.values)
+    assert isinstance(back.indexes['grid'], pd.MultiIndex) and back.indexes['grid'].equals(mi)
+    assert list(back.indexes['ensemble']) == [0, 1, 2, 3]
+    # global weights, plain integer grid: nothing to encode
+    w2 = xrlite.DataArray(rng.normal(size=(3, 3)), dict(ensemble=np.arange(3), ensemble_new=np.arange(3)), ('ensemble', 'ensemble_new'))
+    save_netcdf(w2, path)
+    assert np.array_equal(load_netcdf(path, array=True).values, w2.values)
+    alg = ETKF(weight_save_path=path)
+    st = xrlite.DataArray(np.zeros((1, 1, 3, 5)), dict(ensemble=np.arange(3), grid=np.arange(5)), ('var_name', 'time', 'ensemble', 'grid'))
+    assert np.array_equal(alg._weights_through_store(st, w2.values), w2.values)          # filter.py:159-162: store, load back
+    w3 = rng.normal(size=(5, 3, 3))
+    assert np.array_equal(alg._weights_through_store(st, w3), w3)
+    assert alg.load_weights().dims == ('grid', 'ensemble', 'ensemble_new')
     with pytest.raises(NotImplementedError):
-        ETKF(weight_save_path="weights.nc")
+        load_netcdf(path)
 
 
 def test_validation_errors_and_warnings(golden):
@@ -317,6 +351,43 @@ def test_kernelised_classes_signatures_and_kernel_check():
     assert str(glob) == "Global KETKF(inf_factor=1.5, kernel=LinearKernel)" and glob.smoother
     with pytest.raises(NotImplementedError):
         KETKF(kernel=lambda x, y: x @ y.T)
+
+
+def test_kernel_descriptors_compile_to_programs():
+    """pytassim_b200.kernels: reference constructor signatures and composition operators (kernels/base_kernels.py:40-161)
+    compile to the postfix program of b200da_plan_set_kernel; the float32 quirks of the reference are mirrored."""
+    import torch
+    from pytassim_b200 import _cabi, kernels as K
+    from pytassim_b200.interface import KETKF, LKETKF
+    from pytassim_b200.testing import kernel_cases as kc
+    assert K.GaussKernel(lengthscale=2.).program() == [(_cabi.KOP_GAUSS, 2.0, 0.0)]
+    # rbf.py:103-104: the length scale is computed in the parameter's own type (float32 for the reference's tensor default)
+    ls32 = K.RBFKernel(gamma=torch.tensor(0.3)).program()[0][1]
+    assert ls32 == float((0.5 / torch.tensor(0.3)) ** 0.5) and ls32 != (0.5 / 0.3) ** 0.5
+    assert K.RBFKernel(gamma=0.3).program()[0][1] == (0.5 / 0.3) ** 0.5
+    # scale.py:70-72: the constant is float32-rounded
+    assert K.ScaleKernel(0.01).program() == [(_cabi.KOP_SCALE, float(np.float32(0.01)), 0.0)]
+    comp = K.GaussKernel(3.) * K.ScaleKernel(2.) + K.DiagKernel(0.5)
+    assert [op for op, _, _ in comp.program()] == [_cabi.KOP_GAUSS, _cabi.KOP_SCALE, _cabi.KOP_MUL, _cabi.KOP_DIAG, _cabi.KOP_ADD]
+    assert str(comp) == "GaussKernel(l=3.0)*ScaleKernel(2.0)+DiagKernel(0.5)" and comp.positive_semidefinite
+    assert not K.TanhKernel().positive_semidefinite and not (K.GaussKernel() ** K.ScaleKernel(2.)).positive_semidefinite
+    assert K.PolyKernel(2., 1.).positive_semidefinite and not K.PolyKernel(2.5, 1.).positive_semidefinite
+    for name, build in kc.KERNEL_CASES:
+        prog = build(K, 40).program()
+        depth = 0
+        for op, _, _ in prog:
+            depth += -1 if op >= _cabi.KOP_ADD else 1
+        assert depth == 1 and len(prog) <= _cabi.MAX_KERNEL_OPS, name
+    for cls in (K.OrnsteinUhlenbeckKernel, K.PeriodicKernel):         # L1 kernels are not functions of the Gram
+        with pytest.raises(NotImplementedError):
+            cls(1.0)
+    with pytest.raises(NotImplementedError):
+        K.GaussKernel() + (lambda x, y: x @ y.T)
+    alg = KETKF(kernel=K.RBFKernel(gamma=0.1), inf_factor=1.2)
+    assert str(alg) == "Global KETKF(inf_factor=1.2, kernel=RBFKernel(γ=0.1))" and alg._kernel_key() == tuple(alg.kernel.program())
+    assert LKETKF(kernel=K.LinearKernel())._kernel_key() == ()
+    alg.kernel = K.PolyKernel()                                        # ketkf.py:118-123: the setter swaps the core module
+    assert alg._kernel_key() == ((_cabi.KOP_POLY, 2.0, 1.0),) and alg._engines == {}
 
 
 def test_product_distance_equals_oracle_rows():

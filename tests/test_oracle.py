@@ -228,3 +228,27 @@ def test_multi_row_localization_against_reference(golden):
     np.testing.assert_allclose(w, g["weights"], rtol=1e-12, atol=1e-12)
     idx = np.concatenate([l[0] if isinstance(l, tuple) else l for l in lists])
     np.testing.assert_array_equal(idx, g["csr_idx"])
+
+
+def test_ketkf_kernel_restatements_against_reference(golden):
+    """core/ketkf.py:69-100 with every kernel configuration of pytassim_b200/testing/kernel_cases.py: the numpy restatement
+    of kernels/*.py reproduces ``KETKFModule(kernel)`` of the reference (tests/golden/ketkf_kernels.npz, written by
+    ``oracle/make_golden.py kernels`` from the reference's own modules), global and localized."""
+    from pytassim_b200.testing import kernel_cases as kc
+    g = golden("ketkf_kernels.npz")
+    assert int(g["n_cases"]) == len(kc.PROBLEM_SIZES)
+    for i, (k, p, rho) in enumerate(kc.PROBLEM_SIZES):
+        perts, obs = g["c%d_perts" % i], g["c%d_obs" % i]
+        assert perts.shape == (k, p) and float(g["c%d_rho" % i]) == rho
+        for name, build in kc.KERNEL_CASES:
+            w = orc.ketkf_weights(perts, obs, rho, build(orc, p))
+            np.testing.assert_allclose(w, g["c%d_w_%s" % (i, name)], rtol=1e-11, atol=1e-12, err_msg=name)
+    w = orc.ketkf_weights(g["c0_perts"], g["c0_obs"], 1.1, orc.OrnsteinUhlenbeckKernel(30.))
+    np.testing.assert_allclose(w, g["c0_w_ornuhl"], rtol=1e-11, atol=1e-12)
+    grid_rows = np.stack([np.zeros(40), g["lketkf_grid"]], axis=1)
+    obs_rows = np.stack([np.zeros(40), g["lketkf_obs_grid"]], axis=1)
+    for name, build in kc.KERNEL_CASES:
+        ws = np.stack([orc.lketkf_weights_point(grid_rows[j], g["lketkf_perts"], g["lketkf_innov"][None], obs_rows,
+                                                orc.dist_abs1d, (10.,), build(orc, 20), inf_factor=1.1) for j in range(40)])
+        np.testing.assert_allclose(ws, g["lketkf_weights_" + name], rtol=1e-11, atol=1e-12, err_msg=name)
+        np.testing.assert_allclose(orc.apply_weights(g["lketkf_state"], ws), g["lketkf_analysis_" + name], rtol=1e-11, atol=1e-12)

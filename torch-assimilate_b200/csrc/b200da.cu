@@ -6,6 +6,7 @@
 #include "letkf_kernel.cuh"
 #include "neighbour_kernel.cuh"
 #include "ns_solve_kernel.cuh"
+#include "kernelise_kernel.cuh"
 #include "launch.cuh"
 
 namespace b200da {
@@ -278,6 +279,43 @@ int b200da_plan_set_extra(b200da_plan* pl, int n_extra, const double* extra_radi
     return B200DA_OK;
 }
 
+int b200da_plan_set_kernel(b200da_plan* pl, int n_ops, const int* ops, const double* p0, const double* p1) {
+    if (!pl || n_ops < 0 || n_ops > kMaxKernelOps || (n_ops > 0 && (!ops || !p0 || !p1))) return B200DA_ERR_INVALID;
+    int depth = 0;                                   // the program must be a well-formed postfix expression
+    for (int i = 0; i < n_ops; ++i) {
+        if (ops[i] < B200DA_KOP_LINEAR || ops[i] > B200DA_KOP_POW) return B200DA_ERR_UNSUPPORTED;
+        if (ops[i] >= B200DA_KOP_ADD) { if (depth < 2) return B200DA_ERR_INVALID; --depth; }
+        else if (++depth > kKernelStack) return B200DA_ERR_UNSUPPORTED;
+        if ((ops[i] == B200DA_KOP_GAUSS || ops[i] == B200DA_KOP_RATIONAL) && !(p0[i] != 0.0)) return B200DA_ERR_INVALID;
+    }
+    if (n_ops > 0 && depth != 1) return B200DA_ERR_INVALID;
+    // multiples of 8 run the Gram with one more tile row (innovation row inside the tiles): instantiated up to 16 rows
+    if (n_ops > 0 && pl->k % 8 == 0 && pl->kt > 16) return B200DA_ERR_UNSUPPORTED;
+    pl->kprog = KernelProgram{};
+    pl->kprog.n = n_ops;
+    for (int i = 0; i < n_ops; ++i) { pl->kprog.op[i] = ops[i]; pl->kprog.p0[i] = p0[i]; pl->kprog.p1[i] = p1[i]; }
+    if (n_ops > 0 && pl->use_tc) {
+        // the kernel functions are evaluated on FP64 Gram entries: FP32 plans use the DMMA Gram (FP32 tiles converted on load)
+        const KernelConfig cfg = config_for_kt(pl->kt);
+        pl->use_tc = false; pl->gpb = cfg.g;
+        pl->have_grid = false; pl->have_obs = false;
+    }
+    if (n_ops > 0 && !pl->use_tc) {
+        const KernelConfig cfg = config_for_kt(pl->kt);
+        pl->kernel_name = std::string("letkf_gram_") + (pl->dtype == B200DA_F32 ? "f32in_f64dmma" : "f64") + "_kt" +
+                          std::to_string(pl->kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg) + "+kernelise";
+    }
+    return B200DA_OK;
+}
+
+// Gram slots -> centred kernel matrix + centred kernel column of the observations, in place (kernelise.cuh)
+static int launch_kernelise(b200da_plan* pl, double* cmat, int64_t n_slots, int64_t slot_stride, cudaStream_t st) {
+    const size_t smem = sizeof(double) * 3 * (size_t)(pl->k + 1);
+    k_kernelise<<<(int)std::min<int64_t>(n_slots, 148 * 16), 128, smem, st>>>(cmat, n_slots, slot_stride, pl->k, pl->kprog);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
 int b200da_set_grid(b200da_plan* plan, const double* grid_coord, int64_t n_grid, void* stream) {
     return set_grid_impl(plan, grid_coord, n_grid, (cudaStream_t)stream);
 }
@@ -400,6 +438,7 @@ static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int
         if (pl->use_tc) { if ((rc = launch_tc_gram(pl, P, (int)(e - b), st))) return rc; }
         else if ((rc = dispatch_fused(pl, P, (int)(e - b), st))) return rc;
         if (pl->timing) B200DA_CUDA(cudaEventRecord(eb, st));
+        if (pl->kprog.n > 0 && (rc = launch_kernelise(pl, pl->cmat.as<double>(), n_slots, slot_stride, st))) return rc;
         if (gram_out) {
             k_unpack_gram<<<(int)std::min<int64_t>(n_slots, 148 * 16), 128, 0, st>>>(P.cmat, P.gpos, s0, n_slots, slot_stride, k + 1, gram_out);
             B200DA_LAUNCH_CHECK();
@@ -542,7 +581,8 @@ static int etkf_solve_partials(b200da_plan* pl, int n_partial, void* W, cudaStre
     const int k = pl->k, kp = pl->kp;
     const int f32 = pl->dtype == B200DA_F32 ? 1 : 0;
     int rc;
-    if (n_partial > 0 && pl->solver == B200DA_SOLVER_NEWTON_SCHULZ) {
+    const bool kernelised = pl->kprog.n > 0;
+    if (n_partial > 0 && (pl->solver == B200DA_SOLVER_NEWTON_SCHULZ || kernelised)) {
         // partial Grams -> one tile-packed slot -> the tensor-core Newton-Schulz solve (one matrix, no state update)
         const size_t slot_doubles = (size_t)tri_tiles(pl->kt) * 64;
         if ((rc = pl->etkf_w.ensure(sizeof(Pos4) + sizeof(double) * slot_doubles))) return rc;
@@ -552,6 +592,24 @@ static int etkf_solve_partials(b200da_plan* pl, int n_partial, void* W, cudaStre
         double* slot = reinterpret_cast<double*>(pl->etkf_w.as<unsigned char>() + sizeof(Pos4));
         k_etkf_reduce<<<grid1d((int64_t)(k + 1) * kp, 128), 128, 0, st>>>(pl->etkf_partial.as<double>(), n_partial, kp, k, slot);
         B200DA_LAUNCH_CHECK();
+        if (kernelised && (rc = launch_kernelise(pl, slot, 1, (int64_t)slot_doubles, st))) return rc;
+        if (pl->solver == B200DA_SOLVER_JACOBI) {         // kernelised only: the slot goes through the per-point Jacobi kernel
+            const size_t smem_j = solve_smem_bytes(k);
+            if (smem_j > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
+            SolveParams J{};
+            J.cmat = slot; J.slot_stride = (int64_t)slot_doubles; J.gpos = pl->etkf_w.as<Pos4>(); J.x = nullptr; J.xa = nullptr;
+            J.w_out = W; J.io_f32 = f32; J.stats = nullptr; J.slot_base = 0; J.n_slots = 1; J.n_grid = 0; J.k = k; J.n_slices = 0;
+            J.rho = pl->rho;
+            if (k > 64) {
+                B200DA_CUDA(cudaFuncSetAttribute(k_letkf_solve<512, 1, 2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_j));
+                k_letkf_solve<512, 1, 2, 4, 4><<<1, 512, smem_j, st>>>(J);
+            } else {
+                B200DA_CUDA(cudaFuncSetAttribute(k_letkf_solve<256, 2, 1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_j));
+                k_letkf_solve<256, 2, 1, 4, 2><<<1, 256, smem_j, st>>>(J);
+            }
+            B200DA_LAUNCH_CHECK();
+            return B200DA_OK;
+        }
         NsParams S{};
         S.cmat = slot; S.slot_stride = (int64_t)slot_doubles; S.gpos = pl->etkf_w.as<Pos4>(); S.x = nullptr; S.xa = nullptr;
         S.w_out = W; S.io_f32 = f32; S.stats = nullptr; S.counter = pl->counter.as<unsigned int>();

@@ -119,20 +119,20 @@ __global__ void k_etkf_reduce(const double* __restrict__ partial, int n_partial,
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (k + 1) * kp) return;
     const int r = e / kp, c = e - r * kp;
-    if (c > r || c >= k) return;
+    if (c > r || (c >= k && r != k)) return;                 // (k, k) = d d^T is kept for the kernelised ETKF (kernelise.cuh)
     double s = 0.0;
     for (int p = 0; p < n_partial; ++p) s += partial[(size_t)p * kp * kp + e];
     slot[sym_off(r, c)] = s;
 }
 
-// Sum the partial Grams in a fixed order into a dense (k+1) x (k+1) row-major lower triangle (row k = b, element (k, k) and
-// the upper triangle zero): the all-reduce payload of the observation-sharded global ETKF.
+// Sum the partial Grams in a fixed order into a dense (k+1) x (k+1) row-major lower triangle (row k = b, element (k, k) =
+// d d^T, the upper triangle zero): the all-reduce payload of the observation-sharded global ETKF.
 __global__ void k_etkf_reduce_dense(const double* __restrict__ partial, int n_partial, int kp, int k, double* __restrict__ gram) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (k + 1) * (k + 1)) return;
     const int r = e / (k + 1), c = e - r * (k + 1);
     double s = 0.0;
-    if (c <= r && c < k)
+    if (c <= r)
         for (int p = 0; p < n_partial; ++p) s += partial[(size_t)p * kp * kp + r * kp + c];
     gram[e] = s;
 }
@@ -142,7 +142,7 @@ __global__ void k_etkf_dense_to_partial(const double* __restrict__ gram, int kp,
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= kp * kp) return;
     const int r = e / kp, c = e - r * kp;
-    partial[e] = (r <= k && c <= r && c < k) ? gram[r * (k + 1) + c] : 0.0;
+    partial[e] = (r <= k && c <= r) ? gram[r * (k + 1) + c] : 0.0;
 }
 
 // Sum the partial Grams in a fixed order, eigendecompose, transform; W (k x k) row-major to global memory.

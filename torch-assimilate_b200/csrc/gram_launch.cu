@@ -8,7 +8,8 @@ namespace b200da {
 
 #define B200DA_KT_CASE(KT, G, WPG) case KT: return launch_fused<KT, G, WPG, false>(pl, P, nblocks, st);
 int dispatch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st) {
-    if (pl->k % 8 == 0) return dispatch_fused_brow(pl, P, nblocks, st);
+    // kernelised plans need d.d, which only the in-tile innovation row produces (kernelise.cuh)
+    if (pl->k % 8 == 0 && pl->kprog.n == 0) return dispatch_fused_brow(pl, P, nblocks, st);
     switch (pl->kt) {
         B200DA_KT_CASE(1, 8, 1) B200DA_KT_CASE(2, 8, 1) B200DA_KT_CASE(3, 8, 1) B200DA_KT_CASE(4, 8, 1)
         B200DA_KT_CASE(5, 8, 1) B200DA_KT_CASE(6, 8, 2) B200DA_KT_CASE(7, 8, 2) B200DA_KT_CASE(8, 4, 4)

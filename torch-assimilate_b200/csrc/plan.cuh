@@ -8,6 +8,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "common.cuh"
+#include "kernelise.cuh"
 
 namespace b200da {
 
@@ -81,6 +82,7 @@ struct b200da_plan {
     b200da::DevBuf gext, oext;  // extra coordinate columns in block- / cell-sorted order (b200da_plan_set_extra)
     double ns_stiff = 0.0;      // 0: default (2e3 for FP64 plans, 2e4 for FP32 plans); see NsParams::stiff
     int solver = B200DA_SOLVER_NEWTON_SCHULZ;
+    b200da::KernelProgram kprog{};   // n > 0: kernelised ETKF (b200da_plan_set_kernel)
     bool collect_stats = false;
     // timing
     bool timing = false;

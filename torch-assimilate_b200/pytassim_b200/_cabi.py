@@ -16,6 +16,9 @@ METRIC_ABS1D, METRIC_PERIODIC1D, METRIC_EUCLID, METRIC_HAVERSINE = 0, 1, 2, 3
 TAPER_GC, TAPER_GCINF = 0, 1
 F64, F32 = 0, 1
 SOLVER_NEWTON_SCHULZ, SOLVER_JACOBI = 0, 1
+# b200da_kernel_op
+(KOP_LINEAR, KOP_GAUSS, KOP_POLY, KOP_TANH, KOP_RATIONAL, KOP_SCALE, KOP_DIAG, KOP_ADD, KOP_MUL, KOP_POW) = range(10)
+MAX_KERNEL_OPS = 16
 
 _c = ctypes
 _vp, _i, _i64, _dbl = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
@@ -26,6 +29,7 @@ SIGNATURES = {
     "b200da_plan_create": (_i, [_c.POINTER(_vp), _i, _i, _i, _i, _dp, _i, _dp, _i, _dbl, _dbl, _i, _i]),
     "b200da_plan_destroy": (None, [_vp]),
     "b200da_plan_set_extra": (_i, [_vp, _i, _dp]),
+    "b200da_plan_set_kernel": (_i, [_vp, _i, _c.POINTER(_c.c_int), _dp, _dp]),
     "b200da_set_grid": (_i, [_vp, _vp, _i64, _vp]),
     "b200da_bin_obs": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "b200da_obs_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),

@@ -345,6 +345,28 @@ class LETKFEngine(object):
         _cabi.check(self.lib.b200da_set_solver(self._plan, {"newton": _cabi.SOLVER_NEWTON_SCHULZ, "jacobi": _cabi.SOLVER_JACOBI}[name]))
         return self
 
+    def set_kernel(self, kernel):
+        """Kernelised ETKF (core/ketkf.py:69-100): ``kernel`` is a :mod:`pytassim_b200.kernels` descriptor or None / a
+        ``LinearKernel`` for the plain ETKF.  Kernels that are not positive semi-definite switch the plan to the
+        eigendecomposition solver, which clamps negative eigenvalues as core/utils.py:58 does.  Call before ``set_grid``."""
+        if kernel is None or getattr(kernel, "is_linear", False):
+            prog = []
+        else:
+            if not hasattr(kernel, "program"):
+                raise NotImplementedError("the B200 engine needs a pytassim_b200.kernels descriptor, got {0!r}".format(kernel))
+            prog = list(kernel.program())
+        if len(prog) > _cabi.MAX_KERNEL_OPS:
+            raise NotImplementedError("kernel compositions are limited to {0} operations".format(_cabi.MAX_KERNEL_OPS))
+        n = len(prog)
+        ops = (ctypes.c_int * max(n, 1))(*[int(p[0]) for p in prog])
+        p0 = (ctypes.c_double * max(n, 1))(*[float(p[1]) for p in prog])
+        p1 = (ctypes.c_double * max(n, 1))(*[float(p[2]) for p in prog])
+        _cabi.check(self.lib.b200da_plan_set_kernel(self._plan, n, ops, p0, p1))
+        if n:
+            self.set_solver("newton" if kernel.positive_semidefinite else "jacobi")
+        self.kernel = kernel if n else None
+        return self
+
     def collect_stats(self, on=True):
         _cabi.check(self.lib.b200da_collect_stats(self._plan, 1 if on else 0))
 

@@ -68,9 +68,7 @@ class BaseAssimilation(object):
         self.pre_transform = pre_transform
         self.post_transform = post_transform
         self.dtype = torch.float64
-        if weight_save_path is not None:
-            raise NotImplementedError("weight_save_path (netCDF weight store) is outside the B200 hot path")
-        self.weight_save_path = None
+        self.weight_save_path = weight_save_path
         self.forward_model = forward_model
 
     # -- properties (base.py:86-126) ---------------------------------------------------------------------------
@@ -236,6 +234,36 @@ class BaseAssimilation(object):
             ys.append(y.reshape(-1)); vars_.append(covv.reshape(-1))
         return (np.concatenate(srcs).astype(np.int64), int(n_grid), np.concatenate(ys), np.concatenate(vars_),
                 np.concatenate(infos, axis=0))
+
+    # -- weight store (base.py:280-324) ------------------------------------------------------------------------------
+    def store_weights(self, weights):
+        """base.py:280-300: ``weights`` (DataArray-like with dims ['grid',] 'ensemble', 'ensemble_new') -> netCDF under
+        ``weight_save_path``; MultiIndex dimensions are stored as single-dimensional indexes (utilities/xarray.py:58-90)."""
+        from ..utilities import save_netcdf
+        return save_netcdf(dataset_to_save=weights, save_path=self.weight_save_path)
+
+    def load_weights(self):
+        """base.py:302-324: the stored weights with their MultiIndexes decoded (the reference's dask chunking of the loaded
+        array has no counterpart here: the weights go back to the device in one piece)."""
+        from ..utilities import load_netcdf
+        return load_netcdf(load_path=self.weight_save_path, array=True)
+
+    def _weights_through_store(self, state, weights):
+        """filter.py:159-162: store the estimated weights, load them back, hand the loaded values on to the update.
+        ``weights``: host array (k, k) (global) or (N, k, k) (one matrix per grid point, reference dims grid x ensemble x
+        ensemble_new, interface/letkf.py:143-147)."""
+        from ..xrlite import DataArray
+        ens = state.indexes['ensemble']
+        coords = dict(ensemble=ens, ensemble_new=ens)
+        dims = ('ensemble', 'ensemble_new')
+        if weights.ndim == 3:
+            coords['grid'] = state.indexes['grid']
+            dims = ('grid', ) + dims
+        self.store_weights(DataArray(np.asarray(weights, dtype=np.float64), coords, dims))
+        loaded = self.load_weights()
+        if loaded.dims != dims:
+            loaded = loaded.transpose(*dims)
+        return np.ascontiguousarray(loaded.values)
 
     @abc.abstractmethod
     def update_state(self, state, observations, pseudo_state, analysis_time):

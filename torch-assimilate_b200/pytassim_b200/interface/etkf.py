@@ -33,11 +33,19 @@ class ETKF(FilterAssimilation):
         self._inf_factor = new_factor
         self._engines = {}
 
+    def _kernel_key(self):
+        """Part of the engine cache key that identifies the ensemble-space kernel (KETKF / LKETKF override it)."""
+        return ()
+
+    def _configure_engine(self, engine):
+        """Hook for subclasses: called once on every freshly created engine (KETKF / LKETKF set the kernel program)."""
+        return engine
+
     def _global_engine(self, k, n_slices):
-        key = ('global', k, n_slices, float(self.inf_factor), self.dtype)
+        key = ('global', k, n_slices, float(self.inf_factor), self.dtype, self._kernel_key())
         if key not in self._engines:
-            self._engines[key] = LETKFEngine(k, n_slices, AbsDistance1D(), 1.0, inf_factor=float(self.inf_factor),
-                                             dtype=self.dtype)
+            self._engines[key] = self._configure_engine(
+                LETKFEngine(k, n_slices, AbsDistance1D(), 1.0, inf_factor=float(self.inf_factor), dtype=self.dtype))
         return self._engines[key]
 
     def _prep_engine(self, k, n_slices):
@@ -46,4 +54,6 @@ class ETKF(FilterAssimilation):
     def _analyse_arrays(self, state, x, innov, perts, obs_info):
         eng = self._global_engine(x.shape[1], x.shape[0])
         weights = eng.etkf_weights(perts, innov)                            # etkf.py:99-120
+        if self.weight_save_path is not None:                               # filter.py:159-162
+            weights = self._weights_through_store(state, weights.cpu().numpy())
         return eng.apply_weights(torch.as_tensor(x), weights).cpu().numpy()  # base.py:257-278

@@ -1,20 +1,23 @@
-"""Kernelised ETKF / localized kernelised ETKF on the B200 engine, linear kernel only.
+"""Kernelised ETKF / localized kernelised ETKF on the B200 engine.
 
 Reference: pytassim/interface/ketkf.py:32-123, interface/lketkf.py:40-110, core/ketkf.py:28-100.  With
 ``LinearKernel`` (the reference's default) ``KETKFModule`` reproduces ``ETKFModule`` on centred perturbations (checked with
-the reference's own modules: 7e-16), so the device path is the LETKF / ETKF one; see :mod:`pytassim_b200.kernels`.
+the reference's own modules: 7e-16), so the device path is the LETKF / ETKF one unchanged.  Every other kernel of
+:mod:`pytassim_b200.kernels` (and their ``+``, ``*``, ``**`` compositions) adds one pass between the Gram and the solve
+kernels that turns the augmented Gram into the double-centred kernel matrix (csrc/kernelise.cuh).
 """
 from .etkf import ETKF
 from .letkf import LETKF
-from ..kernels import LinearKernel
+from ..kernels import BaseKernel, LinearKernel
 
 __all__ = ['KETKF', 'LKETKF']
 
 
 def _check_kernel(kernel):
-    if not isinstance(kernel, LinearKernel):
+    if not isinstance(kernel, BaseKernel):
         raise NotImplementedError(
-            "the B200 engine implements the kernelised ETKF for pytassim_b200.kernels.LinearKernel only, got {0!r}".format(kernel))
+            "the B200 engine evaluates kernels on the device from pytassim_b200.kernels descriptors (there is no CPU "
+            "fallback for arbitrary torch modules), got {0!r}".format(kernel))
     return kernel
 
 
@@ -26,6 +29,14 @@ class _KernelMixin(object):
     @kernel.setter
     def kernel(self, new_kernel):                          # interface/ketkf.py:118-123
         self._kernel = _check_kernel(new_kernel).to(dtype=self.dtype, device=self.device)
+        self._engines = {}
+
+    def _kernel_key(self):
+        kernel = self._kernel
+        return () if kernel.is_linear else tuple(kernel.program())
+
+    def _configure_engine(self, engine):
+        return engine.set_kernel(self._kernel)
 
 
 class KETKF(_KernelMixin, ETKF):

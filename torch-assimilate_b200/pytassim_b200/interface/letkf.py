@@ -34,11 +34,12 @@ class LETKF(ETKF):
     def _local_engine(self, k, n_slices, grid_coords):
         loc = self.localization
         key = ('local', k, n_slices, float(self.inf_factor), self.dtype, type(loc).__name__, repr(loc.dist_func),
-               tuple(np.atleast_1d(loc.radius).tolist()), float(loc.epsilon))
+               tuple(np.atleast_1d(loc.radius).tolist()), float(loc.epsilon), self._kernel_key())
         if key not in self._engines:
             self._engines = {kk: v for kk, v in self._engines.items() if kk[0] != 'local'}
-            self._engines[key] = LETKFEngine(k, n_slices, loc.dist_func, loc.radius, epsilon=loc.epsilon,
-                                             inf_factor=float(self.inf_factor), taper=loc.taper, dtype=self.dtype)
+            self._engines[key] = self._configure_engine(
+                LETKFEngine(k, n_slices, loc.dist_func, loc.radius, epsilon=loc.epsilon, inf_factor=float(self.inf_factor),
+                            taper=loc.taper, dtype=self.dtype))
             self._grid_cache = None
         eng = self._engines[key]
         if self._grid_cache is None or self._grid_cache.shape != grid_coords.shape or \
@@ -61,4 +62,11 @@ class LETKF(ETKF):
             obs_coords = obs_info[:, 1:1 + nc]
         eng = self._local_engine(x.shape[1], x.shape[0], np.ascontiguousarray(grid_coords[:, :nc]))
         eng.bin_obs(obs_coords, perts, innov)
+        if self.weight_save_path is not None:
+            # filter.py:159-162: the weights of every grid point leave the device, go through the netCDF store, come back and
+            # are applied by the stand-alone update kernel (b200da_apply_weights) instead of the fused tail of the solve
+            xd = torch.as_tensor(x).to(eng.device)
+            _, weights = eng.analyse(xd, return_weights=True)
+            weights = self._weights_through_store(state, weights.cpu().numpy())
+            return eng.apply_weights(xd, weights).cpu().numpy()
         return eng.analyse(torch.as_tensor(x)).cpu().numpy()

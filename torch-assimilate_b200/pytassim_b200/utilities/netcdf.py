@@ -1,0 +1,142 @@
+"""The on-disk format of exported ensemble weights (``weight_save_path``).
+
+Reference: pytassim/utilities/xarray.py:36-173 (``save_netcdf``, ``load_netcdf``, ``encode_multidim``, ``decode_multidim``) as
+used by ``BaseAssimilation.store_weights`` / ``load_weights`` (pytassim/interface/base.py:280-324) between
+``estimate_weights`` and ``_apply_weights`` (interface/filter.py:157-163).
+
+The reference writes with ``xarray.DataArray.to_netcdf``; xarray and netCDF4 are not part of this image, so the file is
+written directly as netCDF-3 (64-bit offset) with ``scipy.io.netcdf_file`` — the layout xarray's own scipy backend
+produces for an unnamed DataArray: one data variable ``__xarray_dataarray_variable__``, one coordinate variable per indexed
+dimension, and a ``MultiIndex`` dimension encoded as the reference does (xarray.py:78-90): an integer range as the
+dimension coordinate carrying the attribute ``multidim_levels = "name_1;name_2"`` plus one coordinate variable per level
+(listed in the data variable's ``coordinates`` attribute).  Files written here open with ``xarray.open_dataarray`` +
+``decode_multidim`` where xarray exists, and files written by the reference through its scipy backend load here.
+"""
+import numpy as np
+import pandas as pd
+from scipy.io import netcdf_file
+
+from ..xrlite import DataArray
+
+__all__ = ['save_netcdf', 'load_netcdf', 'encode_multidim', 'decode_multidim', 'DATAARRAY_VARIABLE']
+
+DATAARRAY_VARIABLE = '__xarray_dataarray_variable__'        # xarray.backends.api.DATAARRAY_VARIABLE
+_TIME_UNITS = 'seconds since 1970-01-01 00:00:00'
+
+
+def encode_multidim(array):
+    """xarray.py:58-90 on the (values, dims, indexes) protocol: -> (dims coordinates {dim: (values, attrs)}, level coordinates
+    {name: (dim, values)}).  A MultiIndex dimension becomes ``arange(n)`` with ``multidim_levels``; its levels become plain
+    coordinates on that dimension."""
+    dim_coords, level_coords = {}, {}
+    for dim in array.dims:
+        index = array.indexes[dim]
+        if isinstance(index, pd.MultiIndex):
+            names = list(index.names)
+            if any(n is None for n in names):
+                raise ValueError("the levels of the MultiIndex on '{0}' need names to be stored".format(dim))
+            for name in names:
+                level_coords[name] = (dim, np.asarray(index.get_level_values(name)))
+            dim_coords[dim] = (np.arange(len(index)), {'multidim_levels': ';'.join(names)})          # xarray.py:84-89
+        else:
+            dim_coords[dim] = (np.asarray(index), {})
+    return dim_coords, level_coords
+
+
+def _to_nc3(values):
+    """netCDF-3 has no 64-bit integers / booleans / datetimes: the casts xarray's netCDF-3 encoder applies."""
+    values = np.asarray(values)
+    attrs = {}
+    if np.issubdtype(values.dtype, np.datetime64):
+        values = (values.astype('datetime64[ns]') - np.datetime64('1970-01-01T00:00:00', 'ns')) / np.timedelta64(1, 's')
+        values = np.asarray(values, dtype=np.float64)
+        attrs = {'units': _TIME_UNITS, 'calendar': 'proleptic_gregorian'}
+    elif values.dtype == np.bool_:
+        values = values.astype(np.int8)
+        attrs = {'dtype': 'bool'}
+    elif np.issubdtype(values.dtype, np.integer) and values.dtype.itemsize > 4:
+        if values.size and (values.max() > np.iinfo(np.int32).max or values.min() < np.iinfo(np.int32).min):
+            raise ValueError("integer coordinate does not fit netCDF-3's 32-bit integers")
+        values = values.astype(np.int32)
+    elif values.dtype.kind in 'OUS':
+        raise NotImplementedError("string coordinates are not supported by the netCDF-3 weight store")
+    return values, attrs
+
+
+def save_netcdf(dataset_to_save, save_path=None, *args, **kwargs):
+    """xarray.py:36-55 for a DataArray-like (``values``, ``dims``, ``indexes``): encode MultiIndex dimensions, write netCDF-3."""
+    dim_coords, level_coords = encode_multidim(dataset_to_save)
+    values = np.asarray(dataset_to_save.values)
+    nc = netcdf_file(save_path, 'w', version=2)
+    try:
+        for dim, n in zip(dataset_to_save.dims, values.shape):
+            nc.createDimension(dim, int(n))
+        for dim, (coord, attrs) in dim_coords.items():
+            coord, extra = _to_nc3(coord)
+            var = nc.createVariable(dim, coord.dtype, (dim,))
+            var[:] = coord
+            for key, val in dict(attrs, **extra).items():
+                setattr(var, key, val)
+        for name, (dim, coord) in level_coords.items():
+            coord, extra = _to_nc3(coord)
+            var = nc.createVariable(name, coord.dtype, (dim,))
+            var[:] = coord
+            for key, val in extra.items():
+                setattr(var, key, val)
+        data, _ = _to_nc3(values)
+        var = nc.createVariable(DATAARRAY_VARIABLE, data.dtype, tuple(dataset_to_save.dims))
+        var[:] = data
+        if level_coords:
+            var.coordinates = ' '.join(level_coords.keys())
+    finally:
+        nc.close()
+    return None
+
+
+def decode_multidim(dims, coords, attrs):
+    """xarray.py:137-173: dimensions whose coordinate carries ``multidim_levels`` get their MultiIndex back."""
+    indexes = {}
+    for dim in dims:
+        if dim in attrs and 'multidim_levels' in attrs[dim]:
+            names = attrs[dim]['multidim_levels'].split(';')
+            indexes[dim] = pd.MultiIndex.from_arrays([coords[name] for name in names], names=names)      # xarray.py:163-166
+        elif dim in coords:
+            indexes[dim] = pd.Index(coords[dim], name=dim)
+    return indexes
+
+
+def load_netcdf(load_path, array=False, *args, **kwargs):
+    """xarray.py:93-134 with ``array=True`` (the only form the weight store uses): -> DataArray with decoded MultiIndexes."""
+    if not array:
+        raise NotImplementedError("the weight store holds a single DataArray: call load_netcdf(path, array=True)")
+    nc = netcdf_file(load_path, 'r', mmap=False)
+    try:
+        referenced = set()
+        for var in nc.variables.values():
+            referenced.update(str(getattr(var, 'coordinates', b'').decode()).split())
+        data_names = [name for name in nc.variables if name not in nc.dimensions and name not in referenced]
+        if DATAARRAY_VARIABLE in nc.variables:
+            data_name = DATAARRAY_VARIABLE
+        elif len(data_names) == 1:
+            data_name = data_names[0]
+        else:
+            raise ValueError('Given file dataset contains more than one data variable. Please read with '
+                             'xarray.open_dataset and then select the variable or variables you want.')
+        var = nc.variables[data_name]
+        dims = tuple(var.dimensions)
+        values = np.array(var[:], dtype=var[:].dtype.newbyteorder('='))
+        coords, attrs = {}, {}
+        for name, cvar in nc.variables.items():
+            if name == data_name:
+                continue
+            cvals = np.array(cvar[:], dtype=cvar[:].dtype.newbyteorder('='))
+            if cvals.dtype.kind == 'S' and cvals.ndim == 2:                  # netCDF-3 strings: (n, string_length) characters
+                cvals = np.array([b''.join(row).decode().rstrip('\x00') for row in cvals])
+            cattrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in cvar._attributes.items()}
+            if str(cattrs.get('units', '')).startswith('seconds since 1970-01-01'):
+                cvals = (np.datetime64('1970-01-01T00:00:00', 'ns') +
+                         (cvals * 1e9).round().astype('int64').astype('timedelta64[ns]'))
+            coords[name], attrs[name] = cvals, cattrs
+    finally:
+        nc.close()
+    return DataArray(values, decode_multidim(dims, coords, attrs), dims)
