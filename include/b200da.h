@@ -221,6 +221,25 @@ int b200da_etkf_weights_from_gram(b200da_plan* plan, const double* gram, int64_t
 int b200da_apply_weights_cols(b200da_plan* plan, const void* X, const void* W, int per_grid, int64_t col_begin,
                               int64_t col_end, int64_t n_grid, void* Xa, void* stream);
 
+/* ---- iterative ensemble Kalman smoother (IEnKS), one iteration of the weight update -------------------------------- */
+
+/* Replaces IEnKSTransformModule.forward / IEnKSBundleModule.forward (core/ienks.py:117-174) behind
+ * LocalizedIEnKSTransform.inner_loop / LocalizedIEnKSBundle.inner_loop (interface/lienks.py:68-118: localized_module with the
+ * incoming weights skipped by the localization, args_to_skip = (0,)) followed by _apply_weights (interface/base.py:257-278):
+ * like b200da_letkf, but every grid point starts from its incoming weights W_in ((N, k, k) when w_per_grid, else one
+ * (k, k) matrix for all grid points: the prior identity of the first iteration) and takes one step with learning rate
+ * tau in (0, 1].  epsilon > 0 selects the bundle variant (dh_dw = Yn / epsilon, ienks.py:168-174), epsilon <= 0 the
+ * transform variant (dh_dw = Wp^-1 Yn, ienks.py:74-75).  W_out (N, k, k) receives the updated weights, Xa the state
+ * updated with them (either may not be null).  Grid points without local observations keep W_in (ienks.py:143).  The plan's
+ * inf_factor is not used (the IEnKS has none).  k is limited by shared memory (k <= 96). */
+int b200da_letkf_ienks(b200da_plan* plan, const void* X, void* Xa, const void* W_in, int w_per_grid, void* W_out, double tau,
+                       double epsilon, int64_t block_begin, int64_t block_end, void* stream);
+
+/* Replaces IEnKSTransform.inner_loop / IEnKSBundle.inner_loop (interface/ienks.py:96-118): the global (unlocalized) update of
+ * one (k, k) weight matrix from all observations.  m = 0 copies W_in to W_out. */
+int b200da_etkf_ienks_weights(b200da_plan* plan, const void* Yn, const void* d, int64_t m, const void* W_in, double tau,
+                              double epsilon, void* W_out, void* stream);
+
 /* ---- multi-GPU helpers ------------------------------------------------------------------------------------ */
 
 /* Pack / unpack the analysed columns of blocks [block_begin, block_end) between the (n_slices, k, N) layout and

@@ -416,6 +416,82 @@ def lketkf_weights_point(grid_row, normed_perts, normed_obs, obs_rows, dist_func
 
 
 # ----------------------------------------------------------------------------------------------
+# IEnKS weight update  (pytassim/core/ienks.py, pytassim/core/utils.py:96-199)
+# ----------------------------------------------------------------------------------------------
+
+
+def svd(tensor: np.ndarray, reg_value: float = 0.0):
+    """core/utils.py:96-131: ``torch.svd`` (tensor = u diag(s) v^T) with ``s + reg_value``."""
+    u, s, vh = np.linalg.svd(tensor)
+    return u, s + reg_value, vh.T
+
+
+def rev_svd(u: np.ndarray, s: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """core/utils.py:134-150: ``(u * s) v^T``."""
+    return (u * s) @ v.T
+
+
+def ienks_update_weights(weights: np.ndarray, normed_perts: np.ndarray, normed_obs: np.ndarray, tau: float = 1.0,
+                         epsilon: Optional[float] = None):
+    """``IEnKSTransformModule._update_weights`` (core/ienks.py:117-132); ``epsilon`` not None: ``IEnKSBundleModule``
+    (``_get_dh_dw`` :168-174).  weights (k, k), normed_perts (k, p), normed_obs (1, p) -> (w_mean (k, 1), w_perts (k, k))."""
+    ens_size = weights.shape[-2]                                                      # :123
+    weights_deviation = weights - np.eye(ens_size)                                    # :50 diagonal_add(weights, -1)
+    w_mean = weights_deviation.mean(axis=1, keepdims=True)                            # :51
+    w_perts = weights - w_mean                                                        # :52
+    u, s, v = svd(w_perts)                                                            # :62
+    s_inv = 1 / s                                                                     # :63
+    s_prec = np.square(s_inv)                                                         # :64
+    w_perts_inv = rev_svd(u, s_inv, v).T                                              # :65
+    w_prec = rev_svd(u, s_prec, u) * (ens_size - 1)                                   # :66
+    if epsilon is None:
+        dh_dw = w_perts_inv @ normed_perts                                            # :74
+    else:
+        dh_dw = normed_perts / epsilon                                                # :173
+    dlobs_dh = -normed_obs                                                            # :84
+    grad_obs = dh_dw @ dlobs_dh.T                                                     # :85 matrix_product
+    grad = (ens_size - 1) * w_mean + grad_obs                                         # :86-87
+    new_prec = dh_dw @ dh_dw.T                                                        # :96
+    new_prec = new_prec + (ens_size - 1.) * np.eye(ens_size)                          # :97
+    updated_prec = (1 - tau) * w_prec + tau * new_prec                                # :98
+    u, s, v = svd(updated_prec, reg_value=0.0)                                        # :99
+    s_inv = 1 / s                                                                     # :100
+    weights_cov = rev_svd(u, s_inv, v)                                                # :101
+    s_perts = np.sqrt(s_inv * (ens_size - 1))                                         # :102
+    weights_perts = rev_svd(u, s_perts, v)                                            # :103
+    delta_weight = weights_cov @ grad                                                 # :130
+    w_mean = w_mean - tau * delta_weight                                              # :131
+    return w_mean, weights_perts
+
+
+def ienks_weights(weights: np.ndarray, normed_perts: np.ndarray, normed_obs: np.ndarray, tau: float = 1.0,
+                  epsilon: Optional[float] = None) -> np.ndarray:
+    """``IEnKSTransformModule.forward`` / ``IEnKSBundleModule.forward`` (core/ienks.py:134-151): without observations the
+    incoming weights are returned unchanged."""
+    weights = np.asarray(weights, dtype=float)
+    normed_perts = np.asarray(normed_perts, dtype=float)
+    normed_obs = np.asarray(normed_obs, dtype=float)
+    if normed_perts.shape[-1] != normed_obs.shape[-1]:                                # core/base.py:28-38
+        raise ValueError('Observational size between ensemble ({0:d}) and observations '
+                         '({1:d}) do not match!'.format(normed_perts.shape[-1], normed_obs.shape[-1]))
+    weights = weights.reshape(-1, weights.shape[-1])                                  # :142
+    if normed_perts.shape[-1] > 0:                                                    # :143
+        w_mean, w_perts = ienks_update_weights(weights, normed_perts.reshape(-1, normed_perts.shape[-1]),
+                                               normed_obs.reshape(1, -1), tau, epsilon)
+        weights = w_mean + w_perts                                                    # :149
+    return weights
+
+
+def lienks_weights_point(grid_row, weights, normed_perts, normed_obs, obs_rows, dist_func, radius, tau=1.0, epsilon=None,
+                         loc_epsilon=1e-5):
+    """One grid point of the localized IEnKS (interface/lienks.py:68-118): ``localized_module`` with ``args_to_skip=(0,)``
+    localizes the perturbations and innovations but hands the weights through (interface/wrapper.py:86-98)."""
+    luse, lweights = gaspari_cohn_localize(dist_func(grid_row, obs_rows), radius, loc_epsilon)
+    lw = np.sqrt(lweights[luse])
+    return ienks_weights(weights, normed_perts[..., luse] * lw, normed_obs[..., luse] * lw, tau, epsilon)
+
+
+# ----------------------------------------------------------------------------------------------
 # Per-grid-point glue  (pytassim/interface/wrapper.py)
 # ----------------------------------------------------------------------------------------------
 

@@ -229,6 +229,68 @@ def make_kernels_golden():
     print("wrote ketkf_kernels.npz", os.path.getsize(os.path.join(OUT, "ketkf_kernels.npz")))
 
 
+def make_ienks_golden():
+    """tests/golden/ienks.npz: ``IEnKSTransformModule`` / ``IEnKSBundleModule`` of the reference (core/ienks.py, unchanged, by
+    file path) iterated from the prior identity weights on seeded inputs, and the localized IEnKS
+    (wrapper_localization(wrapper_bridge(module)) with args_to_skip=(0,), interface/lienks.py:68-118) on the reference
+    fixtures for three iterations.  The bundle inputs are scaled by epsilon, as the ensemble the reference propagates for the
+    bundle variant is (interface/ienks.py:153-160)."""
+    ref = load_reference_leaves()
+    spec = importlib.util.spec_from_file_location("pytassim.core.ienks", os.path.join(REF, "pytassim/core/ienks.py"))
+    ienks = importlib.util.module_from_spec(spec)
+    sys.modules["pytassim.core.ienks"] = ienks
+    spec.loader.exec_module(ienks)
+    t64 = lambda v: torch.tensor(v, dtype=torch.float64)
+    out = {}
+    rng = np.random.RandomState(777)
+    cases = [(5, 3, 1.0), (10, 40, 1.0), (24, 60, 0.5), (40, 38, 0.8), (50, 200, 1.0)]
+    for i, (k, p, tau) in enumerate(cases):
+        hx = rng.normal(size=(k, p))
+        perts = hx - hx.mean(axis=0, keepdims=True)
+        obs = rng.normal(size=(1, p))
+        out["c{0}_perts".format(i)] = perts; out["c{0}_obs".format(i)] = obs; out["c{0}_tau".format(i)] = np.float64(tau)
+        for variant, eps in (("transform", None), ("bundle", 1e-2)):
+            module = ienks.IEnKSTransformModule(tau=t64(tau)) if eps is None else ienks.IEnKSBundleModule(epsilon=t64(eps), tau=t64(tau))
+            scale = 1.0 if eps is None else eps
+            w = torch.eye(k, dtype=torch.float64)
+            for it in range(3):                             # same observation-space variables every iteration: pins the core only
+                w = module(w, torch.as_tensor(perts * scale), torch.as_tensor(obs))
+                out["c{0}_{1}_w{2}".format(i, variant, it)] = w.numpy().copy()
+        out["c{0}_eps".format(i)] = np.float64(1e-2)
+    out["n_cases"] = np.int64(len(cases))
+    module = ienks.IEnKSTransformModule(tau=t64(0.7))
+    w_in = rng.normal(size=(6, 6))
+    out["empty_in"] = w_in
+    out["empty_w"] = module(torch.as_tensor(w_in), torch.zeros((6, 0), dtype=torch.float64), torch.zeros((1, 0), dtype=torch.float64)).numpy()
+    # localized IEnKS on the fixtures, first time slice (setup of interface/test_lienks.py = test_letkf.py:106-157)
+    fx = read_fixtures()
+    state = fx["state"][:, :1]
+    hx = state[0, 0]
+    mean = hx.mean(axis=0)
+    rc = 1.0 / np.sqrt(np.diag(fx["cov"]))
+    perts = (hx - mean) * rc
+    innov = (fx["obs"][0] - mean) * rc
+    grid_rows = np.stack([np.full(40, fx["t_unix"][0]), fx["grid"]], axis=1)
+    obs_rows = np.stack([np.full(40, fx["t_unix"][0]), fx["obs_grid"]], axis=1)
+    loc = ref.loc_gc.GaspariCohn((10.,), lambda g, o: np.abs(g[1] - np.asarray(o)[:, 1]))
+    smean = state.mean(axis=2, keepdims=True)
+    for variant, eps, tau in (("transform", None, 0.6), ("bundle", 1e-2, 1.0)):
+        module = ienks.IEnKSTransformModule(tau=t64(tau)) if eps is None else ienks.IEnKSBundleModule(epsilon=t64(eps), tau=t64(tau))
+        bridged = ref.wrapper.wrapper_bridge(module, torch.device("cpu"), torch.float64)
+        localized = ref.wrapper.wrapper_localization(bridged, loc)
+        scale = 1.0 if eps is None else eps
+        weights = np.stack([np.eye(10)] * 40)
+        for it in range(3):
+            weights = np.stack([localized(grid_rows[g], weights[g], perts * scale, innov[None], obs_info=obs_rows,
+                                          args_to_skip=(0, )) for g in range(40)])
+            out["l_{0}_w{1}".format(variant, it)] = weights.copy()
+        out["l_{0}_analysis".format(variant)] = smean + np.einsum('vtig,gij->vtjg', state - smean, weights)
+        out["l_{0}_tau".format(variant)] = np.float64(tau)
+    out.update(l_state=state, l_perts=perts, l_innov=innov, l_grid=fx["grid"], l_obs_grid=fx["obs_grid"], l_eps=np.float64(1e-2))
+    np.savez_compressed(os.path.join(OUT, "ienks.npz"), **out)
+    print("wrote ienks.npz", os.path.getsize(os.path.join(OUT, "ienks.npz")))
+
+
 def make_product_golden():
     """tests/golden/product_loc.npz: the reference's GaspariCohn with a dist_func that returns TWO rows (horizontal ring
     distance x |level difference|) and two length scales: localize_obs for a few grid rows, and the LETKF analysis of the
@@ -417,6 +479,10 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ketkf":
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "kernels":
     make_kernels_golden()
+    sys.exit(0)
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ienks":
+    make_ienks_golden()
     sys.exit(0)
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "product":

@@ -1,0 +1,105 @@
+"""IEnKS weight update (transform and bundle variants) on the GPU through the C ABI (b200da_etkf_ienks_weights,
+b200da_letkf_ienks): Gram -> k_ienks_pre -> ensemble-space solve -> k_ienks_keep, against the reference's
+``IEnKSTransformModule`` / ``IEnKSBundleModule`` (tests/golden/ienks.npz, generated from pytassim/core/ienks.py by
+``oracle/make_golden.py ienks``) and against the oracle restatement.  Tolerance: FP64 rtol = atol = 1e-10."""
+import numpy as np
+import pytest
+import torch
+
+import letkf_oracle as orc
+from pytassim_b200.engine import LETKFEngine
+from pytassim_b200.localization import metrics as m
+from pytassim_b200.testing import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+TOL = dict(rtol=1e-10, atol=1e-10)
+VARIANTS = [("transform", None), ("bundle", 1e-2)]
+
+
+@pytest.mark.parametrize("variant,eps", VARIANTS)
+@pytest.mark.parametrize("solver", ["newton", "jacobi"])
+def test_global_ienks_iterations_against_reference(golden, variant, eps, solver):
+    """interface/ienks.py:96-118 -> core/ienks.py:134-174: three iterations from the prior identity, every iterate compared
+    (the device gets the reference's previous iterate, so errors do not accumulate across the comparison)."""
+    g = golden("ienks.npz")
+    for i in range(int(g["n_cases"])):
+        perts, obs, tau = g["c%d_perts" % i], g["c%d_obs" % i], float(g["c%d_tau" % i])
+        k = perts.shape[0]
+        scale = 1.0 if eps is None else eps
+        eng = LETKFEngine(k, 1, m.AbsDistance1D(), 1.0).set_solver(solver)
+        w = np.eye(k)
+        for it in range(3):
+            w_dev = eng.ienks_weights(w, perts * scale, obs.reshape(-1), tau=tau, epsilon=eps).cpu().numpy()
+            ref = g["c%d_%s_w%d" % (i, variant, it)]
+            np.testing.assert_allclose(w_dev, ref, err_msg="case %d iteration %d" % (i, it), **TOL)
+            w = ref
+        # chained on the device: three iterations without the reference in between
+        w = torch.eye(k, dtype=torch.float64, device="cuda")
+        for it in range(3):
+            w = eng.ienks_weights(w, perts * scale, obs.reshape(-1), tau=tau, epsilon=eps)
+        np.testing.assert_allclose(w.cpu().numpy(), g["c%d_%s_w2" % (i, variant)], rtol=1e-9, atol=1e-9)
+    # no observations: the weights are handed through (core/ienks.py:143)
+    eng = LETKFEngine(6, 1, m.AbsDistance1D(), 1.0)
+    w0 = eng.ienks_weights(g["empty_in"], np.zeros((6, 0)), np.zeros(0), tau=0.7).cpu().numpy()
+    assert np.array_equal(w0, g["empty_w"])
+
+
+@pytest.mark.parametrize("variant,eps", VARIANTS)
+def test_localized_ienks_fixture_against_reference(golden, variant, eps):
+    """interface/lienks.py:68-118 on the reference fixtures (GaspariCohn((10.,), |grid - obs|)): three iterations of the
+    per-grid-point weights (first from the prior identity, then from the (N, k, k) weights) and the final analysis."""
+    g = golden("ienks.npz")
+    state, tau = g["l_state"], float(g["l_%s_tau" % variant])
+    scale = 1.0 if eps is None else eps
+    eng = LETKFEngine(10, 2, m.AbsDistance1D(), 10.0)
+    eng.set_grid(g["l_grid"][:, None])
+    eng.bin_obs(g["l_obs_grid"][:, None], g["l_perts"] * scale, g["l_innov"])
+    x = torch.as_tensor(state.reshape(2, 10, 40)).cuda()
+    w = np.eye(10)
+    for it in range(3):
+        xa, w_dev = eng.ienks_step(x, w, tau=tau, epsilon=eps)
+        ref = g["l_%s_w%d" % (variant, it)]
+        np.testing.assert_allclose(w_dev.cpu().numpy(), ref, err_msg="iteration %d" % it, **TOL)
+        w = ref
+    np.testing.assert_allclose(xa.cpu().numpy().reshape(state.shape), g["l_%s_analysis" % variant], **TOL)
+
+
+@pytest.mark.parametrize("k,tau,eps", [(40, 1.0, None), (50, 0.7, None), (24, 0.5, 1e-2), (50, 1.0, 1e-3)])
+def test_localized_ienks_ring_against_oracle(k, tau, eps):
+    """Lorenz-96 ring (2000 grid points, every 2nd observed, a stretch without observations): two chained device iterations
+    against the oracle on a subset of grid points; grid points without local observations keep their incoming weights and
+    their state columns are updated with those (core/ienks.py:143, interface/base.py:257-278)."""
+    n = 2000
+    data = syn.lorenz96_1d(n, k, 2, seed=11)
+    keep = ~((data["obs_rows"][:, 1] > 900) & (data["obs_rows"][:, 1] < 1100))
+    obs_rows, innov = data["obs_rows"][keep], data["normed_obs"][keep]
+    perts = data["normed_perts"][:, keep] * (1.0 if eps is None else eps)
+    eng = LETKFEngine(k, 1, m.PeriodicDistance1D(float(n)), 20.0)
+    eng.set_grid(data["grid_rows"][:, 1:])
+    eng.bin_obs(obs_rows[:, 1:], perts, innov)
+    x = torch.as_tensor(data["state"].reshape(1, k, n)).cuda()
+    rng = np.random.RandomState(3)
+    w_start = np.eye(k) + 0.05 * rng.normal(size=(k, k))          # a non-trivial incoming matrix, the same for every grid point
+    _, w1 = eng.ienks_step(x, w_start, tau=tau, epsilon=eps)
+    xa, w2 = eng.ienks_step(x, w1, tau=tau, epsilon=eps)
+    sel = np.concatenate([np.arange(0, n, 41), np.arange(985, 1015)])
+    dist = orc.make_dist_periodic1d(float(n))
+    ref = []
+    for j in sel:
+        r1 = orc.lienks_weights_point(data["grid_rows"][j], w_start, perts, innov[None], obs_rows, dist, (20.,), tau, eps)
+        ref.append(orc.lienks_weights_point(data["grid_rows"][j], r1, perts, innov[None], obs_rows, dist, (20.,), tau, eps))
+    ref = np.stack(ref)
+    np.testing.assert_allclose(w2.cpu().numpy()[sel], ref, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(w2.cpu().numpy()[1000], w_start)        # no local observation: handed through twice
+    np.testing.assert_allclose(xa.cpu().numpy().reshape(1, 1, k, n)[..., sel], orc.apply_weights(data["state"][..., sel], ref),
+                               rtol=1e-9, atol=1e-9)
+
+
+def test_ienks_argument_checks():
+    eng = LETKFEngine(10, 1, m.AbsDistance1D(), 1.0)
+    with pytest.raises(ValueError):
+        eng.ienks_weights(np.eye(10), np.zeros((10, 4)), np.zeros(4), tau=0.0)        # tau in (0, 1]
+    with pytest.raises(ValueError):
+        eng.ienks_weights(np.eye(10), np.zeros((10, 4)), np.zeros(5))                 # core/base.py:28-38
+    with pytest.raises(NotImplementedError):
+        LETKFEngine(100, 1, m.AbsDistance1D(), 1.0).ienks_weights(np.eye(100), np.zeros((100, 4)), np.zeros(4))   # k <= 96

@@ -100,7 +100,8 @@ def test_kernel_program_validation_and_reset():
     assert set_prog([_cabi.KOP_ADD]) == _cabi.ERR_INVALID                               # nothing to pop
     assert set_prog([_cabi.KOP_LINEAR, _cabi.KOP_LINEAR]) == _cabi.ERR_INVALID          # two values left
     assert set_prog([99]) == _cabi.ERR_UNSUPPORTED
-    assert set_prog([_cabi.KOP_LINEAR] * 9 + [_cabi.KOP_ADD] * 8) == _cabi.ERR_UNSUPPORTED   # stack deeper than 8
+    assert set_prog([_cabi.KOP_LINEAR] * 9 + [_cabi.KOP_ADD] * 7) == _cabi.ERR_UNSUPPORTED   # stack deeper than 8
+    assert set_prog([_cabi.KOP_LINEAR] * 17) == _cabi.ERR_INVALID                        # more than B200DA_MAX_KERNEL_OPS
     rng = np.random.RandomState(5)
     hx = rng.normal(size=(10, 30)); perts = hx - hx.mean(0); obs = rng.normal(size=30)
     w_etkf = eng.etkf_weights(perts, obs).cpu().numpy()

@@ -252,3 +252,31 @@ def test_ketkf_kernel_restatements_against_reference(golden):
                                                 orc.dist_abs1d, (10.,), build(orc, 20), inf_factor=1.1) for j in range(40)])
         np.testing.assert_allclose(ws, g["lketkf_weights_" + name], rtol=1e-11, atol=1e-12, err_msg=name)
         np.testing.assert_allclose(orc.apply_weights(g["lketkf_state"], ws), g["lketkf_analysis_" + name], rtol=1e-11, atol=1e-12)
+
+
+def test_ienks_restatement_against_reference(golden):
+    """core/ienks.py:28-174: the numpy restatement reproduces ``IEnKSTransformModule`` / ``IEnKSBundleModule`` of the reference
+    over three iterations (tests/golden/ienks.npz from ``oracle/make_golden.py ienks``), the hand-through without observations
+    and the localized call with skipped weights (interface/lienks.py:68-118)."""
+    g = golden("ienks.npz")
+    for i in range(int(g["n_cases"])):
+        perts, obs, tau = g["c%d_perts" % i], g["c%d_obs" % i], float(g["c%d_tau" % i])
+        for variant, eps in (("transform", None), ("bundle", float(g["c%d_eps" % i]))):
+            w = np.eye(perts.shape[0])
+            for it in range(3):
+                w = orc.ienks_weights(w, perts * (1.0 if eps is None else eps), obs, tau, eps)
+                np.testing.assert_allclose(w, g["c%d_%s_w%d" % (i, variant, it)], rtol=1e-11, atol=1e-12)
+    assert np.array_equal(orc.ienks_weights(g["empty_in"], np.zeros((6, 0)), np.zeros((1, 0)), 0.7), g["empty_w"])
+    with pytest.raises(ValueError):
+        orc.ienks_weights(np.eye(3), np.zeros((3, 4)), np.zeros((1, 5)))
+    grid_rows = np.stack([np.zeros(40), g["l_grid"]], axis=1)
+    obs_rows = np.stack([np.zeros(40), g["l_obs_grid"]], axis=1)
+    for variant, eps in (("transform", None), ("bundle", float(g["l_eps"]))):
+        tau = float(g["l_%s_tau" % variant])
+        weights = np.stack([np.eye(10)] * 40)
+        for it in range(3):
+            weights = np.stack([orc.lienks_weights_point(grid_rows[j], weights[j], g["l_perts"] * (1.0 if eps is None else eps),
+                                                         g["l_innov"][None], obs_rows, orc.dist_abs1d, (10.,), tau, eps)
+                                for j in range(40)])
+            np.testing.assert_allclose(weights, g["l_%s_w%d" % (variant, it)], rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(orc.apply_weights(g["l_state"], weights), g["l_%s_analysis" % variant], rtol=1e-11, atol=1e-12)

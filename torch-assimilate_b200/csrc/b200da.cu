@@ -7,6 +7,7 @@
 #include "neighbour_kernel.cuh"
 #include "ns_solve_kernel.cuh"
 #include "kernelise_kernel.cuh"
+#include "ienks_kernel.cuh"
 #include "launch.cuh"
 
 namespace b200da {
@@ -372,8 +373,48 @@ int b200da_grid_order(const b200da_plan* plan, int32_t* order_out, void* stream)
     return B200DA_OK;
 }
 
+// incoming weights and parameters of one IEnKS iteration (ienks_kernel.cuh); null: plain (L)ETKF
+struct IenksArgs {
+    const void* w_in;
+    int per_grid;
+    double tau;
+    double eps;     // > 0: bundle variant
+};
+
+static int ienks_check(const b200da_plan* pl, const IenksArgs& ie) {
+    if (!ie.w_in || !(ie.tau > 0.0) || ie.tau > 1.0) return B200DA_ERR_INVALID;
+    if (pl->kprog.n > 0) return B200DA_ERR_UNSUPPORTED;           // the reference has no kernelised IEnKS either
+    if (ienks_smem_bytes(pl->k) > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
+    return B200DA_OK;
+}
+
+static IenksParams ienks_params(const b200da_plan* pl, const IenksArgs& ie, double* cmat, int64_t n_slots, int64_t slot_stride,
+                                const Pos4* gpos, int64_t slot_base, int* empty) {
+    IenksParams I{};
+    I.cmat = cmat; I.n_slots = n_slots; I.slot_stride = slot_stride; I.gpos = gpos; I.slot_base = slot_base;
+    I.w_in = ie.w_in; I.per_grid = ie.per_grid; I.io_f32 = pl->dtype == B200DA_F32 ? 1 : 0; I.k = pl->k;
+    I.tau = ie.tau; I.eps = ie.eps; I.empty = empty;
+    return I;
+}
+
+static int launch_ienks_pre(const b200da_plan* pl, const IenksParams& I, cudaStream_t st) {
+    const size_t smem = ienks_smem_bytes(pl->k);
+    B200DA_CUDA(cudaFuncSetAttribute(k_ienks_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ienks_pre<<<(int)std::min<int64_t>(I.n_slots, 148 * 8), 256, smem, st>>>(I);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
+static int launch_ienks_keep(const b200da_plan* pl, const IenksParams& I, cudaStream_t st) {
+    const size_t smem = sizeof(double) * ((size_t)pl->k * pl->k + pl->k);
+    B200DA_CUDA(cudaFuncSetAttribute(k_ienks_keep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ienks_keep<<<(int)std::min<int64_t>(I.n_slots, 148 * 16), 128, smem, st>>>(I);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
 static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t block_begin, int64_t block_end,
-                      int64_t* n_ambiguous_opt, double* gram_out, void* stream) {
+                      int64_t* n_ambiguous_opt, double* gram_out, void* stream, const IenksArgs* ie = nullptr) {
     if (!pl || (!gram_out && (!X || !Xa))) return B200DA_ERR_INVALID;
     if (!pl->have_grid || !pl->have_obs) return B200DA_ERR_STATE;
     if (block_begin < 0 || block_end > pl->n_blocks || block_begin > block_end) return B200DA_ERR_INVALID;
@@ -439,6 +480,14 @@ static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int
         else if ((rc = dispatch_fused(pl, P, (int)(e - b), st))) return rc;
         if (pl->timing) B200DA_CUDA(cudaEventRecord(eb, st));
         if (pl->kprog.n > 0 && (rc = launch_kernelise(pl, pl->cmat.as<double>(), n_slots, slot_stride, st))) return rc;
+        IenksParams I{};
+        if (ie) {
+            if ((rc = pl->tmp_a.ensure(sizeof(int) * (size_t)n_slots))) return rc;
+            I = ienks_params(pl, *ie, pl->cmat.as<double>(), n_slots, slot_stride, P.gpos, s0, pl->tmp_a.as<int>());
+            I.x = P.x; I.xa = P.xa; I.w_out = P.w_out; I.n_slices = pl->n_slices; I.n_grid = pl->n_grid;
+            if ((rc = launch_ienks_pre(pl, I, st))) return rc;
+        }
+        const double rho_solve = ie ? 1.0 / ie->tau : pl->rho;      // P = A' + tau (k - 1) I  (ienks_kernel.cuh)
         if (gram_out) {
             k_unpack_gram<<<(int)std::min<int64_t>(n_slots, 148 * 16), 128, 0, st>>>(P.cmat, P.gpos, s0, n_slots, slot_stride, k + 1, gram_out);
             B200DA_LAUNCH_CHECK();
@@ -446,7 +495,7 @@ static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int
             SolveParams S{};
             S.cmat = P.cmat; S.slot_stride = slot_stride; S.gpos = P.gpos; S.x = P.x; S.xa = P.xa; S.w_out = P.w_out; S.stats = P.stats;
             S.io_f32 = f32;
-            S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = pl->rho;
+            S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = rho_solve;
             const int grid = (int)std::min<int64_t>(n_slots, 148 * 64);
             if (big) k_letkf_solve<512, 1, 2, 4, 4><<<grid, 512, smem_solve, st>>>(S);
             else k_letkf_solve<256, 2, 1, 4, 2><<<grid, 256, smem_solve, st>>>(S);
@@ -457,11 +506,12 @@ static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int
             S.cmat = P.cmat; S.slot_stride = slot_stride; S.gpos = P.gpos; S.x = P.x; S.xa = P.xa; S.w_out = P.w_out; S.stats = P.stats;
             S.counter = pl->counter.as<unsigned int>();
             S.io_f32 = f32;
-            S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = pl->rho;
+            S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = rho_solve;
             if ((rc = pl->ns_scratch.ensure(ns_scratch_bytes((k + 7) / 8)))) return rc;
             S.scratch = pl->ns_scratch.as<double>(); S.stiff = ns_stiff_ratio(pl);
             if ((rc = dispatch_ns((k + 7) / 8, S, st))) return rc;
         }
+        if (ie && !gram_out && (rc = launch_ienks_keep(pl, I, st))) return rc;
         if (pl->timing) B200DA_CUDA(cudaEventRecord(ec, st));
         b = e;
     }
@@ -472,6 +522,15 @@ static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int
 int b200da_letkf(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int64_t block_begin, int64_t block_end,
                  int64_t* n_ambiguous_opt, void* stream) {
     return letkf_impl(pl, X, Xa, W_opt, block_begin, block_end, n_ambiguous_opt, nullptr, stream);
+}
+
+int b200da_letkf_ienks(b200da_plan* pl, const void* X, void* Xa, const void* W_in, int w_per_grid, void* W_out, double tau,
+                       double epsilon, int64_t block_begin, int64_t block_end, void* stream) {
+    if (!pl) return B200DA_ERR_INVALID;
+    IenksArgs ie{W_in, w_per_grid ? 1 : 0, tau, epsilon};
+    int rc = ienks_check(pl, ie);
+    if (rc) return rc;
+    return letkf_impl(pl, X, Xa, W_out, block_begin, block_end, nullptr, nullptr, stream, &ie);
 }
 
 int b200da_letkf_gram(b200da_plan* pl, double* gram_out, int64_t block_begin, int64_t block_end, void* stream) {
@@ -577,12 +636,17 @@ static int etkf_partial_grams(b200da_plan* pl, const void* Yn, const void* d, in
 }
 
 // stage 2: n_partial partial Grams in pl->etkf_partial -> W (k, k); n_partial = 0 gives sqrt(rho) I
-static int etkf_solve_partials(b200da_plan* pl, int n_partial, void* W, cudaStream_t st) {
+static int etkf_solve_partials(b200da_plan* pl, int n_partial, void* W, cudaStream_t st, const IenksArgs* ie = nullptr) {
     const int k = pl->k, kp = pl->kp;
     const int f32 = pl->dtype == B200DA_F32 ? 1 : 0;
     int rc;
     const bool kernelised = pl->kprog.n > 0;
-    if (n_partial > 0 && (pl->solver == B200DA_SOLVER_NEWTON_SCHULZ || kernelised)) {
+    const double rho_solve = ie ? 1.0 / ie->tau : pl->rho;
+    if (ie && n_partial == 0) {                            // no observations: the weights stay as they are (ienks.py:143-150)
+        B200DA_CUDA(cudaMemcpyAsync(W, ie->w_in, (f32 ? 4 : 8) * (size_t)k * k, cudaMemcpyDeviceToDevice, st));
+        return B200DA_OK;
+    }
+    if (n_partial > 0 && (pl->solver == B200DA_SOLVER_NEWTON_SCHULZ || kernelised || ie)) {
         // partial Grams -> one tile-packed slot -> the tensor-core Newton-Schulz solve (one matrix, no state update)
         const size_t slot_doubles = (size_t)tri_tiles(pl->kt) * 64;
         if ((rc = pl->etkf_w.ensure(sizeof(Pos4) + sizeof(double) * slot_doubles))) return rc;
@@ -593,13 +657,19 @@ static int etkf_solve_partials(b200da_plan* pl, int n_partial, void* W, cudaStre
         k_etkf_reduce<<<grid1d((int64_t)(k + 1) * kp, 128), 128, 0, st>>>(pl->etkf_partial.as<double>(), n_partial, kp, k, slot);
         B200DA_LAUNCH_CHECK();
         if (kernelised && (rc = launch_kernelise(pl, slot, 1, (int64_t)slot_doubles, st))) return rc;
-        if (pl->solver == B200DA_SOLVER_JACOBI) {         // kernelised only: the slot goes through the per-point Jacobi kernel
+        if (ie) {
+            if ((rc = pl->tmp_a.ensure(sizeof(int) * 4))) return rc;
+            IenksParams I = ienks_params(pl, *ie, slot, 1, (int64_t)slot_doubles, pl->etkf_w.as<Pos4>(), 0, pl->tmp_a.as<int>());
+            I.per_grid = 0;
+            if ((rc = launch_ienks_pre(pl, I, st))) return rc;
+        }
+        if (pl->solver == B200DA_SOLVER_JACOBI) {         // kernelised / IEnKS only: the slot goes through the per-point Jacobi kernel
             const size_t smem_j = solve_smem_bytes(k);
             if (smem_j > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
             SolveParams J{};
             J.cmat = slot; J.slot_stride = (int64_t)slot_doubles; J.gpos = pl->etkf_w.as<Pos4>(); J.x = nullptr; J.xa = nullptr;
             J.w_out = W; J.io_f32 = f32; J.stats = nullptr; J.slot_base = 0; J.n_slots = 1; J.n_grid = 0; J.k = k; J.n_slices = 0;
-            J.rho = pl->rho;
+            J.rho = rho_solve;
             if (k > 64) {
                 B200DA_CUDA(cudaFuncSetAttribute(k_letkf_solve<512, 1, 2, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_j));
                 k_letkf_solve<512, 1, 2, 4, 4><<<1, 512, smem_j, st>>>(J);
@@ -613,7 +683,7 @@ static int etkf_solve_partials(b200da_plan* pl, int n_partial, void* W, cudaStre
         NsParams S{};
         S.cmat = slot; S.slot_stride = (int64_t)slot_doubles; S.gpos = pl->etkf_w.as<Pos4>(); S.x = nullptr; S.xa = nullptr;
         S.w_out = W; S.io_f32 = f32; S.stats = nullptr; S.counter = pl->counter.as<unsigned int>();
-        S.slot_base = 0; S.n_slots = 1; S.n_grid = 0; S.k = k; S.n_slices = 0; S.rho = pl->rho;
+        S.slot_base = 0; S.n_slots = 1; S.n_grid = 0; S.k = k; S.n_slices = 0; S.rho = rho_solve;
         if ((rc = pl->ns_scratch.ensure(ns_scratch_bytes((k + 7) / 8)))) return rc;
         S.scratch = pl->ns_scratch.as<double>(); S.stiff = ns_stiff_ratio(pl);
         return dispatch_ns((k + 7) / 8, S, st);
@@ -632,6 +702,18 @@ int b200da_etkf_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t 
     int rc, n_partial = 0;
     if ((rc = etkf_partial_grams(pl, Yn, d, m, m, &n_partial, st))) return rc;
     return etkf_solve_partials(pl, n_partial, W, st);
+}
+
+int b200da_etkf_ienks_weights(b200da_plan* pl, const void* Yn, const void* d, int64_t m, const void* W_in, double tau,
+                              double epsilon, void* W_out, void* stream) {
+    if (!pl || !W_out || m < 0 || (m > 0 && (!Yn || !d))) return B200DA_ERR_INVALID;
+    IenksArgs ie{W_in, 0, tau, epsilon};
+    int rc = ienks_check(pl, ie);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    int n_partial = 0;
+    if ((rc = etkf_partial_grams(pl, Yn, d, m, m, &n_partial, st))) return rc;
+    return etkf_solve_partials(pl, n_partial, W_out, st, &ie);
 }
 
 int b200da_etkf_gram(b200da_plan* pl, const void* Yn, const void* d, int64_t m, int64_t ld_obs, double* gram_out, void* stream) {

@@ -41,6 +41,8 @@ SIGNATURES = {
     "b200da_grid_order": (_i, [_vp, _vp, _vp]),
     "b200da_letkf": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "b200da_letkf_gram": (_i, [_vp, _vp, _i64, _i64, _vp]),
+    "b200da_letkf_ienks": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _dbl, _dbl, _i64, _i64, _vp]),
+    "b200da_etkf_ienks_weights": (_i, [_vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _vp, _vp]),
     "b200da_letkf_host": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "b200da_neighbour_count": (_i, [_vp, _vp, _vp, _vp]),
     "b200da_neighbour_fill": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -170,6 +170,40 @@ class LETKFEngine(object):
             res.append(int(amb.item()))
         return res[0] if len(res) == 1 else tuple(res)
 
+    def ienks_step(self, state, weights, tau=1.0, epsilon=None, out=None, blocks=None):
+        """One localized IEnKS iteration (interface/lienks.py:68-118 -> core/ienks.py:134-151) and the update with the new
+        weights (interface/base.py:257-278).  ``weights``: (k, k) (the prior identity of the first iteration) or (N, k, k);
+        ``epsilon`` None: transform variant, else the bundle variant.  Returns (analysis (n_slices, k, N), weights (N, k, k))."""
+        x = _dev(state, dtype=self.dtype, device=self.device).reshape(self.n_slices, self.k, self.n_grid)
+        w_in = _dev(weights, dtype=self.dtype, device=self.device)
+        per_grid = 1 if w_in.dim() == 3 else 0
+        if tuple(w_in.shape[-2:]) != (self.k, self.k) or (per_grid and w_in.shape[0] != self.n_grid):
+            raise ValueError("weights must be (ens_size, ens_size) or (n_grid, ens_size, ens_size)")
+        xa = torch.empty_like(x) if out is None else out
+        w_out = torch.empty((self.n_grid, self.k, self.k), dtype=self.dtype, device=self.device)
+        b0, b1 = (0, self.n_blocks) if blocks is None else blocks
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_letkf_ienks(self._plan, _ptr(x), _ptr(xa), _ptr(w_in), per_grid, _ptr(w_out), float(tau),
+                                                    -1.0 if epsilon is None else float(epsilon), b0, b1, _stream()))
+        return xa, w_out
+
+    def ienks_weights(self, weights, normed_perts, normed_obs, tau=1.0, epsilon=None):
+        """``IEnKSTransformModule.forward`` / ``IEnKSBundleModule.forward`` on the device (core/ienks.py:134-174): one global
+        (k, k) weight update from all observations."""
+        yn = _dev(normed_perts, dtype=self.dtype, device=self.device)
+        d = _dev(normed_obs, dtype=self.dtype, device=self.device).reshape(-1)
+        if yn.shape[-1] != d.shape[-1]:
+            raise ValueError('Observational size between ensemble ({0:d}) and observations '
+                             '({1:d}) do not match!'.format(yn.shape[-1], d.shape[-1]))
+        w_in = _dev(weights, dtype=self.dtype, device=self.device)
+        if tuple(w_in.shape) != (self.k, self.k):
+            raise ValueError("weights must be (ens_size, ens_size)")
+        w_out = torch.empty_like(w_in)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_etkf_ienks_weights(self._plan, _ptr(yn), _ptr(d), d.shape[0], _ptr(w_in), float(tau),
+                                                           -1.0 if epsilon is None else float(epsilon), _ptr(w_out), _stream()))
+        return w_out
+
     def local_gram(self, blocks=None):
         """(N, k+1, k+1) FP64: the localization-weighted augmented Gram matrix of every grid point (lower triangle),
         i.e. the output of the Gram kernel alone (parity hook; core/etkf.py:68,72 after interface/wrapper.py:91-97)."""
