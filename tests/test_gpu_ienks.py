@@ -103,3 +103,78 @@ def test_ienks_argument_checks():
         eng.ienks_weights(np.eye(10), np.zeros((10, 4)), np.zeros(5))                 # core/base.py:28-38
     with pytest.raises(NotImplementedError):
         LETKFEngine(100, 1, m.AbsDistance1D(), 1.0).ienks_weights(np.eye(100), np.zeros((100, 4)), np.zeros(4))   # k <= 96
+
+
+def _forward_model(st, iter_num):
+    """A weakly non-linear 'model': (analysis state, pseudo state used for the observation equivalents)."""
+    v = np.asarray(st.values)
+    return st, st.copy(data=v + 0.05 * np.tanh(v))
+
+
+@pytest.mark.parametrize("localized", [True, False])
+@pytest.mark.parametrize("eps", [None, 1e-3])
+def test_ienks_interface_classes_against_oracle_loop(golden, localized, eps):
+    """interface/variational.py:105-135 through ``assimilate``: three outer iterations (model propagation of the weighted
+    ensemble, observation operator, correlated-R normalisation, weight update, final update) on the reference fixtures
+    against the same loop written with the oracle's functions."""
+    from pytassim_b200.interface import IEnKSTransform, IEnKSBundle, LocalizedIEnKSTransform, LocalizedIEnKSBundle
+    from pytassim_b200.localization import GaspariCohn, AbsDistance1D
+    from test_host_logic import _fixture_objects
+    g, state, obs = _fixture_objects(golden)
+    ob0 = obs.isel(time=[0])
+    tau, n_iter, k = 0.8, 3, 10
+    loc = GaspariCohn((10.,), AbsDistance1D()) if localized else None
+    if eps is None:
+        alg = LocalizedIEnKSTransform(_forward_model, localization=loc, tau=tau, max_iter=n_iter) if localized \
+            else IEnKSTransform(_forward_model, tau=tau, max_iter=n_iter)
+    else:
+        alg = LocalizedIEnKSBundle(_forward_model, localization=loc, tau=tau, epsilon=eps, max_iter=n_iter) if localized \
+            else IEnKSBundle(_forward_model, tau=tau, epsilon=eps, max_iter=n_iter)
+    ana = alg.assimilate(state, ob0, analysis_time="1992-12-25 00:00")
+    assert ana.dims == state.dims and ana.shape == (2, 1, 10, 40)
+    # the same loop with the oracle
+    st0 = g["state"][:, :1]
+    grid_rows = np.stack([np.zeros(40), g["grid"]], axis=1)
+    obs_rows = np.stack([np.zeros(40), g["obs_grid"]], axis=1)
+    weights = np.stack([np.eye(k)] * 40)
+    for _ in range(n_iter):
+        model_w = weights if eps is None else eps * np.eye(k) + weights.mean(axis=-1, keepdims=True)   # ienks.py:153-160
+        model = orc.apply_weights(st0, model_w)
+        pseudo = model + 0.05 * np.tanh(model)
+        innov, perts = orc.obs_space_variables([pseudo[0, 0][:, None, :]], [g["obs"][:1]], [g["cov"]])
+        if localized:
+            weights = np.stack([orc.lienks_weights_point(grid_rows[j], weights[j], perts, innov[None], obs_rows, orc.dist_abs1d,
+                                                         (10.,), tau, eps) for j in range(40)])
+        else:
+            weights = np.stack([orc.ienks_weights(weights[0], perts, innov[None], tau, eps)] * 40)
+    ref = orc.apply_weights(st0, weights)
+    np.testing.assert_allclose(ana.values, ref, rtol=1e-9, atol=1e-9)
+
+
+def test_ienks_smoother_and_weight_store(golden, tmp_path):
+    """variational.py:132-133 (smoother mode propagates the analysis once more) and :56-80 (weights of every iteration go
+    through the netCDF store when ``weight_save_path`` is set)."""
+    from pytassim_b200.interface import LocalizedIEnKSTransform
+    from pytassim_b200.localization import GaspariCohn, AbsDistance1D
+    from test_host_logic import _fixture_objects
+    g, state, obs = _fixture_objects(golden)
+    ob0 = obs.isel(time=[0])
+    calls = []
+
+    def model(st, iter_num):
+        calls.append(iter_num)
+        return st.copy(data=np.asarray(st.values) * 2.0), st
+
+    path = str(tmp_path / "ienks_weights.nc")
+    kw = dict(localization=GaspariCohn((10.,), AbsDistance1D()), tau=1.0, max_iter=2)
+    plain = LocalizedIEnKSTransform(model, **kw).assimilate(state, ob0, analysis_time="1992-12-25 00:00")
+    assert calls == [0, 1]
+    stored = LocalizedIEnKSTransform(model, weight_save_path=path, smoother=True, **kw)
+    ana = stored.assimilate(state, ob0, analysis_time="1992-12-25 00:00")
+    assert calls == [0, 1, 0, 1, 2]
+    np.testing.assert_allclose(ana.values, 2.0 * plain.values, rtol=1e-12, atol=1e-12)
+    w = stored.load_weights()
+    assert w.dims == ('grid', 'ensemble', 'ensemble_new') and w.shape == (40, 10, 10)
+    # with tau = 1 and an identity model the first iteration is the LETKF without inflation (core/ienks.py vs core/etkf.py)
+    one = LocalizedIEnKSTransform(lambda st, it: (st, st), localization=kw["localization"], tau=1.0, max_iter=1)
+    np.testing.assert_allclose(one.assimilate(state, ob0, analysis_time="1992-12-25 00:00").values, g["a_analysis"], **TOL)

@@ -390,6 +390,34 @@ def test_kernel_descriptors_compile_to_programs():
     assert alg._kernel_key() == ((_cabi.KOP_POLY, 2.0, 1.0),) and alg._engines == {}
 
 
+def test_ienks_classes_signatures_and_bounds():
+    """interface/ienks.py:34-164, interface/lienks.py:40-163: constructor signatures, string forms, tau / epsilon bounds
+    (utilities/decorators.py:51-75) and the bundle's model weights (ienks.py:153-160)."""
+    import torch
+    from pytassim_b200.interface import IEnKSTransform, IEnKSBundle, LocalizedIEnKSTransform, LocalizedIEnKSBundle
+    fm = lambda st, it: (st, st)
+    alg = IEnKSTransform(forward_model=fm, tau=0.5, max_iter=4, smoother=False, gpu=False, pre_transform=None,
+                         post_transform=None, weight_save_path=None)
+    assert str(alg) == "IEnKSTransform(tau=0.5)" and repr(alg) == "IEnKSTransform(0.5)" and alg.max_iter == 4
+    bun = IEnKSBundle(forward_model=fm, tau=1.0, epsilon=1E-4, max_iter=10)
+    assert str(bun) == "IEnKSBundle(epsilon=0.0001, tau=1.0)" and repr(bun) == "IEnKSBundle(0.0001,1.0)"
+    loc = GaspariCohn((10.,), AbsDistance1D())
+    lt = LocalizedIEnKSTransform(forward_model=fm, localization=loc, tau=1.0, max_iter=10, smoother=False, gpu=False,
+                                 pre_transform=None, post_transform=None, chunksize=10, weight_save_path=None)
+    assert str(lt) == "Localized IEnKSTransform(loc=GaspariCohn(l=[10.]), tau=1.0)" and lt.chunks == {"grid": 10}
+    lb = LocalizedIEnKSBundle(forward_model=fm, localization=loc, tau=0.9, epsilon=1E-2)
+    assert repr(lb) == "LIEnKSBundle(GaspariCohn,0.01,0.9)"
+    for bad in (-0.1, 1.5):
+        with pytest.raises(ValueError):
+            alg.tau = bad
+    with pytest.raises(ValueError):
+        bun.epsilon = -1.0
+    w = torch.arange(9, dtype=torch.float64).reshape(3, 3)
+    bun.epsilon = 0.5
+    np.testing.assert_array_equal(bun._get_model_weights(w).numpy(), 0.5 * np.eye(3) + w.numpy().mean(axis=1, keepdims=True))
+    assert alg._get_model_weights(w) is w
+
+
 def test_product_distance_equals_oracle_rows():
     from pytassim_b200.localization import ProductDistance, HaversineDistance
     rng = np.random.RandomState(3)

@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+( timeout 600 python -m pytest tests/test_gpu_ienks.py -m gpu -q 2>&1 | grep -E "^E  |FAILED|passed|failed|Error|error" | head -80 ) > gpurun_out/r34_pytest_new.log 2>&1
+cat gpurun_out/r34_pytest_new.log
