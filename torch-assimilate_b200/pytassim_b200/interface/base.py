@@ -71,7 +71,21 @@ class BaseAssimilation(object):
         self.weight_save_path = weight_save_path
         self.forward_model = forward_model
 
-    # -- properties (base.py:86-126) ---------------------------------------------------------------------------
+    # -- properties (base.py:83-126) ---------------------------------------------------------------------------
+    @property
+    def core_module(self):
+        """base.py:83-85: the device-backed core module of this algorithm (:mod:`pytassim_b200.core`)."""
+        return self._make_core_module()
+
+    def _make_core_module(self):
+        raise NotImplementedError("this assimilation has no core module")
+
+    @property
+    def module(self):
+        """base.py:87-104: the core module bridged to numpy arrays (interface/wrapper.py:29-62)."""
+        from .wrapper import wrapper_bridge
+        return wrapper_bridge(self.core_module, self.device, self.dtype)
+
     @property
     def dtype(self):
         return self._dtype

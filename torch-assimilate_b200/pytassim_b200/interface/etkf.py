@@ -33,6 +33,10 @@ class ETKF(FilterAssimilation):
         self._inf_factor = new_factor
         self._engines = {}
 
+    def _make_core_module(self):
+        from ..core import ETKFModule
+        return ETKFModule(inf_factor=self.inf_factor)
+
     def _kernel_key(self):
         """Part of the engine cache key that identifies the ensemble-space kernel (KETKF / LKETKF override it)."""
         return ()

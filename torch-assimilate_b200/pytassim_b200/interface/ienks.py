@@ -155,6 +155,10 @@ class IEnKSTransform(VarAssimilation):
     def _epsilon_value(self):
         return None
 
+    def _make_core_module(self):
+        from ..core import IEnKSTransformModule
+        return IEnKSTransformModule(tau=self.tau)
+
     def inner_loop(self, engine, state, x_dev, weights, perts, innov, obs_info):     # ienks.py:96-118
         return engine.ienks_weights(weights, perts, innov, tau=float(self.tau), epsilon=self._epsilon_value)
 
@@ -186,6 +190,10 @@ class IEnKSBundle(IEnKSTransform):
     def _epsilon_value(self):
         return float(self.epsilon)
 
+    def _make_core_module(self):
+        from ..core import IEnKSBundleModule
+        return IEnKSBundleModule(epsilon=self.epsilon, tau=self.tau)
+
     def _get_model_weights(self, weights):
         """ienks.py:153-160: ``epsilon * I + mean over ensemble_new`` — the bundle around the current mean weights."""
         k = weights.shape[-1]
@@ -199,6 +207,12 @@ class _LocalizedMixin(object):
     @property
     def chunks(self):
         return dict(grid=self.chunksize)
+
+    @property
+    def localized_module(self):
+        """mixin_local.py:37-42."""
+        from .wrapper import wrapper_localization
+        return wrapper_localization(module=self.module, localization=self.localization)
 
     def _analysis_engine(self, state, k, n_slices):
         loc = self.localization

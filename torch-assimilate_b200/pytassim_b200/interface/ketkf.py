@@ -38,6 +38,10 @@ class _KernelMixin(object):
     def _configure_engine(self, engine):
         return engine.set_kernel(self._kernel)
 
+    def _make_core_module(self):
+        from ..core import KETKFModule
+        return KETKFModule(kernel=self._kernel, inf_factor=self.inf_factor)
+
 
 class KETKF(_KernelMixin, ETKF):
     def __init__(self, kernel=None, inf_factor=1.0, smoother=False, gpu=False, pre_transform=None, post_transform=None,

@@ -31,6 +31,12 @@ class LETKF(ETKF):
     def chunks(self):
         return dict(grid=self.chunksize)                   # mixin_local.py:34-36
 
+    @property
+    def localized_module(self):
+        """mixin_local.py:37-42: one grid point per call (numpy in / out) — the per-grid-point form of the hot loop."""
+        from .wrapper import wrapper_localization
+        return wrapper_localization(module=self.module, localization=self.localization)
+
     def _local_engine(self, k, n_slices, grid_coords):
         loc = self.localization
         key = ('local', k, n_slices, float(self.inf_factor), self.dtype, type(loc).__name__, repr(loc.dist_func),
