@@ -178,3 +178,28 @@ def test_ienks_smoother_and_weight_store(golden, tmp_path):
     # with tau = 1 and an identity model the first iteration is the LETKF without inflation (core/ienks.py vs core/etkf.py)
     one = LocalizedIEnKSTransform(lambda st, it: (st, st), localization=kw["localization"], tau=1.0, max_iter=1)
     np.testing.assert_allclose(one.assimilate(state, ob0, analysis_time="1992-12-25 00:00").values, g["a_analysis"], **TOL)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-4)])
+def test_ienks_first_iteration_is_letkf_at_scale(dtype, tol):
+    """Size-independent identity at the cfg2 size (N = 100 000, k = 40, every 2nd variable observed): from the prior identity
+    weights with tau = 1 the transform IEnKS step is the LETKF without inflation (core/ienks.py:117-132 with W = I reduces to
+    core/etkf.py:57-77), and the bundle step with perturbations scaled by epsilon is the same matrix.  FP32 plans take the
+    tcgen05 Gram in front of the IEnKS pre-pass."""
+    n, k = 100_000, 40
+    data = syn.lorenz96_1d(n, k, 2, seed=42)
+    npd = np.float64 if dtype == torch.float64 else np.float32
+    eng = LETKFEngine(k, 1, m.PeriodicDistance1D(float(n)), 20.0, inf_factor=1.0, dtype=dtype)
+    eng.set_grid(data["grid_rows"][:, 1:])
+    eng.bin_obs(data["obs_rows"][:, 1:], data["normed_perts"].astype(npd), data["normed_obs"].astype(npd))
+    x = torch.as_tensor(data["state"].reshape(1, k, n).astype(npd)).cuda()
+    xa_ref, w_ref = eng.analyse(x, return_weights=True)
+    xa, w = eng.ienks_step(x, np.eye(k), tau=1.0)
+    scale = float(w_ref.abs().max())
+    assert float((w - w_ref).abs().max()) <= tol * scale
+    assert float((xa - xa_ref).abs().max()) <= tol * float(xa_ref.abs().max())
+    if dtype == torch.float64:
+        eps = 2.0 ** -7                                             # a power of two: the scaling is exact
+        eng.bin_obs(data["obs_rows"][:, 1:], data["normed_perts"] * eps, data["normed_obs"])
+        _, wb = eng.ienks_step(x, np.eye(k), tau=1.0, epsilon=eps)
+        assert float((wb - w_ref).abs().max()) <= tol * scale

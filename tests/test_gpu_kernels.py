@@ -130,3 +130,23 @@ def test_kernelised_interface_classes(golden):
     ana = alg.assimilate(st0, ob0).values
     w = orc.ketkf_weights(gk["lketkf_perts"], gk["lketkf_innov"][None], 1.1, BUILD["rational"](orc, 20))
     np.testing.assert_allclose(ana, orc.apply_weights(gk["lketkf_state"], w), **TOL)
+
+
+def test_linear_program_is_letkf_at_scale():
+    """Size-independent identity at the cfg2 size (N = 100 000, k = 40): the kernelise pass with a program that is the linear
+    kernel (centred perturbations: the centring terms vanish, core/ketkf.py:80-92) reproduces the LETKF weights of every grid
+    point; k = 40 also switches the Gram to the variant with the innovation row inside the tiles."""
+    n, k = 100_000, 40
+    data = syn.lorenz96_1d(n, k, 2, seed=42)
+    x = torch.as_tensor(data["state"].reshape(1, k, n)).cuda()
+    res = []
+    for kernel in (None, K.LinearKernel() + K.ScaleKernel(0.)):
+        eng = LETKFEngine(k, 1, m.PeriodicDistance1D(float(n)), 20.0, inf_factor=1.1)
+        if kernel is not None:
+            eng.set_kernel(kernel)
+        eng.set_grid(data["grid_rows"][:, 1:])
+        eng.bin_obs(data["obs_rows"][:, 1:], data["normed_perts"], data["normed_obs"])
+        res.append(eng.analyse(x, return_weights=True))
+    (xa0, w0), (xa1, w1) = res
+    assert float((w1 - w0).abs().max()) <= 1e-10 * float(w0.abs().max())
+    assert float((xa1 - xa0).abs().max()) <= 1e-10 * float(xa0.abs().max())
