@@ -36,6 +36,22 @@ class OracleEngine(object):
         out[:, :, torch.as_tensor(sel)] = torch.as_tensor(ana[0])
         return out
 
+    def ienks_step(self, x, weights, tau=1.0, epsilon=None, out=None, blocks=None):
+        b0, b1 = blocks
+        sel = self.order[self.offsets[b0]:self.offsets[b1]]
+        d = self.data
+        k, n = x.shape[1], x.shape[2]
+        w_in = weights.numpy() if isinstance(weights, torch.Tensor) else np.asarray(weights)
+        w_out = torch.full((n, k, k), float("nan"), dtype=torch.float64)
+        dist_func = orc.make_dist_periodic1d(self.period)
+        for g in sel:
+            w_g = w_in if w_in.ndim == 2 else w_in[g]
+            w_new = orc.lienks_weights_point(d["grid_rows"][g], w_g, d["normed_perts"], d["normed_obs"][None], d["obs_rows"],
+                                             dist_func, (self.radius,), tau, epsilon)
+            w_out[g] = torch.as_tensor(w_new)
+            out[:, :, g] = torch.as_tensor(orc.apply_weights(x.numpy()[None][..., g:g + 1], w_new[None])[0, ..., 0])
+        return out, w_out
+
     def pack_columns(self, xa, b0, b1):
         sel = torch.as_tensor(self.order[self.offsets[b0]:self.offsets[b1]])
         return xa.reshape(-1, xa.shape[-1])[:, sel].contiguous()
@@ -63,6 +79,47 @@ def _worker(rank, world, port, n_grid, ret):
     sh.run(x, out)
     ret[rank] = out.numpy()
     dist.destroy_process_group()
+
+
+def _worker_ienks(rank, world, port, n_grid, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    data = syn.lorenz96_1d(n_grid, 6, 2, seed=22)
+    x = torch.as_tensor(data["state"][0]).clone()
+    sh = ShardedAnalysis(OracleEngine(data, 4.0, 1.0, float(n_grid)))
+    out = torch.full_like(x, float("nan"))
+    weights = torch.eye(6, dtype=torch.float64)
+    for _ in range(2):                                                  # the rank's weights stay on the rank between iterations
+        weights = sh.run_ienks(x, weights, out, tau=0.8)
+    ret[rank] = (out.numpy(), weights.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_ienks_two_ranks_gloo():
+    """Two chained localized IEnKS iterations over two ranks: every rank ends with the whole analysis, each rank holds the
+    weights of its own grid points only (the other rank's entries are never needed and stay NaN)."""
+    n_grid = 43
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_worker_ienks, args=(2, port, n_grid, ret), nprocs=2, join=True)
+    data = syn.lorenz96_1d(n_grid, 6, 2, seed=22)
+    dist_func = orc.make_dist_periodic1d(float(n_grid))
+    ws = np.stack([np.eye(6)] * n_grid)
+    for _ in range(2):
+        ws = np.stack([orc.lienks_weights_point(data["grid_rows"][g], ws[g], data["normed_perts"], data["normed_obs"][None],
+                                                data["obs_rows"], dist_func, (4.0,), 0.8, None) for g in range(n_grid)])
+    ref = orc.apply_weights(data["state"], ws)[0]
+    owned = np.zeros(n_grid, dtype=int)
+    for rank in (0, 1):
+        out, weights = ret[rank]
+        np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12)
+        mine = ~np.isnan(weights[:, 0, 0])
+        np.testing.assert_allclose(weights[mine], ws[mine], rtol=1e-12, atol=1e-12)
+        owned += mine
+    assert np.array_equal(owned, np.ones(n_grid, dtype=int))           # every grid point is owned by exactly one rank
 
 
 def test_block_range_partitions_everything():

@@ -8,7 +8,9 @@ CPU tensors for the host-logic tests).  Grid points are independent given the ob
 data-path collective.
 
 ``engine`` is duck-typed: ``n_blocks``, ``block_offset(b)``, ``analyse(x, out=, blocks=(b0, b1))``,
-``pack_columns(xa, b0, b1) -> (rows, ncols)`` and ``unpack_columns(packed, b0, b1, xa)``.
+``ienks_step(x, weights, tau=, epsilon=, out=, blocks=)``, ``pack_columns(xa, b0, b1) -> (rows, ncols)`` and
+``unpack_columns(packed, b0, b1, xa)``.  An engine with a kernel program (``set_kernel``) shards the same way: the
+kernelise pass is per grid point.
 """
 import torch
 import torch.distributed as dist
@@ -44,6 +46,20 @@ class ShardedAnalysis(object):
         """Analyse this rank's blocks of ``x`` (n_slices, k, N) into ``out`` and fill in every other rank's columns."""
         b0, b1 = self.ranges[self.rank]
         self.engine.analyse(x, out=out, blocks=(b0, b1))
+        return self._gather_columns(out)
+
+    def run_ienks(self, x, weights, out, tau=1.0, epsilon=None):
+        """One localized IEnKS iteration (interface/lienks.py:68-118) on this rank's blocks: ``weights`` is (k, k) or the
+        (N, k, k) array of the previous iteration, of which only this rank's grid points are read.  Returns the updated
+        (N, k, k) weights — valid for this rank's grid points, which is all the next iteration needs here, so the weights are
+        never communicated — and fills ``out`` with the state updated by every rank's weights (all-gathered columns)."""
+        b0, b1 = self.ranges[self.rank]
+        _, new_weights = self.engine.ienks_step(x, weights, tau=tau, epsilon=epsilon, out=out, blocks=(b0, b1))
+        self._gather_columns(out)
+        return new_weights
+
+    def _gather_columns(self, out):
+        b0, b1 = self.ranges[self.rank]
         if self.world == 1:
             return out
         rows = out.shape[0] * out.shape[1]
