@@ -107,7 +107,10 @@ def test_kernel_program_validation_and_reset():
     w_etkf = eng.etkf_weights(perts, obs).cpu().numpy()
     eng.set_kernel(K.LinearKernel() + K.ScaleKernel(0.))          # a program that is the linear kernel: same weights
     np.testing.assert_allclose(eng.etkf_weights(perts, obs).cpu().numpy(), w_etkf, rtol=1e-11, atol=1e-12)
-    eng.set_kernel(None)
+    assert eng.kernel_name.endswith("+kernelise")
+    eng.set_kernel(K.TanhKernel())                                # not positive semi-definite: the plan switches to the Jacobi solver
+    eng.set_kernel(None)                                          # ... and back to the default with the plain ETKF
+    assert "kernelise" not in eng.kernel_name
     assert np.array_equal(eng.etkf_weights(perts, obs).cpu().numpy(), w_etkf)
     with pytest.raises(NotImplementedError):
         LETKFEngine(128, 1, m.AbsDistance1D(), 1.0).set_kernel(K.RBFKernel())           # multiples of 8 up to k = 120

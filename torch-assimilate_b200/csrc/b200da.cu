@@ -301,10 +301,12 @@ int b200da_plan_set_kernel(b200da_plan* pl, int n_ops, const int* ops, const dou
         pl->use_tc = false; pl->gpb = cfg.g;
         pl->have_grid = false; pl->have_obs = false;
     }
-    if (n_ops > 0 && !pl->use_tc) {
+    if (!pl->use_tc) {                                  // name of the DMMA Gram variant that will run (dispatch_fused)
         const KernelConfig cfg = config_for_kt(pl->kt);
-        pl->kernel_name = std::string("letkf_gram_") + (pl->dtype == B200DA_F32 ? "f32in_f64dmma" : "f64") + "_kt" +
-                          std::to_string(pl->kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg) + "+kernelise";
+        const bool brow = pl->k % 8 == 0 && n_ops == 0;
+        pl->kernel_name = std::string("letkf_gram_") + (pl->dtype == B200DA_F32 ? "f32in_f64dmma" : "f64") + (brow ? "_brow" : "") +
+                          "_kt" + std::to_string(brow ? pl->kt - 1 : pl->kt) + "_g" + std::to_string(cfg.g) + "_w" +
+                          std::to_string(cfg.wpg) + (n_ops > 0 ? "+kernelise" : "");
     }
     return B200DA_OK;
 }

@@ -396,8 +396,12 @@ class LETKFEngine(object):
         p0 = (ctypes.c_double * max(n, 1))(*[float(p[1]) for p in prog])
         p1 = (ctypes.c_double * max(n, 1))(*[float(p[2]) for p in prog])
         _cabi.check(self.lib.b200da_plan_set_kernel(self._plan, n, ops, p0, p1))
-        if n:
-            self.set_solver("newton" if kernel.positive_semidefinite else "jacobi")
+        if n and not kernel.positive_semidefinite:
+            self.set_solver("jacobi")
+            self._kernel_forced_jacobi = True
+        elif getattr(self, "_kernel_forced_jacobi", False):       # back to the default solver the previous kernel had replaced
+            self.set_solver("newton")
+            self._kernel_forced_jacobi = False
         self.kernel = kernel if n else None
         return self
 
