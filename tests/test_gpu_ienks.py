@@ -203,3 +203,32 @@ def test_ienks_first_iteration_is_letkf_at_scale(dtype, tol):
         eng.bin_obs(data["obs_rows"][:, 1:], data["normed_perts"] * eps, data["normed_obs"])
         _, wb = eng.ienks_step(x, np.eye(k), tau=1.0, epsilon=eps)
         assert float((wb - w_ref).abs().max()) <= tol * scale
+
+
+@pytest.mark.parametrize("eps", [None, 1e-3])
+def test_localized_ienks_six_chained_iterations(eps):
+    """Error growth over a chain: six localized iterations on the device without the oracle in between (every iteration
+    inverts the previous weights, core/ienks.py:62-65) stay within 1e-9 of the oracle chain."""
+    n, k, tau, n_iter = 600, 24, 0.9, 6
+    data = syn.lorenz96_1d(n, k, 2, seed=19)
+    perts = data["normed_perts"] * (1.0 if eps is None else eps)
+    eng = LETKFEngine(k, 1, m.PeriodicDistance1D(float(n)), 20.0)
+    eng.set_grid(data["grid_rows"][:, 1:])
+    eng.bin_obs(data["obs_rows"][:, 1:], perts, data["normed_obs"])
+    x = torch.as_tensor(data["state"].reshape(1, k, n)).cuda()
+    w = torch.eye(k, dtype=torch.float64, device="cuda")
+    for _ in range(n_iter):
+        xa, w = eng.ienks_step(x, w, tau=tau, epsilon=eps)
+    sel = np.arange(0, n, 23)
+    dist = orc.make_dist_periodic1d(float(n))
+    ref = []
+    for j in sel:
+        r = np.eye(k)
+        for _ in range(n_iter):
+            r = orc.lienks_weights_point(data["grid_rows"][j], r, perts, data["normed_obs"][None], data["obs_rows"], dist, (20.,),
+                                         tau, eps)
+        ref.append(r)
+    ref = np.stack(ref)
+    np.testing.assert_allclose(w.cpu().numpy()[sel], ref, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(xa.cpu().numpy().reshape(1, 1, k, n)[..., sel], orc.apply_weights(data["state"][..., sel], ref),
+                               rtol=1e-9, atol=1e-9)
