@@ -313,8 +313,10 @@ int b200da_plan_set_kernel(b200da_plan* pl, int n_ops, const int* ops, const dou
 
 // Gram slots -> centred kernel matrix + centred kernel column of the observations, in place (kernelise.cuh)
 static int launch_kernelise(b200da_plan* pl, double* cmat, int64_t n_slots, int64_t slot_stride, cudaStream_t st) {
-    const size_t smem = sizeof(double) * 3 * (size_t)(pl->k + 1);
-    k_kernelise<<<(int)std::min<int64_t>(n_slots, 148 * 16), 128, smem, st>>>(cmat, n_slots, slot_stride, pl->k, pl->kprog);
+    const size_t smem = kernelise_smem_bytes(pl->k);
+    if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
+    B200DA_CUDA(cudaFuncSetAttribute(k_kernelise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_kernelise<<<(int)std::min<int64_t>(n_slots, 148 * 16), 256, smem, st>>>(cmat, n_slots, slot_stride, pl->k, pl->kprog);
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }

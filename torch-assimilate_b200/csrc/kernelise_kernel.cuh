@@ -40,11 +40,16 @@ __device__ inline double kernel_eval(const KernelProgram& K, double xy, double x
 
 // One CTA per slot (grid-stride).  Slots whose augmented Gram has a zero diagonal (no local observation) are left alone:
 // the reference returns the inflated prior weights there (core/etkf.py:91-95) and the zero Gram gives exactly that.
-// dynamic shared memory: 3 * (k + 1) doubles.
-__global__ void __launch_bounds__(128) k_kernelise(double* __restrict__ cmat, int64_t n_slots, int64_t slot_stride, int k,
+// Every kernel value is evaluated once (lower triangle, mirrored into a k x (k + 1) shared-memory copy); row means and the
+// centring then work from shared memory.  Dynamic shared memory: kernelise_smem_bytes(k).
+__host__ __device__ inline size_t kernelise_smem_bytes(int k) { return sizeof(double) * ((size_t)k * (k + 1) + 3 * (size_t)(k + 1)); }
+
+__global__ void __launch_bounds__(256) k_kernelise(double* __restrict__ cmat, int64_t n_slots, int64_t slot_stride, int k,
                                                    const KernelProgram K) {
     extern __shared__ double ksm[];
-    double* dg = ksm;                 // [k + 1] diagonal of G
+    const int ld = k + 1;
+    double* Ks = ksm;                 // [k][k + 1] kernel matrix
+    double* dg = Ks + (size_t)k * ld; // [k + 1] diagonal of G
     double* rmean = dg + (k + 1);     // [k] row means of the kernel matrix                          ketkf.py:81
     double* kobs = rmean + (k + 1);   // [k] K(x_i, d)                                               ketkf.py:90
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -53,15 +58,20 @@ __global__ void __launch_bounds__(128) k_kernelise(double* __restrict__ cmat, in
         int nonzero = 0;
         for (int i = tid; i <= k; i += nt) { const double v = C[sym_off(i, i)]; dg[i] = v; nonzero |= (v != 0.0); }
         if (!__syncthreads_or(nonzero)) continue;
+        for (int e = tid; e < k * k; e += nt) {                      // K[i][j] = K[j][i], j <= i                   ketkf.py:80
+            const int i = e / k, j = e - i * k;
+            if (j > i) continue;
+            const double v = kernel_eval(K, C[sym_off(i, j)], dg[i], dg[j], i == j, true);
+            Ks[i * ld + j] = v;
+            Ks[j * ld + i] = v;
+        }
+        // one observation vector: diag.py:66-67 gives zeros unless k == 1
+        for (int i = tid; i < k; i += nt) kobs[i] = kernel_eval(K, C[sym_off(k, i)], dg[i], dg[k], k == 1, k == 1);
+        __syncthreads();
         for (int i = tid; i < k; i += nt) {
-            const double xx = dg[i];
             double sum = 0.0;
-            for (int j = 0; j < k; ++j) {
-                const double g = j <= i ? C[sym_off(i, j)] : C[sym_off(j, i)];
-                sum += kernel_eval(K, g, xx, dg[j], i == j, true);
-            }
+            for (int j = 0; j < k; ++j) sum += Ks[i * ld + j];
             rmean[i] = sum / (double)k;
-            kobs[i] = kernel_eval(K, C[sym_off(k, i)], xx, dg[k], k == 1, k == 1);   // one observation vector: diag.py:66-67 gives zeros unless k == 1
         }
         __syncthreads();
         double mu = 0.0, ko = 0.0;                                   // same order in every thread
@@ -70,9 +80,7 @@ __global__ void __launch_bounds__(128) k_kernelise(double* __restrict__ cmat, in
         // K_c[i, j] = K[i, j] - mean_i K[:, j] - (mean_j K[i, :] - mu)                             ketkf.py:81-85
         for (int e = tid; e < k * k; e += nt) {
             const int i = e / k, j = e - i * k;
-            if (j > i) continue;
-            const size_t off = sym_off(i, j);
-            C[off] = kernel_eval(K, C[off], dg[i], dg[j], i == j, true) - rmean[j] - (rmean[i] - mu);
+            if (j <= i) C[sym_off(i, j)] = Ks[i * ld + j] - rmean[j] - (rmean[i] - mu);
         }
         // k_obs_c[i] = k_obs[i] - mean(k_obs) - (mean_j K[i, :] - mu)                              ketkf.py:91-92
         for (int i = tid; i < k; i += nt) C[sym_off(k, i)] = (kobs[i] - ko) - (rmean[i] - mu);
