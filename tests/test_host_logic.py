@@ -433,3 +433,32 @@ def test_product_distance_equals_oracle_rows():
         ProductDistance(m1)
     with pytest.raises(ValueError):
         ProductDistance(AbsDistance1D(), n_extra=3)
+
+
+def test_netcdf_store_coordinate_encodings(tmp_path):
+    """netCDF-3 has no 64-bit integers, booleans or datetimes: the store applies the casts xarray's netCDF-3 encoder applies
+    (int64 -> int32, datetime64 -> seconds since the epoch with units) and undoes the time encoding on load; a named data
+    variable (a DataArray saved with a name by the reference) is found as the only non-coordinate variable."""
+    from scipy.io import netcdf_file
+    from pytassim_b200.utilities import save_netcdf, load_netcdf
+    t = pd.to_datetime("1992-12-25") + pd.to_timedelta(np.arange(3), unit="h")
+    arr = xrlite.DataArray(np.arange(12.0).reshape(3, 4), dict(time=t, grid=np.arange(4, dtype=np.int64) * 10), ("time", "grid"))
+    path = str(tmp_path / "a.nc")
+    save_netcdf(arr, path)
+    nc = netcdf_file(path, "r", mmap=False)
+    assert nc.variables["grid"][:].dtype.itemsize == 4 and nc.variables["time"].units.decode().startswith("seconds since 1970")
+    nc.close()
+    back = load_netcdf(path, array=True)
+    assert list(pd.DatetimeIndex(back.indexes["time"])) == list(t) and list(back.indexes["grid"]) == [0, 10, 20, 30]
+    assert np.array_equal(back.values, arr.values)
+    with pytest.raises(ValueError):                                  # does not fit 32-bit integers
+        save_netcdf(xrlite.DataArray(np.zeros(2), dict(grid=np.array([0, 2 ** 40])), ("grid", )), path)
+    with pytest.raises(NotImplementedError):                         # string coordinates
+        save_netcdf(xrlite.DataArray(np.zeros(2), dict(var_name=["x", "y"]), ("var_name", )), path)
+    nc = netcdf_file(path, "w", version=2)                           # a file as xarray writes a NAMED DataArray
+    nc.createDimension("ensemble", 2); nc.createDimension("ensemble_new", 2)
+    v = nc.createVariable("ensemble", "i4", ("ensemble", )); v[:] = [0, 1]
+    v = nc.createVariable("weights", "f8", ("ensemble", "ensemble_new")); v[:] = np.eye(2)
+    nc.close()
+    named = load_netcdf(path, array=True)
+    assert named.dims == ("ensemble", "ensemble_new") and np.array_equal(named.values, np.eye(2))
