@@ -232,3 +232,33 @@ def test_localized_ienks_six_chained_iterations(eps):
     np.testing.assert_allclose(w.cpu().numpy()[sel], ref, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(xa.cpu().numpy().reshape(1, 1, k, n)[..., sel], orc.apply_weights(data["state"][..., sel], ref),
                                rtol=1e-9, atol=1e-9)
+
+
+def test_multi_chunk_identities_sphere():
+    """More grid points than one Gram-scratch chunk holds (the scratch is capped at 2 GiB = about 150 000 slots at k = 50, so
+    302 500 points run as three chunks): the IEnKS first iteration and the linear kernel program must reproduce the LETKF
+    weights in every chunk (slot offsets, per-chunk flags and scratch reuse of k_ienks_pre / k_ienks_keep / k_kernelise)."""
+    from pytassim_b200 import kernels as K
+    k = 50
+    data = syn.sphere_latlon(550, 550, k, 200_000, seed=5)
+    n = data["state"].shape[-1]
+    x = torch.as_tensor(data["state"].reshape(1, k, n)).cuda()
+    metric = m.HaversineDistance(6371.0)
+
+    def engine(kernel=None):
+        eng = LETKFEngine(k, 1, metric, 500.0, inf_factor=1.0)
+        if kernel is not None:
+            eng.set_kernel(kernel)
+        eng.set_grid(data["grid_rows"][:, 1:])
+        eng.bin_obs(data["obs_rows"][:, 1:], data["normed_perts"], data["normed_obs"])
+        return eng
+    eng = engine()
+    xa_ref, w_ref = eng.analyse(x, return_weights=True)
+    xa, w = eng.ienks_step(x, np.eye(k), tau=1.0)
+    scale = float(w_ref.abs().max())
+    assert float((w - w_ref).abs().max()) <= 1e-10 * scale
+    assert float((xa - xa_ref).abs().max()) <= 1e-10 * float(xa_ref.abs().max())
+    del w, xa
+    xa2, w2 = engine(K.LinearKernel() + K.ScaleKernel(0.)).analyse(x, return_weights=True)
+    assert float((w2 - w_ref).abs().max()) <= 1e-10 * scale
+    assert float((xa2 - xa_ref).abs().max()) <= 1e-10 * float(xa_ref.abs().max())
