@@ -230,7 +230,9 @@ int b200da_apply_weights_cols(b200da_plan* plan, const void* X, const void* W, i
  * (k, k) matrix for all grid points: the prior identity of the first iteration) and takes one step with learning rate
  * tau in (0, 1].  epsilon > 0 selects the bundle variant (dh_dw = Yn / epsilon, ienks.py:168-174), epsilon <= 0 the
  * transform variant (dh_dw = Wp^-1 Yn, ienks.py:74-75).  W_out (N, k, k) receives the updated weights, Xa the state
- * updated with them (either may not be null).  Grid points without local observations keep W_in (ienks.py:143).  The plan's
+ * updated with them (either may not be null).  Grid points without local observations keep W_in (ienks.py:143); they are
+ * recognised by an all-zero Gram diagonal and innovation row, so local observations whose localized perturbations and
+ * innovations are all exactly zero count as none.  The plan's
  * inf_factor is not used (the IEnKS has none).  k is limited by shared memory (k <= 96). */
 int b200da_letkf_ienks(b200da_plan* plan, const void* X, void* Xa, const void* W_in, int w_per_grid, void* W_out, double tau,
                        double epsilon, int64_t block_begin, int64_t block_end, void* stream);
