@@ -43,6 +43,21 @@ def test_cabi_binding_covers_header():
     assert lib.b200da_launch_count() >= 0
 
 
+def test_cabi_constants_match_header_enums():
+    """The Python constants of the binding are the enum values of include/b200da.h (guards against ABI drift)."""
+    import re
+    text = open(os.path.join(ROOT, "include", "b200da.h")).read()
+    enums = {name: int(val) for name, val in re.findall(r"\b(B200DA_[A-Z0-9_]+)\s*=\s*(-?\d+)", text)}
+    for name, val in enums.items():
+        short = name[len("B200DA_"):]
+        if hasattr(_cabi, short):
+            assert getattr(_cabi, short) == val, name
+    for short in ("KOP_LINEAR", "KOP_GAUSS", "KOP_POLY", "KOP_TANH", "KOP_RATIONAL", "KOP_SCALE", "KOP_DIAG", "KOP_ADD", "KOP_MUL",
+                  "KOP_POW", "METRIC_HAVERSINE", "TAPER_GCINF", "F32", "SOLVER_JACOBI", "ERR_UNSUPPORTED"):
+        assert "B200DA_" + short in enums and enums["B200DA_" + short] == getattr(_cabi, short), short
+    assert int(re.search(r"#define B200DA_MAX_KERNEL_OPS (\d+)", text).group(1)) == _cabi.MAX_KERNEL_OPS
+
+
 def test_plan_create_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
