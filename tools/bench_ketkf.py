@@ -37,7 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--only", default=None, help="cfg2 | cfg3: run one workload (the short command wrapped by ncu)")
+    ap.add_argument("--only", default=None, help="cfg2 | cfg3 | cfg3b: run one workload (the short command wrapped by ncu)")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -48,6 +48,9 @@ def main():
     torch.cuda.set_device(0)
     works = [("cfg2: L96 ring N=100000 k=40 M=50000 c=20", syn.lorenz96_1d(100000, 40, 2, seed=42), m.PeriodicDistance1D(100000.0), 20.0, 38),
              ("cfg3/11: sphere 300x300 k=50 M=225000 c=1000km", syn.sphere_latlon(300, 300, 50, 225000, seed=42), m.HaversineDistance(6371.0), 1000.0, 5100)]
+    if args.only == "cfg3b":             # a third of cfg3 in each direction of the grid: p about 17 000 local observations
+        works = [("cfg3b: sphere 550x550 k=50 M=750000 c=1000km", syn.sphere_latlon(550, 550, 50, 750000, seed=42),
+                  m.HaversineDistance(6371.0), 1000.0, 17000)]
     works = [w for w in works if args.only is None or w[0].startswith(args.only)]
     for name, data, metric, radius, p in works:
         k, n = data["state"].shape[2], data["state"].shape[3]
