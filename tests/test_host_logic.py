@@ -477,3 +477,82 @@ def test_netcdf_store_coordinate_encodings(tmp_path):
     nc.close()
     named = load_netcdf(path, array=True)
     assert named.dims == ("ensemble", "ensemble_new") and np.array_equal(named.values, np.eye(2))
+
+
+def _emulate_program(prog, xy, xx, yy, diag, same_set):
+    """numpy emulation of the postfix interpreter of csrc/kernelise_kernel.cuh (kernel_eval) — the semantics of the program the
+    descriptors compile to, checked here without a GPU against the oracle's restatement of pytassim/kernels."""
+    from pytassim_b200 import _cabi as c
+    st = []
+    for op, a, b in prog:
+        if op == c.KOP_LINEAR:
+            st.append(xy)
+        elif op == c.KOP_GAUSS:
+            st.append(np.exp(-(np.maximum((xx + yy - 2.0 * xy) / (a * a), 0.0) / 2.0)))
+        elif op == c.KOP_POLY:
+            st.append(np.power(xy + b, a))
+        elif op == c.KOP_TANH:
+            st.append(np.tanh(a * xy + b))
+        elif op == c.KOP_RATIONAL:
+            st.append(np.power(1.0 + np.maximum((xx + yy - 2.0 * xy) / (a * a), 0.0) / (2.0 * b), -b))
+        elif op == c.KOP_SCALE:
+            st.append(np.full_like(xy, a))
+        elif op == c.KOP_DIAG:
+            st.append(np.where(diag & same_set, a, 0.0))
+        else:
+            y, x = st.pop(), st.pop()
+            st.append(x + y if op == c.KOP_ADD else x * y if op == c.KOP_MUL else np.power(x, y))
+    assert len(st) == 1
+    return st[0]
+
+
+def test_kernel_programs_reproduce_reference_kernels_from_the_gram(golden):
+    """Every kernel configuration: descriptor -> program -> (emulated) evaluation on entries of the augmented Gram, double
+    centring as k_kernelise does it, weights by the oracle's evd route == the reference's ``KETKFModule(kernel)`` output
+    (tests/golden/ketkf_kernels.npz).  This is the algebra the device path relies on: kernels as functions of the Gram."""
+    from pytassim_b200 import kernels as K
+    from pytassim_b200.testing import kernel_cases as kc
+    g = golden("ketkf_kernels.npz")
+    for i, (k, p, rho) in enumerate(kc.PROBLEM_SIZES):
+        perts, obs = g["c%d_perts" % i], g["c%d_obs" % i]
+        aug = np.concatenate([perts, obs], axis=0)
+        gram = aug @ aug.T
+        dg = np.diag(gram)
+        for name, build in kc.KERNEL_CASES:
+            prog = build(K, p).program()
+            kp = _emulate_program(prog, gram[:k, :k], dg[:k, None], dg[None, :k], np.eye(k, dtype=bool), True)
+            ko = _emulate_program(prog, gram[:k, k:], dg[:k, None], dg[None, k:], np.zeros((k, 1), dtype=bool), False)
+            rmean = kp.mean(axis=1, keepdims=True)
+            mu = rmean.mean()
+            kc_mat = kp - rmean.T - (rmean - mu)                                     # core/ketkf.py:81-85
+            ko_c = ko - ko.mean() - (rmean - mu)                                    # :91-92
+            evals, evects, evals_inv = orc.evd(kc_mat, (k - 1) / rho)
+            w = orc.rev_evd(evals_inv, evects) @ ko_c + orc.rev_evd(np.sqrt((k - 1) * evals_inv), evects)
+            np.testing.assert_allclose(w, g["c%d_w_%s" % (i, name)], rtol=1e-10, atol=1e-10, err_msg="%s k=%d" % (name, k))
+
+
+def test_ienks_gram_reformulation_reproduces_reference(golden):
+    """The algebra behind k_ienks_pre (csrc/ienks_kernel.cuh), in numpy: from the Gram C = Yn Yn^T, b = Yn d^T and the incoming
+    weights, A' = (1 - tau)(k - 1) T^T T + tau S C S^T, b' = P w - tau grad, then the ETKF solve with inflation 1 / tau — equals
+    the reference's SVD-based ``IEnKSTransformModule`` / ``IEnKSBundleModule`` over three iterations (tests/golden/ienks.npz)."""
+    g = golden("ienks.npz")
+
+    def step(w_in, yn, d, tau, eps):
+        k = w_in.shape[0]
+        c, b = yn @ yn.T, yn @ d.ravel()
+        w = (w_in - np.eye(k)).mean(axis=1)                                         # core/ienks.py:50-51
+        t = np.linalg.inv(w_in - w[:, None])                                        # :62-65
+        scs, sb = (t @ c @ t.T, t @ b) if eps is None else (c / eps / eps, b / eps)   # :74-75 / :173
+        a = (1 - tau) * (k - 1) * t.T @ t + tau * scs
+        a = 0.5 * (a + a.T)
+        alpha = tau * (k - 1)
+        b_slot = (a + alpha * np.eye(k)) @ w - tau * ((k - 1) * w - sb)
+        evals, evects, evals_inv = orc.evd(a, alpha)                                # the solve kernels: rho = 1 / tau
+        return (orc.rev_evd(evals_inv, evects) @ b_slot)[:, None] + orc.rev_evd(np.sqrt((k - 1) * evals_inv), evects)
+    for i in range(int(g["n_cases"])):
+        perts, obs, tau = g["c%d_perts" % i], g["c%d_obs" % i], float(g["c%d_tau" % i])
+        for variant, eps in (("transform", None), ("bundle", float(g["c%d_eps" % i]))):
+            w = np.eye(perts.shape[0])
+            for it in range(3):
+                w = step(w, perts * (1.0 if eps is None else eps), obs, tau, eps)
+                np.testing.assert_allclose(w, g["c%d_%s_w%d" % (i, variant, it)], rtol=1e-10, atol=1e-10)
