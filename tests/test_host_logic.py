@@ -556,3 +556,40 @@ def test_ienks_gram_reformulation_reproduces_reference(golden):
             for it in range(3):
                 w = step(w, perts * (1.0 if eps is None else eps), obs, tau, eps)
                 np.testing.assert_allclose(w, g["c%d_%s_w%d" % (i, variant, it)], rtol=1e-10, atol=1e-10)
+
+
+def test_inplace_gauss_jordan_as_in_ienks_pre():
+    """numpy emulation of the inversion inside k_ienks_pre (csrc/ienks_kernel.cuh): in-place Gauss-Jordan with row pivoting,
+    the pivot chosen on the upper 32 bits of |a| (any pivot within 2^-20 of the largest), the unit column folded into the
+    scaled pivot row, the moved row read from its staging copy, and the row swaps undone as column swaps in reverse order."""
+    def invert(a):
+        a = a.copy()
+        k = len(a)
+        pivs = np.zeros(k, dtype=int)
+        for c in range(k):
+            keys = (np.abs(a[c:, c]).view(np.uint64) >> np.uint64(32)).astype(np.uint32)   # __double2hiint(fabs(.))
+            pr = c + int(np.argmax(keys))
+            pivs[c] = pr
+            pinv = 1.0 / a[pr, c]
+            rowa = np.where(np.arange(k) == c, 1.0, a[pr]) * pinv
+            rowc, colv = a[c].copy(), a[:, c].copy()
+            for r in range(k):
+                if r == c:
+                    a[r] = rowa
+                    continue
+                moved = r == pr
+                src = rowc if moved else a[r]
+                f = rowc[c] if moved else colv[r]
+                a[r] = np.where(np.arange(k) == c, 0.0, src) - f * rowa
+        for c in range(k - 1, -1, -1):
+            p = pivs[c]
+            if p != c:
+                a[:, [c, p]] = a[:, [p, c]]
+        return a
+    rng = np.random.RandomState(8)
+    for k in (2, 3, 10, 40, 50, 96):
+        m_ = rng.normal(size=(k, k))
+        np.testing.assert_allclose(invert(m_) @ m_, np.eye(k), atol=1e-9 * np.linalg.cond(m_))
+        np.testing.assert_allclose(invert(m_), np.linalg.inv(m_), rtol=0, atol=1e-12 * np.linalg.cond(m_) * np.abs(np.linalg.inv(m_)).max())
+    perm = np.eye(5)[[3, 0, 4, 1, 2]] * np.array([2., -3., 0.5, 4., 1.])              # needs a swap at every step
+    np.testing.assert_allclose(invert(perm), np.linalg.inv(perm), atol=1e-15)
