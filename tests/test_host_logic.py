@@ -593,3 +593,54 @@ def test_inplace_gauss_jordan_as_in_ienks_pre():
         np.testing.assert_allclose(invert(m_), np.linalg.inv(m_), rtol=0, atol=1e-12 * np.linalg.cond(m_) * np.abs(np.linalg.inv(m_)).max())
     perm = np.eye(5)[[3, 0, 4, 1, 2]] * np.array([2., -3., 0.5, 4., 1.])              # needs a swap at every step
     np.testing.assert_allclose(invert(perm), np.linalg.inv(perm), atol=1e-15)
+
+
+class _OracleIenksEngine(object):
+    """CPU stand-in for the engine behind ``VarAssimilation.update_state`` (test infrastructure: the oracle does the numerics)
+    so that the control flow of the outer loop (interface/variational.py:105-135) is exercised without a GPU."""
+    device = torch.device("cpu")
+
+    def apply_weights(self, x, weights):
+        return torch.as_tensor(orc.apply_weights(x.numpy()[:, None], weights.numpy())[:, 0])
+
+    def ienks_weights(self, weights, perts, innov, tau=1.0, epsilon=None):
+        return torch.as_tensor(orc.ienks_weights(weights.numpy(), np.asarray(perts), np.asarray(innov)[None], tau, epsilon))
+
+
+def test_ienks_outer_loop_control_flow(golden, monkeypatch):
+    """tests/unit_tests/interface/test_ienks.py:143-161, 215-237 of the reference: a given pseudo state skips the first model
+    propagation, later iterations propagate; max_iter = 1 with an identity model equals the ETKF without inflation; smoother
+    mode propagates the analysis once more (variational.py:132-133); the bundle variant propagates epsilon * I + mean weights."""
+    from pytassim_b200.interface import IEnKSTransform, IEnKSBundle
+    g, state, obs = _fixture_objects(golden)
+    ob_last = obs.isel(time=[2])
+    t_last = "1992-12-25 02:00"
+    monkeypatch.setattr(IEnKSTransform, "_analysis_engine", lambda self, st, k, n_slices: _OracleIenksEngine())
+    calls = []
+
+    def model(st, iter_num):
+        calls.append((iter_num, np.asarray(st.values).copy()))
+        return st, st
+    st_last = state.isel(time=[2])
+    alg = IEnKSTransform(model, tau=1.0, max_iter=1)
+    ana = alg.assimilate(state, ob_last, st_last, analysis_time=t_last)            # pseudo state given: no propagation
+    assert calls == []
+    innov, perts = orc.obs_space_variables([g["state"][0, 2][:, None, :]], [g["obs"][2:3]], [g["cov"]])
+    ref = orc.apply_weights(g["state"][:, 2:3], orc.etkf_weights(perts, innov, 1.0))
+    np.testing.assert_allclose(ana.values, ref, rtol=1e-10, atol=1e-10)           # == ETKF (test_ienks.py:215-237)
+    assert list(ana.indexes["time"]) == [pd.Timestamp(t_last)]
+    alg.max_iter = 2
+    alg.assimilate(state, ob_last, st_last, analysis_time=t_last)
+    assert [c[0] for c in calls] == [1]                                             # test_ienks.py:153-161
+    del calls[:]
+    alg.smoother = True
+    alg.assimilate(state, ob_last, None, analysis_time=t_last)
+    assert [c[0] for c in calls] == [0, 1, 2]                                       # two iterations + the smoother propagation
+    np.testing.assert_allclose(calls[0][1], g["state"][:, 2:3], rtol=0, atol=1e-13)  # prior weights = identity
+    del calls[:]
+    bun = IEnKSBundle(model, tau=1.0, epsilon=1e-2, max_iter=1)
+    bun.assimilate(state, ob_last, None, analysis_time=t_last)
+    mean = g["state"][:, 2:3].mean(axis=2, keepdims=True)
+    np.testing.assert_allclose(calls[0][1], mean + 1e-2 * (g["state"][:, 2:3] - mean), rtol=0, atol=1e-13)   # ienks.py:153-160
+    with pytest.raises(KeyError):
+        alg.update_state(state, [ob_last], None, pd.Timestamp("2000-01-01"))
