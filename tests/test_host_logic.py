@@ -644,3 +644,33 @@ def test_ienks_outer_loop_control_flow(golden, monkeypatch):
     np.testing.assert_allclose(calls[0][1], mean + 1e-2 * (g["state"][:, 2:3] - mean), rtol=0, atol=1e-13)   # ienks.py:153-160
     with pytest.raises(KeyError):
         alg.update_state(state, [ob_last], None, pd.Timestamp("2000-01-01"))
+
+
+def test_kernelised_interface_configures_engines(golden, monkeypatch):
+    """KETKF / LKETKF hand their kernel to every engine they create and drop cached engines when the kernel changes
+    (interface/ketkf.py:118-123 swaps the core module); the plain ETKF / LETKF never set a program."""
+    from pytassim_b200 import kernels as K
+    from pytassim_b200.interface import KETKF, etkf as etkf_mod
+    created = []
+
+    class StubEngine(object):
+        def __init__(self, k, n_slices, metric, radius, **kwargs):
+            self.k, self.kernel_set = k, []
+            created.append(self)
+
+        def set_kernel(self, kernel):
+            self.kernel_set.append(kernel)
+            return self
+    monkeypatch.setattr(etkf_mod, "LETKFEngine", StubEngine)
+    alg = KETKF(kernel=K.RBFKernel(gamma=0.1), inf_factor=1.1)
+    eng = alg._global_engine(10, 2)
+    assert alg._global_engine(10, 2) is eng and len(created) == 1 and eng.kernel_set == [alg.kernel]
+    alg.kernel = K.PolyKernel()
+    eng2 = alg._global_engine(10, 2)
+    assert eng2 is not eng and eng2.kernel_set == [alg.kernel]
+    alg.inf_factor = 1.3                                         # etkf.py:93-97: a new core module -> new engines
+    assert alg._global_engine(10, 2) is not eng2
+    plain = ETKF(inf_factor=1.1)
+    assert plain._global_engine(10, 2).kernel_set == [] and plain._kernel_key() == ()
+    lin = KETKF()                                                # default LinearKernel: handed over, compiles to no program
+    assert lin._global_engine(10, 2).kernel_set[0].is_linear and lin._kernel_key() == ()
