@@ -1,5 +1,5 @@
 """The reference's plug-in points (3) and (4) on the device: ``core_module(normed_perts, normed_obs)``,
-``assimilation.module`` (numpy bridge, interface/wrapper.py:29-62) and ``assimilation.localized_module`` (one grid point per
+``assimilation.module`` (numpy bridge, the reference's interface/wrapper.py:29-62) and ``assimilation.localized_module`` (one grid point per
 call, interface/wrapper.py:64-98), mirroring tests/unit_tests/core/test_etkf.py, test_ketkf.py, test_ienks.py and
 interface/test_letkf.py of the reference.  Expected values: golden vectors from the reference's own modules."""
 import numpy as np

@@ -674,3 +674,32 @@ def test_kernelised_interface_configures_engines(golden, monkeypatch):
     assert plain._global_engine(10, 2).kernel_set == [] and plain._kernel_key() == ()
     lin = KETKF()                                                # default LinearKernel: handed over, compiles to no program
     assert lin._global_engine(10, 2).kernel_set[0].is_linear and lin._kernel_key() == ()
+
+
+def test_per_point_call_forms_with_stub_module():
+    """interface/per_point.py against the reference's closures (interface/wrapper.py:54-62, 86-98) on stand-ins: the bridge
+    returns the first argument's dtype, the localized form selects and scales every argument except the skipped ones."""
+    from pytassim_b200.interface.per_point import NumpyBridge, LocalObservations
+    seen = {}
+
+    def core(*tensors):
+        seen["args"] = tensors
+        return tensors[0].sum() * torch.eye(2, dtype=tensors[0].dtype)
+    bridge = NumpyBridge(core, torch.device("cpu"), torch.float64)
+    out = bridge(np.ones((2, 3), dtype=np.float32), np.zeros((1, 3), dtype=np.float32))
+    assert out.dtype == np.float32 and np.array_equal(out, 6.0 * np.eye(2))
+    assert all(t.dtype == torch.float64 for t in seen["args"])
+
+    class Loc(object):
+        def localize_obs(self, grid_info, obs_info):
+            assert grid_info == "row" and obs_info == "info"
+            return np.array([True, False, True, True]), np.array([0.25, 0.0, 1.0, 0.04])
+    calls = []
+    lm = LocalObservations(lambda *a: calls.append(a) or "w", Loc())
+    weights, perts, innov = np.eye(2), np.arange(8.0).reshape(2, 4), np.arange(4.0)[None]
+    assert lm("row", weights, perts, innov, obs_info="info", args_to_skip=(0, )) == "w"
+    w_arg, p_arg, i_arg = calls[0]
+    assert w_arg is weights
+    np.testing.assert_allclose(p_arg, perts[:, [0, 2, 3]] * np.array([0.5, 1.0, 0.2]))
+    np.testing.assert_allclose(i_arg, innov[:, [0, 2, 3]] * np.array([0.5, 1.0, 0.2]))
+    assert LocalObservations(lambda *a: a, None)("row", 1, 2, obs_info=None) == (1, 2)        # wrapper.py:87: no localization

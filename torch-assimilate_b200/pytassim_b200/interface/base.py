@@ -83,8 +83,8 @@ class BaseAssimilation(object):
     @property
     def module(self):
         """base.py:87-104: the core module bridged to numpy arrays (interface/wrapper.py:29-62)."""
-        from .wrapper import wrapper_bridge
-        return wrapper_bridge(self.core_module, self.device, self.dtype)
+        from .per_point import NumpyBridge
+        return NumpyBridge(self.core_module, self.device, self.dtype)
 
     @property
     def dtype(self):

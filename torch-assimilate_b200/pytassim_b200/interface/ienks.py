@@ -211,8 +211,8 @@ class _LocalizedMixin(object):
     @property
     def localized_module(self):
         """mixin_local.py:37-42."""
-        from .wrapper import wrapper_localization
-        return wrapper_localization(module=self.module, localization=self.localization)
+        from .per_point import LocalObservations
+        return LocalObservations(module=self.module, localization=self.localization)
 
     def _analysis_engine(self, state, k, n_slices):
         loc = self.localization

@@ -34,8 +34,8 @@ class LETKF(ETKF):
     @property
     def localized_module(self):
         """mixin_local.py:37-42: one grid point per call (numpy in / out) — the per-grid-point form of the hot loop."""
-        from .wrapper import wrapper_localization
-        return wrapper_localization(module=self.module, localization=self.localization)
+        from .per_point import LocalObservations
+        return LocalObservations(module=self.module, localization=self.localization)
 
     def _local_engine(self, k, n_slices, grid_coords):
         loc = self.localization
