@@ -1,18 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — LETKF analysed grid points / s on B200 (BASELINE.json metric), with roofline and CPU baseline.
+"""bench.py — LETKF analysed grid points / s on B200 (BASELINE.json metric), with roofline, CPU baseline and parity sample.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg1|small] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg1|cfg4|cfg5_k16|...] [--dtype f64|f32]
+                    [--impl reference] [--no-secondary] [--secondary a,b,...]
 
-One "step" is one full LETKF analysis of the workload: observation binning + fused analysis kernel (+ for
-N > 1 the broadcast of the observation-space arrays from rank 0 and the all-gather of the analysis).
-`value` is measured with every input already resident in HBM; `e2e` goes through the host-buffer entry point
-(`b200da_letkf_host`: pinned host arrays in, host array out, copies inside the timed region).
-`--impl reference` times the reference's CPU algorithm (the numpy/LAPACK oracle port, oracle/letkf_oracle.py —
-the reference itself is pure Python and cannot be imported without xarray/dask) on all host cores on a bounded
-sample of the same workload.
+One "step" is one full analysis of the workload: observation binning + Gram + ensemble-space solve + update (+ for N > 1
+the broadcast of the observation-space arrays from rank 0 and the all-gather of the analysis; + the ambiguity protocol of
+include/b200da.h, one stream synchronisation).  `value` is measured with every input already resident in HBM; `e2e` goes
+through the host-buffer entry point (`b200da_letkf_host`: pinned host arrays in, host array out, copies inside the timed
+region).  The headline line is cfg3 FP64 (BASELINE.json configs[2], the configuration the metric is quoted on); the default
+invocation appends `secondary`: one entry per other BASELINE configuration (cfg1, cfg2, cfg3 FP32 plan, cfg4 global ETKF,
+cfg5 k = 16/32/64/128 x FP32/FP64), each with its own roofline, clock record, e2e and CPU baseline.
+
+`--impl reference` times the reference's own CPU code: the unmodified leaf modules of the reference installed under
+baseline/_ref (wrapper_localization(wrapper_bridge(ETKFModule)) + GaspariCohn.localize_obs per grid point, numpy update),
+loaded by file path because the package itself needs xarray / dask (absent); when baseline/_ref is missing it falls back to
+the numpy port (oracle/letkf_oracle.py).  All host cores, bounded samples.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -24,18 +31,45 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "torch-assimilate_b200"))
 
+METRIC, UNIT = "letkf_analysed_gridpoints_per_sec", "gridpoints/s"
+
 WORKLOADS = {
-    # name: (description, generator kwargs, metric ctor, GC radius, inflation)
     "cfg3": dict(desc="cfg3: synthetic global 1000x1000 lat-lon grid (1M points), k=50, 2.5M obs uniform on the sphere, "
                       "haversine GC c=1000 km, inf_factor 1.1, FP64",
                  kind="sphere", nlat=1000, nlon=1000, k=50, n_obs=2_500_000, radius=1000.0, rho=1.1),
     "cfg2": dict(desc="cfg2: Lorenz-96 ring N=100k, k=40, every 2nd variable observed, periodic GC c=20, inf_factor 1.1, FP64",
                  kind="ring", n_grid=100_000, k=40, stride=2, radius=20.0, rho=1.1),
-    "cfg1": dict(desc="cfg1: Lorenz-96 ring N=40, k=50, all observed, periodic GC c=5, inf_factor 1.1, FP64",
+    "cfg1": dict(desc="cfg1: Lorenz-96 ring N=40, k=50, all observed, periodic GC c=5, inf_factor 1.1, FP64 "
+                      "(examples/benchmark_letkf.py shape)",
                  kind="ring", n_grid=40, k=50, stride=1, radius=5.0, rho=1.1),
-    "small": dict(desc="small: 100x200 lat-lon grid, k=50, 50k obs, haversine GC c=1000 km (smoke-sized cfg3)",
+    "small": dict(desc="small: 100x200 lat-lon grid, k=50, 50k obs, haversine GC c=1000 km (smoke-sized cfg3), FP64",
                   kind="sphere", nlat=100, nlon=200, k=50, n_obs=50_000, radius=1000.0, rho=1.1),
+    "cfg4": dict(desc="cfg4: global ETKF without localization, state 10M elements x k=100 members, 1M observations (every 10th "
+                      "element, R = I), inf_factor 1.1, FP64",
+                 kind="global", n_grid=10_000_000, k=100, n_obs=1_000_000, rho=1.1),
+    "cfg4small": dict(desc="cfg4small: global ETKF, state 200k elements x k=100, 20k observations, FP64 (smoke-sized cfg4)",
+                      kind="global", n_grid=200_000, k=100, n_obs=20_000, rho=1.1),
 }
+for _k in (16, 32, 64, 128):
+    WORKLOADS["cfg5_k{0}".format(_k)] = dict(
+        desc="cfg5: cfg3 geometry (1000x1000 lat-lon grid, 2.5M obs, haversine GC c=1000 km, inf_factor 1.1) with k={0}, "
+             "FP64".format(_k),
+        kind="sphere", nlat=1000, nlon=1000, k=_k, n_obs=2_500_000, radius=1000.0, rho=1.1)
+
+# default secondary entries: (key, workload, dtype, share of the grid-point blocks analysed per step)
+SECONDARY = [
+    ("cfg3_f32", "cfg3", "f32", 1.0), ("cfg2_f64", "cfg2", "f64", 1.0), ("cfg2_f32", "cfg2", "f32", 1.0),
+    ("cfg1_f64", "cfg1", "f64", 1.0), ("cfg4_f64", "cfg4", "f64", 1.0), ("cfg4_f32", "cfg4", "f32", 1.0),
+    ("cfg5_k16_f64", "cfg5_k16", "f64", 1.0), ("cfg5_k16_f32", "cfg5_k16", "f32", 1.0),
+    ("cfg5_k32_f64", "cfg5_k32", "f64", 1.0), ("cfg5_k32_f32", "cfg5_k32", "f32", 1.0),
+    ("cfg5_k64_f64", "cfg5_k64", "f64", 0.25), ("cfg5_k64_f32", "cfg5_k64", "f32", 1.0),
+    ("cfg5_k128_f64", "cfg5_k128", "f64", 0.10), ("cfg5_k128_f32", "cfg5_k128", "f32", 0.25),
+]
+SECONDARY_MULTI = ("cfg3_f32", "cfg2_f64", "cfg4_f64")       # what the N > 1 runs repeat
+
+
+def desc_of(w, dtype):
+    return w["desc"] if dtype == "f64" else w["desc"].replace("FP64", "FP32 arrays in HBM")
 
 
 def make_workload(name):
@@ -43,8 +77,10 @@ def make_workload(name):
     w = WORKLOADS[name]
     if w["kind"] == "sphere":
         data = syn.sphere_latlon(w["nlat"], w["nlon"], w["k"], w["n_obs"], seed=42)
-    else:
+    elif w["kind"] == "ring":
         data = syn.lorenz96_1d(w["n_grid"], w["k"], w["stride"], seed=42)
+    else:
+        data = None                       # cfg4: generated on the device (8 GB state); the CPU legs draw their own sample
     return w, data
 
 
@@ -63,34 +99,73 @@ def oracle_dist(w, data):
     return orc, orc.make_dist_periodic1d(data["period"])
 
 
-# ---- CPU baseline: the reference algorithm (oracle port) on the host cores -----------------------------------
+# ---- CPU legs: the reference's own leaf modules (baseline/_ref) or the numpy port, on the host cores ------------------------
 _G = {}
+REF_ROOT = os.path.join(ROOT, "baseline", "_ref")
+
+
+def load_reference():
+    """The unmodified reference leaves (core/etkf.py, core/utils.py, localization/gaspari_cohn.py, interface/wrapper.py ...)
+    from baseline/_ref by file path (oracle/make_golden.py: load_reference_leaves), or None when not installed."""
+    if "ref" in _G:
+        return _G["ref"]
+    ref = None
+    if os.path.exists(os.path.join(REF_ROOT, "pytassim", "core", "etkf.py")):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import make_golden
+            ref = make_golden.load_reference_leaves(REF_ROOT)
+        except Exception as exc:                     # pragma: no cover - reported in the JSON line
+            sys.stderr.write("[bench] reference leaves not loadable: {0!r}\n".format(exc))
+            ref = None
+    _G["ref"] = ref
+    return ref
 
 
 def _cpu_init():
     try:
         from threadpoolctl import threadpool_limits
-        _G["limit"] = threadpool_limits(limits=1)       # reference advice: OMP_NUM_THREADS=1 per worker
+        _G["limit"] = threadpool_limits(limits=1)       # reference advice: OMP_NUM_THREADS=1 per worker (docs etkf.rst:55-57)
+        import torch
+        torch.set_num_threads(1)
     except Exception:
         pass
 
 
 def _cpu_chunk(sel):
-    orc, dist, w, data = _G["orc"], _G["dist"], _G["w"], _G["data"]
-    ana, _ = orc.letkf_analysis(data["state"], data["normed_perts"], data["normed_obs"], data["grid_rows"],
-                                data["obs_rows"], dist, w["radius"], inf_factor=w["rho"], grid_subset=sel)
+    orc, dist, w, data, ref = _G["orc"], _G["dist"], _G["w"], _G["data"], _G.get("ref_use")
+    if ref is not None:
+        # the reference's hot loop with the reference's own functions (interface/letkf.py:127-143): per grid point
+        # wrapper_localization(wrapper_bridge(ETKFModule), GaspariCohn)(grid_row, Yn, d, obs_info=...), then the numpy form of
+        # _apply_weights (interface/base.py:257-278)
+        import torch
+        if "ref_module" not in _G or _G.get("ref_module_w") is not w:
+            module = ref.core_etkf.ETKFModule(inf_factor=torch.tensor(w["rho"], dtype=torch.float64))
+            bridged = ref.wrapper.wrapper_bridge(module, torch.device("cpu"), torch.float64)
+            _G["ref_module"] = ref.wrapper.wrapper_localization(bridged, ref.loc_gc.GaspariCohn((w["radius"],), dist))
+            _G["ref_module_w"] = w
+        localized = _G["ref_module"]
+        weights = np.stack([localized(data["grid_rows"][g], data["normed_perts"], data["normed_obs"], obs_info=data["obs_rows"])
+                            for g in sel], axis=0)
+        st = data["state"][..., sel]
+        mean = st.mean(axis=2, keepdims=True)
+        ana = mean + np.einsum("vtig,gij->vtjg", st - mean, weights)
+    else:
+        ana, _ = orc.letkf_analysis(data["state"], data["normed_perts"], data["normed_obs"], data["grid_rows"],
+                                    data["obs_rows"], dist, w["radius"], inf_factor=w["rho"], grid_subset=sel)
     return float(ana.sum())
 
 
-def cpu_reference_rate(w, data, target_seconds=15.0, max_points=None):
-    """Grid points / s of the reference algorithm on all host cores; bounded sample of evenly spaced grid points."""
+def cpu_reference_rate(w, data, target_seconds=15.0, max_points=None, use_reference=True):
+    """Grid points / s of the reference loop on all host cores; bounded sample of evenly spaced grid points."""
     import multiprocessing as mp
     orc, dist = oracle_dist(w, data)
-    _G.update(orc=orc, dist=dist, w=w, data=data)
+    ref = load_reference() if use_reference else None
+    _G.update(orc=orc, dist=dist, w=w, data=data, ref_use=ref)
     cores = len(os.sched_getaffinity(0))
     n_grid = data["state"].shape[-1]
-    # calibrate on a few points in this process
     probe = np.linspace(0, n_grid - 1, 2, dtype=np.int64)
+    _cpu_chunk(probe[:1])
     t0 = time.perf_counter(); _cpu_chunk(probe[:1]); _cpu_chunk(probe[1:]); per_point = (time.perf_counter() - t0) / 2
     n_pts = int(min(n_grid, max(cores, target_seconds * cores / max(per_point, 1e-6))))
     if max_points:
@@ -107,10 +182,48 @@ def cpu_reference_rate(w, data, target_seconds=15.0, max_points=None):
         t0 = time.perf_counter()
         pool.map(_cpu_chunk, chunks * passes)
         dt = time.perf_counter() - t0
-    return dict(value=len(sel) * passes / dt, unit="gridpoints/s", cores=cores, kind="port",
-                sample="{0} evenly spaced grid points of {1}{4} on {2} processes x 1 thread, numpy+LAPACK port of the "
-                       "reference loop (localize_obs over all obs -> sqrt(w) gather -> ETKF weights -> update), "
-                       "{3:.1f} s wall".format(len(sel), n_grid, cores, dt, " x {0} passes".format(passes) if passes > 1 else ""))
+    what = ("the reference's own leaf modules from baseline/_ref (GaspariCohn.localize_obs over all obs -> "
+            "wrapper_localization(wrapper_bridge(ETKFModule)) -> numpy update; torch.symeig shimmed to torch.linalg.eigh)"
+            if ref is not None else
+            "numpy+LAPACK port of the reference loop (localize_obs over all obs -> sqrt(w) gather -> ETKF weights -> update)")
+    return dict(value=len(sel) * passes / dt, unit=UNIT, cores=cores, kind="reference" if ref is not None else "port",
+                sample="{0} evenly spaced grid points of {1}{4} on {2} processes x 1 thread, {5}, {3:.1f} s wall".format(
+                    len(sel), n_grid, cores, dt, " x {0} passes".format(passes) if passes > 1 else "", what))
+
+
+def cpu_etkf_rate(w, sample_cols=1_000_000, use_reference=True):
+    """cfg4 on the host: the reference's ETKFModule on the whole (k, M) observation arrays with all cores as torch threads
+    (one call, interface/etkf.py:99-120), then the numpy einsum update (interface/base.py:257-278) on a sample of the state
+    columns, extrapolated linearly to N."""
+    import torch
+    k, n, m = w["k"], w["n_grid"], w["n_obs"]
+    cores = len(os.sched_getaffinity(0))
+    rnd = np.random.RandomState(42)
+    cols = min(n, sample_cols)
+    x = rnd.normal(size=(1, 1, k, cols))
+    hx = rnd.normal(size=(k, m))
+    yn = hx - hx.mean(axis=0, keepdims=True)
+    d = rnd.normal(size=m) * 0.5
+    ref = load_reference() if use_reference else None
+    torch.set_num_threads(cores)
+    t0 = time.perf_counter()
+    if ref is not None:
+        module = ref.core_etkf.ETKFModule(inf_factor=torch.tensor(w["rho"], dtype=torch.float64))
+        W = module(torch.from_numpy(yn), torch.from_numpy(d)).numpy()
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import letkf_oracle as orc
+        W = orc.etkf_weights(yn, d, w["rho"])
+    t_w = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    mean = x.mean(axis=2, keepdims=True)
+    ana = mean + np.einsum("vtig,ij->vtjg", x - mean, W)
+    t_u = (time.perf_counter() - t0) * (n / cols)
+    assert np.isfinite(ana).all()
+    return dict(value=n / (t_w + t_u), unit=UNIT, cores=cores, kind="reference" if ref is not None else "port",
+                sample="ETKF weights from the full (k={0}, M={1}) observation arrays ({2:.2f} s, torch with {3} threads) + numpy "
+                       "einsum update on {4} of {5} state columns extrapolated linearly ({6:.2f} s for all)".format(
+                           k, m, t_w, cores, cols, n, t_u))
 
 
 # ---- clocks ------------------------------------------------------------------------------------------------------
@@ -118,17 +231,22 @@ class ClockSampler(object):
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index=0, period_ms=100):
+        self.rows, self.proc, self.gpu, self.period = [], None, gpu_index, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:      # the first sample marks the sampler as running
+                time.sleep(0.01)
+            self.first = len(self.rows)
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -136,19 +254,21 @@ class ClockSampler(object):
 
     def stop(self):
         if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"], samples=0)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        smax = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.rows[max(0, getattr(self, "first", 1) - 1):]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        smax = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) < 9:
                 continue
             for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
                 if r[col].lower().startswith("active"):
                     reasons.add(name)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(smax) if smax else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), power_w_max=max(pw) if pw else None)
 
 
 def measure_fp64_peak(torch, seconds=1.5):
@@ -178,6 +298,13 @@ def measure_fp64_peak(torch, seconds=1.5):
     return flops / best * 1e-9, flops * reps / e0.elapsed_time(e1) * 1e-9
 
 
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 _JSON_FD = None
 
 
@@ -199,75 +326,72 @@ def _emit(line):
         os.write(_JSON_FD, payload)
 
 
-def main():
-    _reserve_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="plan dtype (state / obs-space arrays in HBM)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
+def _log(msg):
+    sys.stderr.write("[bench] " + msg + "\n"); sys.stderr.flush()
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    metric_name, unit = "letkf_analysed_gridpoints_per_sec", "gridpoints/s"
 
-    # ------------------------------------------------------------------------------------------------------------
-    # reference arm: the reference's CPU algorithm on the host cores (rank 0 only)
-    # ------------------------------------------------------------------------------------------------------------
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        w, data = make_workload(args.workload)
-        vals, info = [], None
-        for _ in range(max(1, args.warmup > 0)):
-            cpu_reference_rate(w, data, target_seconds=3.0)
-        t_all = time.perf_counter()
-        for _ in range(args.steps):
-            info = cpu_reference_rate(w, data, target_seconds=12.0)
-            vals.append(info["value"])
-        v = float(np.mean(vals))
-        info["value"] = v
-        line = {"metric": metric_name, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1000.0 * (time.perf_counter() - t_all) / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "impl": "reference", "config": {"workload": w["desc"], "inputs": "host resident"},
-                "cpu_baseline": info,
-                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        _emit(line)
-        return
+class Ctx(object):
+    """Process-wide state of the B200 arm: rank / world, device, measured peaks."""
 
-    # ------------------------------------------------------------------------------------------------------------
-    # B200 arm
-    # ------------------------------------------------------------------------------------------------------------
-    w, data = (None, None)
-    if rank == 0:
-        w, data = make_workload(args.workload)
-    else:
-        w = WORKLOADS[args.workload]
-    cpu_info = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_info = cpu_reference_rate(w, data, target_seconds=12.0)      # before CUDA is initialised (fork safety)
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.peak_burst = self.peak_sus = None
 
-    import torch
-    import torch.distributed as dist
+    def init_cuda(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            # NCCL writes its version banner to STDOUT when NCCL_DEBUG is VERSION: keep stdout to the one JSON line
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"
+            dist.init_process_group("nccl", device_id=self.dev)
+        if self.rank == 0:
+            self.peak_burst, self.peak_sus = measure_fp64_peak(torch)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+
+def sample_blocks(n_blocks, fraction, pieces=8):
+    """Evenly spaced block ranges that together cover ``fraction`` of the blocks (work per block is uniform on the sphere
+    only in the mean: spread the sample from pole to pole)."""
+    if fraction >= 1.0:
+        return [(0, n_blocks)]
+    per = max(1, int(n_blocks * fraction / pieces))
+    starts = np.linspace(0, n_blocks - per, pieces, dtype=np.int64)
+    return [(int(s), int(s) + per) for s in starts]
+
+
+# ---- one localized workload on the B200 ------------------------------------------------------------------------------
+def run_letkf(ctx, wname, dtype, steps, warmup, e2e_steps, data=None, fraction=1.0, parity_points=8, cpu_info=None,
+              min_seconds=0.0):
+    torch, dist = ctx.torch, ctx.dist
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
     from pytassim_b200.engine import LETKFEngine, launch_count
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # NCCL writes its version banner to STDOUT when NCCL_DEBUG is VERSION: keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-
+    from pytassim_b200.parallel import ShardedAnalysis
+    from pytassim_b200.localization import metrics as mm
+    w = WORKLOADS[wname]
+    if rank == 0 and data is None:
+        w, data = make_workload(wname)
     k = w["k"]
-    # shapes travel from rank 0
+    f64 = torch.float64
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    ndt = np.float64 if dtype == "f64" else np.float32
+    esz = 8 if dtype == "f64" else 4
     if world > 1:
         shp = torch.zeros(4, dtype=torch.int64, device=dev)
         if rank == 0:
@@ -277,10 +401,6 @@ def main():
     else:
         n_grid, n_obs, n_coord = data["state"].shape[-1], data["normed_obs"].shape[0], data["grid_rows"].shape[1] - 1
 
-    f64 = torch.float64
-    tdt = torch.float64 if args.dtype == "f64" else torch.float32
-    ndt = np.float64 if args.dtype == "f64" else np.float32
-    esz = 8 if args.dtype == "f64" else 4
     if rank == 0:
         x_host = torch.from_numpy(np.ascontiguousarray(data["state"].reshape(1, k, n_grid), dtype=ndt)).pin_memory()
         y_host = torch.from_numpy(np.ascontiguousarray(data["normed_perts"], dtype=ndt)).pin_memory()
@@ -297,108 +417,102 @@ def main():
         oc_dev = torch.empty((n_obs, n_coord), dtype=f64, device=dev)
     if world > 1:
         dist.broadcast(gc_dev, 0)          # the grid is static: part of the plan, outside the timed region
-
-    if rank == 0:
-        metric = make_metric(w, data)
-        mdesc = torch.tensor([metric.metric_id, metric.n_coord] + [0], dtype=f64, device=dev)
-        mpar = torch.tensor(list(metric.params) + [0.0], dtype=f64, device=dev)[:1]
-    else:
-        mdesc = torch.zeros(3, dtype=f64, device=dev); mpar = torch.zeros(1, dtype=f64, device=dev)
-    if world > 1:
-        dist.broadcast(mdesc, 0); dist.broadcast(mpar, 0)
-        from pytassim_b200.localization import metrics as mm
-        if rank != 0:
-            metric = mm.HaversineDistance(float(mpar[0])) if int(mdesc[0]) == 3 else mm.PeriodicDistance1D(float(mpar[0]))
+    period = float(n_grid)
+    metric = mm.HaversineDistance(6371.0) if w["kind"] == "sphere" else mm.PeriodicDistance1D(period)
 
     eng = LETKFEngine(k, 1, metric, w["radius"], inf_factor=w["rho"], dtype=tdt)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     eng.set_grid(gc_dev)
+    torch.cuda.synchronize()
+    set_grid_ms = (time.perf_counter() - t0) * 1e3
     eng.enable_timing(True)
-    from pytassim_b200.parallel import ShardedAnalysis
-    sharded = ShardedAnalysis(eng)
-    nb = eng.n_blocks
-    b0, b1 = sharded.ranges[rank]
-    xa_dev = torch.empty_like(x_dev)
 
-    kernel_ms, gram_ms, solve_ms = [], [], []
-
-    def step(record=False):
-        # rank 0 owns the inputs: broadcast obs-space arrays + state once per step (no-op for one GPU)
-        sharded.broadcast_inputs([oc_dev, y_dev, d_dev, x_dev])
-        eng.bin_obs(oc_dev, y_dev, d_dev)
-        sharded.run(x_dev, xa_dev)
-        if record:
-            kernel_ms.append(eng.last_kernel_ms())
-            gm, sm = eng.last_phase_ms()
-            gram_ms.append(gm); solve_ms.append(sm)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # algorithmic work: sum over grid points of the local observation counts (exact, from the neighbour count kernel)
+    # algorithmic work: local observation count of every grid point (exact, from the neighbour-count kernel)
+    if world > 1:
+        for t in (oc_dev, y_dev, d_dev, x_dev):
+            dist.broadcast(t, 0)
     eng.bin_obs(oc_dev, y_dev, d_dev)
-    import ctypes
-    from pytassim_b200 import _cabi
-    counts = torch.zeros(n_grid, dtype=torch.int64, device=dev)
-    namb = torch.zeros(1, dtype=torch.int64, device=dev)
-    _cabi.check(eng.lib.b200da_neighbour_count(eng._plan, ctypes.c_void_p(counts.data_ptr()), ctypes.c_void_p(namb.data_ptr()),
-                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-    order = torch.empty(n_grid, dtype=torch.int32, device=dev)
-    _cabi.check(eng.lib.b200da_grid_order(eng._plan, ctypes.c_void_p(order.data_ptr()),
-                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-    s0, s1 = eng.block_offset(b0), eng.block_offset(b1)
-    my_pairs = int(counts[order[s0:s1].long()].sum().item())
-    my_points = s1 - s0
+    counts, _ = eng.neighbour_counts()
+    sharded = ShardedAnalysis(eng, weights=counts if fraction >= 1.0 else None)
+    b0, b1 = sharded.ranges[rank]
+    my_ranges = [(b0, b1)] if fraction >= 1.0 else sample_blocks(eng.n_blocks, fraction)
+    order = eng.grid_order()
+    counts_sorted = counts[order.long()]
+    my_pairs = my_points = 0
+    for (c0, c1) in my_ranges:
+        s0, s1 = eng.block_offset(c0), eng.block_offset(c1)
+        my_pairs += int(counts_sorted[s0:s1].sum().item())
+        my_points += s1 - s0
     flops_gram = 2.0 * k * k * my_pairs + 2.0 * k * my_pairs
     flops_solve = (13.0 * k ** 3 + 2.0 * k * k) * my_points
-    flops_local = flops_gram + flops_solve
     p_mean = float(counts.double().mean().item())
-    del counts, order
+    del counts_sorted, order
+    xa_dev = torch.empty_like(x_dev)
+    kernel_ms, gram_ms, solve_ms, amb = [], [], [], []
 
-    peak_burst = peak_sus = None
-    if rank == 0:
-        peak_burst, peak_sus = measure_fp64_peak(torch)
+    def step(record=False):
+        if fraction >= 1.0:
+            # rank 0 owns the inputs: broadcast obs-space arrays + state once per step (no-op for one GPU)
+            sharded.broadcast_inputs([oc_dev, y_dev, d_dev, x_dev])
+            eng.bin_obs(oc_dev, y_dev, d_dev)
+            sharded.run(x_dev, xa_dev)
+            if record:
+                kernel_ms.append(eng.last_kernel_ms())
+                gm, sm = eng.last_phase_ms()
+                gram_ms.append(gm); solve_ms.append(sm); amb.append(dict(eng.last_ambiguous))
+        else:
+            eng.bin_obs(oc_dev, y_dev, d_dev)
+            km = gm = sm = 0.0
+            for (c0, c1) in my_ranges:
+                eng.analyse(x_dev, out=xa_dev, blocks=(c0, c1))
+                if record:
+                    km += eng.last_kernel_ms(); a, b = eng.last_phase_ms(); gm += a; sm += b
+            if record:
+                kernel_ms.append(km); gram_ms.append(gm); solve_ms.append(sm); amb.append(dict(eng.last_ambiguous))
 
-    for _ in range(args.warmup):
+    for _ in range(max(warmup, 1)):
         step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    ctx.barrier()
+    if min_seconds > 0.0:                       # short workloads: enough steps for the clock sampler to see the run
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); step(); e1.record(); ctx.barrier()
+        est = ctx.max_over_ranks([e0.elapsed_time(e1)])[0]
+        steps = int(max(steps, min(20000, math.ceil(min_seconds * 1e3 / max(est, 1e-3)))))
+    sampler = ClockSampler(ctx.local_rank).start() if rank == 0 else None
     l0 = launch_count()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(record=True)
     e1.record()
-    barrier()
-    elapsed_ms = e0.elapsed_time(e1)
+    ctx.barrier()
     launches = launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([elapsed_ms, float(np.mean(kernel_ms)), float(np.mean(gram_ms)), float(np.mean(solve_ms))], dtype=f64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, kern_ms, g_ms, s_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
-    ms_per_step = elapsed_ms / args.steps
-    value = n_grid / (ms_per_step * 1e-3)
+    elapsed_ms, kern_ms, g_ms, s_ms = ctx.max_over_ranks([e0.elapsed_time(e1), float(np.mean(kernel_ms)), float(np.mean(gram_ms)),
+                                                          float(np.mean(solve_ms))])
+    ms_per_step = elapsed_ms / steps
+    n_points = n_grid if fraction >= 1.0 else my_points
+    value = n_points / (ms_per_step * 1e-3)
 
-    # end to end through the host-buffer entry point (N = 1: rank 0 owns everything)
+    # ---- end to end through the host-buffer entry point -------------------------------------------------------------
     e2e = None
-    if world == 1:
+    if fraction < 1.0:
+        e2e = {"value": None, "unit": UNIT, "note": "block-sampled run: the host-buffer entry point analyses the whole grid; "
+                                                    "not measured for this entry"}
+    elif world == 1:
         out_host = torch.empty_like(x_host).pin_memory()
         eng.analyse_host(x_host, oc_host, y_host, d_host, out=out_host)          # warm (allocates staging)
         torch.cuda.synchronize()
+        n_e2e = e2e_steps if min_seconds <= 0.0 else int(max(e2e_steps, min(2000, math.ceil(0.5 * min_seconds * 1e3 / ms_per_step))))
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
+        for _ in range(n_e2e):
             eng.analyse_host(x_host, oc_host, y_host, d_host, out=out_host)
         torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
+        dt = (time.perf_counter() - t0) / n_e2e
         h2d = x_host.numel() * esz + y_host.numel() * esz + d_host.numel() * esz + oc_host.numel() * 8
-        e2e = {"value": n_grid / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.numel() * esz),
-               "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "api": "LETKFEngine.analyse_host -> b200da_letkf_host"}
-        # sanity: the e2e result equals the device-resident result
+        e2e = {"value": n_grid / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_host.numel() * esz),
+               "ms_per_step": dt * 1e3, "steps": n_e2e, "api": "LETKFEngine.analyse_host -> b200da_letkf_host"}
         e2e["max_abs_diff_vs_device_path"] = float((out_host - xa_dev.cpu()).abs().max())
     else:
         # N > 1: inputs start in rank 0's pinned host memory, result is read back on rank 0
@@ -410,89 +524,410 @@ def main():
             if rank == 0:
                 out_host.copy_(xa_dev, non_blocking=True)
         out_host = torch.empty((1, k, n_grid), dtype=tdt).pin_memory() if rank == 0 else None
-        e2e_step(); barrier()
+        e2e_step(); ctx.barrier()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
+        for _ in range(e2e_steps):
             e2e_step()
-        barrier()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        tt = torch.tensor([dt], dtype=f64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt[0])
+        ctx.barrier()
+        dt = ctx.max_over_ranks([(time.perf_counter() - t0) / e2e_steps])[0]
         if rank == 0:
             h2d = x_host.numel() * esz + y_host.numel() * esz + d_host.numel() * esz + oc_host.numel() * 8
-            e2e = {"value": n_grid / dt, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n_grid * k * esz),
-                   "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "api": "pinned host -> rank 0 -> NCCL broadcast -> analyse -> all-gather -> host"}
+            e2e = {"value": n_grid / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n_grid * k * esz),
+                   "ms_per_step": dt * 1e3, "steps": e2e_steps,
+                   "api": "pinned host -> rank 0 -> NCCL broadcast -> analyse -> all-gather -> host"}
 
+    # ---- parity sample against the oracle, outside every timed region (rank 0; the analysis is complete on every rank) ----
+    parity = None
+    if rank == 0 and parity_points > 0 and fraction >= 1.0:
+        orc, odist = oracle_dist(w, data)
+        sel = np.unique(np.linspace(0, n_grid - 1, parity_points, dtype=np.int64))
+        o_state = data["state"].astype(ndt).astype(np.float64)
+        o_y = data["normed_perts"].astype(ndt).astype(np.float64)
+        o_d = data["normed_obs"].astype(ndt).astype(np.float64)
+        ref, _, lists = orc.letkf_analysis(o_state, o_y, o_d, data["grid_rows"], data["obs_rows"], odist, w["radius"],
+                                           inf_factor=w["rho"], grid_subset=sel, return_lists=True)
+        got = xa_dev[..., torch.as_tensor(sel, device=dev)].double().cpu().numpy().reshape(ref.shape)
+        off, idx, _, _, _ = eng.neighbour_lists(with_weights=False, subset=sel)
+        off, idx = off.cpu().numpy(), idx.cpu().numpy()
+        lists_equal = all(np.array_equal(idx[off[g]:off[g + 1]], lists[n]) for n, g in enumerate(sel))
+        parity = {"n": int(sel.size), "max_rel": float(np.abs(got - ref).max() / np.abs(ref).max()),
+                  "tolerance": 1e-10 if dtype == "f64" else 1e-4, "lists_equal": bool(lists_equal),
+                  "n_ambiguous": int(amb[-1]["n"]) if amb else None, "n_ambiguous_flipped": int(amb[-1]["flipped"]) if amb else None,
+                  "against": "oracle/letkf_oracle.py on the same (dtype-rounded) inputs, evenly spaced grid points"}
+
+    if rank != 0:
+        return None
+    tc_path = "tcgen05" in eng.kernel_name
+    kt = k // 8 if k % 8 == 0 else (k + 1 + 7) // 8        # multiples of 8: the innovation row is accumulated by FMAs
+    exec_ratio = ((kt * (kt + 1) // 2) * 128.0 + (2.0 * k if k % 8 == 0 else 0.0)) / (2.0 * k * k + 2.0 * k)
+    exec_note = ("executed DMMA FLOPs (lower-triangle 8x8 tiles of the padded [Yn; d] Gram) / algorithmic FLOPs = {0:.3f}".format(exec_ratio))
+    kname = eng.kernel_name
+    er = eng.extra_rows
+    if er and not tc_path:
+        ktd = (k + 1 - er) // 8
+        exec_ratio = ((ktd * (ktd + 1) // 2) * 128.0) / (2.0 * k * k + 2.0 * k)
+        exec_note = ("executed DMMA FLOPs ({0} lower-triangle 8x8 tiles of rows 0..{1}) / algorithmic FLOPs = {2:.3f}; the last {3} "
+                     "row(s) of [Yn; d] are accumulated by DFMA".format(ktd * (ktd + 1) // 2, ktd * 8 - 1, exec_ratio, er))
+    peak_used = ctx.peak_sus
+    peak_src = ("measured live: cuBLAS DGEMM 8192^3 via torch.matmul, sustained {0:.2f} / burst {1:.2f} TFLOP/s (FP64 DMMA pipe; "
+                "MEASURED_PEAKS.json has no FP64 entry)".format(ctx.peak_sus, ctx.peak_burst))
+    if tc_path:
+        mp = measured_peaks()
+        if mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops"):
+            peak_used = float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops"))
+            peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3, seconds-long loop), of measured"
+        else:
+            peak_used, peak_src = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md), of fallback"
+        import re
+        mt = re.search(r"_n(\d+)x(\d+)", kname)                 # pair columns per CTA x column chunks, from the kernel name
+        nc, n_chunks = int(mt.group(1)), int(mt.group(2))
+        exec_ratio = 3.0 * 2.0 * nc * n_chunks / (2.0 * k * k + 2.0 * k)
+        exec_note = ("executed tensor FLOPs per accepted (grid point, obs) pair = 3 bf16 MMAs (hi*hi + hi*lo + lo*hi) x 2 x {0} "
+                     "pair columns; / algorithmic FLOPs = {1:.3f} (candidates rejected per grid point but kept for the "
+                     "128-point block add to the executed side)".format(nc * n_chunks, exec_ratio))
+    # dominant kernel of the step
+    gram_dominant = g_ms >= s_ms
+    latency_bound = n_grid < 148 * 8
+    if gram_dominant:
+        achieved = flops_gram / (g_ms * 1e-3) * 1e-12
+        dom = dict(kernel=kname, kernel_ms=g_ms, algorithmic_flops_per_launch=flops_gram,
+                   flop_model="Gram kernel: sum_g 2k^2 p_g + 2k p_g (SURVEY.md 8d; full k x k Gram counted, the kernel computes "
+                              "the lower triangle), p_g from the neighbour-count kernel, rank 0's share")
+    else:
+        achieved = flops_solve / (s_ms * 1e-3) * 1e-12
+        peak_used, peak_src = ctx.peak_sus, ("measured live: cuBLAS DGEMM 8192^3 via torch.matmul, sustained {0:.2f} TFLOP/s (the "
+                                             "solve runs on the FP64 tensor pipe for both plan dtypes)".format(ctx.peak_sus))
+        dom = dict(kernel="k_letkf_solve_ns (Newton-Schulz inverse square root + transform + update)", kernel_ms=s_ms,
+                   algorithmic_flops_per_launch=flops_solve,
+                   flop_model="solve kernel: (13 k^3 + 2 k^2 n_s) per grid point, LAPACK-equivalent (SURVEY.md 8d: syev 9k^3 + "
+                              "2 rev_evd 4k^3 + update); the Newton-Schulz iteration executes more")
+        exec_ratio, exec_note = None, "LAPACK-equivalent FLOPs; see solver"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_{0}{1}.json".format(wname, "" if dtype == "f64" else "_f32"))
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "latency" if latency_bound else "tensor", "achieved": achieved, "peak": peak_used, "unit": "TFLOP/s",
+                "frac": None if latency_bound else (achieved / peak_used if peak_used else None), "traffic": traffic,
+                "fp64_dgemm_peak_tflops": ctx.peak_sus, "peak_source": peak_src,
+                "kernel_share_of_step": dom["kernel_ms"] / ms_per_step,
+                "executed_frac": (achieved * exec_ratio / peak_used) if (peak_used and exec_ratio) else None,
+                "executed_note": exec_note,
+                "gram_kernel": {"name": kname, "kernel_ms": g_ms, "algorithmic_flops_per_launch": flops_gram,
+                                "achieved_tflops": flops_gram / (g_ms * 1e-3) * 1e-12 if g_ms > 0 else None,
+                                "share_of_step": g_ms / ms_per_step},
+                "solve_kernel": {"name": "k_letkf_solve_ns (Newton-Schulz inverse square root + transform + update)", "kernel_ms": s_ms,
+                                 "algorithmic_flops_per_launch": flops_solve,
+                                 "achieved_tflops": flops_solve / (s_ms * 1e-3) * 1e-12 if s_ms > 0 else None,
+                                 "share_of_step": s_ms / ms_per_step},
+                "path": {"achieved_tflops": (flops_gram + flops_solve) / (kern_ms * 1e-3) * 1e-12, "kernel_ms": kern_ms,
+                         "frac": (flops_gram + flops_solve) / (kern_ms * 1e-3) * 1e-12 / ctx.peak_sus if (ctx.peak_sus and not tc_path) else None,
+                         "flop_model": "sum_g 2k^2 p_g + 2k p_g + 13k^3 + 2k^2 n_s (SURVEY.md 8d)"}}
+    if latency_bound:
+        roofline["note"] = ("{0} grid points = {0} CTAs of work on 148 SMs: less than one wave, launch-latency bound; time "
+                            "reported, no roofline claim (SURVEY.md 8d)".format(n_grid))
+    roofline.update(dom)
+    if world == 1:
+        l2 = ("inputs exceed L2 (staged obs copy {0:.0f} MB + state {1:.0f} MB vs 126 MB)".format(
+                  n_obs * eng.k * esz * 1.12 / 1e6, n_grid * k * esz / 1e6) if n_obs * k * esz > 2e8 else
+              "inputs fit in L2; no flush (workload is latency/compute bound, not DRAM bound)")
+    else:
+        l2 = "inputs exceed L2" if n_obs * k * esz > 2e8 else "inputs fit in L2; no flush"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": dtype, "data": "synthetic",
+        "config": {"workload": desc_of(w, dtype), "n_grid": n_grid, "n_obs": n_obs, "ens_size": k, "mean_local_obs": p_mean,
+                   "sharding": "grid-point blocks split over {0} GPU(s) in contiguous ranges balanced by local-observation "
+                               "count; obs broadcast from rank 0, analysis all-gathered".format(world),
+                   "l2": l2, "kernel": kname},
+        "roofline": roofline,
+        "solver": "FP64 Newton-Schulz (k x k solve and update in FP64 for both plan dtypes)",
+        "set_grid_ms": set_grid_ms,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity_sample": parity,
+    }
+    if fraction < 1.0:
+        line["config"]["block_sample"] = ("{0:.0%} of the grid-point blocks per step ({1} grid points in {2} evenly spaced ranges "
+                                          "from pole to pole); value = analysed grid points / time".format(fraction, my_points, len(my_ranges)))
+    if cpu_info is not None:
+        line["cpu_baseline"] = cpu_info
+    del eng, sharded, x_dev, y_dev, d_dev, oc_dev, xa_dev, gc_dev
+    torch.cuda.empty_cache()
+    return line
+
+
+# ---- cfg4: global ETKF -----------------------------------------------------------------------------------------------
+def run_etkf(ctx, wname, dtype, steps, warmup, e2e_steps, cpu_info=None, min_seconds=0.0):
+    torch, dist = ctx.torch, ctx.dist
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    from pytassim_b200.engine import LETKFEngine, launch_count
+    from pytassim_b200.localization.metrics import AbsDistance1D
+    from pytassim_b200.parallel import ShardedETKF
+    w = WORKLOADS[wname]
+    k, n, m = w["k"], w["n_grid"], w["n_obs"]
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    esz = 8 if dtype == "f64" else 4
+    # every rank builds the same synthetic arrays (same seed) and reads only its observation / state ranges
+    g = torch.Generator(device=dev); g.manual_seed(42)
+    x = torch.randn((1, k, n), dtype=tdt, device=dev, generator=g)
+    stride = max(1, n // m)
+    hx = x[0, :, ::stride][:, :m].to(torch.float64)                   # identity H on every stride-th element
+    yn = (hx - hx.mean(dim=0, keepdim=True)).to(tdt).contiguous()     # R = I
+    d = (torch.randn(m, dtype=torch.float64, device=dev, generator=g) * 0.5).to(tdt)
+    del hx
+    eng = LETKFEngine(k, 1, AbsDistance1D(), 1.0, inf_factor=w["rho"], dtype=tdt)
+    sh = ShardedETKF(eng)
+    xa = torch.empty_like(x)
+
+    def step():
+        sh.run(x, yn, d, xa, gather=True)
+    for _ in range(max(warmup, 1)):
+        step()
+    ctx.barrier()
+    if min_seconds > 0.0:
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); step(); e1.record(); ctx.barrier()
+        est = ctx.max_over_ranks([e0.elapsed_time(e1)])[0]
+        steps = int(max(steps, min(5000, math.ceil(min_seconds * 1e3 / max(est, 1e-3)))))
+    # per-kernel times (one untimed pass, CUDA events on the launch stream)
+    ev = [torch.cuda.Event(True) for _ in range(4)]
+    m0, m1 = sh.ranges(m)[rank]
+    c0, c1 = sh.ranges(n)[rank]
+    ev[0].record(); gram = eng.etkf_gram(yn, d, obs_range=(m0, m1))
+    if world > 1:
+        dist.all_reduce(gram)
+    ev[1].record(); wts = eng.etkf_weights_from_gram(gram, m); ev[2].record()
+    eng.apply_weights_cols(x, wts, c0, c1, xa); ev[3].record(); ev[3].synchronize()
+    t_gram, t_solve, t_upd = ctx.max_over_ranks([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])])
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank).start() if rank == 0 else None
+    l0 = launch_count()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    ctx.barrier()
+    launches = launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ctx.max_over_ranks([e0.elapsed_time(e1)])[0] / steps
+    # parity property at full size: the sharded result equals the single-call result on this rank (N > 1), and the weights
+    # satisfy the defining identities of core/etkf.py:57-77:  W_p^2 (C + a I) = (k - 1) I,  (C + a I) w_mean = b
+    gram_full = eng.etkf_gram(yn, d).double()
+    C = gram_full[:k, :k]; C = torch.tril(C) + torch.tril(C, -1).t(); b = gram_full[k, :k]
+    W = eng.etkf_weights(yn, d).double()
+    a = (k - 1) / w["rho"]
+    A = C + a * torch.eye(k, dtype=torch.float64, device=dev)
+    wbar = torch.linalg.solve(A, b)
+    Wp = W - wbar[:, None]
+    ident = float(((Wp @ Wp @ A) / (k - 1) - torch.eye(k, dtype=torch.float64, device=dev)).abs().max())
+    ref = eng.apply_weights(x, eng.etkf_weights(yn, d))
+    shard_err = float((xa - ref).abs().max() / ref.abs().max())
+    del ref
+    e2e = None
     if rank == 0:
-        achieved = flops_gram / (g_ms * 1e-3) * 1e-12            # dominant kernel: the DMMA Gram kernel
-        kt = k // 8 if k % 8 == 0 else (k + 1 + 7) // 8        # multiples of 8: the innovation row is accumulated by FMAs
-        exec_ratio = ((kt * (kt + 1) // 2) * 128.0 + (2.0 * k if k % 8 == 0 else 0.0)) / (2.0 * k * k + 2.0 * k)
-        tc_path = "tcgen05" in eng.kernel_name
-        peak_used, peak_src = peak_sus, ("measured live: cuBLAS DGEMM 8192^3 via torch.matmul, sustained {0:.2f} / burst {1:.2f} "
-                                         "TFLOP/s (FP64 DMMA pipe; MEASURED_PEAKS.json has no FP64 entry)".format(peak_sus, peak_burst))
-        exec_note = ("executed DMMA FLOPs (lower-triangle 8x8 tiles of the padded [Yn; d] Gram) / algorithmic "
-                     "FLOPs = {0:.3f}".format(exec_ratio))
-        if tc_path:
-            # FP32 plan: bf16 hi/lo split operands on the tcgen05 tensor cores -> the bf16 dense peak of MEASURED_PEAKS.json
-            try:
-                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-                peak_used = float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops"))
-                peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3, seconds-long loop), of measured"
-            except Exception:
-                peak_used, peak_src = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md), of fallback"
-            n_cols = (k + 1) * (k + 2) // 2
-            n_chunks = -(-n_cols // 512)
-            nc = -(-(-(-n_cols // n_chunks)) // 32) * 32
-            exec_ratio = 3.0 * 2.0 * nc * n_chunks / (2.0 * k * k + 2.0 * k)
-            exec_note = ("executed tensor FLOPs per accepted (grid point, obs) pair = 3 bf16 MMAs (hi*hi + hi*lo + lo*hi) x 2 x {0} "
-                         "pair columns; / algorithmic FLOPs = {1:.3f} (candidates rejected per grid point but kept for the "
-                         "128-point block add to the executed side)".format(nc * n_chunks, exec_ratio))
-        path_tflops = flops_local / (kern_ms * 1e-3) * 1e-12      # Gram + solve kernels together
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_{0}{1}.json".format(args.workload, "" if args.dtype == "f64" else "_f32"))
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        line = {
-            "metric": metric_name, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": w["desc"] if args.dtype == "f64" else w["desc"].replace("FP64", "FP32 arrays in HBM"), "n_grid": n_grid, "n_obs": n_obs, "ens_size": k, "mean_local_obs": p_mean,
-                       "sharding": "grid-point blocks split contiguously over {0} GPU(s); obs broadcast from rank 0, "
-                                   "analysis all-gathered".format(world),
-                       "l2": "inputs exceed L2 (staged obs copy {0:.0f} MB + state {1:.0f} MB vs 126 MB)".format(
-                           n_obs * eng.k * esz * 1.12 / 1e6, n_grid * k * esz / 1e6) if n_obs * k * esz > 2e8 else
-                             "inputs fit in L2; no flush (workload is latency/compute bound, not DRAM bound)",
-                       "kernel": eng.kernel_name},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_used, "unit": "TFLOP/s",
-                         "frac": achieved / peak_used if peak_used else None, "traffic": traffic,
-                         "kernel": eng.kernel_name, "kernel_ms": g_ms,
-                         "algorithmic_flops_per_launch": flops_gram,
-                         "flop_model": "Gram kernel: sum_g 2k^2 p_g + 2k p_g (SURVEY.md 8d; full k x k Gram counted, the kernel "
-                                       "computes the lower triangle), p_g from the neighbour-count kernel, rank 0's share",
-                         "fp64_dgemm_peak_tflops": peak_sus,
-                         "peak_source": peak_src,
-                         "kernel_share_of_step": g_ms / ms_per_step,
-                         "executed_frac": (achieved * exec_ratio / peak_used) if peak_used else None,
-                         "executed_note": exec_note,
-                         "solve_kernel": {"name": "k_letkf_solve_ns (Newton-Schulz inverse square root + transform + update)", "kernel_ms": s_ms,
-                                          "algorithmic_flops_per_launch": flops_solve,
-                                          "achieved_tflops": flops_solve / (s_ms * 1e-3) * 1e-12 if s_ms > 0 else None,
-                                          "share_of_step": s_ms / ms_per_step},
-                         "path": {"achieved_tflops": path_tflops, "frac": path_tflops / peak_used if peak_used else None,
-                                  "kernel_ms": kern_ms,
-                                  "flop_model": "sum_g 2k^2 p_g + 2k p_g + 13k^3 + 2k^2 n_s (SURVEY.md 8d)"}},
-            "solver": "FP64 Newton-Schulz (k x k solve and update in FP64 for both plan dtypes)",
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        }
-        if cpu_info is not None:
-            line["cpu_baseline"] = cpu_info
+        need = 2 * x.numel() * esz + yn.numel() * esz
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 0
+        if world > 1:
+            e2e = {"value": None, "unit": UNIT, "note": "N > 1: the e2e leg of cfg4 is measured at N = 1 only"}
+        elif avail > 2.5 * need:
+            xh = torch.empty(x.shape, dtype=tdt).pin_memory(); xh.copy_(x)
+            yh = torch.empty(yn.shape, dtype=tdt).pin_memory(); yh.copy_(yn)
+            dh = torch.empty(d.shape, dtype=tdt).pin_memory(); dh.copy_(d)
+            oh = torch.empty(x.shape, dtype=tdt).pin_memory()
+            xd, yd, dd = torch.empty_like(x), torch.empty_like(yn), torch.empty_like(d)
+
+            def e2e_step():
+                xd.copy_(xh, non_blocking=True); yd.copy_(yh, non_blocking=True); dd.copy_(dh, non_blocking=True)
+                wt = eng.etkf_weights(yd, dd)
+                eng.apply_weights(xd, wt, out=xa)
+                oh.copy_(xa, non_blocking=True)
+            e2e_step(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / e2e_steps
+            e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": int(need - x.numel() * esz + d.numel() * esz),
+                   "d2h_bytes_per_step": int(x.numel() * esz), "ms_per_step": dt * 1e3, "steps": e2e_steps,
+                   "api": "pinned host -> LETKFEngine.etkf_weights + apply_weights (b200da_etkf_weights, b200da_apply_weights) -> host"}
+            del xh, yh, dh, oh, xd, yd, dd
+        else:
+            e2e = {"value": None, "unit": UNIT, "note": "not measured: {0:.0f} GB of pinned host memory needed, {1:.0f} GB "
+                                                        "available".format(need / 1e9, avail / 1e9)}
+    if rank != 0:
+        return None
+    hbm = float(measured_peaks().get("hbm_gbs", 6550.0))
+    upd_flops = 2.0 * k * k * (c1 - c0)
+    upd_bytes = 2.0 * k * (c1 - c0) * esz
+    line = {
+        "metric": METRIC, "value": n / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype,
+        "data": "synthetic (generated on the device, seed 42)",
+        "state_elements_per_sec": n * k / (ms_per_step * 1e-3),
+        "config": {"workload": desc_of(w, dtype), "n_grid": n, "n_obs": m, "ens_size": k,
+                   "sharding": "observation-sharded Gram -> all-reduce of (k+1)^2 doubles -> redundant k x k solve -> state-sharded "
+                               "update -> all-gather of the analysis ({0} GPU(s))".format(world),
+                   "l2": "inputs exceed L2 (state {0:.1f} GB)".format(n * k * esz / 1e9) if n * k * esz > 2e8 else "inputs fit in L2; no flush",
+                   "kernel": "k_etkf_gram + k_letkf_solve_ns + k_apply_global"},
+        "roofline": {"bound": "tensor", "kernel": "k_apply_global (update Xa = W'^T X as a streaming DMMA GEMM)", "kernel_ms": t_upd,
+                     "achieved": upd_flops / (t_upd * 1e-3) * 1e-12, "peak": ctx.peak_sus, "unit": "TFLOP/s",
+                     "frac": upd_flops / (t_upd * 1e-3) * 1e-12 / ctx.peak_sus if ctx.peak_sus else None, "traffic": None,
+                     "algorithmic_flops_per_launch": upd_flops, "flop_model": "2 k^2 per state column of this rank (SURVEY.md 8d)",
+                     "peak_source": "measured live: cuBLAS DGEMM 8192^3 via torch.matmul, sustained",
+                     "hbm": {"achieved_gbs": upd_bytes / (t_upd * 1e-3) * 1e-9, "peak_gbs": hbm,
+                             "frac": upd_bytes / (t_upd * 1e-3) * 1e-9 / hbm, "algorithmic_bytes_per_launch": upd_bytes,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs, of measured"},
+                     "kernel_share_of_step": t_upd / ms_per_step,
+                     "phases_ms": {"gram_plus_allreduce": t_gram, "solve": t_solve, "update": t_upd}},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "parity_sample": {"identity_residual_Wp2_A_over_km1_minus_I": ident, "sharded_vs_single_max_rel": shard_err,
+                          "tolerance": 1e-10 if dtype == "f64" else 1e-4,
+                          "against": "defining identities of core/etkf.py:57-77 on the device Gram (size-independent property; "
+                                     "tests/test_gpu_parity.py checks the same kernels against the oracle at reduced size)"},
+    }
+    if cpu_info is not None:
+        line["cpu_baseline"] = cpu_info
+    del x, xa, yn, d, eng
+    torch.cuda.empty_cache()
+    return line
+
+
+def secondary_plan(args, world):
+    if args.no_secondary:
+        return []
+    if args.secondary:
+        keys = [s for s in args.secondary.split(",") if s]
+        return [e for e in SECONDARY if e[0] in keys]
+    if args.workload != "cfg3" or args.dtype != "f64":
+        return []
+    if world > 1:
+        return [e for e in SECONDARY if e[0] in SECONDARY_MULTI]
+    return list(SECONDARY)
+
+
+def main():
+    _reserve_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="plan dtype (state / obs-space arrays in HBM)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="only the headline workload")
+    ap.add_argument("--secondary", default="", help="comma-separated secondary entries to run instead of the default set")
+    ap.add_argument("--fraction", type=float, default=1.0, help="share of the grid-point blocks analysed per step (headline)")
+    ap.add_argument("--parity-points", type=int, default=12)
+    args = ap.parse_args()
+    ctx = Ctx()
+    rank, world = ctx.rank, ctx.world
+    plan = secondary_plan(args, world)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # reference arm: the reference's CPU code on the host cores (rank 0 only)
+    # ------------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w, data = make_workload(args.workload)
+        vals, info = [], None
+        t_all = time.perf_counter()
+        if w["kind"] == "global":
+            for _ in range(args.steps):
+                info = cpu_etkf_rate(w); vals.append(info["value"])
+        else:
+            for _ in range(max(1, args.warmup > 0)):
+                cpu_reference_rate(w, data, target_seconds=3.0)
+            t_all = time.perf_counter()
+            for _ in range(args.steps):
+                info = cpu_reference_rate(w, data, target_seconds=12.0)
+                vals.append(info["value"])
+        v = float(np.mean(vals))
+        info["value"] = v
+        ms = 1000.0 * (time.perf_counter() - t_all) / args.steps
+        sec = {}
+        done = {}
+        for key, wname, dtype, _ in plan:                     # the CPU code is FP64 throughout: one sample per workload
+            if wname not in done:
+                _log("reference sample " + wname)
+                ws, ds = make_workload(wname)
+                done[wname] = cpu_etkf_rate(ws) if ws["kind"] == "global" else cpu_reference_rate(ws, ds, target_seconds=4.0)
+                del ds
+            sec[key] = {"value": done[wname]["value"], "unit": UNIT, "cpu_baseline": done[wname],
+                        "config": {"workload": desc_of(WORKLOADS[wname], "f64")}}
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": desc_of(w, "f64"), "inputs": "host resident"},
+                "cpu_baseline": info,
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        if sec:
+            line["secondary"] = sec
+        _emit(line)
+        return
+
+    # ------------------------------------------------------------------------------------------------------------
+    # B200 arm.  Phase A (before CUDA is initialised: the CPU pool forks): CPU baselines on bounded samples, N = 1 only
+    # ------------------------------------------------------------------------------------------------------------
+    w = WORKLOADS[args.workload]
+    datasets, cpu = {}, {}
+    if rank == 0:
+        names = [args.workload] + [e[1] for e in plan]
+        for wname in dict.fromkeys(names):
+            ww, dd = make_workload(wname)
+            datasets[wname] = dd
+            if world == 1 and not args.no_cpu_baseline:
+                _log("cpu baseline sample " + wname)
+                tgt = 12.0 if wname == args.workload else 3.0
+                cpu[wname] = cpu_etkf_rate(ww) if ww["kind"] == "global" else cpu_reference_rate(ww, dd, target_seconds=tgt)
+    ctx.init_cuda()
+
+    _log("headline " + args.workload)
+    if w["kind"] == "global":
+        line = run_etkf(ctx, args.workload, args.dtype, args.steps, args.warmup, args.e2e_steps, cpu_info=cpu.get(args.workload))
+    else:
+        line = run_letkf(ctx, args.workload, args.dtype, args.steps, args.warmup, args.e2e_steps,
+                         data=datasets.pop(args.workload, None) if args.workload not in [e[1] for e in plan] else datasets.get(args.workload),
+                         fraction=args.fraction, parity_points=args.parity_points, cpu_info=cpu.get(args.workload))
+    sec = {}
+    remaining = [e[1] for e in plan]
+    for key, wname, dtype, fraction in plan:
+        _log("secondary " + key)
+        ws = WORKLOADS[wname]
+        t0 = time.perf_counter()
+        try:
+            if ws["kind"] == "global":
+                ent = run_etkf(ctx, wname, dtype, 5, 3, 1, cpu_info=cpu.get(wname), min_seconds=2.0)
+            else:
+                big = ws["kind"] == "sphere"
+                ent = run_letkf(ctx, wname, dtype, 3 if big else 5, 1 if big else 3, 1, data=datasets.get(wname), fraction=fraction,
+                                parity_points=6 if big else 8, cpu_info=cpu.get(wname), min_seconds=2.0)
+        except Exception as exc:                                # one failing entry must not take the headline with it
+            ent = {"error": repr(exc)}
+            if world > 1:
+                raise
+        remaining.remove(wname)
+        if wname not in remaining:
+            datasets.pop(wname, None)
+        if ent is not None:
+            ent["wall_s"] = time.perf_counter() - t0
+            sec[key] = ent
+    if rank == 0:
+        if sec:
+            line["secondary"] = sec
         _emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

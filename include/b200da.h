@@ -35,6 +35,11 @@
 extern "C" {
 #endif
 
+/* The library is built with -fvisibility=hidden: only the entry points declared here are exported. */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
 typedef struct b200da_plan b200da_plan;
 
 typedef enum {
@@ -46,7 +51,9 @@ typedef enum {
     B200DA_ERR_NO_DEVICE = -4,    /* no CUDA device or not sm_100: there is no CPU fallback                   */
     B200DA_ERR_CUDA = -5,         /* a CUDA runtime call failed; see b200da_last_cuda_error()                 */
     B200DA_ERR_STATE = -6,        /* call order: set_grid and bin_obs must precede letkf / neighbour_*         */
-    B200DA_ERR_NOMEM = -7
+    B200DA_ERR_NOMEM = -7,
+    B200DA_ERR_OVERFLOW = -8      /* a grid-point block needed more candidate cell columns than the kernels hold (reported by
+                                     b200da_pending_status): the analysis of that launch is invalid                        */
 } b200da_status;
 
 /* Distance functions.  The reference takes an arbitrary Python `dist_func` (localization/gaspari_cohn.py:60-69,125);
@@ -154,6 +161,8 @@ int64_t b200da_num_grid(const b200da_plan* plan);
 int64_t b200da_num_obs(const b200da_plan* plan);
 /* first grid slot (position in the block-sorted order) of block b, b in [0, num_blocks]; host query */
 int64_t b200da_block_offset(const b200da_plan* plan, int64_t block);
+/* all num_blocks + 1 offsets at once into a HOST array */
+int b200da_block_offsets(const b200da_plan* plan, int64_t* offsets_host);
 /* copies the block-sorted grid order (N int32: slot -> original grid index) to a device buffer */
 int b200da_grid_order(const b200da_plan* plan, int32_t* order_out, void* stream);
 
@@ -181,6 +190,10 @@ int b200da_letkf_gram(b200da_plan* plan, double* gram_out, int64_t block_begin, 
 int b200da_letkf_host(b200da_plan* plan, const double* obs_coord_host, const void* Yn_host, const void* d_host,
                       int64_t n_obs, const void* X_host, void* Xa_host, void* stream);
 
+/* After b200da_letkf_host: analyse blocks [block_begin, block_end) again from the inputs still staged on the device (with
+ * the overrides set since) and download the analysis again — the repeat step of the ambiguity protocol below. */
+int b200da_letkf_host_blocks(b200da_plan* plan, void* Xa_host, int64_t block_begin, int64_t block_end, void* stream);
+
 /* Local-observation index lists = np.nonzero(use_obs)[0] of GaspariCohn.localize_obs
  * (localization/gaspari_cohn.py:135) for every grid point, as CSR in ORIGINAL grid order, ascending obs id.
  * Two passes: count -> caller scans -> fill.  w_opt receives the taper weights (before sqrt);
@@ -189,9 +202,30 @@ int b200da_letkf_host(b200da_plan* plan, const double* obs_coord_host, const voi
 int b200da_neighbour_count(b200da_plan* plan, int64_t* counts, int64_t* n_ambiguous_opt, void* stream);
 int b200da_neighbour_fill(b200da_plan* plan, const int64_t* offsets, int32_t* idx, double* w_opt,
                           uint8_t* ambiguous_opt, void* stream);
+/* (grid points with offsets[g + 1] == offsets[g] are skipped by the fill pass: zero the counts of the grid points that are
+ * not wanted before the scan to materialise the lists of a subset only — the full CSR of cfg3 has 5.7e10 entries) */
 /* All pairs (grid index, obs index, w) inside the ambiguity band, accepted or not; capacity-limited. */
 int b200da_neighbour_ambiguous(b200da_plan* plan, int64_t capacity, int64_t* grid_idx, int64_t* obs_idx,
                                double* w, int64_t* n_found, void* stream);
+
+/* The ambiguity protocol for the mask `use_obs = weights > epsilon` of GaspariCohn.localize_obs (localization/
+ * gaspari_cohn.py:135).  The reference evaluates the taper with numpy's `**`, whose last bits depend on the host's numpy
+ * build; the device evaluates the same polynomial by Horner's rule.  The two values agree to ~1e-15, so the mask can differ
+ * only for pairs with |w - epsilon| < 1e-13.  b200da_letkf records every such pair it meets (FP64 taper path; up to 4096):
+ *   b200da_pending_status      synchronises the stream, copies the recorded pairs (original grid index, original obs index,
+ *                              unmasked device taper value) to HOST arrays, resets the record, and returns
+ *                              B200DA_ERR_OVERFLOW if a kernel since the last call had to drop candidate cells (see
+ *                              b200da_status).  *n_found_host may exceed `capacity` / 4096: then only that many were kept;
+ *   b200da_plan_set_overrides  hands the host's decisions back (HOST arrays): the weight of pair i becomes w_host[i]
+ *                              (0 = not a local observation) in b200da_letkf*, b200da_letkf_gram and the neighbour lists
+ *                              until the next b200da_bin_obs / b200da_set_grid; n = 0 clears the list;
+ *   b200da_blocks_of_grid      the block that holds each original grid index (HOST arrays), so that only the blocks whose
+ *                              mask changed are analysed again. */
+int b200da_pending_status(b200da_plan* plan, int64_t capacity, int64_t* grid_idx_host, int64_t* obs_idx_host, double* w_host,
+                          int64_t* n_found_host, void* stream);
+int b200da_plan_set_overrides(b200da_plan* plan, int64_t n, const int64_t* grid_idx_host, const int64_t* obs_idx_host,
+                              const double* w_host, void* stream);
+int b200da_blocks_of_grid(b200da_plan* plan, int64_t n, const int64_t* grid_idx_host, int64_t* block_host, void* stream);
 
 /* ---- global ETKF (no localization) ------------------------------------------------------------------------ */
 
@@ -245,11 +279,12 @@ int b200da_etkf_ienks_weights(b200da_plan* plan, const void* Yn, const void* d, 
 /* ---- multi-GPU helpers ------------------------------------------------------------------------------------ */
 
 /* Pack / unpack the analysed columns of blocks [block_begin, block_end) between the (n_slices, k, N) layout and
- * a dense (n_slices * k, n_cols) buffer in block-sorted order: the all-gather payload of the grid-sharded run. */
+ * a (n_slices * k, n_cols) buffer with row stride ld >= n_cols elements (0: dense) in block-sorted order: the all-gather
+ * payload of the grid-sharded run, packed straight into / scattered straight out of a slot of the gather buffer. */
 int b200da_pack_columns(b200da_plan* plan, const void* Xa, int64_t block_begin, int64_t block_end, void* packed,
-                        void* stream);
+                        int64_t ld, void* stream);
 int b200da_unpack_columns(b200da_plan* plan, const void* packed, int64_t block_begin, int64_t block_end, void* Xa,
-                          void* stream);
+                          int64_t ld, void* stream);
 
 /* ---- misc -------------------------------------------------------------------------------------------------- */
 
@@ -258,6 +293,8 @@ const char* b200da_last_cuda_error(void);
 int b200da_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t b200da_launch_count(void);
+/* rows of the augmented [Yn; d] that the FP64 Gram kernel of this plan accumulates with DFMA next to its DMMA tiles */
+int b200da_gram_extra_rows(const b200da_plan* plan);
 /* name of the Gram kernel configuration chosen for the plan, e.g. "letkf_gram_f64_kt7_g8_w2" */
 const char* b200da_kernel_name(const b200da_plan* plan);
 /* device time (ms) of the last b200da_letkf main-kernel launch on this plan, measured with CUDA events on
@@ -274,6 +311,10 @@ int b200da_collect_stats(b200da_plan* plan, int on);
 /* choose the ensemble-space solver of b200da_letkf (b200da_solver) */
 int b200da_set_solver(b200da_plan* plan, int solver);
 int b200da_get_stats(b200da_plan* plan, int64_t* out8);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 
 #ifdef __cplusplus
 }

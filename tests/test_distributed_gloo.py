@@ -52,9 +52,17 @@ class OracleEngine(object):
             out[:, :, g] = torch.as_tensor(orc.apply_weights(x.numpy()[None][..., g:g + 1], w_new[None])[0, ..., 0])
         return out, w_out
 
-    def pack_columns(self, xa, b0, b1):
+    def pack_columns(self, xa, b0, b1, out=None):
         sel = torch.as_tensor(self.order[self.offsets[b0]:self.offsets[b1]])
-        return xa.reshape(-1, xa.shape[-1])[:, sel].contiguous()
+        packed = xa.reshape(-1, xa.shape[-1])[:, sel].contiguous()
+        if out is None:
+            return packed
+        out.copy_(packed)                     # a strided slot of the all-gather buffer
+        return out
+
+    def block_costs(self, counts):
+        c = np.asarray(counts, dtype=np.float64)[self.order]
+        return np.array([c[self.offsets[b]:self.offsets[b + 1]].sum() for b in range(self.n_blocks)])
 
     def unpack_columns(self, packed, b0, b1, xa):
         sel = torch.as_tensor(self.order[self.offsets[b0]:self.offsets[b1]])

@@ -62,6 +62,14 @@ CASES = [
     (128, lambda: syn.lorenz96_1d(140, 128, 1, seed=9), lambda m: m.PeriodicDistance1D(140.0), 8.0, lambda: orc.make_dist_periodic1d(140.0)),
     (5, lambda: syn.lorenz96_1d(90, 5, 1, seed=10), lambda m: m.AbsDistance1D(), 6.0, lambda: orc.dist_abs1d),
     (16, lambda: syn.sphere_latlon(20, 40, 16, 3000, seed=11), lambda m: m.HaversineDistance(6371.0), 1800.0, lambda: orc.make_dist_haversine(6371.0)),
+    # the FP64 Gram keeps (k + 1) mod 8 = 1, 2 or 3 trailing rows of [Yn; d] on the DFMA pipe (letkf_kernel.cuh, ER): one case
+    # per remainder and warp layout (kt <= 5: one warp per grid point, <= 7: two, <= 10: four, beyond: eight)
+    (9, lambda: syn.lorenz96_1d(200, 9, 1, seed=15), lambda m: m.PeriodicDistance1D(200.0), 7.0, lambda: orc.make_dist_periodic1d(200.0)),
+    (26, lambda: syn.lorenz96_1d(300, 26, 1, seed=16), lambda m: m.AbsDistance1D(), 11.0, lambda: orc.dist_abs1d),
+    (49, lambda: syn.sphere_latlon(20, 40, 49, 3000, seed=17), lambda m: m.HaversineDistance(6371.0), 1500.0, lambda: orc.make_dist_haversine(6371.0)),
+    (58, lambda: syn.lorenz96_1d(260, 58, 1, seed=18), lambda m: m.PeriodicDistance1D(260.0), 14.0, lambda: orc.make_dist_periodic1d(260.0)),
+    (73, lambda: syn.lorenz96_1d(180, 73, 1, seed=19), lambda m: m.PeriodicDistance1D(180.0), 9.0, lambda: orc.make_dist_periodic1d(180.0)),
+    (122, lambda: syn.lorenz96_1d(130, 122, 1, seed=20), lambda m: m.PeriodicDistance1D(130.0), 8.0, lambda: orc.make_dist_periodic1d(130.0)),
 ]
 
 

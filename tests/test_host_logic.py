@@ -468,8 +468,11 @@ def test_netcdf_store_coordinate_encodings(tmp_path):
     assert np.array_equal(back.values, arr.values)
     with pytest.raises(ValueError):                                  # does not fit 32-bit integers
         save_netcdf(xrlite.DataArray(np.zeros(2), dict(grid=np.array([0, 2 ** 40])), ("grid", )), path)
-    with pytest.raises(NotImplementedError):                         # string coordinates
-        save_netcdf(xrlite.DataArray(np.zeros(2), dict(var_name=["x", "y"]), ("var_name", )), path)
+    # string labels: character arrays with a trailing string<n> dimension, as xarray's netCDF-3 encoder writes them
+    save_netcdf(xrlite.DataArray(np.arange(6.0).reshape(2, 3), dict(var_name=["x", "temperature"], grid=np.arange(3)),
+                                 ("var_name", "grid")), path)
+    lab = load_netcdf(path, array=True)
+    assert list(lab.indexes["var_name"]) == ["x", "temperature"] and np.array_equal(lab.values, np.arange(6.0).reshape(2, 3))
     nc = netcdf_file(path, "w", version=2)                           # a file as xarray writes a NAMED DataArray
     nc.createDimension("ensemble", 2); nc.createDimension("ensemble_new", 2)
     v = nc.createVariable("ensemble", "i4", ("ensemble", )); v[:] = [0, 1]
@@ -477,6 +480,31 @@ def test_netcdf_store_coordinate_encodings(tmp_path):
     nc.close()
     named = load_netcdf(path, array=True)
     assert named.dims == ("ensemble", "ensemble_new") and np.array_equal(named.values, np.eye(2))
+
+
+def test_netcdf_store_beyond_the_fixed_variable_limit(tmp_path, monkeypatch):
+    """Per-grid-point weights of 2 GiB or more (N ~ 168 000 at k = 40) exceed scipy's signed 32-bit ``vsize`` of a fixed
+    netCDF-3 variable: they are written with ``grid`` as the record dimension.  The limit is lowered here so that the same
+    code path runs on a small array; the file must round-trip, MultiIndex included, and a 1-D array over the limit (no
+    dimension to make records of) must raise a clear error instead of struct.error."""
+    from scipy.io import netcdf_file
+    from pytassim_b200.utilities import netcdf as store
+    rng = np.random.RandomState(1)
+    mi = pd.MultiIndex.from_product((np.arange(7) * 0.5, [0.0, 180.0]), names=['lat', 'lon'])
+    w = xrlite.DataArray(rng.normal(size=(14, 5, 5)), dict(grid=mi, ensemble=np.arange(5), ensemble_new=np.arange(5)),
+                         ('grid', 'ensemble', 'ensemble_new'))
+    monkeypatch.setattr(store, "FIXED_VARIABLE_LIMIT", 1000)          # 14 x 5 x 5 x 8 = 2800 bytes > limit
+    path = str(tmp_path / "big.nc")
+    store.save_netcdf(w, path)
+    nc = netcdf_file(path, 'r', mmap=False)
+    assert nc.dimensions['grid'] is None and nc.variables[store.DATAARRAY_VARIABLE].isrec      # record layout
+    nc.close()
+    back = store.load_netcdf(path, array=True)
+    assert np.array_equal(back.values, w.values) and back.indexes['grid'].equals(mi)
+    with pytest.raises(ValueError, match="2 GiB"):
+        store.save_netcdf(xrlite.DataArray(np.zeros(400), dict(grid=np.arange(400)), ('grid', )), path)
+    # the real limit: sizes are checked up front, nothing of this size is allocated here
+    assert store.FIXED_VARIABLE_LIMIT == 1000 and 168_000 * 40 * 40 * 8 > 2 ** 31 - 4
 
 
 def _emulate_program(prog, xy, xx, yy, diag, same_set):
@@ -703,3 +731,27 @@ def test_per_point_call_forms_with_stub_module():
     np.testing.assert_allclose(p_arg, perts[:, [0, 2, 3]] * np.array([0.5, 1.0, 0.2]))
     np.testing.assert_allclose(i_arg, innov[:, [0, 2, 3]] * np.array([0.5, 1.0, 0.2]))
     assert LocalObservations(lambda *a: a, None)("row", 1, 2, obs_info=None) == (1, 2)        # wrapper.py:87: no localization
+
+
+# ---- ambiguity protocol: the host decision rule is the reference's expression ----------------------------------------
+def test_host_decision_is_bit_equal_to_the_reference_expression(golden):
+    """``BaseLocalization.host_decision`` (the rule applied to pairs the device cannot decide) against the oracle's
+    restatement of gaspari_cohn.py:97-136 / :216-254, which tests/test_oracle.py pins to reference-generated goldens."""
+    rnd = np.random.RandomState(0)
+    obs_rows = np.stack([np.zeros(500), rnd.uniform(-30.0, 70.0, size=500)], axis=1)
+    grid_row = np.array([0.0, 20.0])
+    loc = GaspariCohn((10.0,), AbsDistance1D())
+    use, w = loc.host_decision(grid_row, obs_rows)
+    use_ref, w_ref = orc.gaspari_cohn_localize(orc.dist_abs1d(grid_row, obs_rows), (10.0,), 1e-5)
+    np.testing.assert_array_equal(use, use_ref)
+    np.testing.assert_array_equal(w, w_ref)
+    loc = GaspariCohnInf(10.0, AbsDistance1D())
+    use, w = loc.host_decision(grid_row, obs_rows)
+    use_ref, w_ref = orc.gaspari_cohn_inf_localize(orc.dist_abs1d(grid_row, obs_rows), 10.0, 1e-5)
+    np.testing.assert_array_equal(use, use_ref)
+    np.testing.assert_array_equal(w, w_ref)
+    # one pair at a time (how the protocol calls it) gives the same bits as the vector call
+    for j in (3, 77, 256):
+        u1, w1 = GaspariCohn((10.0,), AbsDistance1D()).host_decision(grid_row, obs_rows[j:j + 1])
+        ua, wa = GaspariCohn((10.0,), AbsDistance1D()).host_decision(grid_row, obs_rows)
+        assert u1[0] == ua[j] and w1[0] == wa[j]

@@ -161,6 +161,97 @@ __global__ void __launch_bounds__(512) k_gramlike(double* out, int iters) {
     if (s == 123.456) out[0] = s;
 }
 
+// Do DFMA and DMMA co-issue?  ND independent DMMA chains + NF independent DFMA chains per iteration, interleaved: if the two
+// instruction classes had their own datapaths the mixed loop would take max(t_dmma, t_dfma), if they share the FP64 units it
+// takes t_dmma + t_dfma.
+template <int ND, int NF>
+__global__ void __launch_bounds__(256) k_mix(double* out, int iters, double a, double b) {
+    double c[ND > 0 ? ND : 1][2];
+    double f[NF > 0 ? NF : 1];
+#pragma unroll
+    for (int i = 0; i < (ND > 0 ? ND : 1); ++i) { c[i][0] = threadIdx.x; c[i][1] = i; }
+#pragma unroll
+    for (int i = 0; i < (NF > 0 ? NF : 1); ++i) f[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < (ND > NF ? ND : NF); ++i) {
+            if (i < ND) dmma884(c[i][0], c[i][1], a, b);
+            if (i < NF) f[i] = fma(f[i], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < (ND > 0 ? ND : 1); ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < (NF > 0 ? NF : 1); ++i) s += f[i];
+    if (s == 123.456) out[0] = s;
+}
+
+// The k = 50 Gram inner loop with the last three rows of [Yn; d] on the DFMA pipe (letkf_kernel.cuh, ER = 3): 6 tile rows =
+// 21 lower-triangle tiles split 10 / 11 over the two warps of a grid point + 3 x 3 column FMAs per warp + the 6 pair terms.
+template <int HALF>
+__device__ __forceinline__ void gramlike_er_body(const double* sm, const double* wt, int iters, int lane, double (&c)[11][2],
+                                                 double (&e)[3][3], double (&p)[6]) {
+    const int S = 60, T = 64;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 2
+        for (int ks = 0; ks < T / 4; ++ks) {
+            const int j = ks * 4 + (lane & 3);
+            const double w = wt[j];
+            double f[6], x[3], wx[3];
+#pragma unroll
+            for (int t = 0; t < 6; ++t) f[t] = sm[j * S + t * 8 + (lane >> 2)];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { x[q] = sm[j * S + 48 + q]; wx[q] = w * x[q]; }
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) e[q][t] = fma(f[HALF * 3 + t], wx[q], e[q][t]);
+            if (HALF == 0) {
+                int n = 0;
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int q2 = 0; q2 <= q; ++q2) { p[n] = fma(wx[q], x[q2], p[n]); ++n; }
+            }
+            int idx = 0, n = 0;
+#pragma unroll
+            for (int mt = 0; mt < 6; ++mt) {
+#pragma unroll
+                for (int nt = 0; nt <= mt; ++nt) {
+                    if ((idx >= 10) == (HALF == 1)) { dmma884(c[n][0], c[n][1], f[mt] * w, f[nt]); ++n; }
+                    ++idx;
+                }
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(512) k_gramlike_er(double* out, int iters) {
+    extern __shared__ double sm[];
+    const int S = 60, T = 64;
+    for (int i = threadIdx.x; i < T * S + 8 * T; i += blockDim.x) sm[i] = (i % 97) * 1e-3;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = warp >> 1;
+    double c[11][2], e[3][3], p[6];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) { c[i][0] = 0; c[i][1] = 0; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { e[i][0] = 0; e[i][1] = 0; e[i][2] = 0; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) p[i] = 0;
+    const double* wt = sm + T * S + g * T;
+    if (warp & 1) gramlike_er_body<1>(sm, wt, iters, lane, c, e, p); else gramlike_er_body<0>(sm, wt, iters, lane, c, e, p);
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 11; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s += e[i][0] + e[i][1] + e[i][2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s += p[i];
+    if (s == 123.456) out[0] = s;
+}
+
 template <typename F>
 static double time_ms(F launch) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -205,6 +296,33 @@ int main() {
         double ms = time_ms([&] { k_gramlike<<<sms, 512, smem>>>(out, it2); });
         // 16 warps x 16 k-steps x 14 DMMA x 256 FMA x 2
         printf(", \"gramlike_tflops\": %.2f", (double)sms * 16 * it2 * 16 * 14 * 256 * 2 / ms * 1e-9);
+    }
+    {
+        // co-issue probe at 4 CTAs of 256 threads per SM (8 warps per scheduler)
+        const int grid = sms * 4, block = 256;
+        const double t_d = time_ms([&] { k_mix<8, 0><<<grid, block>>>(out, iters, 1.0000001, 1e-9); });
+        const double t_f8 = time_ms([&] { k_mix<0, 8><<<grid, block>>>(out, iters, 1.0000001, 1e-9); });
+        const double t_m8 = time_ms([&] { k_mix<8, 8><<<grid, block>>>(out, iters, 1.0000001, 1e-9); });
+        const double t_f16 = time_ms([&] { k_mix<0, 16><<<grid, block>>>(out, iters, 1.0000001, 1e-9); });
+        const double t_m16 = time_ms([&] { k_mix<8, 16><<<grid, block>>>(out, iters, 1.0000001, 1e-9); });
+        printf(", \"coissue\": {\"dmma8_ms\": %.3f, \"dfma8_ms\": %.3f, \"dmma8_dfma8_ms\": %.3f, \"dfma16_ms\": %.3f, "
+               "\"dmma8_dfma16_ms\": %.3f, \"overlap_8\": %.3f, \"overlap_16\": %.3f, \"note\": \"overlap = (t_dmma + t_dfma - "
+               "t_mixed) / min(t_dmma, t_dfma): 1 = separate datapaths, 0 = one shared FP64 datapath\"}",
+               t_d, t_f8, t_m8, t_f16, t_m16, (t_d + t_f8 - t_m8) / (t_d < t_f8 ? t_d : t_f8),
+               (t_d + t_f16 - t_m16) / (t_d < t_f16 ? t_d : t_f16));
+    }
+    {
+        const int smem = (64 * 60 + 8 * 64) * 8;
+        CK(cudaFuncSetAttribute(k_gramlike_er, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int it2 = 256;
+        double ms = time_ms([&] { k_gramlike_er<<<sms, 512, smem>>>(out, it2); });
+        // algorithmic Gram FLOPs of k = 50 per observation and grid point: 2 * 51 * 51 (full square incl. the d row)
+        printf(", \"gramlike_er3_ms\": %.3f, \"gramlike_er3_alg_tflops\": %.2f", ms,
+               (double)sms * 8 * it2 * 64 * (2.0 * 50 * 50 + 2.0 * 50) / ms * 1e-9);
+        const int smem0 = (64 * 60 + 8 * 64) * 8;
+        double ms0 = time_ms([&] { k_gramlike<<<sms, 512, smem0>>>(out, it2); });
+        printf(", \"gramlike_kt7_ms\": %.3f, \"gramlike_kt7_alg_tflops\": %.2f", ms0,
+               (double)sms * 8 * it2 * 64 * (2.0 * 50 * 50 + 2.0 * 50) / ms0 * 1e-9);
     }
     printf("}\n");
     return 0;

@@ -62,6 +62,16 @@ static KernelConfig config_for_kt(int kt) {
 }
 constexpr int kMaxKt = 17;
 
+// name of the DMMA Gram variant that will run for the plan (dispatch_fused) and its number of DFMA rows
+static void name_dmma_kernel(b200da_plan* pl) {
+    const KernelConfig cfg = config_for_kt(pl->kt);
+    const int er = gram_extra_rows(pl);
+    pl->gram_er = er;
+    pl->kernel_name = std::string("letkf_gram_") + (pl->dtype == B200DA_F32 ? "f32in_f64dmma" : "f64") +
+                      (er > 0 ? "_er" + std::to_string(er) : std::string()) + "_kt" + std::to_string(er > 0 ? pl->kt - 1 : pl->kt) +
+                      "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg) + (pl->kprog.n > 0 ? "+kernelise" : "");
+}
+
 template <int KT>
 static int launch_etkf_gram(int f32, const void* yn, const void* d, int64_t m, int64_t ld, int k, int ncta, int64_t chunk,
                             double* partial, cudaStream_t st) {
@@ -150,6 +160,8 @@ static NeighbourParams neighbour_params(const b200da_plan* pl) {
     P.cell_start = pl->cell_start.as<int>();
     P.n_obs = pl->n_obs;
     P.cut_pad = pl->geom.cut_bin * (1.0 + 1e-9) + 1e-300;
+    P.status = pl->devstat.as<PlanStatus>();
+    P.over = pl->over_list.as<PairRec>(); P.n_over = pl->n_over;
     return P;
 }
 
@@ -186,6 +198,7 @@ const char* b200da_strerror(int status) {
         case B200DA_ERR_CUDA: return "CUDA runtime error";
         case B200DA_ERR_STATE: return "call order: set_grid and bin_obs must precede this call";
         case B200DA_ERR_NOMEM: return "out of device memory";
+        case B200DA_ERR_OVERFLOW: return "a grid-point block needs more candidate cell columns than the kernels hold: results are invalid";
         default: return "unknown status";
     }
 }
@@ -210,9 +223,9 @@ int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int
     const KernelConfig cfg = config_for_kt(kt);
     pl->gpb = cfg.g;
     pl->use_tc = (dtype == B200DA_F32 && k >= 8);
-    pl->kernel_name = std::string("letkf_gram_") + (dtype == B200DA_F32 ? "f32in_f64dmma" : "f64") + (k % 8 == 0 ? "_brow" : "") +
-                      "_kt" + std::to_string(k % 8 == 0 ? kt - 1 : kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
+    name_dmma_kernel(pl);
     if (pl->use_tc) {
+        pl->gram_er = 0;
         int n_cols, n_chunks, nc;
         tc_chunking(k, &n_cols, &n_chunks, &nc);
         pl->gpb = 128;
@@ -244,6 +257,10 @@ int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int
     if (cudaEventCreate(&pl->ev0) != cudaSuccess || cudaEventCreate(&pl->ev1) != cudaSuccess) {
         delete pl; return B200DA_ERR_CUDA;
     }
+    if (pl->devstat.ensure(sizeof(PlanStatus)) || pl->amb_list.ensure(sizeof(PairRec) * kAmbCapacity) ||
+        pl->over_list.ensure(sizeof(PairRec) * 16) || cudaMemset(pl->devstat.p, 0, sizeof(PlanStatus)) != cudaSuccess) {
+        b200da_plan_destroy(pl); return B200DA_ERR_NOMEM;
+    }
     *plan = pl;
     return B200DA_OK;
 }
@@ -253,7 +270,8 @@ void b200da_plan_destroy(b200da_plan* pl) {
     DevBuf* bufs[] = {&pl->gpos, &pl->gorder, &pl->block_off, &pl->opos, &pl->cell_start, &pl->ys, &pl->tmp_keys,
                       &pl->tmp_cell, &pl->tmp_count, &pl->tmp_a, &pl->tmp_b, &pl->tmp_pos, &pl->host_stage_obs,
                       &pl->host_stage_y, &pl->host_stage_d, &pl->host_stage_x, &pl->host_stage_xa, &pl->etkf_partial,
-                      &pl->etkf_w, &pl->stats, &pl->cmat, &pl->counter, &pl->ns_scratch, &pl->gext, &pl->oext};
+                      &pl->etkf_w, &pl->stats, &pl->cmat, &pl->counter, &pl->ns_scratch, &pl->gext, &pl->oext,
+                      &pl->devstat, &pl->amb_list, &pl->over_list};
     for (cudaEvent_t ev : pl->ev_pool) cudaEventDestroy(ev);
     for (DevBuf* b : bufs) b->release();
     if (pl->ev0) cudaEventDestroy(pl->ev0);
@@ -273,8 +291,7 @@ int b200da_plan_set_extra(b200da_plan* pl, int n_extra, const double* extra_radi
         // DMMA Gram (FP32 tiles converted on load)
         const KernelConfig cfg = config_for_kt(pl->kt);
         pl->use_tc = false; pl->gpb = cfg.g;
-        pl->kernel_name = std::string("letkf_gram_f32in_f64dmma") + (pl->k % 8 == 0 ? "_brow" : "") + "_kt" +
-                          std::to_string(pl->k % 8 == 0 ? pl->kt - 1 : pl->kt) + "_g" + std::to_string(cfg.g) + "_w" + std::to_string(cfg.wpg);
+        name_dmma_kernel(pl);
     }
     pl->have_grid = false; pl->have_obs = false;
     return B200DA_OK;
@@ -301,13 +318,7 @@ int b200da_plan_set_kernel(b200da_plan* pl, int n_ops, const int* ops, const dou
         pl->use_tc = false; pl->gpb = cfg.g;
         pl->have_grid = false; pl->have_obs = false;
     }
-    if (!pl->use_tc) {                                  // name of the DMMA Gram variant that will run (dispatch_fused)
-        const KernelConfig cfg = config_for_kt(pl->kt);
-        const bool brow = pl->k % 8 == 0 && n_ops == 0;
-        pl->kernel_name = std::string("letkf_gram_") + (pl->dtype == B200DA_F32 ? "f32in_f64dmma" : "f64") + (brow ? "_brow" : "") +
-                          "_kt" + std::to_string(brow ? pl->kt - 1 : pl->kt) + "_g" + std::to_string(cfg.g) + "_w" +
-                          std::to_string(cfg.wpg) + (n_ops > 0 ? "+kernelise" : "");
-    }
+    if (!pl->use_tc) name_dmma_kernel(pl);
     return B200DA_OK;
 }
 
@@ -322,11 +333,15 @@ static int launch_kernelise(b200da_plan* pl, double* cmat, int64_t n_slots, int6
 }
 
 int b200da_set_grid(b200da_plan* plan, const double* grid_coord, int64_t n_grid, void* stream) {
+    if (plan) { plan->slot_of_host.clear(); plan->n_over = 0; }
     return set_grid_impl(plan, grid_coord, n_grid, (cudaStream_t)stream);
 }
 
 int b200da_bin_obs(b200da_plan* plan, const double* obs_coord, const void* Yn, const void* d, int64_t n_obs, void* stream) {
     if (!plan) return B200DA_ERR_INVALID;
+    // new observations: decisions and records of the ambiguity protocol refer to the previous set
+    plan->n_over = 0;
+    B200DA_CUDA(cudaMemsetAsync(&plan->devstat.as<PlanStatus>()->amb_found, 0, sizeof(unsigned long long), (cudaStream_t)stream));
     if (plan->dtype == B200DA_F32)
         return bin_obs_impl<float>(plan, obs_coord, (const float*)Yn, (const float*)d, n_obs, (cudaStream_t)stream);
     return bin_obs_impl<double>(plan, obs_coord, (const double*)Yn, (const double*)d, n_obs, (cudaStream_t)stream);
@@ -369,6 +384,13 @@ int64_t b200da_block_offset(const b200da_plan* plan, int64_t block) {
     if (!plan || !plan->have_grid || block < 0 || block > plan->n_blocks) return -1;
     return plan->block_off_host[(size_t)block];
 }
+int b200da_block_offsets(const b200da_plan* plan, int64_t* offsets_host) {
+    if (!plan || !offsets_host) return B200DA_ERR_INVALID;
+    if (!plan->have_grid) return B200DA_ERR_STATE;
+    for (size_t b = 0; b <= (size_t)plan->n_blocks; ++b) offsets_host[b] = plan->block_off_host[b];
+    return B200DA_OK;
+}
+int b200da_gram_extra_rows(const b200da_plan* plan) { return plan ? plan->gram_er : 0; }
 int b200da_grid_order(const b200da_plan* plan, int32_t* order_out, void* stream) {
     if (!plan || !order_out) return B200DA_ERR_INVALID;
     if (!plan->have_grid) return B200DA_ERR_STATE;
@@ -438,6 +460,9 @@ static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int
     P.block_begin = (int)block_begin;
     P.k = pl->k; P.n_slices = pl->n_slices; P.rho = pl->rho;
     P.cut_pad = pl->geom.cut_bin * (1.0 + 1e-9) + 1e-300;
+    P.status = pl->devstat.as<PlanStatus>();
+    P.amb_list = pl->amb_list.as<PairRec>();
+    P.over = pl->over_list.as<PairRec>(); P.n_over = pl->n_over;
     P.stats = nullptr;
     if (pl->collect_stats) {
         int rc = pl->stats.ensure(sizeof(unsigned long long) * 16);
@@ -570,6 +595,19 @@ int b200da_letkf_host(b200da_plan* pl, const double* obs_coord_host, const void*
     return B200DA_OK;
 }
 
+int b200da_letkf_host_blocks(b200da_plan* pl, void* Xa_host, int64_t block_begin, int64_t block_end, void* stream) {
+    if (!pl || !Xa_host) return B200DA_ERR_INVALID;
+    if (!pl->have_grid || !pl->have_obs || !pl->host_stage_x.p || !pl->host_stage_xa.p) return B200DA_ERR_STATE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t es = pl->dtype == B200DA_F32 ? sizeof(float) : sizeof(double);
+    const size_t xbytes = es * (size_t)pl->n_slices * pl->k * (size_t)pl->n_grid;
+    int rc;
+    if ((rc = b200da_letkf(pl, pl->host_stage_x.p, pl->host_stage_xa.p, nullptr, block_begin, block_end, nullptr, stream))) return rc;
+    B200DA_CUDA(cudaMemcpyAsync(Xa_host, pl->host_stage_xa.p, xbytes, cudaMemcpyDeviceToHost, st));
+    B200DA_CUDA(cudaStreamSynchronize(st));
+    return B200DA_OK;
+}
+
 int b200da_neighbour_count(b200da_plan* pl, int64_t* counts, int64_t* n_ambiguous_opt, void* stream) {
     if (!pl || !counts) return B200DA_ERR_INVALID;
     if (!pl->have_grid || !pl->have_obs) return B200DA_ERR_STATE;
@@ -602,7 +640,7 @@ int b200da_neighbour_fill(b200da_plan* pl, const int64_t* offsets, int32_t* idx,
     B200DA_LAUNCH_CHECK();
     k_neighbour_finalize<<<nblk, 128, 0, st>>>(pl->geom, pl->gpos.as<Pos4>(), pl->opos.as<Pos4>(), pl->gext.as<double>(),
                                                  pl->oext.as<double>(), (const long long*)offsets,
-                                               P.keys, pl->n_grid, idx, w_opt, ambiguous_opt);
+                                               P.keys, pl->n_grid, idx, w_opt, ambiguous_opt, P.over, P.n_over);
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
@@ -617,6 +655,67 @@ int b200da_neighbour_ambiguous(b200da_plan* pl, int64_t capacity, int64_t* grid_
     P.capacity = capacity; P.amb_grid = (long long*)grid_idx; P.amb_obs = (long long*)obs_idx; P.amb_w = w;
     P.amb_found = (unsigned long long*)n_found;
     return launch_neighbours<2>(pl, P, st);
+}
+
+int b200da_pending_status(b200da_plan* pl, int64_t capacity, int64_t* grid_idx_host, int64_t* obs_idx_host, double* w_host,
+                          int64_t* n_found_host, void* stream) {
+    if (!pl || !n_found_host || capacity < 0 || (capacity > 0 && (!grid_idx_host || !obs_idx_host || !w_host))) return B200DA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    PlanStatus hs{};
+    B200DA_CUDA(cudaMemcpyAsync(&hs, pl->devstat.p, sizeof(PlanStatus), cudaMemcpyDeviceToHost, st));
+    B200DA_CUDA(cudaStreamSynchronize(st));
+    *n_found_host = (int64_t)hs.amb_found;
+    const int64_t n = std::min<int64_t>(std::min<int64_t>((int64_t)hs.amb_found, kAmbCapacity), capacity);
+    if (n > 0) {
+        std::vector<PairRec> rec((size_t)n);
+        B200DA_CUDA(cudaMemcpyAsync(rec.data(), pl->amb_list.p, sizeof(PairRec) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        B200DA_CUDA(cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < n; ++i) { grid_idx_host[i] = rec[(size_t)i].gid; obs_idx_host[i] = rec[(size_t)i].oid; w_host[i] = rec[(size_t)i].w; }
+    }
+    if (hs.amb_found || hs.error) B200DA_CUDA(cudaMemsetAsync(pl->devstat.p, 0, sizeof(PlanStatus), st));
+    if (hs.error & kStatusRunOverflow) return B200DA_ERR_OVERFLOW;
+    return B200DA_OK;
+}
+
+int b200da_plan_set_overrides(b200da_plan* pl, int64_t n, const int64_t* grid_idx_host, const int64_t* obs_idx_host,
+                              const double* w_host, void* stream) {
+    if (!pl || n < 0 || n > kAmbCapacity || (n > 0 && (!grid_idx_host || !obs_idx_host || !w_host))) return B200DA_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    pl->n_over = 0;
+    if (n == 0) return B200DA_OK;
+    int rc;
+    std::vector<PairRec> rec((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (grid_idx_host[i] < 0 || grid_idx_host[i] >= pl->n_grid || obs_idx_host[i] < 0 || obs_idx_host[i] >= pl->n_obs ||
+            !(w_host[i] >= 0.0)) return B200DA_ERR_INVALID;
+        rec[(size_t)i].gid = grid_idx_host[i]; rec[(size_t)i].oid = obs_idx_host[i]; rec[(size_t)i].w = w_host[i];
+    }
+    B200DA_CUDA(cudaStreamSynchronize(st));                    // kernels in flight may still read the previous list
+    if ((rc = pl->over_list.ensure(sizeof(PairRec) * (size_t)n))) return rc;
+    B200DA_CUDA(cudaMemcpyAsync(pl->over_list.p, rec.data(), sizeof(PairRec) * (size_t)n, cudaMemcpyHostToDevice, st));
+    B200DA_CUDA(cudaStreamSynchronize(st));                    // rec is a stack-lifetime staging buffer
+    pl->n_over = (int)n;
+    return B200DA_OK;
+}
+
+int b200da_blocks_of_grid(b200da_plan* pl, int64_t n, const int64_t* grid_idx_host, int64_t* block_host, void* stream) {
+    if (!pl || n < 0 || (n > 0 && (!grid_idx_host || !block_host))) return B200DA_ERR_INVALID;
+    if (!pl->have_grid) return B200DA_ERR_STATE;
+    if (pl->slot_of_host.size() != (size_t)pl->n_grid) {
+        std::vector<int32_t> order((size_t)pl->n_grid);
+        B200DA_CUDA(cudaMemcpyAsync(order.data(), pl->gorder.p, sizeof(int32_t) * (size_t)pl->n_grid, cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream));
+        B200DA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        pl->slot_of_host.assign((size_t)pl->n_grid, 0);
+        for (int64_t s = 0; s < pl->n_grid; ++s) pl->slot_of_host[(size_t)order[(size_t)s]] = (int32_t)s;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        if (grid_idx_host[i] < 0 || grid_idx_host[i] >= pl->n_grid) return B200DA_ERR_INVALID;
+        const int32_t slot = pl->slot_of_host[(size_t)grid_idx_host[i]];
+        const auto it = std::upper_bound(pl->block_off_host.begin(), pl->block_off_host.end(), slot);
+        block_host[i] = (int64_t)(it - pl->block_off_host.begin()) - 1;
+    }
+    return B200DA_OK;
 }
 
 // stage 1 of the global ETKF: per-CTA partial Grams of an observation range into pl->etkf_partial; returns the number of partials
@@ -778,28 +877,31 @@ int b200da_apply_weights_cols(b200da_plan* pl, const void* X, const void* W, int
     return apply_weights_impl(pl, x, w, per_grid, col_end - col_begin, n_grid, xa, (cudaStream_t)stream);
 }
 
-static int pack_impl(b200da_plan* pl, const void* xa, int64_t b0, int64_t b1, void* packed, int unpack, cudaStream_t st) {
+static int pack_impl(b200da_plan* pl, const void* xa, int64_t b0, int64_t b1, void* packed, int64_t ld, int unpack,
+                     cudaStream_t st) {
     if (!pl || !xa || !packed) return B200DA_ERR_INVALID;
     if (!pl->have_grid) return B200DA_ERR_STATE;
     if (b0 < 0 || b1 > pl->n_blocks || b0 > b1) return B200DA_ERR_INVALID;
     const int64_t s0 = pl->block_off_host[(size_t)b0], s1 = pl->block_off_host[(size_t)b1];
     const int64_t ncols = s1 - s0;
     if (ncols == 0) return B200DA_OK;
+    if (ld <= 0) ld = ncols;
+    if (ld < ncols) return B200DA_ERR_INVALID;
     const int rows = pl->n_slices * pl->k;
     if (rows > 65535) return B200DA_ERR_UNSUPPORTED;
     dim3 grid((unsigned)grid1d(ncols, 256), (unsigned)rows);
     if (pl->dtype == B200DA_F32)
-        k_pack_columns<float><<<grid, 256, 0, st>>>((const float*)xa, pl->gorder.as<int>(), s0, ncols, rows, pl->n_grid, (float*)packed, unpack);
+        k_pack_columns<float><<<grid, 256, 0, st>>>((const float*)xa, pl->gorder.as<int>(), s0, ncols, rows, pl->n_grid, (float*)packed, ld, unpack);
     else
-        k_pack_columns<double><<<grid, 256, 0, st>>>((const double*)xa, pl->gorder.as<int>(), s0, ncols, rows, pl->n_grid, (double*)packed, unpack);
+        k_pack_columns<double><<<grid, 256, 0, st>>>((const double*)xa, pl->gorder.as<int>(), s0, ncols, rows, pl->n_grid, (double*)packed, ld, unpack);
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
-int b200da_pack_columns(b200da_plan* pl, const void* Xa, int64_t b0, int64_t b1, void* packed, void* stream) {
-    return pack_impl(pl, Xa, b0, b1, packed, 0, (cudaStream_t)stream);
+int b200da_pack_columns(b200da_plan* pl, const void* Xa, int64_t b0, int64_t b1, void* packed, int64_t ld, void* stream) {
+    return pack_impl(pl, Xa, b0, b1, packed, ld, 0, (cudaStream_t)stream);
 }
-int b200da_unpack_columns(b200da_plan* pl, const void* packed, int64_t b0, int64_t b1, void* Xa, void* stream) {
-    return pack_impl(pl, Xa, b0, b1, const_cast<void*>(packed), 1, (cudaStream_t)stream);
+int b200da_unpack_columns(b200da_plan* pl, const void* packed, int64_t b0, int64_t b1, void* Xa, int64_t ld, void* stream) {
+    return pack_impl(pl, Xa, b0, b1, const_cast<void*>(packed), ld, 1, (cudaStream_t)stream);
 }
 
 int b200da_set_solver(b200da_plan* pl, int solver) {

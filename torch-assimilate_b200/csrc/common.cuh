@@ -42,6 +42,24 @@ struct __align__(32) Pos4 {     // bin-space position + payload (original index,
     long long id;
 };
 
+// One (grid point, observation) pair in ORIGINAL indices with a taper value: the records of the ambiguity protocol.  The Gram
+// kernel appends every pair whose taper value lies inside the ambiguity band to the plan's list (the mask w > eps of
+// gaspari_cohn.py:135 is then decided on the host with the reference's own numpy expression); the host hands its decisions
+// back as overrides: `w` replaces the device's weight of that pair (0 = not a local observation).
+struct PairRec { long long gid; long long oid; double w; };
+constexpr int kAmbCapacity = 4096;          // recorded ambiguous pairs per plan between two b200da_pending_status calls
+
+// device-side status words of a plan
+enum { kStatusRunOverflow = 1 };            // a block needed more than kMaxRuns candidate cell columns: results invalid
+struct PlanStatus { unsigned int error; unsigned int pad; unsigned long long amb_found; };
+
+__device__ __forceinline__ double apply_override(const PairRec* __restrict__ over, int n_over, long long gid, long long oid,
+                                                 double w) {
+    for (int o = 0; o < n_over; ++o)
+        if (over[o].oid == oid && over[o].gid == gid) w = over[o].w;
+    return w;
+}
+
 __host__ __device__ inline double deg2rad(double d) { return d * 0.017453292519943295; }
 
 // Coordinates (struct of arrays, n_coord rows of length n) -> bin-space position.
@@ -196,6 +214,15 @@ __device__ __forceinline__ double pair_weight(const Geometry& g, double gx, doub
     }
     ambiguous = fabs(w - g.eps) < kAmbiguityBand;
     return (w > g.eps) ? w : 0.0;                          // gaspari_cohn.py:135
+}
+
+// the taper value itself (no mask): what the ambiguity records carry
+__device__ __forceinline__ double pair_weight_raw(const Geometry& g, double gx, double gy, double gz,
+                                                  double ox, double oy, double oz, const double* __restrict__ ge,
+                                                  const double* __restrict__ oe) {
+    double w = taper_eval(g.taper, metric_distance(g, gx, gy, gz, ox, oy, oz) / g.radius);
+    for (int e = 0; e < g.n_ext; ++e) w = __dmul_rn(w, taper_eval(g.taper, fabs(ge[e] - oe[e]) / g.ext_radius[e]));
+    return w;
 }
 
 // ---- state / weight I/O in the plan's dtype --------------------------------------------------------------------

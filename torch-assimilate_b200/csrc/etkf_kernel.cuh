@@ -310,13 +310,13 @@ __global__ void __launch_bounds__(kApplyWarps * 32, apply_min_ctas<T>(MT)) k_app
 // (n_rows, N) <-> dense (n_rows, n_cols) in block-sorted order: the all-gather payload of the grid-sharded run
 template <typename T>
 __global__ void k_pack_columns(const T* __restrict__ xa, const int* __restrict__ order, int64_t slot0, int64_t n_cols,
-                               int n_rows, int64_t n_grid, T* __restrict__ packed, int unpack) {
+                               int n_rows, int64_t n_grid, T* __restrict__ packed, int64_t ld, int unpack) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (c >= n_cols || r >= n_rows) return;
     const int64_t gi = order[slot0 + c];
-    if (unpack) const_cast<T*>(xa)[(int64_t)r * n_grid + gi] = packed[(int64_t)r * n_cols + c];
-    else packed[(int64_t)r * n_cols + c] = xa[(int64_t)r * n_grid + gi];
+    if (unpack) const_cast<T*>(xa)[(int64_t)r * n_grid + gi] = packed[(int64_t)r * ld + c];
+    else packed[(int64_t)r * ld + c] = xa[(int64_t)r * n_grid + gi];
 }
 
 }  // namespace b200da

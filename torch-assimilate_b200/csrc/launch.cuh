@@ -6,6 +6,15 @@ namespace b200da {
 
 constexpr size_t kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
 
+// rows of [Yn; d] the DMMA Gram accumulates by DFMA: (k + 1) mod 8 when that is 1..3; kernelised plans keep every row in the
+// tiles (they need d.d, which only the in-tile innovation row produces, kernelise.cuh)
+inline int gram_extra_rows(const b200da_plan* pl) {
+    const int e = (pl->k + 1) % 8;
+    if (pl->kprog.n > 0 || pl->k < 8 || e < 1 || e > 3) return 0;
+    if (const char* v = getenv("B200DA_GRAM_ER_MAX")) { if (e > atoi(v)) return 0; }
+    return e;
+}
+
 struct LetkfParams;
 struct NsParams;
 int dispatch_fused(b200da_plan* pl, const LetkfParams& P, int nblocks, cudaStream_t st);

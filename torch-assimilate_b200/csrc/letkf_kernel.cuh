@@ -21,6 +21,9 @@
 
 namespace b200da {
 
+#ifndef B200DA_GRAM_UNROLL
+#define B200DA_GRAM_UNROLL 2
+#endif
 constexpr int kTileObs = 64;      // observations per staged tile
 // ring depth of the staged tiles: 3, or 2 when three FP64 tiles of a large ensemble would not fit in shared memory
 template <typename T, int KPT> __host__ __device__ constexpr int gram_stages() { return (sizeof(T) == 8 && KPT > 14) ? 2 : 3; }
@@ -49,6 +52,10 @@ struct LetkfParams {
     int n_slices;
     double rho;
     double cut_pad;            // padded cutoff in bin space
+    PlanStatus* status;        // plan-owned: error flags, number of recorded ambiguous pairs
+    PairRec* amb_list;         // [kAmbCapacity] pairs inside the ambiguity band met by this launch (FP64 taper path)
+    const PairRec* over;       // [n_over] host decisions that replace the device weight of a pair
+    int n_over;
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -70,14 +77,32 @@ __host__ __device__ constexpr int tile_ld() {
     return sizeof(T) == 8 ? KT * 8 + 4 : KT * 8 + ((8 - (KT * 8) % 32 + 32) % 32);
 }
 
-// BROW: the ensemble size is a multiple of 8, so the innovation row d (row k of the augmented matrix) would cost a whole
-// extra row of tiles; instead b = sum_j w_j d_j y_j is accumulated with plain FMAs next to the DMMA tiles of C.
-template <typename T, int KT, int WPG, int SUB, bool BROW>
+// Ownership of the KT (KT + 1) / 2 lower-triangle tiles (row-major index idx) and of the KT column tiles of the extra rows
+// among the WPG warps of a grid point: contiguous ranges, so a warp touches as few tile rows (A fragments f * w) as possible.
+template <int KT, int WPG, int SUB>
+__host__ __device__ constexpr bool gram_tile_owned(int idx) {
+    return idx >= (KT * (KT + 1) / 2) * SUB / WPG && idx < (KT * (KT + 1) / 2) * (SUB + 1) / WPG;
+}
+template <int KT, int WPG, int SUB>
+__host__ __device__ constexpr bool gram_col_owned(int t) { return t >= KT * SUB / WPG && t < KT * (SUB + 1) / WPG; }
+template <int KT, int WPG> __host__ __device__ constexpr int gram_acc() { return (KT * (KT + 1) / 2 + WPG - 1) / WPG; }
+template <int KT, int WPG> __host__ __device__ constexpr int gram_ecols() { return (KT + WPG - 1) / WPG; }
+
+// ER ("extra rows"): the augmented matrix [Yn; d] has k + 1 = 8 KT + ER rows.  Rows 0 .. 8 KT - 1 are ensemble members and run
+// on the DMMA pipe as KT (KT + 1) / 2 lower-triangle 8 x 8 tiles; the last ER rows (ER - 1 members and the innovation row d)
+// would cost a whole extra row of KT + 1 tiles for ER of its 8 rows, so their ER (8 KT) + ER (ER + 1) / 2 dot products are
+// accumulated with plain DFMAs instead (k = 50: 21 tiles + 3 rows instead of 28 tiles).  ER = 0: every row sits in a tile
+// (k + 1 <= 8 KT; kernelised plans, which need d.d from the tiles' diagonal, and remainders of 4..7 rows).
+//   eacc[e][n]  partial sums (over this lane's observations) of row 8 KT + e against column n-th owned column tile * 8 + lane / 4
+//   pacc[p]     the pairs among the extra rows, p = e (e + 1) / 2 + e2, e2 <= e (warp SUB 0 only)
+template <typename T, int KT, int WPG, int SUB, int ER>
 __device__ __forceinline__ void gram_tile(const T* __restrict__ ytile, const double* __restrict__ wrow,
-                                          double (&acc)[(KT * (KT + 1) / 2 + WPG - 1) / WPG][2],
-                                          double (&bacc)[(KT + WPG - 1) / WPG], int lane) {
-    constexpr int LDY = tile_ld<T, KT + (BROW ? 1 : 0)>();
-#pragma unroll 2
+                                          double (&acc)[gram_acc<KT, WPG>()][2],
+                                          double (&eacc)[ER > 0 ? ER : 1][gram_ecols<KT, WPG>()],
+                                          double (&pacc)[ER > 0 ? ER * (ER + 1) / 2 : 1], int lane) {
+    constexpr int LDY = tile_ld<T, KT + (ER > 0 ? 1 : 0)>();
+    constexpr int kUnroll = B200DA_GRAM_UNROLL;
+#pragma unroll kUnroll
     for (int ks = 0; ks < kTileObs / 4; ++ks) {
         const int j = ks * 4 + (lane & 3);
         const double w = wrow[j];
@@ -86,12 +111,24 @@ __device__ __forceinline__ void gram_tile(const T* __restrict__ ytile, const dou
         double f[KT];
 #pragma unroll
         for (int t = 0; t < KT; ++t) f[t] = (double)yr[t * 8];
-        if constexpr (BROW) {
-            const double wd = w * (double)ytile[j * LDY + KT * 8];
-            int nb = 0;
+        if constexpr (ER > 0) {
+            double x[ER], wx[ER];
 #pragma unroll
-            for (int t = 0; t < KT; ++t)
-                if (t % WPG == SUB) { bacc[nb] = fma(f[t], wd, bacc[nb]); ++nb; }
+            for (int e = 0; e < ER; ++e) { x[e] = (double)ytile[j * LDY + KT * 8 + e]; wx[e] = w * x[e]; }
+#pragma unroll
+            for (int e = 0; e < ER; ++e) {
+                int nb = 0;
+#pragma unroll
+                for (int t = 0; t < KT; ++t)
+                    if (gram_col_owned<KT, WPG, SUB>(t)) { eacc[e][nb] = fma(f[t], wx[e], eacc[e][nb]); ++nb; }
+            }
+            if constexpr (SUB == 0) {
+                int p = 0;
+#pragma unroll
+                for (int e = 0; e < ER; ++e)
+#pragma unroll
+                    for (int e2 = 0; e2 <= e; ++e2) { pacc[p] = fma(wx[e], x[e2], pacc[p]); ++p; }
+            }
         }
         int idx = 0, n = 0;
 #pragma unroll
@@ -99,55 +136,47 @@ __device__ __forceinline__ void gram_tile(const T* __restrict__ ytile, const dou
             const double fw = f[mt] * w;
 #pragma unroll
             for (int nt = 0; nt <= mt; ++nt) {
-                if (idx % WPG == SUB) { dmma884(acc[n][0], acc[n][1], fw, f[nt]); ++n; }
+                if (gram_tile_owned<KT, WPG, SUB>(idx)) { dmma884(acc[n][0], acc[n][1], fw, f[nt]); ++n; }
                 ++idx;
             }
         }
     }
 }
 
-// accumulators -> symmetric A (k x k, leading dimension lda) and b (row k of the augmented Gram)
-template <int KT, int WPG, int SUB>
-__device__ __forceinline__ void dump_tiles(const double (&acc)[(KT * (KT + 1) / 2 + WPG - 1) / WPG][2],
-                                           double* __restrict__ A, int lda, double* __restrict__ bvec, int k, int lane) {
-    int idx = 0, n = 0;
-#pragma unroll
-    for (int mt = 0; mt < KT; ++mt) {
-#pragma unroll
-        for (int nt = 0; nt <= mt; ++nt) {
-            if (idx % WPG == SUB) {
-                const int r = mt * 8 + (lane >> 2);
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = nt * 8 + (lane & 3) * 2 + e;
-                    const double v = acc[n][e];
-                    if (r < k && c <= r) { A[r * lda + c] = v; A[c * lda + r] = v; }
-                    else if (r == k && c < k) bvec[c] = v;
-                }
-                ++n;
-            }
-            ++idx;
-        }
-    }
-}
-
 // accumulators -> global scratch in the tile-packed layout (common.cuh): one 512-byte tile per accumulator pair set,
-// rows 0..k-1 = C (diagonal tiles hold the full 8x8 product), row k = b
-template <int KT, int WPG, int SUB, bool BROW>
-__device__ __forceinline__ void dump_tiles_global(const double (&acc)[(KT * (KT + 1) / 2 + WPG - 1) / WPG][2],
-                                                  double (&bacc)[(KT + WPG - 1) / WPG], double* __restrict__ C, int lane) {
+// rows 0..k-1 = C (diagonal tiles hold the full 8x8 product), row k = b; the extra rows land in tile row KT
+template <int KT, int WPG, int SUB, int ER>
+__device__ __forceinline__ void dump_tiles_global(const double (&acc)[gram_acc<KT, WPG>()][2],
+                                                  double (&eacc)[ER > 0 ? ER : 1][gram_ecols<KT, WPG>()],
+                                                  double (&pacc)[ER > 0 ? ER * (ER + 1) / 2 : 1], double* __restrict__ C, int lane) {
     const int r = lane >> 2, c = (lane & 3) * 2;
-    if constexpr (BROW) {                       // row k = KT * 8 of the augmented matrix: first row of tile row KT
-        int nb = 0;
+    if constexpr (ER > 0) {                     // rows KT * 8 + e of the augmented matrix: rows e of tile row KT
 #pragma unroll
-        for (int t = 0; t < KT; ++t) {
-            if (t % WPG == SUB) {
-                double v = bacc[nb];
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if ((lane & 3) == 0) C[tile_off(KT, t) + tile_elem(0, r)] = v;
-                ++nb;
+        for (int e = 0; e < ER; ++e) {
+            int nb = 0;
+#pragma unroll
+            for (int t = 0; t < KT; ++t) {
+                if (gram_col_owned<KT, WPG, SUB>(t)) {
+                    double v = eacc[e][nb];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    if ((lane & 3) == 0) C[tile_off(KT, t) + tile_elem(e, r)] = v;
+                    ++nb;
+                }
             }
+        }
+        if constexpr (SUB == 0) {
+            int p = 0;
+#pragma unroll
+            for (int e = 0; e < ER; ++e)
+#pragma unroll
+                for (int e2 = 0; e2 <= e; ++e2) {
+                    double v = pacc[p];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    if (lane == 0) C[tile_off(KT, KT) + tile_elem(e, e2)] = v;
+                    ++p;
+                }
         }
     }
     int idx = 0, n = 0;
@@ -155,7 +184,7 @@ __device__ __forceinline__ void dump_tiles_global(const double (&acc)[(KT * (KT 
     for (int mt = 0; mt < KT; ++mt) {
 #pragma unroll
         for (int nt = 0; nt <= mt; ++nt) {
-            if (idx % WPG == SUB) {
+            if (gram_tile_owned<KT, WPG, SUB>(idx)) {
                 *reinterpret_cast<double2*>(C + tile_off(mt, nt) + tile_elem(r, c)) = make_double2(acc[n][0], acc[n][1]);
                 ++n;
             }
@@ -180,7 +209,7 @@ struct BlockHeader {
 template <int G>
 __device__ void setup_block(BlockHeader<G>& H, const Geometry& g, const Pos4* __restrict__ gpos,
                             const int* __restrict__ block_off, const int* __restrict__ cell_start, int64_t n_obs,
-                            double cut_pad, int blk) {
+                            double cut_pad, int blk, PlanStatus* status) {
     const int tid = threadIdx.x;
     const int slot0 = block_off[blk];
     const int ng = block_off[blk + 1] - slot0;
@@ -231,7 +260,10 @@ __device__ void setup_block(BlockHeader<G>& H, const Geometry& g, const Pos4* __
             for (int cx_ = lo[0]; cx_ <= hi[0]; ++cx_)
                 for (int cy_ = lo[1]; cy_ <= hi[1]; ++cy_)
                     for (int q = 0; q < nz; ++q) {
-                        if (nr >= kMaxRuns) break;
+                        if (nr >= kMaxRuns) {         // never silently drop candidates: the host turns this into an error
+                            if (status) atomicOr(&status->error, (unsigned)kStatusRunOverflow);
+                            break;
+                        }
                         const int base = (cx_ * g.nc[1] + cy_) * g.nc[2];
                         const int s = cell_start[base + zr[q][0]];
                         const int e = cell_start[base + zr[q][1] + 1];
@@ -246,20 +278,32 @@ __device__ void setup_block(BlockHeader<G>& H, const Geometry& g, const Pos4* __
 
 }
 
-template <typename T, int KT, int G, int WPG, bool BROW>
+template <typename T, int KT, int G, int WPG, int ER>
 __host__ __device__ constexpr size_t gram_smem_bytes() {
-    constexpr int KPT = KT + (BROW ? 1 : 0), S = gram_stages<T, KPT>();
+    constexpr int KPT = KT + (ER > 0 ? 1 : 0), S = gram_stages<T, KPT>();
     return sizeof(double) * ((size_t)S * G * kTileObs) + sizeof(T) * ((size_t)S * kTileObs * tile_ld<T, KPT>());
 }
 
-template <typename T, int KT, int G, int WPG, bool BROW>
+// run-time warp index -> compile-time SUB (the accumulator arrays stay in registers only if every access is static)
+#define B200DA_FOR_SUB(WPG_, sub_, CALL)                                                                            \
+    do {                                                                                                             \
+        if constexpr ((WPG_) == 1) { CALL(0); }                                                                      \
+        else if constexpr ((WPG_) == 2) { if ((sub_) == 0) { CALL(0); } else { CALL(1); } }                          \
+        else if constexpr ((WPG_) == 4) {                                                                            \
+            switch (sub_) { case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; default: CALL(3); break; } \
+        } else {                                                                                                     \
+            switch (sub_) { case 0: CALL(0); break; case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; \
+                            case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; default: CALL(7); break; } \
+        }                                                                                                            \
+    } while (0)
+
+template <typename T, int KT, int G, int WPG, int ER>
 __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParams P) {
     constexpr int NT = G * WPG * 32;
-    constexpr int KPT = KT + (BROW ? 1 : 0);                  // 8-row tiles of the staged [Yn; d] rows
+    constexpr int KPT = KT + (ER > 0 ? 1 : 0);                // 8-row tiles of the staged [Yn; d] rows
     constexpr int kStages = gram_stages<T, KPT>();
     constexpr int KP = KPT * 8, LDY = tile_ld<T, KPT>();
-    constexpr int NTILES = KT * (KT + 1) / 2;
-    constexpr int ACC = (NTILES + WPG - 1) / WPG;
+    constexpr int ACC = gram_acc<KT, WPG>(), ECOLS = gram_ecols<KT, WPG>(), NP = ER > 0 ? ER * (ER + 1) / 2 : 1;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     BlockHeader<G>& H = *reinterpret_cast<BlockHeader<G>*>(smem_raw);
     unsigned char* work = smem_raw + ((sizeof(BlockHeader<G>) + 31) & ~size_t(31));
@@ -272,16 +316,21 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
     const int my_g = warp / WPG, my_sub = warp % WPG;
     const int blk = P.block_begin + blockIdx.x;
     const long long t_start = clock64();
-    setup_block<G>(H, g, P.gpos, P.block_off, P.cell_start, P.n_obs, P.cut_pad, blk);
+    setup_block<G>(H, g, P.gpos, P.block_off, P.cell_start, P.n_obs, P.cut_pad, blk, P.status);
     const int ng = H.ng;
     const long long t_setup = clock64();
 
     double acc[ACC][2];
 #pragma unroll
     for (int i = 0; i < ACC; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
-    double bacc[(KT + WPG - 1) / WPG];
+    double eacc[ER > 0 ? ER : 1][ECOLS];
 #pragma unroll
-    for (int i = 0; i < (KT + WPG - 1) / WPG; ++i) bacc[i] = 0.0;
+    for (int e = 0; e < (ER > 0 ? ER : 1); ++e)
+#pragma unroll
+        for (int i = 0; i < ECOLS; ++i) eacc[e][i] = 0.0;
+    double pacc[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) pacc[i] = 0.0;
 
     // ------------------------------------------------------------------------------------------------------------
     // Gram phase
@@ -337,9 +386,19 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
                 const int so = H.ring[(ring_head + slot) & (kRing - 1)];
                 const Pos4 po = P.opos[so];
                 bool amb;
-                w = pair_weight(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z,
-                                P.gext + (size_t)(P.block_off[blk] + gi) * g.n_ext, P.oext + (size_t)so * g.n_ext, amb);
-                if (amb) ++my_amb;
+                const double* ge = P.gext + (size_t)(P.block_off[blk] + gi) * g.n_ext;
+                const double* oe = P.oext + (size_t)so * g.n_ext;
+                w = pair_weight(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, ge, oe, amb);
+                if (amb) {                                 // rare: hand the pair to the host for the reference's own decision
+                    ++my_amb;
+                    const unsigned long long at = atomicAdd(&P.status->amb_found, 1ull);
+                    if (at < (unsigned long long)kAmbCapacity) {
+                        PairRec rec; rec.gid = H.gp[gi].id; rec.oid = po.id;
+                        rec.w = pair_weight_raw(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, ge, oe);
+                        P.amb_list[at] = rec;
+                    }
+                }
+                if (P.n_over > 0) w = apply_override(P.over, P.n_over, H.gp[gi].id, po.id, w);
             }
             wst[q] = w;
         }
@@ -359,29 +418,9 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
             const int stage = consumed % kStages;
             const T* yst = ybuf + (size_t)stage * kTileObs * LDY;
             const double* wrow = wbuf + ((size_t)stage * G + my_g) * kTileObs;
-            if constexpr (WPG == 1) gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane);
-            else if constexpr (WPG == 2) {
-                if (my_sub == 0) gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane);
-                else gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane);
-            } else if constexpr (WPG == 4) {
-                switch (my_sub) {
-                    case 0: gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane); break;
-                    case 1: gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane); break;
-                    case 2: gram_tile<T, KT, WPG, 2, BROW>(yst, wrow, acc, bacc, lane); break;
-                    default: gram_tile<T, KT, WPG, 3, BROW>(yst, wrow, acc, bacc, lane); break;
-                }
-            } else {
-                switch (my_sub) {
-                    case 0: gram_tile<T, KT, WPG, 0, BROW>(yst, wrow, acc, bacc, lane); break;
-                    case 1: gram_tile<T, KT, WPG, 1, BROW>(yst, wrow, acc, bacc, lane); break;
-                    case 2: gram_tile<T, KT, WPG, 2, BROW>(yst, wrow, acc, bacc, lane); break;
-                    case 3: gram_tile<T, KT, WPG, 3, BROW>(yst, wrow, acc, bacc, lane); break;
-                    case 4: gram_tile<T, KT, WPG, 4, BROW>(yst, wrow, acc, bacc, lane); break;
-                    case 5: gram_tile<T, KT, WPG, 5, BROW>(yst, wrow, acc, bacc, lane); break;
-                    case 6: gram_tile<T, KT, WPG, 6, BROW>(yst, wrow, acc, bacc, lane); break;
-                    default: gram_tile<T, KT, WPG, 7, BROW>(yst, wrow, acc, bacc, lane); break;
-                }
-            }
+#define B200DA_GT(S) gram_tile<T, KT, WPG, S, ER>(yst, wrow, acc, eacc, pacc, lane)
+            B200DA_FOR_SUB(WPG, my_sub, B200DA_GT);
+#undef B200DA_GT
         }
     };
     // Half of the warps of every scheduler (warp id bit 2) stage the tile after next BEFORE their share of the tensor work
@@ -424,29 +463,9 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
     // ------------------------------------------------------------------------------------------------------------
     if (my_g < ng) {
         double* C = P.cmat + (size_t)((int64_t)P.block_off[blk] + my_g - P.slot_base) * (size_t)(tri_tiles(KPT) * 64);
-        if constexpr (WPG == 1) dump_tiles_global<KT, WPG, 0, BROW>(acc, bacc, C, lane);
-        else if constexpr (WPG == 2) {
-            if (my_sub == 0) dump_tiles_global<KT, WPG, 0, BROW>(acc, bacc, C, lane);
-            else dump_tiles_global<KT, WPG, 1, BROW>(acc, bacc, C, lane);
-        } else if constexpr (WPG == 4) {
-            switch (my_sub) {
-                case 0: dump_tiles_global<KT, WPG, 0, BROW>(acc, bacc, C, lane); break;
-                case 1: dump_tiles_global<KT, WPG, 1, BROW>(acc, bacc, C, lane); break;
-                case 2: dump_tiles_global<KT, WPG, 2, BROW>(acc, bacc, C, lane); break;
-                default: dump_tiles_global<KT, WPG, 3, BROW>(acc, bacc, C, lane); break;
-            }
-        } else {
-            switch (my_sub) {
-                case 0: dump_tiles_global<KT, WPG, 0, BROW>(acc, bacc, C, lane); break;
-                case 1: dump_tiles_global<KT, WPG, 1, BROW>(acc, bacc, C, lane); break;
-                case 2: dump_tiles_global<KT, WPG, 2, BROW>(acc, bacc, C, lane); break;
-                case 3: dump_tiles_global<KT, WPG, 3, BROW>(acc, bacc, C, lane); break;
-                case 4: dump_tiles_global<KT, WPG, 4, BROW>(acc, bacc, C, lane); break;
-                case 5: dump_tiles_global<KT, WPG, 5, BROW>(acc, bacc, C, lane); break;
-                case 6: dump_tiles_global<KT, WPG, 6, BROW>(acc, bacc, C, lane); break;
-                default: dump_tiles_global<KT, WPG, 7, BROW>(acc, bacc, C, lane); break;
-            }
-        }
+#define B200DA_DT(S) dump_tiles_global<KT, WPG, S, ER>(acc, eacc, pacc, C, lane)
+        B200DA_FOR_SUB(WPG, my_sub, B200DA_DT);
+#undef B200DA_DT
     }
     if (P.stats && tid == 0) {
         const long long t_end = clock64();

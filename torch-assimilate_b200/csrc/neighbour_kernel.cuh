@@ -18,6 +18,9 @@ struct NeighbourParams {
     const int* cell_start;
     int64_t n_obs;
     double cut_pad;
+    PlanStatus* status;                 // plan-owned error flags
+    const PairRec* over;                // host decisions of the ambiguity protocol (MODE 0 / 1 lists reflect them)
+    int n_over;
     // MODE 0: counts
     long long* counts;                  // [N] original grid order
     unsigned long long* n_ambiguous;    // or null
@@ -37,7 +40,7 @@ __global__ void __launch_bounds__(256) k_neighbours(const NeighbourParams P) {
     __shared__ int cnt[G];
     const Geometry& g = P.g;
     const int tid = threadIdx.x;
-    setup_block<G>(H, g, P.gpos, P.block_off, P.cell_start, P.n_obs, P.cut_pad, blockIdx.x);
+    setup_block<G>(H, g, P.gpos, P.block_off, P.cell_start, P.n_obs, P.cut_pad, blockIdx.x, P.status);
     if (tid < G) cnt[tid] = 0;
     __syncthreads();
     const int ng = H.ng, n_runs = H.n_runs, cand_total = H.cand_total;
@@ -56,13 +59,15 @@ __global__ void __launch_bounds__(256) k_neighbours(const NeighbourParams P) {
             bool amb;
             const double* ge = P.gext + (size_t)(P.block_off[blockIdx.x] + gi) * g.n_ext;
             const double* oe = P.oext + (size_t)s * g.n_ext;
-            const double w = pair_weight(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, ge, oe, amb);
+            double w = pair_weight(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, ge, oe, amb);
+            if (MODE != 2 && P.n_over > 0) w = apply_override(P.over, P.n_over, H.gp[gi].id, po.id, w);
             if (MODE == 0) {
                 if (w > 0.0) atomicAdd(&cnt[gi], 1);
                 if (amb) ++my_amb;
             } else if (MODE == 1) {
-                if (w > 0.0) {
-                    const long long og = H.gp[gi].id;
+                const long long og = H.gp[gi].id;
+                // grid points the caller gave no room (offsets[og + 1] == offsets[og]: not selected) are skipped
+                if (w > 0.0 && P.offsets[og + 1] > P.offsets[og]) {
                     const int at = atomicAdd(&P.cursor[og], 1);
                     P.keys[P.offsets[og] + at] = ((unsigned long long)(unsigned)po.id << 32) | (unsigned)s;
                 }
@@ -70,11 +75,8 @@ __global__ void __launch_bounds__(256) k_neighbours(const NeighbourParams P) {
                 if (amb) {
                     const unsigned long long at = atomicAdd(P.amb_found, 1ull);
                     if ((long long)at < P.capacity) {
-                        const double dist = metric_distance(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z);
                         P.amb_grid[at] = H.gp[gi].id; P.amb_obs[at] = po.id;
-                        double wa = taper_eval(g.taper, dist / g.radius);
-                        for (int e = 0; e < g.n_ext; ++e) wa = __dmul_rn(wa, taper_eval(g.taper, fabs(ge[e] - oe[e]) / g.ext_radius[e]));
-                        P.amb_w[at] = wa;
+                        P.amb_w[at] = pair_weight_raw(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, ge, oe);
                     }
                 }
             }
@@ -92,7 +94,7 @@ __global__ void k_neighbour_finalize(Geometry g, const Pos4* __restrict__ gpos, 
                                      const double* __restrict__ gext, const double* __restrict__ oext,
                                      const long long* __restrict__ offsets, const unsigned long long* __restrict__ keys,
                                      int64_t n_grid, int* __restrict__ idx, double* __restrict__ w_out,
-                                     unsigned char* __restrict__ amb_out) {
+                                     unsigned char* __restrict__ amb_out, const PairRec* __restrict__ over, int n_over) {
     for (int64_t slot = blockIdx.x; slot < n_grid; slot += gridDim.x) {
         const Pos4 gp = gpos[slot];
         const long long beg = offsets[gp.id], end = offsets[gp.id + 1];
@@ -103,8 +105,9 @@ __global__ void k_neighbour_finalize(Geometry g, const Pos4* __restrict__ gpos, 
                 const unsigned so = (unsigned)(key & 0xffffffffull);
                 const Pos4 po = opos[so];
                 bool amb;
-                const double w = pair_weight(g, gp.x, gp.y, gp.z, po.x, po.y, po.z, gext + (size_t)slot * g.n_ext,
-                                             oext + (size_t)so * g.n_ext, amb);
+                double w = pair_weight(g, gp.x, gp.y, gp.z, po.x, po.y, po.z, gext + (size_t)slot * g.n_ext,
+                                       oext + (size_t)so * g.n_ext, amb);
+                if (n_over > 0) w = apply_override(over, n_over, gp.id, po.id, w);
                 if (w_out) w_out[e] = w;
                 if (amb_out) amb_out[e] = amb ? 1 : 0;
             }

@@ -61,6 +61,7 @@ struct b200da_plan {
     int kp = 0;            // padded row length of the staging copy: 8 * kt
     int gpb = 8;           // grid points per block (CTA) of the fused kernel
     bool use_tc = false;   // FP32 plan with k >= 32: tcgen05 Gram kernel, 128 grid points per block
+    int gram_er = 0;       // rows of [Yn; d] the DMMA Gram accumulates by DFMA next to its tiles (letkf_kernel.cuh: ER)
     double rho = 1.0;
     b200da::Geometry geom{};
     // grid side
@@ -80,6 +81,12 @@ struct b200da_plan {
     b200da::DevBuf host_stage_obs, host_stage_y, host_stage_d, host_stage_x, host_stage_xa;
     b200da::DevBuf etkf_partial, etkf_w, stats, cmat, counter, ns_scratch;
     b200da::DevBuf gext, oext;  // extra coordinate columns in block- / cell-sorted order (b200da_plan_set_extra)
+    // ambiguity protocol and device-side error flags (common.cuh: PlanStatus, PairRec)
+    b200da::DevBuf devstat;     // PlanStatus
+    b200da::DevBuf amb_list;    // PairRec[kAmbCapacity] recorded by the Gram kernel
+    b200da::DevBuf over_list;   // PairRec[n_over] host decisions (b200da_plan_set_overrides)
+    int n_over = 0;
+    std::vector<int32_t> slot_of_host;   // original grid index -> block-sorted slot (lazily built for b200da_blocks_of_grid)
     double ns_stiff = 0.0;      // 0: default (2e3 for FP64 plans, 2e4 for FP32 plans); see NsParams::stiff
     int solver = B200DA_SOLVER_NEWTON_SCHULZ;
     b200da::KernelProgram kprog{};   // n > 0: kernelised ETKF (b200da_plan_set_kernel)

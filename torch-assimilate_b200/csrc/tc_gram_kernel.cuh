@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
     uint64_t* all_done = S.bars + 4 + 2 * kTcYStages;
 
     // ---- one-time set-up: candidate runs of the block, barriers, tensor memory ----------------------------------------
-    setup_block<kTcM>(H, g, L.gpos, L.block_off, L.cell_start, L.n_obs, L.cut_pad, blk);
+    setup_block<kTcM>(H, g, L.gpos, L.block_off, L.cell_start, L.n_obs, L.cut_pad, blk, L.status);
     if (tid == 0) {
         mbar_init(&op_full[0], kTcGenWarps); mbar_init(&op_full[1], kTcGenWarps);
         mbar_init(&op_free[0], 1); mbar_init(&op_free[1], 1);

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200da.so")
 
 OK = 0
-ERR_INVALID, ERR_SIZE, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
+ERR_INVALID, ERR_SIZE, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_OVERFLOW = -1, -2, -3, -4, -5, -6, -7, -8
 
 METRIC_ABS1D, METRIC_PERIODIC1D, METRIC_EUCLID, METRIC_HAVERSINE = 0, 1, 2, 3
 TAPER_GC, TAPER_GCINF = 0, 1
@@ -44,16 +44,22 @@ SIGNATURES = {
     "b200da_letkf_ienks": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _dbl, _dbl, _i64, _i64, _vp]),
     "b200da_etkf_ienks_weights": (_i, [_vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _vp, _vp]),
     "b200da_letkf_host": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "b200da_letkf_host_blocks": (_i, [_vp, _vp, _i64, _i64, _vp]),
     "b200da_neighbour_count": (_i, [_vp, _vp, _vp, _vp]),
     "b200da_neighbour_fill": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "b200da_neighbour_ambiguous": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "b200da_pending_status": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "b200da_plan_set_overrides": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "b200da_blocks_of_grid": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "b200da_etkf_weights": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "b200da_apply_weights": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp]),
     "b200da_etkf_gram": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "b200da_etkf_weights_from_gram": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "b200da_apply_weights_cols": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i64, _vp, _vp]),
-    "b200da_pack_columns": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
-    "b200da_unpack_columns": (_i, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "b200da_pack_columns": (_i, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "b200da_unpack_columns": (_i, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
+    "b200da_block_offsets": (_i, [_vp, _vp]),
+    "b200da_gram_extra_rows": (_i, [_vp]),
     "b200da_strerror": (_c.c_char_p, [_i]),
     "b200da_last_cuda_error": (_c.c_char_p, []),
     "b200da_version": (_i, []),

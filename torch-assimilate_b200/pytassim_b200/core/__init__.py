@@ -39,8 +39,13 @@ class BaseModule(object):
     def _inflation(self):
         return 1.0
 
+    def _config_key(self):
+        """What ``_configure`` puts on the engine (the kernel program of KETKFModule): part of the cache key, so reassigning
+        ``module.kernel`` or changing a kernel's parameters takes effect on the next call, as in the reference."""
+        return None
+
     def _engine(self, ens_size, dtype):
-        key = (int(ens_size), dtype, float(self._inflation()))
+        key = (int(ens_size), dtype, float(self._inflation()), self._config_key())
         if key not in self._engines:
             self._engines = {key: self._configure(LETKFEngine(int(ens_size), 1, AbsDistance1D(), 1.0,
                                                               inf_factor=float(self._inflation()), dtype=dtype))}
@@ -92,6 +97,12 @@ class KETKFModule(ETKFModule):
 
     def _configure(self, engine):
         return engine.set_kernel(self.kernel)
+
+    def _config_key(self):
+        k = self.kernel
+        if k is None or getattr(k, "is_linear", False) or not hasattr(k, "program"):
+            return None
+        return tuple((int(op), float(a), float(b)) for op, a, b in k.program())
 
 
 class IEnKSTransformModule(BaseModule):

@@ -68,6 +68,13 @@ class LETKFEngine(object):
         self.n_grid = 0
         self.n_obs = 0
         self._keep = {}
+        self.epsilon = float(epsilon)
+        self.taper = taper
+        self.radius = radius
+        self._gc = None                 # (N, n_coord) grid coordinates as given to set_grid (device)
+        self._oc = None                 # (M, n_coord) observation coordinates as given to bin_obs (device or host)
+        self._overrides = {}            # (grid index, obs index) -> decided weight, since the last bin_obs
+        self.last_ambiguous = dict(n=0, flipped=0)
 
     def __del__(self):
         plan = getattr(self, "_plan", None)
@@ -92,6 +99,7 @@ class LETKFEngine(object):
             _cabi.check(self.lib.b200da_set_grid(self._plan, _ptr(soa), gc.shape[0], _stream()))
         self.n_grid = int(gc.shape[0])
         self.n_blocks = int(self.lib.b200da_num_blocks(self._plan))
+        self._gc, self._oc, self._overrides = gc, None, {}
         return self
 
     def bin_obs(self, obs_coords, normed_perts, normed_obs):
@@ -112,6 +120,7 @@ class LETKFEngine(object):
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.b200da_bin_obs(self._plan, _ptr(soa), _ptr(yn), _ptr(d), d.shape[0], _stream()))
         self.n_obs = int(d.shape[0])
+        self._oc, self._overrides = oc, {}
         return self
 
     def obs_prep(self, ens_obs, observations, variance):
@@ -152,8 +161,13 @@ class LETKFEngine(object):
         return yn, d
 
     # -- hot path ----------------------------------------------------------------------------------------------
-    def analyse(self, state, out=None, return_weights=False, blocks=None, count_ambiguous=False):
-        """state (n_slices, k, N) on the device -> analysis of the same shape (interface/base.py:257-278)."""
+    def analyse(self, state, out=None, return_weights=False, blocks=None, count_ambiguous=False, resolve_ambiguous=True):
+        """state (n_slices, k, N) on the device -> analysis of the same shape (interface/base.py:257-278).
+
+        ``resolve_ambiguous`` (default): after the launch, pairs whose taper value the device found within 1e-13 of epsilon
+        are decided on the host with the reference's numpy expression and, where the decision differs from the device's, the
+        affected blocks are analysed again with the host's decision (:meth:`resolve_ambiguous`; one stream synchronisation).
+        ``last_ambiguous`` holds the counts."""
         x = _dev(state, dtype=self.dtype, device=self.device).reshape(self.n_slices, self.k, self.n_grid)
         xa = torch.empty_like(x) if out is None else out
         if xa.dtype != self.dtype or not xa.is_contiguous():
@@ -163,6 +177,9 @@ class LETKFEngine(object):
         b0, b1 = (0, self.n_blocks) if blocks is None else blocks
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.b200da_letkf(self._plan, _ptr(x), _ptr(xa), _ptr(w), b0, b1, _ptr(amb), _stream()))
+            if resolve_ambiguous:
+                self.resolve_ambiguous(lambda c0, c1: _cabi.check(
+                    self.lib.b200da_letkf(self._plan, _ptr(x), _ptr(xa), _ptr(w), c0, c1, None, _stream())), (b0, b1))
         res = [xa]
         if return_weights:
             res.append(w)
@@ -183,8 +200,11 @@ class LETKFEngine(object):
         w_out = torch.empty((self.n_grid, self.k, self.k), dtype=self.dtype, device=self.device)
         b0, b1 = (0, self.n_blocks) if blocks is None else blocks
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.b200da_letkf_ienks(self._plan, _ptr(x), _ptr(xa), _ptr(w_in), per_grid, _ptr(w_out), float(tau),
-                                                    -1.0 if epsilon is None else float(epsilon), b0, b1, _stream()))
+            def launch(c0, c1):
+                _cabi.check(self.lib.b200da_letkf_ienks(self._plan, _ptr(x), _ptr(xa), _ptr(w_in), per_grid, _ptr(w_out), float(tau),
+                                                        -1.0 if epsilon is None else float(epsilon), c0, c1, _stream()))
+            launch(b0, b1)
+            self.resolve_ambiguous(launch, (b0, b1))
         return xa, w_out
 
     def ienks_weights(self, weights, normed_perts, normed_obs, tau=1.0, epsilon=None):
@@ -241,18 +261,108 @@ class LETKFEngine(object):
             return ctypes.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else ctypes.c_void_p(a.ctypes.data)
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.b200da_letkf_host(self._plan, hp(oc_soa), hp(yn), hp(d), m, hp(x), hp(out), _stream()))
-        self.n_obs = m
+            self.n_obs = m
+            self._oc, self._overrides = (oc_soa, "soa"), {}
+
+            def redo(c0, c1):                        # rare: a host decision differs from the device's -> those blocks again
+                _cabi.check(self.lib.b200da_letkf_host_blocks(self._plan, hp(out), c0, c1, _stream()))
+            self.resolve_ambiguous(redo, (0, self.n_blocks))
         return out
 
+    # -- ambiguity protocol (include/b200da.h; SURVEY.md hard part 1) -------------------------------------------------------
+    def pending_status(self):
+        """(n_found, grid idx, obs idx, device taper value) of the pairs the Gram kernel met inside the ambiguity band since
+        the last call; raises if a kernel had to drop candidate cells (B200DA_ERR_OVERFLOW).  Synchronises the stream."""
+        cap = 4096
+        gi = np.empty(cap, dtype=np.int64); oi = np.empty(cap, dtype=np.int64); w = np.empty(cap, dtype=np.float64)
+        n = ctypes.c_int64(0)
+        _cabi.check(self.lib.b200da_pending_status(self._plan, cap, gi.ctypes.data_as(_cabi._vp), oi.ctypes.data_as(_cabi._vp),
+                                                   w.ctypes.data_as(_cabi._vp), ctypes.byref(n), _stream()))
+        nf = min(int(n.value), cap)
+        return int(n.value), gi[:nf], oi[:nf], w[:nf]
+
+    def _host_rows(self, gi, oi):
+        """[t, coords...] rows of the given grid points / observations for the host decision."""
+        idx_g = torch.as_tensor(gi, device=self._gc.device)
+        grid = self._gc[idx_g].cpu().numpy()
+        if isinstance(self._oc, tuple):                       # (n_coord, M) host array of analyse_host
+            soa = self._oc[0]
+            soa = soa.numpy() if isinstance(soa, torch.Tensor) else soa
+            obs = np.ascontiguousarray(soa[:, oi].T)
+        else:
+            obs = self._oc[torch.as_tensor(oi, device=self._oc.device)].cpu().numpy()
+        zg = np.zeros((grid.shape[0], 1)); zo = np.zeros((obs.shape[0], 1))
+        return np.concatenate([zg, grid], axis=1), np.concatenate([zo, obs], axis=1)
+
+    def set_overrides(self, pairs):
+        """pairs: dict (grid index, obs index) -> weight (0 = not a local observation); replaces the list on the plan."""
+        n = len(pairs)
+        gi = np.asarray([p[0] for p in pairs], dtype=np.int64)
+        oi = np.asarray([p[1] for p in pairs], dtype=np.int64)
+        w = np.asarray([pairs[p] for p in pairs], dtype=np.float64)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_plan_set_overrides(self._plan, n, gi.ctypes.data_as(_cabi._vp), oi.ctypes.data_as(_cabi._vp),
+                                                           w.ctypes.data_as(_cabi._vp), _stream()))
+        self._overrides = dict(pairs)
+
+    def blocks_of_grid(self, grid_idx):
+        gi = np.ascontiguousarray(grid_idx, dtype=np.int64)
+        out = np.empty(gi.shape[0], dtype=np.int64)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_blocks_of_grid(self._plan, gi.shape[0], gi.ctypes.data_as(_cabi._vp),
+                                                       out.ctypes.data_as(_cabi._vp), _stream()))
+        return out
+
+    def resolve_ambiguous(self, relaunch, blocks):
+        """Second half of the ambiguity protocol, after a launch over ``blocks``: read the pairs the device could not decide,
+        evaluate ``weights > epsilon`` for them with the reference's numpy expression on the host
+        (localization/gaspari_cohn.py:120-135 via ``BaseLocalization.host_decision``), hand the decisions to the plan and call
+        ``relaunch(b, b + 1)`` for every block in which a decision differs from the device's.  Returns the number of pairs."""
+        n, gi, oi, wdev = self.pending_status()
+        self.last_ambiguous = dict(n=n, flipped=0)
+        if n == 0:
+            return 0
+        if n > gi.shape[0]:
+            raise _cabi.B200DAError("{0} (grid point, observation) pairs lie within 1e-13 of epsilon, more than the {1} the "
+                                    "engine records: the localization is degenerate for this geometry".format(n, gi.shape[0]))
+        from .localization.gaspari_cohn import GaspariCohn, GaspariCohnInf
+        loc = (GaspariCohnInf if self.taper == "gcinf" else GaspariCohn)(self.radius, self.metric, self.epsilon)
+        grid_rows, obs_rows = self._host_rows(gi, oi)
+        pairs = dict(self._overrides)
+        flipped = []
+        for g in np.unique(gi):
+            sel = np.nonzero(gi == g)[0]
+            use, w_ref = loc.host_decision(grid_rows[sel[0]], obs_rows[sel])
+            for q, j in enumerate(sel):
+                key = (int(g), int(oi[j]))
+                dev_use = (pairs[key] > 0.0) if key in pairs else bool(wdev[j] > self.epsilon)
+                pairs[key] = float(w_ref[q]) if use[q] else 0.0
+                if bool(use[q]) != dev_use:
+                    flipped.append(int(g))
+        self.set_overrides(pairs)
+        self.last_ambiguous = dict(n=n, flipped=len(flipped))
+        if flipped:
+            b0, b1 = blocks
+            for b in np.unique(self.blocks_of_grid(np.asarray(flipped, dtype=np.int64))):
+                if b0 <= b < b1:
+                    relaunch(int(b), int(b) + 1)
+            self.pending_status()                             # the repeated blocks record the same pairs again: drop them
+        return n
+
     # -- neighbour lists -----------------------------------------------------------------------------------------
-    def neighbour_lists(self, with_weights=True):
+    def neighbour_lists(self, with_weights=True, subset=None):
         """CSR (offsets int64[N+1], idx int32[nnz], w float64[nnz], ambiguous uint8[nnz], n_ambiguous) of the
         local observations of every grid point, ascending obs index = ``np.nonzero(use_obs)[0]``
-        (localization/gaspari_cohn.py:135)."""
+        (localization/gaspari_cohn.py:135).  ``subset``: grid indices whose lists are materialised (the others get empty
+        segments) — at cfg3 size the full CSR would have 5.7e10 entries."""
         counts = torch.zeros(self.n_grid, dtype=torch.int64, device=self.device)
         namb = torch.zeros(1, dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.b200da_neighbour_count(self._plan, _ptr(counts), _ptr(namb), _stream()))
+            if subset is not None:
+                keep = torch.zeros(self.n_grid, dtype=torch.int64, device=self.device)
+                keep[torch.as_tensor(np.asarray(subset, dtype=np.int64), device=self.device)] = 1
+                counts = counts * keep
             offsets = torch.zeros(self.n_grid + 1, dtype=torch.int64, device=self.device)
             offsets[1:] = torch.cumsum(counts, 0)
             nnz = int(offsets[-1].item())
@@ -350,22 +460,60 @@ class LETKFEngine(object):
     def block_offset(self, block):
         return int(self.lib.b200da_block_offset(self._plan, int(block)))
 
-    def pack_columns(self, xa, b0, b1):
+    def pack_columns(self, xa, b0, b1, out=None):
+        """Columns of blocks [b0, b1) of ``xa`` (n_slices, k, N) -> dense (n_slices * k, ncols) in block-sorted order; ``out``
+        may be a view with a row stride (a slot of the all-gather buffer)."""
         ncols = self.block_offset(b1) - self.block_offset(b0)
-        packed = torch.empty((self.n_slices * self.k, ncols), dtype=self.dtype, device=self.device)
+        rows = self.n_slices * self.k
+        packed = torch.empty((rows, ncols), dtype=self.dtype, device=self.device) if out is None else out
+        if tuple(packed.shape) != (rows, ncols) or packed.stride(1) != 1 or packed.dtype != self.dtype:
+            raise ValueError("pack target must be ({0}, {1}) with unit column stride".format(rows, ncols))
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.b200da_pack_columns(self._plan, _ptr(xa), b0, b1, _ptr(packed), _stream()))
+            _cabi.check(self.lib.b200da_pack_columns(self._plan, _ptr(xa), b0, b1, _ptr(packed), int(packed.stride(0)), _stream()))
         return packed
 
     def unpack_columns(self, packed, b0, b1, xa):
+        if packed.stride(1) != 1:
+            packed = packed.contiguous()
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.b200da_unpack_columns(self._plan, _ptr(packed), b0, b1, _ptr(xa), _stream()))
+            _cabi.check(self.lib.b200da_unpack_columns(self._plan, _ptr(packed), b0, b1, _ptr(xa), int(packed.stride(0)), _stream()))
         return xa
+
+    def neighbour_counts(self):
+        """(counts int64[N] in original grid order, n_ambiguous): local observations per grid point
+        (b200da_neighbour_count; the exact p_g of the FLOP model, and the work measure of the multi-GPU split)."""
+        counts = torch.zeros(self.n_grid, dtype=torch.int64, device=self.device)
+        namb = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_neighbour_count(self._plan, _ptr(counts), _ptr(namb), _stream()))
+        return counts, int(namb.item())
+
+    def grid_order(self):
+        """int32[N]: block-sorted slot -> original grid index."""
+        order = torch.empty(self.n_grid, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.b200da_grid_order(self._plan, _ptr(order), _stream()))
+        return order
+
+    def block_costs(self, counts):
+        """Work per block for the multi-GPU split: sum over the block's grid points of (local observations + a constant
+        for the k x k solve: 13 k^3 FLOP against 2 k^2 per observation, weighted by the ~4x lower FLOP rate of the solve)."""
+        c = torch.as_tensor(counts, device=self.device).double()[self.grid_order().long()] + 26.0 * self.k
+        cum = torch.cat([torch.zeros(1, dtype=torch.float64, device=self.device), torch.cumsum(c, 0)])
+        host = np.empty(self.n_blocks + 1, dtype=np.int64)
+        _cabi.check(self.lib.b200da_block_offsets(self._plan, host.ctypes.data_as(_cabi._vp)))
+        offs = torch.as_tensor(host, device=self.device)
+        return (cum[offs[1:]] - cum[offs[:-1]]).cpu().numpy()
 
     # -- introspection ---------------------------------------------------------------------------------------------
     @property
     def kernel_name(self):
         return self.lib.b200da_kernel_name(self._plan).decode()
+
+    @property
+    def extra_rows(self):
+        """Rows of [Yn; d] the FP64 Gram kernel accumulates with DFMA next to the DMMA tiles (0: all rows in the tiles)."""
+        return int(self.lib.b200da_gram_extra_rows(self._plan))
 
     def enable_timing(self, on=True):
         _cabi.check(self.lib.b200da_enable_timing(self._plan, 1 if on else 0))

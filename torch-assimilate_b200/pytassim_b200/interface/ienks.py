@@ -149,7 +149,13 @@ class IEnKSTransform(VarAssimilation):
 
     @tau.setter
     def tau(self, new_tau):                                                          # ienks.py:88-94
-        self._tau = _bounded(new_tau, self.dtype, 0.0, 1.0)
+        tau = _bounded(new_tau, self.dtype, 0.0, 1.0)
+        if not float(tau) > 0.0:
+            # the reference accepts tau = 0 (a step that leaves the mean weights where they are); the device kernels solve with
+            # inflation 1 / tau (csrc/ienks_kernel.cuh), so reject it here, where it is set, instead of failing in assimilate()
+            raise ValueError("tau = 0 (no update of the mean weights) is not supported by the B200 IEnKS kernels: "
+                             "use a learning rate in (0, 1]")
+        self._tau = tau
 
     @property
     def _epsilon_value(self):
@@ -226,7 +232,7 @@ class _LocalizedMixin(object):
             if grid_coords.shape[1] < nc:
                 raise ValueError("the metric needs {0} coordinate column(s)".format(nc))
         grid_coords = np.ascontiguousarray(grid_coords[:, :nc])
-        key = ('local', k, n_slices, self.dtype, type(loc).__name__, repr(loc.dist_func), tuple(np.atleast_1d(loc.radius).tolist()),
+        key = ('local', k, n_slices, self.dtype, type(loc).__name__, loc.dist_func.cache_key(), tuple(np.atleast_1d(loc.radius).tolist()),
                float(loc.epsilon))
         if key not in self._engines:
             self._engines = {kk: v for kk, v in self._engines.items() if kk[0] != 'local'}

@@ -39,7 +39,7 @@ class LETKF(ETKF):
 
     def _local_engine(self, k, n_slices, grid_coords):
         loc = self.localization
-        key = ('local', k, n_slices, float(self.inf_factor), self.dtype, type(loc).__name__, repr(loc.dist_func),
+        key = ('local', k, n_slices, float(self.inf_factor), self.dtype, type(loc).__name__, loc.dist_func.cache_key(),
                tuple(np.atleast_1d(loc.radius).tolist()), float(loc.epsilon), self._kernel_key())
         if key not in self._engines:
             self._engines = {kk: v for kk, v in self._engines.items() if kk[0] != 'local'}

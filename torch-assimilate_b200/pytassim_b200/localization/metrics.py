@@ -29,6 +29,11 @@ class _Metric(object):
     def __repr__(self):
         return "{0}({1})".format(type(self).__name__, ", ".join(str(p) for p in self.params))
 
+    def cache_key(self):
+        """Everything that distinguishes two metric objects for the engine (plans are cached per key)."""
+        return (type(self).__name__, int(self.metric_id), int(self.n_coord), int(getattr(self, "n_extra", 0)),
+                tuple(float(p) for p in self.params), bool(getattr(self, "zero_coords", False)))
+
 
 class AbsDistance1D(_Metric):
     """|x_g - x_o| on one coordinate (examples/benchmark_letkf.py:85-87, testing/dummy.py:142-151)."""
@@ -104,8 +109,11 @@ class HaversineDistance(_Metric):
 
 class ProductDistance(_Metric):
     """Several distance rows: row 0 is ``primary`` on the first ``primary.n_coord`` coordinate columns, rows 1.. are
-    ``|x_g - x_o|`` on the following ``n_extra`` columns (vertical level, time offset, ...; at most 2).  ``GaspariCohn`` takes
-    one ``length_scale`` entry per row and multiplies the tapers (pytassim/localization/gaspari_cohn.py:124-134)."""
+    ``|x_g - x_o|`` on the following ``n_extra`` coordinate columns (vertical level, ...; at most 2).  ``GaspariCohn`` takes
+    one ``length_scale`` entry per row and multiplies the tapers (pytassim/localization/gaspari_cohn.py:124-134).  Columns are
+    the coordinate levels AFTER the time column of the grid / observation rows (interface/mixin_local.py:45-69): the time
+    column itself is not handed to the device (``LETKF._analyse_arrays`` drops it), so a temporal taper needs the time offset
+    as an explicit coordinate level of the grid index and the observation info."""
 
     def __init__(self, primary, n_extra=1):
         if not isinstance(primary, _Metric) or isinstance(primary, ProductDistance) or getattr(primary, "zero_coords", False):

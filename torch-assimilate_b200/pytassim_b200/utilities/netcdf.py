@@ -11,6 +11,12 @@ dimension, and a ``MultiIndex`` dimension encoded as the reference does (xarray.
 dimension coordinate carrying the attribute ``multidim_levels = "name_1;name_2"`` plus one coordinate variable per level
 (listed in the data variable's ``coordinates`` attribute).  Files written here open with ``xarray.open_dataarray`` +
 ``decode_multidim`` where xarray exists, and files written by the reference through its scipy backend load here.
+
+Size.  A fixed-size netCDF-3 variable is limited to 2 GiB in scipy's writer (the ``vsize`` field is packed as a signed
+32-bit integer); per-grid-point weights ``(N, k, k)`` float64 pass that at N ~ 168 000 for k = 40.  Arrays of 2 GiB or more
+are therefore written with their FIRST dimension (``grid``) as the record (unlimited) dimension — one record per grid point,
+no limit on the number of records; xarray reads record variables like any other.  String labels are stored the way xarray's
+netCDF-3 encoder stores them: character arrays with a trailing ``string<n>`` dimension.
 """
 import numpy as np
 import pandas as pd
@@ -22,6 +28,7 @@ __all__ = ['save_netcdf', 'load_netcdf', 'encode_multidim', 'decode_multidim', '
 
 DATAARRAY_VARIABLE = '__xarray_dataarray_variable__'        # xarray.backends.api.DATAARRAY_VARIABLE
 _TIME_UNITS = 'seconds since 1970-01-01 00:00:00'
+FIXED_VARIABLE_LIMIT = 2 ** 31 - 4                           # bytes; larger arrays go to the record layout (see above)
 
 
 def encode_multidim(array):
@@ -59,33 +66,55 @@ def _to_nc3(values):
             raise ValueError("integer coordinate does not fit netCDF-3's 32-bit integers")
         values = values.astype(np.int32)
     elif values.dtype.kind in 'OUS':
-        raise NotImplementedError("string coordinates are not supported by the netCDF-3 weight store")
+        enc = [v if isinstance(v, bytes) else str(v).encode('utf-8') for v in values.ravel()]
+        width = max([len(v) for v in enc] + [1])
+        chars = np.zeros((len(enc), width), dtype='S1')
+        for i, v in enumerate(enc):
+            chars[i, :len(v)] = np.frombuffer(v, dtype='S1')
+        values = chars.reshape(values.shape + (width,))
+        attrs = {'_Encoding': 'utf-8'}
     return values, attrs
+
+
+def _create(nc, name, values, dims):
+    """createVariable for plain and for character data (trailing ``string<n>`` dimension, shared between variables)."""
+    if values.dtype.kind == 'S':
+        sdim = 'string{0}'.format(values.shape[-1])
+        if sdim not in nc.dimensions:
+            nc.createDimension(sdim, int(values.shape[-1]))
+        var = nc.createVariable(name, 'c', tuple(dims) + (sdim,))
+    else:
+        var = nc.createVariable(name, values.dtype, tuple(dims))
+    var[:] = values
+    return var
 
 
 def save_netcdf(dataset_to_save, save_path=None, *args, **kwargs):
     """xarray.py:36-55 for a DataArray-like (``values``, ``dims``, ``indexes``): encode MultiIndex dimensions, write netCDF-3."""
     dim_coords, level_coords = encode_multidim(dataset_to_save)
     values = np.asarray(dataset_to_save.values)
+    data, _ = _to_nc3(values)
+    record_dim = None
+    if data.nbytes > FIXED_VARIABLE_LIMIT:
+        if data.ndim < 2 or data[0].nbytes > FIXED_VARIABLE_LIMIT:
+            raise ValueError("the netCDF-3 weight store holds arrays whose slices along the first dimension stay below 2 GiB; "
+                             "got shape {0} of {1}".format(data.shape, data.dtype))
+        record_dim = dataset_to_save.dims[0]
     nc = netcdf_file(save_path, 'w', version=2)
     try:
         for dim, n in zip(dataset_to_save.dims, values.shape):
-            nc.createDimension(dim, int(n))
+            nc.createDimension(dim, None if dim == record_dim else int(n))
         for dim, (coord, attrs) in dim_coords.items():
             coord, extra = _to_nc3(coord)
-            var = nc.createVariable(dim, coord.dtype, (dim,))
-            var[:] = coord
+            var = _create(nc, dim, coord, (dim,))
             for key, val in dict(attrs, **extra).items():
                 setattr(var, key, val)
         for name, (dim, coord) in level_coords.items():
             coord, extra = _to_nc3(coord)
-            var = nc.createVariable(name, coord.dtype, (dim,))
-            var[:] = coord
+            var = _create(nc, name, coord, (dim,))
             for key, val in extra.items():
                 setattr(var, key, val)
-        data, _ = _to_nc3(values)
-        var = nc.createVariable(DATAARRAY_VARIABLE, data.dtype, tuple(dataset_to_save.dims))
-        var[:] = data
+        var = _create(nc, DATAARRAY_VARIABLE, data, tuple(dataset_to_save.dims))
         if level_coords:
             var.coordinates = ' '.join(level_coords.keys())
     finally:
@@ -114,7 +143,8 @@ def load_netcdf(load_path, array=False, *args, **kwargs):
         referenced = set()
         for var in nc.variables.values():
             referenced.update(str(getattr(var, 'coordinates', b'').decode()).split())
-        data_names = [name for name in nc.variables if name not in nc.dimensions and name not in referenced]
+        data_names = [name for name in nc.variables if name not in nc.dimensions and name not in referenced
+                      and not name.startswith('string')]
         if DATAARRAY_VARIABLE in nc.variables:
             data_name = DATAARRAY_VARIABLE
         elif len(data_names) == 1:
@@ -131,7 +161,7 @@ def load_netcdf(load_path, array=False, *args, **kwargs):
                 continue
             cvals = np.array(cvar[:], dtype=cvar[:].dtype.newbyteorder('='))
             if cvals.dtype.kind == 'S' and cvals.ndim == 2:                  # netCDF-3 strings: (n, string_length) characters
-                cvals = np.array([b''.join(row).decode().rstrip('\x00') for row in cvals])
+                cvals = np.array([b''.join(row).decode('utf-8').rstrip('\x00') for row in cvals])
             cattrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in cvar._attributes.items()}
             if str(cattrs.get('units', '')).startswith('seconds since 1970-01-01'):
                 cvals = (np.datetime64('1970-01-01T00:00:00', 'ns') +
