@@ -13,6 +13,7 @@
 namespace b200da {
 thread_local std::string g_last_cuda_error;
 int64_t g_launch_count = 0;
+int g_debug_sync = [] { const char* e = getenv("B200DA_DEBUG_SYNC"); return e ? atoi(e) : 0; }();
 
 // host copies of the tapers (only used to locate the cutoff radius r with w(r) = eps)
 static double host_taper(int taper, double r) {
@@ -271,7 +272,7 @@ void b200da_plan_destroy(b200da_plan* pl) {
                       &pl->tmp_cell, &pl->tmp_count, &pl->tmp_a, &pl->tmp_b, &pl->tmp_pos, &pl->host_stage_obs,
                       &pl->host_stage_y, &pl->host_stage_d, &pl->host_stage_x, &pl->host_stage_xa, &pl->etkf_partial,
                       &pl->etkf_w, &pl->stats, &pl->cmat, &pl->counter, &pl->ns_scratch, &pl->gext, &pl->oext,
-                      &pl->devstat, &pl->amb_list, &pl->over_list};
+                      &pl->devstat, &pl->amb_list, &pl->over_list, &pl->tc_centre};
     for (cudaEvent_t ev : pl->ev_pool) cudaEventDestroy(ev);
     for (DevBuf* b : bufs) b->release();
     if (pl->ev0) cudaEventDestroy(pl->ev0);
@@ -337,13 +338,45 @@ int b200da_set_grid(b200da_plan* plan, const double* grid_coord, int64_t n_grid,
     return set_grid_impl(plan, grid_coord, n_grid, (cudaStream_t)stream);
 }
 
+static int etkf_partial_grams(b200da_plan* pl, const void* Yn, const void* d, int64_t m, int64_t ld, int* ncta_out, cudaStream_t st);
+
+// Centring constants of the tcgen05 Gram (tc_gram_kernel.cuh): c[(a, b)] = mean over ALL observations of y_a y_b, i.e. the
+// unlocalized augmented Gram (the global-ETKF Gram kernel, etkf_kernel.cuh) divided by M, in pair-column order.
+__global__ void k_tc_centre(const double* __restrict__ partial, int n_partial, int kp, int k, int64_t m, int n_cols,
+                            float* __restrict__ centre) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n_cols) return;
+    int a = (int)((sqrtf(8.0f * (float)col + 1.0f) - 1.0f) * 0.5f);
+    while (a * (a + 1) / 2 > col) --a;
+    while ((a + 1) * (a + 2) / 2 <= col) ++a;
+    const int b = col - a * (a + 1) / 2;
+    double s = 0.0;
+    for (int p = 0; p < n_partial; ++p) s += partial[(size_t)p * kp * kp + a * kp + b];
+    centre[col] = m > 0 ? (float)(s / (double)m) : 0.f;
+}
+static int tc_centre_constants(b200da_plan* pl, const void* Yn, const void* d, int64_t m, cudaStream_t st) {
+    const int n_cols = (pl->k + 1) * (pl->k + 2) / 2;
+    int rc, n_partial = 0;
+    if ((rc = pl->tc_centre.ensure(sizeof(float) * (size_t)(n_cols + 512)))) return rc;
+    if (m <= 0) { B200DA_CUDA(cudaMemsetAsync(pl->tc_centre.p, 0, sizeof(float) * (size_t)(n_cols + 512), st)); return B200DA_OK; }
+    if ((rc = etkf_partial_grams(pl, Yn, d, m, m, &n_partial, st))) return rc;
+    B200DA_CUDA(cudaMemsetAsync(pl->tc_centre.p, 0, sizeof(float) * (size_t)(n_cols + 512), st));
+    k_tc_centre<<<(n_cols + 127) / 128, 128, 0, st>>>(pl->etkf_partial.as<double>(), n_partial, pl->kp, pl->k, m, n_cols,
+                                                       pl->tc_centre.as<float>());
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+
 int b200da_bin_obs(b200da_plan* plan, const double* obs_coord, const void* Yn, const void* d, int64_t n_obs, void* stream) {
     if (!plan) return B200DA_ERR_INVALID;
     // new observations: decisions and records of the ambiguity protocol refer to the previous set
     plan->n_over = 0;
     B200DA_CUDA(cudaMemsetAsync(&plan->devstat.as<PlanStatus>()->amb_found, 0, sizeof(unsigned long long), (cudaStream_t)stream));
-    if (plan->dtype == B200DA_F32)
-        return bin_obs_impl<float>(plan, obs_coord, (const float*)Yn, (const float*)d, n_obs, (cudaStream_t)stream);
+    if (plan->dtype == B200DA_F32) {
+        int rc = bin_obs_impl<float>(plan, obs_coord, (const float*)Yn, (const float*)d, n_obs, (cudaStream_t)stream);
+        if (rc == B200DA_OK && plan->use_tc) rc = tc_centre_constants(plan, Yn, d, n_obs, (cudaStream_t)stream);
+        return rc;
+    }
     return bin_obs_impl<double>(plan, obs_coord, (const double*)Yn, (const double*)d, n_obs, (cudaStream_t)stream);
 }
 

@@ -24,10 +24,20 @@ extern int64_t g_launch_count;
         }                                                                                                     \
     } while (0)
 
+// B200DA_DEBUG_SYNC=1 in the environment: every launch is followed by a device synchronisation, so that a faulting kernel is
+// named (file:line) in b200da_last_cuda_error instead of surfacing at a later API call.
+extern int g_debug_sync;
 #define B200DA_LAUNCH_CHECK()                                                                                \
     do {                                                                                                      \
         ++::b200da::g_launch_count;                                                                           \
         B200DA_CUDA(cudaGetLastError());                                                                      \
+        if (::b200da::g_debug_sync) {                                                                         \
+            cudaError_t err__ = cudaDeviceSynchronize();                                                      \
+            if (err__ != cudaSuccess) {                                                                       \
+                ::b200da::g_last_cuda_error = std::string("kernel launched at " __FILE__ ":") + std::to_string(__LINE__) + ": " + cudaGetErrorString(err__); \
+                return B200DA_ERR_CUDA;                                                                       \
+            }                                                                                                 \
+        }                                                                                                     \
     } while (0)
 
 // Grow-only device buffer owned by the plan.
@@ -80,6 +90,7 @@ struct b200da_plan {
     b200da::DevBuf tmp_keys, tmp_cell, tmp_count, tmp_a, tmp_b, tmp_pos;
     b200da::DevBuf host_stage_obs, host_stage_y, host_stage_d, host_stage_x, host_stage_xa;
     b200da::DevBuf etkf_partial, etkf_w, stats, cmat, counter, ns_scratch;
+    b200da::DevBuf tc_centre;   // FP32 tcgen05 plans: centring constant of every pair column (b200da.cu: tc_centre_constants)
     b200da::DevBuf gext, oext;  // extra coordinate columns in block- / cell-sorted order (b200da_plan_set_extra)
     // ambiguity protocol and device-side error flags (common.cuh: PlanStatus, PairRec)
     b200da::DevBuf devstat;     // PlanStatus

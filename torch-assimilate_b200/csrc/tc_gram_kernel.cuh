@@ -18,7 +18,12 @@
 //
 // Precision.  Operands are split into two bfloat16 terms (x = hi + lo, 16 significant bits) and the product is
 // accumulated as hi*hi + hi*lo + lo*hi in FP32 (3 kind::f16 MMAs per 16 observations; the dropped lo*lo term is 2^-18
-// relative).  The taper is read from a per-CTA table of the weight as a function of the SQUARED bin-space distance
+// relative).  The FP32 accumulation of the tensor core truncates: over the ~3 500 accumulation steps of a cfg3 grid point
+// (p ~ 56 000) a sum of same-sign terms comes out 4e-4 too small (measured, tools/diag_tc_gram.py: every diagonal entry
+// biased by -4.1e-4 relative, off-diagonal entries by the same fraction of their own magnitude).  The accumulators are
+// therefore kept small: every pair column is centred, Z[(a,b), j] = y_aj y_bj - c_ab with c_ab the mean of y_a y_b over
+// ALL observations (b200da.cu: tc_centre_constants), and the epilogue adds c_ab * sum_j w_gj back in FP64, the sum of the
+// weights being accumulated by the generator threads on the CUDA cores (FP64).  The taper is read from a per-CTA table of the weight as a function of the SQUARED bin-space distance
 // (2048 intervals, linear interpolation, error < 1e-6; built in FP64 from the same taper code as the FP64 path, mask
 // w > eps included), evaluated on FP32 positions relative to the block centre: a pair costs 3 subtractions, 3 FMAs, one
 // table read and one FMA instead of a square root, an arc sine and two polynomials.  The k x k solve and the update stay
@@ -62,6 +67,7 @@ struct TcParams {
     int asin_poly;     // closed form, haversine: chord / 2 stays below 0.3, asin by its series
     float r_scale;     // closed form, distance -> r: 1 / radius (haversine: 2 R / radius, applied to asin(chord / 2))
     float eps;
+    const float* centre;   // [n_cols] centring constant of every pair column (see "Precision")
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------
@@ -164,10 +170,11 @@ __device__ __forceinline__ float pair_weight_f32(const float2* __restrict__ tab,
 // taper weights of one grid point for the 8 observations ot[0..7] -> bf16 hi / lo
 template <int DIST>
 __device__ __forceinline__ void w_chunk(const float4* __restrict__ ot, const float2* __restrict__ tab, float xs, float period,
-                                        float gx, float gy, float gz, uint4& hi, uint4& lo) {
+                                        float gx, float gy, float gz, uint4& hi, uint4& lo, float& wsum) {
     float w[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) w[jj] = pair_weight_f32<DIST>(tab, xs, period, gx, gy, gz, ot[jj]);
+    wsum = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
     split8(w, hi, lo);
 }
 
@@ -228,10 +235,11 @@ __device__ __forceinline__ float pair_weight_closed(float r_scale, float eps, fl
 }
 template <int DIST, int TAPER>
 __device__ __forceinline__ void w_chunk_closed(const float4* __restrict__ ot, float r_scale, float eps, float period, float gx,
-                                               float gy, float gz, uint4& hi, uint4& lo) {
+                                               float gy, float gz, uint4& hi, uint4& lo, float& wsum) {
     float w[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) w[jj] = pair_weight_closed<DIST, TAPER>(r_scale, eps, period, gx, gy, gz, ot[jj]);
+    wsum = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
     split8(w, hi, lo);
 }
 
@@ -488,6 +496,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
         const bool c_ok = tid < nc && my_col < P.n_cols;
         int ca = 0, cb = 0;
         if (c_ok) col_to_pair(my_col, ca, cb);
+        const float ncz = c_ok ? -P.centre[my_col] : 0.f;            // minus the centring constant of this thread's pair column
+        double wsum_acc = 0.0;                                      // sum of this thread's taper weights (grid point my_g)
         const int dist_kind = g.metric == B200DA_METRIC_PERIODIC1D ? kTcPeriodic
                             : g.metric == B200DA_METRIC_ABS1D ? kTcAbs : kTcSq3;
         const float xs = (float)kTcTab / P.q_max, period = P.period, r_scale = P.r_scale, eps = P.eps;
@@ -513,17 +523,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
             {
                 const float4* ot = S.otile + yst * kTcObs + my_kc * 8;
                 uint4 hi, lo;
+                float ws8;
                 switch (wmode) {                                   // uniform over the launch
-                    case 0: w_chunk<kTcSq3>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo); break;
-                    case 1: w_chunk<kTcAbs>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo); break;
-                    case 2: w_chunk<kTcPeriodic>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo); break;
-#define B200DA_TC_W(D, T) case 8 + (D) * 2 + (T): w_chunk_closed<D, T>(ot, r_scale, eps, period, gxr, gyr, gzr, hi, lo); break;
+                    case 0: w_chunk<kTcSq3>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo, ws8); break;
+                    case 1: w_chunk<kTcAbs>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo, ws8); break;
+                    case 2: w_chunk<kTcPeriodic>(ot, wtab, xs, period, gxr, gyr, gzr, hi, lo, ws8); break;
+#define B200DA_TC_W(D, T) case 8 + (D) * 2 + (T): w_chunk_closed<D, T>(ot, r_scale, eps, period, gxr, gyr, gzr, hi, lo, ws8); break;
                     B200DA_TC_W(kTcHavPoly, 0) B200DA_TC_W(kTcHavPoly, 1) B200DA_TC_W(kTcHavAsin, 0) B200DA_TC_W(kTcHavAsin, 1)
                     B200DA_TC_W(kTcEuclid, 0) B200DA_TC_W(kTcEuclid, 1) B200DA_TC_W(kTcAbsF, 0) B200DA_TC_W(kTcAbsF, 1)
                     B200DA_TC_W(kTcPeriodicF, 0)
-                    default: w_chunk_closed<kTcPeriodicF, 1>(ot, r_scale, eps, period, gxr, gyr, gzr, hi, lo); break;
+                    default: w_chunk_closed<kTcPeriodicF, 1>(ot, r_scale, eps, period, gxr, gyr, gzr, hi, lo, ws8); break;
 #undef B200DA_TC_W
                 }
+                wsum_acc += (double)ws8;
                 if constexpr (kTcATmem) {
                     // this thread's row (grid point) = its tensor-memory lane; 8 bf16 = 4 columns at K offset my_kc * 8
                     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)kTcMaxCols + (uint32_t)st * 32 +
@@ -548,7 +560,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
                 float4 a0 = ya[0], a1 = ya[1], b0 = yb[0], b1 = yb[1];
 #pragma unroll
                 for (int kc = 0; kc < kTcObs / 8; ++kc) {
-                    const float z[8] = {a0.x * b0.x, a0.y * b0.y, a0.z * b0.z, a0.w * b0.w, a1.x * b1.x, a1.y * b1.y, a1.z * b1.z, a1.w * b1.w};
+                    const float z[8] = {fmaf(a0.x, b0.x, ncz), fmaf(a0.y, b0.y, ncz), fmaf(a0.z, b0.z, ncz), fmaf(a0.w, b0.w, ncz),
+                                        fmaf(a1.x, b1.x, ncz), fmaf(a1.y, b1.y, ncz), fmaf(a1.z, b1.z, ncz), fmaf(a1.w, b1.w, ncz)};
                     if (kc + 1 < kTcObs / 8) { a0 = ya[2 * kc + 2]; a1 = ya[2 * kc + 3]; b0 = yb[2 * kc + 2]; b1 = yb[2 * kc + 3]; }
                     uint4 hi, lo;
                     split8(z, hi, lo);
@@ -578,8 +591,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
         // ---- epilogue: tensor memory -> FP64 tile-packed Gram scratch of the solve kernel ------------------------------------
         mbar_wait(all_done, 0);
         tc_fence_after();
+        // sum of the weights of every grid point: four partial sums (observation chunks) through the idle operand stage
+        double* wpart = reinterpret_cast<double*>(S.b_hi);
+        wpart[my_kc * kTcM + my_g] = wsum_acc;
+        asm volatile("bar.sync 1, %0;" :: "n"(kTcGenThreads) : "memory");
         const int lq = warp & 3, cw = warp >> 2;                  // TMEM lane quarter of this warp, column group
         const int gi = lq * 32 + lane;
+        const double wsum = (wpart[gi] + wpart[kTcM + gi]) + (wpart[2 * kTcM + gi] + wpart[3 * kTcM + gi]);
         const int64_t slot = (int64_t)L.block_off[blk] + gi - L.slot_base;
         const int kt = (k1 + 7) >> 3;
         double* C = L.cmat + (size_t)(gi < ng ? slot : 0) * (size_t)(tri_tiles(kt) * 64);
@@ -602,7 +620,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_tc_gram(const TcParams P) {
                 col_to_pair(col, a, b);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    if (col + i < P.n_cols) C[sym_off(a, b)] = (double)__uint_as_float(v[i]);
+                    if (col + i < P.n_cols) C[sym_off(a, b)] = fma((double)__ldg(P.centre + col + i), wsum, (double)__uint_as_float(v[i]));
                     if (++b > a) { ++a; b = 0; }
                 }
             }

@@ -30,6 +30,8 @@ int launch_tc_gram(b200da_plan* pl, const LetkfParams& L, int nblocks, cudaStrea
     P.asin_poly = (g.metric == B200DA_METRIC_HAVERSINE && g.cut_bin <= 0.4) ? 1 : 0;
     P.r_scale = (float)(g.metric == B200DA_METRIC_HAVERSINE ? 2.0 * g.sphere_r / g.radius : 1.0 / g.radius);
     P.eps = (float)g.eps;
+    P.centre = pl->tc_centre.as<float>();
+    if (!P.centre) return B200DA_ERR_STATE;
     if (const char* e = getenv("B200DA_TC_WTABLE")) P.w_closed = atoi(e) ? 0 : 1;
     P.n_load = kTcYStages;
     while (P.n_load > 2 && tc_smem_bytes(P.kp, P.nc, P.n_load) > kMaxSmem) --P.n_load;
