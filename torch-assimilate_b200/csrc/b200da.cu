@@ -570,7 +570,7 @@ static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int
             S.io_f32 = f32;
             S.slot_base = s0; S.n_slots = n_slots; S.n_grid = pl->n_grid; S.k = k; S.n_slices = pl->n_slices; S.rho = rho_solve;
             if ((rc = pl->ns_scratch.ensure(ns_scratch_bytes((k + 7) / 8)))) return rc;
-            S.scratch = pl->ns_scratch.as<double>(); S.stiff = ns_stiff_ratio(pl);
+            S.scratch = pl->ns_scratch.as<double>(); S.stiff = ns_stiff_ratio(pl); S.conv = pl->dtype == B200DA_F32 ? 3e-4 : 2e-8;
             if ((rc = dispatch_ns((k + 7) / 8, S, st))) return rc;
         }
         if (ie && !gram_out && (rc = launch_ienks_keep(pl, I, st))) return rc;
@@ -821,7 +821,7 @@ static int etkf_solve_partials(b200da_plan* pl, int n_partial, void* W, cudaStre
         S.w_out = W; S.io_f32 = f32; S.stats = nullptr; S.counter = pl->counter.as<unsigned int>();
         S.slot_base = 0; S.n_slots = 1; S.n_grid = 0; S.k = k; S.n_slices = 0; S.rho = rho_solve;
         if ((rc = pl->ns_scratch.ensure(ns_scratch_bytes((k + 7) / 8)))) return rc;
-        S.scratch = pl->ns_scratch.as<double>(); S.stiff = ns_stiff_ratio(pl);
+        S.scratch = pl->ns_scratch.as<double>(); S.stiff = ns_stiff_ratio(pl); S.conv = pl->dtype == B200DA_F32 ? 3e-4 : 2e-8;
         return dispatch_ns((k + 7) / 8, S, st);
     }
     const size_t smem = solve_smem_bytes(k);

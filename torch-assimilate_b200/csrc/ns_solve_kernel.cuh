@@ -17,7 +17,7 @@
 // clamp(min=0) (core/utils.py:58) only removes rounding noise of the same size as this kernel's own rounding.
 // With mu = eig(g M) in [g lo, g], g = 3 / (1 + sqrt(lo) + lo) equalises f(g lo) = f(g), f(mu) = mu (3 - mu)^2 / 4,
 // which is the largest lower bound reachable in one step; lo <- f(g lo).  The iteration count follows from the
-// bound alone (no data-dependent test): it stops when 1 - lo < 2e-8, i.e. when the next step leaves an error
+// bound alone (no data-dependent test): it stops when 1 - lo < 2e-8 (FP32 plans: 3e-4), i.e. when the next step leaves an error
 // of order (1 - lo)^2 below the FP64 rounding level.
 //
 // Layout.  Every matrix of the iteration is a polynomial in A, hence symmetric: only the lower-triangle 8x8
@@ -244,6 +244,7 @@ struct NsParams {
     double rho;
     double* scratch;           // per group (blockIdx.x * GROUPS + group) ns_scratch_doubles(KT) doubles: stiff matrices only
     double stiff;              // spectral-bound ratio s / a above which the two-level solve is used
+    double conv;               // the iteration takes its last step when 1 - lo < conv (error afterwards ~ conv^2): 2e-8, FP32 plans 3e-4
 };
 
 // doubles of global scratch per group: fixed-up A and B (tile-packed symmetric) + one full tile grid
@@ -348,7 +349,7 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
             lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
         }
         for (; iters < 64; ++iters) {
-            const bool last = (1.0 - lo) < 2e-8;
+            const bool last = (1.0 - lo) < P.conv;
             g = 3.0 / (1.0 + sqrt(lo) + lo);
             sg = sqrt(g);
             sym_gemm_sub<KT, WPM, SUB>(Z, Y, fo, acc);                    // M = Z Y
