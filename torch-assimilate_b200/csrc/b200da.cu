@@ -29,6 +29,85 @@ static double host_taper(int taper, double r) {
     return 0.0;
 }
 
+// ---- tabulated taper of the Gram kernels (common.cuh: TaperTab) ---------------------------------------------------------------
+// piece `seg` of the taper as an analytic function of r (each piece is evaluated with its own formula also slightly outside
+// its interval, so that the interpolation nodes next to a breakpoint never pick the neighbouring piece)
+static long double taper_piece(int taper, int seg, long double r) {
+    const long double r2 = r * r, r3 = r2 * r, r4 = r3 * r, r5 = r4 * r;
+    if (taper == B200DA_TAPER_GCINF) {
+        switch (seg) {
+            case 0: return -28.0L * r5 / 33 + 8.0L * r4 / 11 + 20.0L * r3 / 11 - 80.0L * r2 / 33 + 1;
+            case 1: return 20.0L * r5 / 33 - 16.0L * r4 / 11 + 100.0L * r2 / 33 - 45.0L * r / 11 + 51.0L / 22 - 7.0L / (44 * r);
+            case 2: return -4.0L * r5 / 11 + 16.0L * r4 / 11 - 10.0L * r3 / 11 - 100.0L * r2 / 33 + 5 * r - 61.0L / 22 + 115.0L / (132 * r);
+            default: return 4.0L * r5 / 33 - 8.0L * r4 / 11 + 10.0L * r3 / 11 + 80.0L * r2 / 33 - 80.0L * r / 11 + 64.0L / 11 - 32.0L / (33 * r);
+        }
+    }
+    if (seg == 0) return -0.25L * r5 + 0.5L * r4 + 0.625L * r3 - 5.0L / 3 * r2 + 1;
+    return r5 / 12 - 0.5L * r4 + 0.625L * r3 + 5.0L / 3 * r2 - 5 * r + 4 - 2.0L / 3 / r;
+}
+// Builds the table for the plan's geometry; leaves pl->tt.coef null (direct evaluation) when the table does not apply: a
+// haversine support that reaches beyond a third of the sphere (the chord is a poor coordinate near the antipode), a degenerate
+// radius, or B200DA_TAPER_TABLE=0 in the environment.
+static int build_taper_table(b200da_plan* pl) {
+    const Geometry& g = pl->geom;
+    pl->tt = TaperTab{};
+    if (const char* e = getenv("B200DA_TAPER_TABLE")) { if (!atoi(e)) return B200DA_OK; }
+    if (!(g.radius > 0.0) || !std::isfinite(g.radius)) return B200DA_OK;
+    const bool hav = g.metric == B200DA_METRIC_HAVERSINE;
+    const int nseg = g.taper == B200DA_TAPER_GCINF ? 4 : 2;
+    const long double dr = 2.0L / nseg;
+    if (hav && 2.0 * g.radius / g.sphere_r > 2.0 * M_PI / 3.0) return B200DA_OK;
+    auto u_of_r = [&](long double r) -> long double {            // bin-space distance at taper argument r
+        return hav ? 2.0L * sinl(0.5L * r * (long double)g.radius / (long double)g.sphere_r) : r * (long double)g.radius;
+    };
+    auto r_of_u = [&](long double u) -> long double {
+        return hav ? 2.0L * (long double)g.sphere_r * asinl(0.5L * u) / (long double)g.radius : u / (long double)g.radius;
+    };
+    TaperTab tt{};
+    tt.nseg = nseg;
+    tt.nint = 256 / nseg;                                         // 128 intervals per unit of r
+    std::vector<double> coef((size_t)nseg * tt.nint * 6);
+    for (int sg = 0; sg <= nseg; ++sg) tt.ub[sg] = (double)u_of_r(dr * sg);
+    static const long double kPi = 3.14159265358979323846264338327950288L;
+    for (int sg = 0; sg < nseg; ++sg) {
+        const long double ua = tt.ub[sg], ub = tt.ub[sg + 1];      // the device locates the segment with these rounded values
+        if (!(ub > ua)) return B200DA_OK;
+        const long double h = (ub - ua) / tt.nint;
+        tt.scale[sg] = (double)(1.0L / h);
+        for (int i = 0; i < tt.nint; ++i) {
+            // the device computes x = (u - ub[s]) * scale[s], i = floor(x), t = 2 (x - i) - 1: interval i is [ua + i / scale, ...)
+            const long double inv = 1.0L / (long double)tt.scale[sg];
+            const long double mid = ua + (i + 0.5L) * inv, half = 0.5L * inv;
+            long double f[6], a[6];
+            for (int j = 0; j < 6; ++j) {
+                const long double t = cosl((2 * j + 1) * kPi / 12);
+                long double r = r_of_u(mid + half * t);
+                if (r < 1e-30L) r = 1e-30L;
+                f[j] = taper_piece(g.taper, sg, r);
+            }
+            for (int kk = 0; kk < 6; ++kk) {                      // Chebyshev coefficients of the interpolant
+                long double acc = 0;
+                for (int j = 0; j < 6; ++j) acc += f[j] * cosl(kk * (2 * j + 1) * kPi / 12);
+                a[kk] = acc * (kk == 0 ? 1.0L / 6 : 2.0L / 6);
+            }
+            // T0..T5 -> monomials in t
+            double* c = &coef[((size_t)sg * tt.nint + i) * 6];
+            c[0] = (double)(a[0] - a[2] + a[4]);
+            c[1] = (double)(a[1] - 3 * a[3] + 5 * a[5]);
+            c[2] = (double)(2 * a[2] - 8 * a[4]);
+            c[3] = (double)(4 * a[3] - 20 * a[5]);
+            c[4] = (double)(8 * a[4]);
+            c[5] = (double)(16 * a[5]);
+        }
+    }
+    int rc = pl->taper_tab.ensure(sizeof(double) * coef.size());
+    if (rc) return rc;
+    B200DA_CUDA(cudaMemcpy(pl->taper_tab.p, coef.data(), sizeof(double) * coef.size(), cudaMemcpyHostToDevice));
+    tt.coef = pl->taper_tab.as<double>();
+    pl->tt = tt;
+    return B200DA_OK;
+}
+
 // smallest r (padded) beyond which the taper never exceeds eps: the tapers decrease monotonically on (0, 2)
 static double cutoff_radius(int taper, double eps) {
     if (!(eps > 0.0)) return 2.0;
@@ -258,6 +337,7 @@ int b200da_plan_create(b200da_plan** plan, int k, int n_slices, int n_coord, int
     if (cudaEventCreate(&pl->ev0) != cudaSuccess || cudaEventCreate(&pl->ev1) != cudaSuccess) {
         delete pl; return B200DA_ERR_CUDA;
     }
+    if (int rc = build_taper_table(pl)) { b200da_plan_destroy(pl); return rc; }
     if (pl->devstat.ensure(sizeof(PlanStatus)) || pl->amb_list.ensure(sizeof(PairRec) * kAmbCapacity) ||
         pl->over_list.ensure(sizeof(PairRec) * 16) || cudaMemset(pl->devstat.p, 0, sizeof(PlanStatus)) != cudaSuccess) {
         b200da_plan_destroy(pl); return B200DA_ERR_NOMEM;
@@ -272,7 +352,7 @@ void b200da_plan_destroy(b200da_plan* pl) {
                       &pl->tmp_cell, &pl->tmp_count, &pl->tmp_a, &pl->tmp_b, &pl->tmp_pos, &pl->host_stage_obs,
                       &pl->host_stage_y, &pl->host_stage_d, &pl->host_stage_x, &pl->host_stage_xa, &pl->etkf_partial,
                       &pl->etkf_w, &pl->stats, &pl->cmat, &pl->counter, &pl->ns_scratch, &pl->gext, &pl->oext,
-                      &pl->devstat, &pl->amb_list, &pl->over_list, &pl->tc_centre};
+                      &pl->devstat, &pl->amb_list, &pl->over_list, &pl->tc_centre, &pl->taper_tab};
     for (cudaEvent_t ev : pl->ev_pool) cudaEventDestroy(ev);
     for (DevBuf* b : bufs) b->release();
     if (pl->ev0) cudaEventDestroy(pl->ev0);
@@ -496,6 +576,7 @@ static int letkf_impl(b200da_plan* pl, const void* X, void* Xa, void* W_opt, int
     P.status = pl->devstat.as<PlanStatus>();
     P.amb_list = pl->amb_list.as<PairRec>();
     P.over = pl->over_list.as<PairRec>(); P.n_over = pl->n_over;
+    P.tt = pl->geom.n_ext == 0 ? pl->tt : TaperTab{};              // several distance rows: direct evaluation, row by row
     P.stats = nullptr;
     if (pl->collect_stats) {
         int rc = pl->stats.ensure(sizeof(unsigned long long) * 16);

@@ -216,6 +216,56 @@ __device__ __forceinline__ double pair_weight(const Geometry& g, double gx, doub
     return (w > g.eps) ? w : 0.0;                          // gaspari_cohn.py:135
 }
 
+// ---- tabulated taper of the Gram kernels -----------------------------------------------------------------------------------
+// The direct evaluation above costs ~150 FP64 instructions per (grid point, observation) pair for the haversine metric (a
+// square root, an arc sine, two divisions, the polynomial) on the datapath the DMMA instructions need.  The Gram kernels
+// therefore read the weight as a function of the BIN-SPACE distance u (chord length for haversine, the metric's own distance
+// otherwise) from a table: the pieces of the taper (breakpoints r = 1, 2 or 0.5, 1, 1.5, 2) map to u-segments, every segment
+// is cut into `nint` equal intervals, and every interval carries the degree-5 interpolant of w(u) through 6 Chebyshev nodes
+// (coefficients in t = 2 (u - u_left) / h - 1, computed on the host in long double; b200da.cu: build_taper_table).  The
+// interpolation error is below 1e-16 for radii up to a third of the sphere, i.e. smaller than the rounding of the direct
+// evaluation; the mask w > eps is applied to the tabulated value, and pairs inside the ambiguity band go to the host as before.
+// The neighbour-list kernels keep the direct evaluation (their weights are compared with numpy's).
+constexpr int kTaperSegMax = 4;
+struct TaperTab {
+    const double* coef;              // [nseg * nint][6], null: direct evaluation
+    int nseg, nint;
+    double ub[kTaperSegMax + 1];     // u at the breakpoints, ub[0] = 0, ub[nseg] = u where the taper reaches 0
+    double scale[kTaperSegMax];      // nint / (ub[s + 1] - ub[s])
+};
+__host__ __device__ inline size_t taper_tab_doubles(const TaperTab& tt) { return tt.coef ? (size_t)tt.nseg * tt.nint * 6 : 0; }
+
+// bin-space distance of the pair, the argument of the table
+__device__ __forceinline__ double taper_tab_arg(const Geometry& g, double gx, double gy, double gz, double ox, double oy, double oz) {
+    switch (g.metric) {
+        case B200DA_METRIC_ABS1D: return fabs(gz - oz);
+        case B200DA_METRIC_PERIODIC1D: { const double d = fabs(gz - oz); return fmin(d, g.period - d); }
+        default: {                  // EUCLID (unused leading coordinates are 0 in bin space) and HAVERSINE (chord)
+            const double dx = ox - gx, dy = oy - gy, dz = oz - gz;
+            return sqrt(fma(dx, dx, fma(dy, dy, dz * dz)));
+        }
+    }
+}
+__device__ __forceinline__ double taper_tab_eval(const TaperTab& tt, const double* __restrict__ tab, double u) {
+    if (!(u < tt.ub[tt.nseg])) return 0.0;                  // beyond the support (and NaN distances, gaspari_cohn.py:128)
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < kTaperSegMax; ++i) if (i < tt.nseg && u >= tt.ub[i]) s = i;
+    const double x = (u - tt.ub[s]) * tt.scale[s];
+    const int i = min(__double2int_rd(x), tt.nint - 1);
+    const double t = fma(2.0, x - (double)i, -1.0);
+    const double2* c = reinterpret_cast<const double2*>(tab + (size_t)(s * tt.nint + i) * 6);
+    const double2 c01 = c[0], c23 = c[1], c45 = c[2];
+    return fma(t, fma(t, fma(t, fma(t, fma(t, c45.y, c45.x), c23.y), c23.x), c01.y), c01.x);
+}
+// pair_weight with the tabulated taper (single distance row only)
+__device__ __forceinline__ double pair_weight_tab(const Geometry& g, const TaperTab& tt, const double* __restrict__ tab,
+                                                  double gx, double gy, double gz, double ox, double oy, double oz, bool& ambiguous) {
+    const double w = taper_tab_eval(tt, tab, taper_tab_arg(g, gx, gy, gz, ox, oy, oz));
+    ambiguous = fabs(w - g.eps) < kAmbiguityBand;
+    return (w > g.eps) ? w : 0.0;                          // gaspari_cohn.py:135
+}
+
 // the taper value itself (no mask): what the ambiguity records carry
 __device__ __forceinline__ double pair_weight_raw(const Geometry& g, double gx, double gy, double gz,
                                                   double ox, double oy, double oz, const double* __restrict__ ge,

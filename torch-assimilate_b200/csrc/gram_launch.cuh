@@ -7,7 +7,7 @@ namespace b200da {
 template <typename T, int KT, int G, int WPG, int ER>
 static int launch_fused_t(const LetkfParams& P, int nblocks, cudaStream_t st) {
     const size_t hdr = (sizeof(BlockHeader<G>) + 31) & ~size_t(31);
-    const size_t smem = hdr + gram_smem_bytes<T, KT, G, WPG, ER>();
+    const size_t smem = hdr + gram_smem_bytes<T, KT, G, WPG, ER>() + sizeof(double) * taper_tab_doubles(P.tt);
     if (smem > kMaxSmem) return B200DA_ERR_UNSUPPORTED;
     auto kern = k_letkf_gram<T, KT, G, WPG, ER>;
     B200DA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

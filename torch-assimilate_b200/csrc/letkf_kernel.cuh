@@ -56,6 +56,7 @@ struct LetkfParams {
     PairRec* amb_list;         // [kAmbCapacity] pairs inside the ambiguity band met by this launch (FP64 taper path)
     const PairRec* over;       // [n_over] host decisions that replace the device weight of a pair
     int n_over;
+    TaperTab tt;               // tabulated taper (common.cuh); tt.coef null: direct evaluation
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -298,7 +299,7 @@ __host__ __device__ constexpr size_t gram_smem_bytes() {
     } while (0)
 
 template <typename T, int KT, int G, int WPG, int ER>
-__global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParams P) {
+__global__ void __launch_bounds__(G * WPG * 32, (KT <= 4 && G * WPG <= 8) ? 2 : 1) k_letkf_gram(const LetkfParams P) {
     constexpr int NT = G * WPG * 32;
     constexpr int KPT = KT + (ER > 0 ? 1 : 0);                // 8-row tiles of the staged [Yn; d] rows
     constexpr int kStages = gram_stages<T, KPT>();
@@ -309,7 +310,14 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
     unsigned char* work = smem_raw + ((sizeof(BlockHeader<G>) + 31) & ~size_t(31));
     double* wbuf = reinterpret_cast<double*>(work);                       // [S][G][TS]
     T* ybuf = reinterpret_cast<T*>(wbuf + (size_t)kStages * G * kTileObs);   // [S][TS][LDY]
+    double* ttab = reinterpret_cast<double*>(work + gram_smem_bytes<T, KT, G, WPG, ER>());   // [nseg * nint][6] taper table
     const T* ys = reinterpret_cast<const T*>(P.ys);
+    const bool use_tab = P.tt.coef != nullptr;
+    if (use_tab) {                                   // made visible by the barriers of setup_block
+        const int n2 = (int)(taper_tab_doubles(P.tt) >> 1);
+        for (int i = threadIdx.x; i < n2; i += G * WPG * 32)
+            reinterpret_cast<double2*>(ttab)[i] = reinterpret_cast<const double2*>(P.tt.coef)[i];
+    }
 
     const Geometry& g = P.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -388,7 +396,8 @@ __global__ void __launch_bounds__(G * WPG * 32, 1) k_letkf_gram(const LetkfParam
                 bool amb;
                 const double* ge = P.gext + (size_t)(P.block_off[blk] + gi) * g.n_ext;
                 const double* oe = P.oext + (size_t)so * g.n_ext;
-                w = pair_weight(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, ge, oe, amb);
+                if (use_tab) w = pair_weight_tab(g, P.tt, ttab, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, amb);
+                else w = pair_weight(g, H.gp[gi].x, H.gp[gi].y, H.gp[gi].z, po.x, po.y, po.z, ge, oe, amb);
                 if (amb) {                                 // rare: hand the pair to the host for the reference's own decision
                     ++my_amb;
                     const unsigned long long at = atomicAdd(&P.status->amb_found, 1ull);

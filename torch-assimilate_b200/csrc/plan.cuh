@@ -90,6 +90,8 @@ struct b200da_plan {
     b200da::DevBuf tmp_keys, tmp_cell, tmp_count, tmp_a, tmp_b, tmp_pos;
     b200da::DevBuf host_stage_obs, host_stage_y, host_stage_d, host_stage_x, host_stage_xa;
     b200da::DevBuf etkf_partial, etkf_w, stats, cmat, counter, ns_scratch;
+    b200da::DevBuf taper_tab;   // tabulated taper of the Gram kernels (b200da.cu: build_taper_table)
+    b200da::TaperTab tt{};
     b200da::DevBuf tc_centre;   // FP32 tcgen05 plans: centring constant of every pair column (b200da.cu: tc_centre_constants)
     b200da::DevBuf gext, oext;  // extra coordinate columns in block- / cell-sorted order (b200da_plan_set_extra)
     // ambiguity protocol and device-side error flags (common.cuh: PlanStatus, PairRec)
