@@ -679,7 +679,9 @@ def run_etkf(ctx, wname, dtype, steps, warmup, e2e_steps, cpu_info=None, min_sec
     del hx
     eng = LETKFEngine(k, 1, AbsDistance1D(), 1.0, inf_factor=w["rho"], dtype=tdt)
     sh = ShardedETKF(eng)
-    xa = torch.empty_like(x)
+    xa = sh.alloc_output(x.shape, tdt, dev)      # symmetric memory for N > 1: the update kernel writes into every rank's array
+    fused_gather = world > 1 and getattr(sh, "_peers", None) is not None
+    sh.fused_stores = os.environ.get("B200DA_ETKF_FUSED_STORES", "0") == "1"
 
     def step():
         sh.run(x, yn, d, xa, gather=True)
@@ -713,6 +715,19 @@ def run_etkf(ctx, wname, dtype, steps, warmup, e2e_steps, cpu_info=None, min_sec
     launches = launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ctx.max_over_ranks([e0.elapsed_time(e1)])[0] / steps
+    sharded_ms = None
+    if world > 1:                                # the analysed columns left where they were computed (no copy to the other ranks)
+        for _ in range(2):
+            sh.run(x, yn, d, xa, gather=False)
+        ctx.barrier()
+        e0.record()
+        for _ in range(steps):
+            sh.run(x, yn, d, xa, gather=False)
+        e1.record()
+        ctx.barrier()
+        sharded_ms = ctx.max_over_ranks([e0.elapsed_time(e1)])[0] / steps
+        sh.run(x, yn, d, xa, gather=True)        # the complete analysis again for the checks below
+        ctx.barrier()
     # parity property at full size: the sharded result equals the single-call result on this rank (N > 1), and the weights
     # satisfy the defining identities of core/etkf.py:57-77:  W_p^2 (C + a I) = (k - 1) I,  (C + a I) w_mean = b
     gram_full = eng.etkf_gram(yn, d).double()
@@ -773,7 +788,12 @@ def run_etkf(ctx, wname, dtype, steps, warmup, e2e_steps, cpu_info=None, min_sec
         "state_elements_per_sec": n * k / (ms_per_step * 1e-3),
         "config": {"workload": desc_of(w, dtype), "n_grid": n, "n_obs": m, "ens_size": k,
                    "sharding": "observation-sharded Gram -> all-reduce of (k+1)^2 doubles -> redundant k x k solve -> state-sharded "
-                               "update -> all-gather of the analysis ({0} GPU(s))".format(world),
+                               "update{1} ({0} GPU(s))".format(world, "" if world == 1 else (
+                                   (" whose kernel stores every analysed tile into the analysis array of every rank over NVLink "
+                                    "peer memory (b200da_apply_weights_cols_peers: update and all-gather in one kernel)" if sh.fused_stores
+                                    else " in 8 column pieces, each pushed into the analysis array of every rank (symmetric memory, NVLink "
+                                         "peer stores on a copy stream) while the next piece is computed") if fused_gather
+                                   else " -> all-gather of the analysis (NCCL)")),
                    "l2": "inputs exceed L2 (state {0:.1f} GB)".format(n * k * esz / 1e9) if n * k * esz > 2e8 else "inputs fit in L2; no flush",
                    "kernel": "k_etkf_gram + k_letkf_solve_ns + k_apply_global"},
         "roofline": {"bound": "tensor", "kernel": "k_apply_global (update Xa = W'^T X as a streaming DMMA GEMM)", "kernel_ms": t_upd,
@@ -792,6 +812,12 @@ def run_etkf(ctx, wname, dtype, steps, warmup, e2e_steps, cpu_info=None, min_sec
                           "against": "defining identities of core/etkf.py:57-77 on the device Gram (size-independent property; "
                                      "tests/test_gpu_parity.py checks the same kernels against the oracle at reduced size)"},
     }
+    if sharded_ms is not None:
+        line["sharded"] = {"value": n / (sharded_ms * 1e-3), "unit": UNIT, "ms_per_step": sharded_ms,
+                           "note": "the same analysis with every rank keeping only its own column range (what a sharded consumer "
+                                   "needs); `value` delivers the whole (k, N) analysis to every rank, which moves (N - N / G) k "
+                                   "elements into each GPU over NVLink (900 GB/s per direction) - for cfg4 on 8 GPUs 7 GB = 7.8 ms, "
+                                   "next to 9.4 ms for the whole HBM-bound update on one GPU"}
     if cpu_info is not None:
         line["cpu_baseline"] = cpu_info
     del x, xa, yn, d, eng

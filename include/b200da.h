@@ -254,6 +254,19 @@ int b200da_etkf_gram(b200da_plan* plan, const void* Yn, const void* d, int64_t n
 int b200da_etkf_weights_from_gram(b200da_plan* plan, const double* gram, int64_t n_obs_total, void* W, void* stream);
 int b200da_apply_weights_cols(b200da_plan* plan, const void* X, const void* W, int per_grid, int64_t col_begin,
                               int64_t col_end, int64_t n_grid, void* Xa, void* stream);
+/* The same update of columns [col_begin, col_end) with one (k, k) W, fused with the all-gather of the state-sharded global
+ * ETKF: every analysed tile is stored into Xa AND into the n_peers (<= 7) arrays Xa_peers[i] of the same shape that live in
+ * the memory of other GPUs of the node (peer-accessible device pointers, e.g. from CUDA IPC / symmetric memory), straight from
+ * the kernel's registers over NVLink.  Replaces "update, then gather the chunks" of the reference's dask graph
+ * (interface/etkf.py:99-120, xr.apply_ufunc over grid chunks + compute()).  The caller orders the ranks (a barrier after the
+ * call before anyone reads its Xa). */
+/* Columns [col_begin, col_end) of a (rows, ld) row-major array from src to dst (either may be peer memory of another GPU of the
+ * node): one strided copy on the copy engines (cudaMemcpy2DAsync), the transport of the overlapped update + all-gather in
+ * pytassim_b200/parallel.py (ShardedETKF).  No plan needed. */
+int b200da_peer_copy_cols(void* dst, const void* src, int64_t rows, int64_t ld, int64_t col_begin, int64_t col_end,
+                          int elem_bytes, void* stream);
+int b200da_apply_weights_cols_peers(b200da_plan* plan, const void* X, const void* W, int64_t col_begin, int64_t col_end,
+                                    int64_t n_grid, void* Xa, int n_peers, void* const* Xa_peers, void* stream);
 
 /* ---- iterative ensemble Kalman smoother (IEnKS), one iteration of the weight update -------------------------------- */
 

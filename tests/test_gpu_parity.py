@@ -335,7 +335,14 @@ def test_sharded_etkf_entry_points(dtype, tol):
     for c0, c1 in ((0, 333), (333, 4001), (4001, n)):
         eng.apply_weights_cols(x, w_whole, c0, c1, out2)
     assert torch.equal(out2, xa_whole)
+    # the update fused with the gather: the kernel stores the same columns into further ("peer") analysis arrays
+    out_a, out_b, out_c = (torch.full_like(x, float("nan")) for _ in range(3))
+    for c0, c1 in ((0, 333), (333, 4001), (4001, n)):
+        eng.apply_weights_cols(x, w_whole, c0, c1, out_a, peers=[out_b, out_c])
+    assert torch.equal(out_a, xa_whole) and torch.equal(out_b, xa_whole) and torch.equal(out_c, xa_whole)
     wg = w_whole[None].repeat(n, 1, 1).contiguous()
+    with pytest.raises(ValueError):
+        eng.apply_weights_cols(x, wg, 0, n, out_a, peers=[out_b])
     out3 = torch.full_like(x, float("nan"))
     for c0, c1 in ((0, 5000), (5000, n)):
         eng.apply_weights_cols(x, wg, c0, c1, out3)

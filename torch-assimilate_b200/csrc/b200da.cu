@@ -179,7 +179,7 @@ static int dispatch_etkf_gram(int kt, int f32, const void* yn, const void* d, in
 
 template <int MT>
 static int launch_apply_global(int f32, const void* x, const void* w, int k, int n_rows, int64_t n_grid, int64_t ld, void* xa,
-                               cudaStream_t st) {
+                               const ApplyPeers& peers, cudaStream_t st) {
     const size_t esz = f32 ? 4 : 8;
     const int vec_ok = ((ld * (int64_t)esz) % (2 * esz) == 0 && (reinterpret_cast<uintptr_t>(xa) % (2 * esz)) == 0) ? 1 : 0;
     const size_t smem = sizeof(double) * (size_t)MT * 8 * apply_lda(k);
@@ -196,16 +196,16 @@ static int launch_apply_global(int f32, const void* x, const void* w, int k, int
     }
     const int grid = (int)std::min<int64_t>((n_chunks + kApplyWarps - 1) / kApplyWarps, 148 * (int64_t)std::max(occ, 1));
     if (f32) {
-        k_apply_global<float, MT><<<grid, kApplyWarps * 32, smem, st>>>((const float*)x, (const float*)w, k, n_rows, n_grid, ld, vec_ok, (float*)xa);
+        k_apply_global<float, MT><<<grid, kApplyWarps * 32, smem, st>>>((const float*)x, (const float*)w, k, n_rows, n_grid, ld, vec_ok, (float*)xa, peers);
     } else {
-        k_apply_global<double, MT><<<grid, kApplyWarps * 32, smem, st>>>((const double*)x, (const double*)w, k, n_rows, n_grid, ld, vec_ok, (double*)xa);
+        k_apply_global<double, MT><<<grid, kApplyWarps * 32, smem, st>>>((const double*)x, (const double*)w, k, n_rows, n_grid, ld, vec_ok, (double*)xa, peers);
     }
     B200DA_LAUNCH_CHECK();
     return B200DA_OK;
 }
-#define B200DA_AG_CASE(MT) case MT: return launch_apply_global<MT>(f32, x, w, k, n_rows, n_grid, ld, xa, st);
+#define B200DA_AG_CASE(MT) case MT: return launch_apply_global<MT>(f32, x, w, k, n_rows, n_grid, ld, xa, peers, st);
 static int dispatch_apply_global(int f32, const void* x, const void* w, int k, int n_rows, int64_t n_grid, int64_t ld, void* xa,
-                                 cudaStream_t st) {
+                                 const ApplyPeers& peers, cudaStream_t st) {
     switch ((k + 7) / 8) {
         B200DA_AG_CASE(1) B200DA_AG_CASE(2) B200DA_AG_CASE(3) B200DA_AG_CASE(4) B200DA_AG_CASE(5) B200DA_AG_CASE(6)
         B200DA_AG_CASE(7) B200DA_AG_CASE(8) B200DA_AG_CASE(9) B200DA_AG_CASE(10) B200DA_AG_CASE(11) B200DA_AG_CASE(12)
@@ -958,9 +958,10 @@ int b200da_etkf_weights_from_gram(b200da_plan* pl, const double* gram, int64_t n
 }
 
 static int apply_weights_impl(b200da_plan* pl, const void* X, const void* W, int per_grid, int64_t n_grid, int64_t ld, void* Xa,
-                              cudaStream_t st) {
+                              cudaStream_t st, const ApplyPeers& peers = ApplyPeers{}) {
     const int k = pl->k;
-    if (!per_grid) return dispatch_apply_global(pl->dtype == B200DA_F32, X, W, k, pl->n_slices, n_grid, ld, Xa, st);
+    if (!per_grid) return dispatch_apply_global(pl->dtype == B200DA_F32, X, W, k, pl->n_slices, n_grid, ld, Xa, peers, st);
+    if (peers.n > 0) return B200DA_ERR_UNSUPPORTED;
     const size_t smem = 0;
     if (pl->dtype == B200DA_F32) {
         B200DA_CUDA(cudaFuncSetAttribute(k_apply_weights<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
@@ -989,6 +990,35 @@ int b200da_apply_weights_cols(b200da_plan* pl, const void* X, const void* W, int
     unsigned char* xa = static_cast<unsigned char*>(Xa) + (size_t)col_begin * esz;
     const unsigned char* w = static_cast<const unsigned char*>(W) + (per_grid ? (size_t)col_begin * pl->k * pl->k * esz : 0);
     return apply_weights_impl(pl, x, w, per_grid, col_end - col_begin, n_grid, xa, (cudaStream_t)stream);
+}
+
+int b200da_apply_weights_cols_peers(b200da_plan* pl, const void* X, const void* W, int64_t col_begin, int64_t col_end,
+                                    int64_t n_grid, void* Xa, int n_peers, void* const* Xa_peers, void* stream) {
+    if (!pl || !X || !W || !Xa || n_grid <= 0 || col_begin < 0 || col_end > n_grid || col_begin > col_end || n_peers < 0 ||
+        n_peers > 7 || (n_peers > 0 && !Xa_peers)) return B200DA_ERR_INVALID;
+    if (col_begin == col_end) return B200DA_OK;
+    const size_t esz = pl->dtype == B200DA_F32 ? 4 : 8;
+    ApplyPeers peers{};
+    peers.n = n_peers;
+    for (int i = 0; i < n_peers; ++i) {
+        if (!Xa_peers[i]) return B200DA_ERR_INVALID;
+        peers.p[i] = static_cast<unsigned char*>(Xa_peers[i]) + (size_t)col_begin * esz;
+    }
+    const unsigned char* x = static_cast<const unsigned char*>(X) + (size_t)col_begin * esz;
+    unsigned char* xa = static_cast<unsigned char*>(Xa) + (size_t)col_begin * esz;
+    return apply_weights_impl(pl, x, W, 0, col_end - col_begin, n_grid, xa, (cudaStream_t)stream, peers);
+}
+
+int b200da_peer_copy_cols(void* dst, const void* src, int64_t rows, int64_t ld, int64_t col_begin, int64_t col_end,
+                          int elem_bytes, void* stream) {
+    if (!dst || !src || rows <= 0 || ld <= 0 || col_begin < 0 || col_end > ld || col_begin > col_end ||
+        (elem_bytes != 4 && elem_bytes != 8)) return B200DA_ERR_INVALID;
+    if (col_begin == col_end) return B200DA_OK;
+    const size_t es = (size_t)elem_bytes;
+    B200DA_CUDA(cudaMemcpy2DAsync(static_cast<unsigned char*>(dst) + (size_t)col_begin * es, (size_t)ld * es,
+                                  static_cast<const unsigned char*>(src) + (size_t)col_begin * es, (size_t)ld * es,
+                                  (size_t)(col_end - col_begin) * es, (size_t)rows, cudaMemcpyDefault, (cudaStream_t)stream));
+    return B200DA_OK;
 }
 
 static int pack_impl(b200da_plan* pl, const void* xa, int64_t b0, int64_t b1, void* packed, int64_t ld, int unpack,

@@ -228,9 +228,14 @@ __host__ __device__ inline int apply_lda(int k) {          // leading dimension 
     while ((lda & 15) != 4) lda += 4;
     return lda;
 }
+// Further destinations of the analysed columns: the same array in the memory of other GPUs of the node (peer pointers, already
+// offset to this rank's first column).  The update kernel then IS the all-gather of the state-sharded global ETKF: every tile
+// it produces goes to the local analysis and over NVLink to every peer, overlapped with the DMMA work of the next tile.
+struct ApplyPeers { void* p[7]; int n; };
 template <typename T, int MT>
 __global__ void __launch_bounds__(kApplyWarps * 32, apply_min_ctas<T>(MT)) k_apply_global(const T* __restrict__ x, const T* __restrict__ w, int k, int n_rows,
-                                                                 int64_t n_grid, int64_t ld, int vec_ok, T* __restrict__ xa) {
+                                                                 int64_t n_grid, int64_t ld, int vec_ok, T* __restrict__ xa,
+                                                                 const ApplyPeers peers) {
     constexpr int kApplyNTW = apply_ntw<T>(MT);
     extern __shared__ double wsm_raw[];
     double* At = wsm_raw;                                   // [MT * 8][lda]: At[j][i] = W'[i][j]
@@ -260,7 +265,6 @@ __global__ void __launch_bounds__(kApplyWarps * 32, apply_min_ctas<T>(MT)) k_app
     const int64_t n_chunks = (n_grid + kApplyNTW * 8 - 1) / (kApplyNTW * 8);
     for (int srow = 0; srow < n_rows; ++srow) {
         const T* xs = x + (int64_t)srow * k * ld;
-        T* xo = xa + (int64_t)srow * k * ld;
         for (int64_t ch = (int64_t)blockIdx.x * kApplyWarps + warp; ch < n_chunks; ch += (int64_t)gridDim.x * kApplyWarps) {
             const int64_t g0 = ch * (kApplyNTW * 8);
             double acc[MT][kApplyNTW][2];
@@ -292,13 +296,16 @@ __global__ void __launch_bounds__(kApplyWarps * 32, apply_min_ctas<T>(MT)) k_app
                 for (int nt = 0; nt < kApplyNTW; ++nt) {
                     const int64_t g = g0 + nt * 8 + q * 2;
                     if (j < k) {
-                        T* dst = xo + (int64_t)j * ld + g;
-                        if (g + 1 < n_grid && vec_ok) {
-                            if constexpr (sizeof(T) == 8) *reinterpret_cast<double2*>(dst) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-                            else *reinterpret_cast<float2*>(dst) = make_float2((float)acc[mt][nt][0], (float)acc[mt][nt][1]);
-                        } else {
-                            if (g < n_grid) dst[0] = (T)acc[mt][nt][0];
-                            if (g + 1 < n_grid) dst[1] = (T)acc[mt][nt][1];
+                        const int64_t off = (int64_t)srow * k * ld + (int64_t)j * ld + g;
+                        for (int pd = -1; pd < peers.n; ++pd) {
+                            T* dst = (pd < 0 ? xa : static_cast<T*>(peers.p[pd])) + off;
+                            if (g + 1 < n_grid && vec_ok) {
+                                if constexpr (sizeof(T) == 8) *reinterpret_cast<double2*>(dst) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                                else *reinterpret_cast<float2*>(dst) = make_float2((float)acc[mt][nt][0], (float)acc[mt][nt][1]);
+                            } else {
+                                if (g < n_grid) dst[0] = (T)acc[mt][nt][0];
+                                if (g + 1 < n_grid) dst[1] = (T)acc[mt][nt][1];
+                            }
                         }
                     }
                 }

@@ -56,6 +56,8 @@ SIGNATURES = {
     "b200da_etkf_gram": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "b200da_etkf_weights_from_gram": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "b200da_apply_weights_cols": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i64, _vp, _vp]),
+    "b200da_peer_copy_cols": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i, _vp]),
+    "b200da_apply_weights_cols_peers": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i, _vp, _vp]),
     "b200da_pack_columns": (_i, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "b200da_unpack_columns": (_i, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "b200da_block_offsets": (_i, [_vp, _vp]),

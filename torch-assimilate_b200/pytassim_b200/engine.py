@@ -442,21 +442,42 @@ class LETKFEngine(object):
             _cabi.check(self.lib.b200da_etkf_weights_from_gram(self._plan, _ptr(g), int(n_obs_total), _ptr(w), _stream()))
         return w
 
-    def apply_weights_cols(self, state, weights, col_begin, col_end, out):
+    def apply_weights_cols(self, state, weights, col_begin, col_end, out, peers=None):
         """``_apply_weights`` (interface/base.py:257-278) on grid columns [col_begin, col_end) of ``state`` (n_slices, k, N)
-        into the same columns of ``out``; the other columns of ``out`` are left untouched."""
+        into the same columns of ``out``; the other columns of ``out`` are left untouched.  ``peers``: tensors of ``out``'s shape
+        and dtype in the memory of other GPUs (peer-accessible, e.g. symmetric memory) that receive the same columns from the
+        kernel itself — the all-gather of the state-sharded global ETKF fused into the update (one (k, k) W only)."""
         x = _dev(state, dtype=self.dtype, device=self.device)
         n_grid = x.shape[-1]
         w = _dev(weights, dtype=self.dtype, device=self.device)
         per_grid = 1 if w.dim() == 3 else 0
         if out.dtype != self.dtype or not out.is_contiguous() or out.numel() != x.numel():
             raise ValueError("out must be a contiguous {0} tensor of the state's shape".format(self.dtype))
+        if peers:
+            if per_grid:
+                raise ValueError("peer destinations need one (ens_size, ens_size) weight matrix")
+            for t in peers:
+                if t.dtype != self.dtype or not t.is_contiguous() or t.numel() != x.numel():
+                    raise ValueError("peer destinations must be contiguous {0} tensors of the state's shape".format(self.dtype))
+            arr = (ctypes.c_void_p * len(peers))(*[t.data_ptr() for t in peers])
+            with torch.cuda.device(self.device):
+                _cabi.check(self.lib.b200da_apply_weights_cols_peers(self._plan, _ptr(x), _ptr(w), int(col_begin), int(col_end), n_grid,
+                                                                     _ptr(out), len(peers), arr, _stream()))
+            return out
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.b200da_apply_weights_cols(self._plan, _ptr(x), _ptr(w), per_grid, int(col_begin), int(col_end),
                                                            n_grid, _ptr(out), _stream()))
         return out
 
     # -- multi-GPU helpers --------------------------------------------------------------------------------------
+    def peer_copy_cols(self, dst, src, col_begin, col_end, stream=None):
+        """Columns [col_begin, col_end) of the (rows, N) view of ``src`` into the same place of ``dst`` (a tensor of the same
+        shape, possibly in another GPU's memory) with one strided copy-engine transfer on ``stream`` (default: current)."""
+        n = src.shape[-1]
+        rows = src.numel() // n
+        st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+        _cabi.check(self.lib.b200da_peer_copy_cols(_ptr(dst), _ptr(src), rows, n, int(col_begin), int(col_end), src.element_size(), st))
+
     def block_offset(self, block):
         return int(self.lib.b200da_block_offset(self._plan, int(block)))
 

@@ -167,6 +167,10 @@ class ShardedETKF(object):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.align = int(align)
         self._recv = None
+        self._peers = None
+        self._copy_stream = None
+        self.pieces = 8                  # column pieces of the overlapped update + peer copies (symmetric outputs)
+        self.fused_stores = False        # True: peer stores from inside the update kernel (measured slower: 16-byte NVLink stores)
 
     def ranges(self, n):
         """Contiguous split of n columns into world ranges whose boundaries are multiples of ``align`` (16-byte aligned rows
@@ -188,12 +192,68 @@ class ShardedETKF(object):
             dist.all_reduce(gram, op=dist.ReduceOp.SUM, group=self.group)
         return self.engine.etkf_weights_from_gram(gram, m)
 
+    def alloc_output(self, shape, dtype, device):
+        """An analysis array every rank of the group can write into: symmetric memory (CUDA peer mappings over NVLink,
+        ``torch.distributed._symmetric_memory``) when the node offers it, else an ordinary tensor.  With a symmetric output
+        ``run(..., gather=True)`` needs no collective after the update: the update kernel stores every analysed tile into the
+        output of every rank (``b200da_apply_weights_cols_peers``)."""
+        self._peers = None
+        if self.world > 1 and torch.device(device).type == "cuda":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                group = self.group if self.group is not None else dist.group.WORLD
+                out = symm.empty(*tuple(int(v) for v in shape), dtype=dtype, device=device)
+                hdl = symm.rendezvous(out, group=group)
+                peers = [hdl.get_buffer(r, tuple(shape), dtype) for r in range(self.world) if r != self.rank]
+                self._peers = (out.data_ptr(), peers, hdl)
+                return out
+            except Exception as exc:                          # no NVLink peer access / unsupported build: plain gather path
+                self._peers = None
+                self.symmetric_error = repr(exc)
+        return torch.empty(tuple(shape), dtype=dtype, device=device)
+
     def run(self, x, normed_perts, normed_obs, out, gather=True):
         """x, out: (n_slices, k, N).  Updates this rank's column range of ``out`` (all columns when ``gather``)."""
         w = self.weights(normed_perts, normed_obs)
         n = int(x.shape[-1])
         cols = self.ranges(n)
         c0, c1 = cols[self.rank]
+        peers = getattr(self, "_peers", None)
+        if gather and self.world > 1 and peers is not None and peers[0] == out.data_ptr() and w.dim() == 2:
+            if self.fused_stores:
+                # the update kernel itself stores every tile into every rank's array (b200da_apply_weights_cols_peers)
+                self.engine.apply_weights_cols(x, w, c0, c1, out, peers=peers[1])
+            else:
+                # update in column pieces; behind each piece a copy stream pushes it into every peer's array over NVLink
+                # (row-contiguous 16-byte stores of whole lines) while the next piece is computed
+                rows = out.shape[0] * out.shape[1]
+                flat = out.view(rows, n)
+                pflat = [p.view(rows, n) for p in peers[1]]
+                main = torch.cuda.current_stream()
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=out.device)
+                side = self._copy_stream
+                npiece = max(1, min(self.pieces, (c1 - c0) // (64 * self.align)))
+                units = (c1 - c0 + self.align - 1) // self.align
+                for i in range(npiece):
+                    a = c0 + min(c1 - c0, (units * i // npiece) * self.align)
+                    b = c0 + min(c1 - c0, (units * (i + 1) // npiece) * self.align)
+                    if b <= a:
+                        continue
+                    self.engine.apply_weights_cols(x, w, a, b, out)
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    if hasattr(self.engine, "peer_copy_cols"):
+                        for pt in peers[1]:                   # copy engines: one strided transfer per peer and piece
+                            self.engine.peer_copy_cols(pt, out, a, b, stream=side)
+                    else:
+                        with torch.cuda.stream(side):
+                            for pf in pflat:
+                                pf[:, a:b].copy_(flat[:, a:b], non_blocking=True)
+                main.wait_stream(side)
+            peers[2].barrier()                                # every rank's stores have landed before anyone reads its output
+            return out
         self.engine.apply_weights_cols(x, w, c0, c1, out)
         if gather and self.world > 1:
             self._gather(out, cols)
