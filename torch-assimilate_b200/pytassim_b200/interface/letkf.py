@@ -2,7 +2,7 @@
 import numpy as np
 import torch
 
-from .base import index_to_array
+from .base import index_to_array, to_host
 from .etkf import ETKF
 from ..engine import LETKFEngine
 
@@ -74,5 +74,5 @@ class LETKF(ETKF):
             xd = torch.as_tensor(x).to(eng.device)
             _, weights = eng.analyse(xd, return_weights=True)
             weights = self._weights_through_store(state, weights.cpu().numpy())
-            return eng.apply_weights(xd, weights).cpu().numpy()
-        return eng.analyse(torch.as_tensor(x)).cpu().numpy()
+            return to_host(eng.apply_weights(xd, weights))
+        return to_host(eng.analyse(torch.as_tensor(x)))

@@ -43,7 +43,12 @@ class DataArray(object):
         for dim, idx in indexers.items():
             ax = self.dims.index(dim)
             idx = np.atleast_1d(idx)
-            values = np.take(values, idx, axis=ax)
+            if idx.dtype.kind in "iu" and idx.size > 0 and idx[0] >= 0 and np.array_equal(idx, np.arange(idx[0], idx[0] + idx.size)):
+                sl = [slice(None)] * values.ndim            # a contiguous run of positions: a view, no copy of the data
+                sl[ax] = slice(int(idx[0]), int(idx[0]) + idx.size)
+                values = values[tuple(sl)]
+            else:
+                values = np.take(values, idx, axis=ax)
             coords[dim] = self.indexes[dim][idx]
         return DataArray(values, coords, self.dims)
 
