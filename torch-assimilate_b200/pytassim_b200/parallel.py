@@ -230,9 +230,9 @@ class ShardedETKF(object):
                 flat = out.view(rows, n)
                 pflat = [p.view(rows, n) for p in peers[1]]
                 main = torch.cuda.current_stream()
-                if self._copy_stream is None:
-                    self._copy_stream = torch.cuda.Stream(device=out.device)
-                side = self._copy_stream
+                if self._copy_stream is None:                 # one copy stream per peer: the transfers to different GPUs overlap
+                    self._copy_stream = [torch.cuda.Stream(device=out.device) for _ in peers[1]]
+                sides = self._copy_stream
                 npiece = max(1, min(self.pieces, (c1 - c0) // (64 * self.align)))
                 units = (c1 - c0 + self.align - 1) // self.align
                 for i in range(npiece):
@@ -243,15 +243,17 @@ class ShardedETKF(object):
                     self.engine.apply_weights_cols(x, w, a, b, out)
                     ev = torch.cuda.Event()
                     ev.record(main)
-                    side.wait_event(ev)
-                    if hasattr(self.engine, "peer_copy_cols"):
-                        for pt in peers[1]:                   # copy engines: one strided transfer per peer and piece
-                            self.engine.peer_copy_cols(pt, out, a, b, stream=side)
-                    else:
-                        with torch.cuda.stream(side):
-                            for pf in pflat:
-                                pf[:, a:b].copy_(flat[:, a:b], non_blocking=True)
-                main.wait_stream(side)
+                    for q in range(len(sides)):               # start with a different peer on every rank: no incast on one GPU
+                        j = (q + self.rank) % len(sides)
+                        side = sides[j]
+                        side.wait_event(ev)
+                        if hasattr(self.engine, "peer_copy_cols"):
+                            self.engine.peer_copy_cols(peers[1][j], out, a, b, stream=side)     # copy engine, strided
+                        else:
+                            with torch.cuda.stream(side):
+                                pflat[j][:, a:b].copy_(flat[:, a:b], non_blocking=True)
+                for side in sides:
+                    main.wait_stream(side)
             peers[2].barrier()                                # every rank's stores have landed before anyone reads its output
             return out
         self.engine.apply_weights_cols(x, w, c0, c1, out)
