@@ -197,11 +197,12 @@ __device__ __forceinline__ void store_tiles_sub(double* __restrict__ S, const do
                 const double v0 = acc[n][0] * scale, v1 = acc[n][1] * scale;
                 if (mt != nt) {
                     *reinterpret_cast<double2*>(tp + tile_elem(r, c)) = make_double2(v0, v1);
-                } else {
-                    if (c < r) { tp[tile_elem(r, c)] = v0; tp[tile_elem(c, r)] = v0; }
-                    else if (c == r) tp[tile_elem(r, c)] = v0 + diag;
-                    if (c + 1 < r) { tp[tile_elem(r, c + 1)] = v1; tp[tile_elem(c + 1, r)] = v1; }
-                    else if (c + 1 == r) tp[tile_elem(r, c + 1)] = v1 + diag;
+                } else {                       // four predicated stores, no divergent branches
+                    const double d0 = c == r ? v0 + diag : v0, d1 = c + 1 == r ? v1 + diag : v1;
+                    if (c <= r) tp[tile_elem(r, c)] = d0;
+                    if (c < r) tp[tile_elem(c, r)] = v0;
+                    if (c + 1 <= r) tp[tile_elem(r, c + 1)] = d1;
+                    if (c + 1 < r) tp[tile_elem(c + 1, r)] = v1;
                 }
                 ++n;
             }
@@ -325,13 +326,13 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         double lo = fmin(lo_abs * inv_sc, 1.0);
         double g = 3.0 / (1.0 + sqrt(lo) + lo);
         double sg = sqrt(g);
+        // e = tile * 64 + tile_elem(r, c); the tile coordinates (mt, nt) are stepped along with e (GT <= 128: at most two tiles
+        // per step) instead of being recovered from the tile index with a square root
+        int tile = gtid >> 6, mt = tile, nt = 0;
+        if (tile > 0) { mt = 1; nt = tile - 1; if (tile > 2) { mt = 2; nt = tile - 3; } }     // tiles 0..3: (0,0) (1,0) (1,1) (2,0)
         for (int e = gtid; e < MAT; e += GT) {
-            const int tile = e >> 6, r = (e >> 3) & 7, c = (e & 7) ^ ((r & 2) << 1);   // e = tile*64 + tile_elem(r, c)
-            // tile -> (mt, nt): diagonal tiles sit at mt (mt + 3) / 2
-            int mt = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
-            while (mt * (mt + 1) / 2 > tile) --mt;
-            while ((mt + 1) * (mt + 2) / 2 <= tile) ++mt;
-            const int nt = tile - mt * (mt + 1) / 2;
+            for (; tile < (e >> 6); ++tile) { if (++nt > mt) { ++mt; nt = 0; } }
+            const int r = (e >> 3) & 7, c = (e & 7) ^ ((r & 2) << 1);
             const bool on_diag = (mt == nt) && (r == c);
             double y = (Y[e] + (on_diag ? shift : 0.0)) * inv_sc;
             if (on_diag && mt * 8 + r >= k) y = 1.0;                 // padding: decoupled unit eigenvalues
@@ -376,9 +377,9 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         // ---- one level: D = A^(-1/2) = Z / sqrt(s) ---------------------------------------------------------------------
         iters = inv_sqrt(0.0, s, alpha);
         const double zs = sqrt(1.0 / s);
-        for (int e = gtid; e < k * k; e += GT) {
-            const int i = e / k, j = e - i * k;
+        for (int e = gtid, i = gtid / k, j = gtid - (gtid / k) * k; e < k * k; e += GT) {
             D[i * LDW + j] = sym_get(Z, i, j) * zs;
+            for (j += GT; j >= k; j -= k) ++i;
         }
     } else {
         // ---- stiff matrix (s / a above P.stiff): two levels.  Every product of the iteration is stored as a symmetric matrix
@@ -420,11 +421,11 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         store_full_sub<KT, WPM, SUB, true>(gF, acc, lane);
         ns_sync<WPM>(bar_id);
         const double zs = 0.5 * sqrt(1.0 / s2);
-        for (int e = gtid; e < k * k; e += GT) {
-            const int i = e / k, j = e - i * k;
+        for (int e = gtid, i = gtid / k, j = gtid - (gtid / k) * k; e < k * k; e += GT) {
             const double fij = __ldcg(gF + ((i >> 3) * KT + (j >> 3)) * 64 + tile_elem(i & 7, j & 7));
             const double fji = __ldcg(gF + ((j >> 3) * KT + (i >> 3)) * 64 + tile_elem(j & 7, i & 7));
             D[i * LDW + j] = (fij + fji) * zs;
+            for (j += GT; j >= k; j -= k) ++i;
         }
     }
     if (P.stats && gtid == 0) { atomicAdd(P.stats + 2, (unsigned long long)iters); atomicAdd(P.stats + 3, 1ull); }
@@ -468,11 +469,11 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
     const double sk = sqrt((double)(k - 1));
     const int64_t gi = P.gpos[P.slot_base + slot].id;
     const int f32 = P.io_f32;
-    for (int e = gtid; e < k * k; e += GT) {                      // W = w_mean 1^T + sqrt(k-1) D     core/etkf.py:75-76,102
-        const int i = e / k, j = e - i * k;
+    for (int e = gtid, i = gtid / k, j = gtid - (gtid / k) * k; e < k * k; e += GT) {   // W = w_mean 1^T + sqrt(k-1) D   core/etkf.py:75-76,102
         const double w = fma(sk, D[i * LDW + j], wbar[i]);
         D[i * LDW + j] = w;
         if (P.w_out) st_io(P.w_out, gi * (int64_t)k * k + e, w, f32);
+        for (j += GT; j >= k; j -= k) ++i;
     }
     ns_sync<WPM>(bar_id);
     // ---- x_a[s, j, g] = mean + sum_i (x[s, i, g] - mean) W[i][j]                                interface/base.py:257-278
