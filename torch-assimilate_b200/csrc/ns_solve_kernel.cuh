@@ -119,7 +119,10 @@ __device__ __forceinline__ void sym_gemm_sub(const double* L, const double* R, c
                                              double (&acc)[NsCfg<KT, WPM>::OWN][2]) {
 #pragma unroll
     for (int i = 0; i < NsCfg<KT, WPM>::OWN; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
-#pragma unroll 1
+    // small matrices: fully unrolled, every fragment offset a compile-time constant (the run-time selection between a tile and
+    // its transpose was 14 % of the instructions at k = 40); larger ones keep the loop (code size, registers)
+    constexpr int kUnrollKt = KT <= 6 ? KT : 1;
+#pragma unroll kUnrollKt
     for (int kt = 0; kt < KT; ++kt) {
         gemm_kstep<KT, WPM, SUB, 0, LM, RM>(L, R, kt, fo, acc);
         gemm_kstep<KT, WPM, SUB, 1, LM, RM>(L, R, kt, fo, acc);
