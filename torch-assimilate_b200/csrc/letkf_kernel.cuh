@@ -351,21 +351,30 @@ __global__ void __launch_bounds__(G * WPG * 32, (KT <= 4 && G * WPG <= 8) ? 2 : 
     unsigned long long my_amb = 0;
 
     // 1. refill the survivor ring (CTA-collective: two barriers per pass of NT candidates; needed once every few tiles)
+    // The position of this thread's candidate of the NEXT refill pass is fetched one pass ahead (s_next, px / py / pz): the
+    // L2 latency of that load (the one long wait of a pass: all warps sit in the pass together, the DMMA pipe idles) is hidden
+    // behind the tiles computed in between.
+    int s_next = -1;
+    double px = 0.0, py = 0.0, pz = 0.0;
+    auto fetch_next = [&]() {
+        const int c = cand_pos + tid;
+        s_next = -1;
+        if (c < cand_total) {
+            int lo_ = 0, hi_ = n_runs;            // run_pref[lo_] <= c < run_pref[hi_]
+            while (hi_ - lo_ > 1) {
+                const int mid = (lo_ + hi_) >> 1;
+                if (H.run_pref[mid] <= c) lo_ = mid; else hi_ = mid;
+            }
+            s_next = H.run_start[lo_] + (c - H.run_pref[lo_]);
+            const Pos4 po = P.opos[s_next];
+            px = po.x; py = po.y; pz = po.z;
+        }
+    };
+    fetch_next();
     auto refill = [&]() {
         while (ring_tail - ring_head < kTileObs && cand_pos < cand_total) {
-            const int c = cand_pos + tid;
-            bool keep = false;
-            int s = 0;
-            if (c < cand_total) {
-                int lo_ = 0, hi_ = n_runs;            // run_pref[lo_] <= c < run_pref[hi_]
-                while (hi_ - lo_ > 1) {
-                    const int mid = (lo_ + hi_) >> 1;
-                    if (H.run_pref[mid] <= c) lo_ = mid; else hi_ = mid;
-                }
-                s = H.run_start[lo_] + (c - H.run_pref[lo_]);
-                const Pos4 po = P.opos[s];
-                keep = bin_distance(g, bcx, bcy, bcz, po.x, po.y, po.z) <= reach;
-            }
+            const int s = s_next;
+            const bool keep = s >= 0 && bin_distance(g, bcx, bcy, bcz, px, py, pz) <= reach;
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             if (lane == 0) H.warp_counts[warp] = __popc(bal);
             __syncthreads();
@@ -380,6 +389,7 @@ __global__ void __launch_bounds__(G * WPG * 32, (KT <= 4 && G * WPG <= 8) ? 2 : 
             __syncthreads();
             ring_tail += total;
             cand_pos += NT;
+            fetch_next();
         }
     };
     // 2. + 3. this thread's share of the next tile (no barrier inside): localization weights, one (slot, grid point) pair per
