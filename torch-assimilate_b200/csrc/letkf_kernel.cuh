@@ -107,7 +107,7 @@ __device__ __forceinline__ void gram_tile(const T* __restrict__ ytile, const dou
     for (int ks = 0; ks < kTileObs / 4; ++ks) {
         const int j = ks * 4 + (lane & 3);
         const double w = wrow[j];
-        if (__all_sync(0xffffffffu, w == 0.0)) continue;
+        if (__all_sync(0xffffffffu, ((__double2hiint(w) << 1) | __double2loint(w)) == 0)) continue;    // w == 0 on the integer pipe (the FP64 pipe is the busy one)
         const T* yr = ytile + j * LDY + (lane >> 2);
         double f[KT];
 #pragma unroll
