@@ -297,8 +297,10 @@ __global__ void __launch_bounds__(kApplyWarps * 32, apply_min_ctas<T>(MT)) k_app
                     const int64_t g = g0 + nt * 8 + q * 2;
                     if (j < k) {
                         const int64_t off = (int64_t)srow * k * ld + (int64_t)j * ld + g;
-                        for (int pd = -1; pd < peers.n; ++pd) {
-                            T* dst = (pd < 0 ? xa : static_cast<T*>(peers.p[pd])) + off;
+#pragma unroll
+                        for (int pd = -1; pd < 7; ++pd) {     // unrolled: static indices into the kernel parameter (no local copy)
+                            if (pd >= peers.n) break;
+                            T* dst = (pd < 0 ? xa : static_cast<T*>(peers.p[pd < 0 ? 0 : pd])) + off;
                             if (g + 1 < n_grid && vec_ok) {
                                 if constexpr (sizeof(T) == 8) *reinterpret_cast<double2*>(dst) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
                                 else *reinterpret_cast<float2*>(dst) = make_float2((float)acc[mt][nt][0], (float)acc[mt][nt][1]);
