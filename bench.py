@@ -231,7 +231,7 @@ class ClockSampler(object):
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0, period_ms=100):
+    def __init__(self, gpu_index=0, period_ms=int(os.environ.get("B200DA_CLOCK_PERIOD_MS", "100"))):
         self.rows, self.proc, self.gpu, self.period = [], None, gpu_index, period_ms
 
     def start(self):
@@ -411,11 +411,16 @@ def run_letkf(ctx, wname, dtype, steps, warmup, e2e_steps, data=None, fraction=1
         oc_dev = oc_host.to(dev).t().contiguous()                                                     # (M, n_coord)
     else:
         gc_dev = torch.empty((n_grid, n_coord), dtype=f64, device=dev)
-        x_dev = torch.empty((1, k, n_grid), dtype=tdt, device=dev)
-        y_dev = torch.empty((k, n_obs), dtype=tdt, device=dev)
-        d_dev = torch.empty((n_obs,), dtype=tdt, device=dev)
-        oc_dev = torch.empty((n_obs, n_coord), dtype=f64, device=dev)
+    inbuf = None
     if world > 1:
+        # the per-analysis inputs are views of ONE flat buffer: they reach the other ranks with one transport call per step
+        from pytassim_b200.parallel import InputBuffer
+        inbuf = InputBuffer([((n_obs, n_coord), f64), ((k, n_obs), tdt), ((n_obs,), tdt), ((1, k, n_grid), tdt)], dev, world,
+                            rank=rank, mode=os.environ.get("B200DA_INPUT_TRANSPORT", "broadcast"))
+        if rank == 0:
+            for v, src in zip(inbuf.views, (oc_dev, y_dev, d_dev, x_dev)):
+                v.copy_(src)
+        oc_dev, y_dev, d_dev, x_dev = inbuf.views
         dist.broadcast(gc_dev, 0)          # the grid is static: part of the plan, outside the timed region
     period = float(n_grid)
     metric = mm.HaversineDistance(6371.0) if w["kind"] == "sphere" else mm.PeriodicDistance1D(period)
@@ -430,33 +435,47 @@ def run_letkf(ctx, wname, dtype, steps, warmup, e2e_steps, data=None, fraction=1
 
     # algorithmic work: local observation count of every grid point (exact, from the neighbour-count kernel)
     if world > 1:
-        for t in (oc_dev, y_dev, d_dev, x_dev):
-            dist.broadcast(t, 0)
+        inbuf.broadcast(0)
     eng.bin_obs(oc_dev, y_dev, d_dev)
     counts, _ = eng.neighbour_counts()
     sharded = ShardedAnalysis(eng, weights=counts if fraction >= 1.0 else None)
-    b0, b1 = sharded.ranges[rank]
-    my_ranges = [(b0, b1)] if fraction >= 1.0 else sample_blocks(eng.n_blocks, fraction)
     order = eng.grid_order()
     counts_sorted = counts[order.long()]
-    my_pairs = my_points = 0
-    for (c0, c1) in my_ranges:
-        s0, s1 = eng.block_offset(c0), eng.block_offset(c1)
-        my_pairs += int(counts_sorted[s0:s1].sum().item())
-        my_points += s1 - s0
-    flops_gram = 2.0 * k * k * my_pairs + 2.0 * k * my_pairs
-    flops_solve = (13.0 * k ** 3 + 2.0 * k * k) * my_points
+
+    def work_of_rank():
+        """This rank's block ranges and their algorithmic work (the ranges move when the split is re-cut after a warm-up step)."""
+        b0, b1 = sharded.ranges[rank]
+        ranges = [(b0, b1)] if fraction >= 1.0 else sample_blocks(eng.n_blocks, fraction)
+        pairs = points = 0
+        for (c0, c1) in ranges:
+            s0, s1 = eng.block_offset(c0), eng.block_offset(c1)
+            pairs += int(counts_sorted[s0:s1].sum().item())
+            points += s1 - s0
+        return ranges, 2.0 * k * k * pairs + 2.0 * k * pairs, (13.0 * k ** 3 + 2.0 * k * k) * points, points
+    my_ranges, flops_gram, flops_solve, my_points = work_of_rank()
     p_mean = float(counts.double().mean().item())
-    del counts_sorted, order
     xa_dev = torch.empty_like(x_dev)
     kernel_ms, gram_ms, solve_ms, amb = [], [], [], []
+
+    phases = os.environ.get("B200DA_BENCH_PHASES", "0") == "1"
+    phase_ms = []
 
     def step(record=False):
         if fraction >= 1.0:
             # rank 0 owns the inputs: broadcast obs-space arrays + state once per step (no-op for one GPU)
-            sharded.broadcast_inputs([oc_dev, y_dev, d_dev, x_dev])
+            if phases and record:
+                pe = [torch.cuda.Event(True) for _ in range(4)]
+                pe[0].record()
+            sharded.broadcast_inputs(inbuf if inbuf is not None else [oc_dev, y_dev, d_dev, x_dev])
+            if phases and record:
+                pe[1].record()
             eng.bin_obs(oc_dev, y_dev, d_dev)
+            if phases and record:
+                pe[2].record()
             sharded.run(x_dev, xa_dev)
+            if phases and record:
+                pe[3].record(); pe[3].synchronize()
+                phase_ms.append([pe[i].elapsed_time(pe[i + 1]) for i in range(3)] + [eng.last_kernel_ms()])
             if record:
                 kernel_ms.append(eng.last_kernel_ms())
                 gm, sm = eng.last_phase_ms()
@@ -473,6 +492,10 @@ def run_letkf(ctx, wname, dtype, steps, warmup, e2e_steps, data=None, fraction=1
 
     for _ in range(max(warmup, 1)):
         step()
+        if world > 1 and fraction >= 1.0 and n_grid >= 100_000:
+            sharded.rebalance(eng.last_kernel_ms())      # feedback on the work split: same network and grid every step
+    my_ranges, flops_gram, flops_solve, my_points = work_of_rank()
+    del counts_sorted, order
     ctx.barrier()
     if min_seconds > 0.0:                       # short workloads: enough steps for the clock sampler to see the run
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
@@ -480,6 +503,7 @@ def run_letkf(ctx, wname, dtype, steps, warmup, e2e_steps, data=None, fraction=1
         est = ctx.max_over_ranks([e0.elapsed_time(e1)])[0]
         steps = int(max(steps, min(20000, math.ceil(min_seconds * 1e3 / max(est, 1e-3)))))
     sampler = ClockSampler(ctx.local_rank).start() if rank == 0 else None
+    ctx.barrier()                                # rank 0 waited for the sampler's first row: nobody starts the clock early
     l0 = launch_count()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
@@ -488,6 +512,9 @@ def run_letkf(ctx, wname, dtype, steps, warmup, e2e_steps, data=None, fraction=1
     e1.record()
     ctx.barrier()
     launches = launch_count() - l0
+    if phases and phase_ms:
+        pm = np.mean(np.asarray(phase_ms), axis=0)
+        _log("rank {0} phases ms: transport {1:.2f} bin_obs {2:.2f} analyse+gather {3:.2f} (kernels {4:.2f})".format(rank, *pm))
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms, kern_ms, g_ms, s_ms = ctx.max_over_ranks([e0.elapsed_time(e1), float(np.mean(kernel_ms)), float(np.mean(gram_ms)),
                                                           float(np.mean(solve_ms))])
@@ -641,7 +668,9 @@ def run_letkf(ctx, wname, dtype, steps, warmup, e2e_steps, data=None, fraction=1
         "dtype": dtype, "data": "synthetic",
         "config": {"workload": desc_of(w, dtype), "n_grid": n_grid, "n_obs": n_obs, "ens_size": k, "mean_local_obs": p_mean,
                    "sharding": "grid-point blocks split over {0} GPU(s) in contiguous ranges balanced by local-observation "
-                               "count; obs broadcast from rank 0, analysis all-gathered".format(world),
+                               "count and re-cut after every warm-up step from the ranks' measured times; inputs from rank 0 as one flat buffer "
+                               "({1}), analysis all-gathered".format(
+                                   world, "n/a" if inbuf is None else inbuf.mode),
                    "l2": l2, "kernel": kname},
         "roofline": roofline,
         "solver": "FP64 Newton-Schulz (k x k solve and update in FP64 for both plan dtypes)",
@@ -705,6 +734,7 @@ def run_etkf(ctx, wname, dtype, steps, warmup, e2e_steps, cpu_info=None, min_sec
     t_gram, t_solve, t_upd = ctx.max_over_ranks([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])])
     ctx.barrier()
     sampler = ClockSampler(ctx.local_rank).start() if rank == 0 else None
+    ctx.barrier()                                # rank 0 waited for the sampler's first row: nobody starts the clock early
     l0 = launch_count()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
