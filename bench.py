@@ -460,13 +460,14 @@ def run_letkf(ctx, wname, dtype, steps, warmup, e2e_steps, data=None, fraction=1
     phases = os.environ.get("B200DA_BENCH_PHASES", "0") == "1"
     phase_ms = []
 
-    def step(record=False):
+    def step(record=False, transport=True):
         if fraction >= 1.0:
             # rank 0 owns the inputs: broadcast obs-space arrays + state once per step (no-op for one GPU)
             if phases and record:
                 pe = [torch.cuda.Event(True) for _ in range(4)]
                 pe[0].record()
-            sharded.broadcast_inputs(inbuf if inbuf is not None else [oc_dev, y_dev, d_dev, x_dev])
+            if transport:
+                sharded.broadcast_inputs(inbuf if inbuf is not None else [oc_dev, y_dev, d_dev, x_dev])
             if phases and record:
                 pe[1].record()
             eng.bin_obs(oc_dev, y_dev, d_dev)
@@ -542,26 +543,96 @@ def run_letkf(ctx, wname, dtype, steps, warmup, e2e_steps, data=None, fraction=1
                "ms_per_step": dt * 1e3, "steps": n_e2e, "api": "LETKFEngine.analyse_host -> b200da_letkf_host"}
         e2e["max_abs_diff_vs_device_path"] = float((out_host - xa_dev.cpu()).abs().max())
     else:
-        # N > 1: inputs start in rank 0's pinned host memory, result is read back on rank 0
+        # N > 1: the inputs sit in host memory of the node (POSIX shared memory written by rank 0, page-locked by every rank):
+        # every rank uploads 1 / N of the bytes over its own PCIe link, one in-place all-gather over NVLink completes the
+        # buffer on every GPU; after the analysis every rank downloads 1 / N of the result into the shared output.  Falls back
+        # to "rank 0 uploads everything, broadcast" when the shared segment cannot be page-locked.
+        from multiprocessing import shared_memory, resource_tracker
+
+        def shared_pinned(nbytes, tag):
+            name = [None]
+            if rank == 0:
+                name[0] = "b200da_{0}_{1}".format(os.getpid(), tag)
+                seg = shared_memory.SharedMemory(name=name[0], create=True, size=nbytes)
+            dist.broadcast_object_list(name, 0)
+            if rank != 0:
+                seg = shared_memory.SharedMemory(name=name[0])
+                try:
+                    resource_tracker.unregister(seg._name, "shared_memory")      # rank 0 owns (and unlinks) the segment
+                except Exception:
+                    pass
+            t = torch.from_numpy(np.ndarray((nbytes,), dtype=np.uint8, buffer=seg.buf))
+            ok = int(torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)) == 0
+            return seg, t, ok
+        in_bytes = inbuf.nbytes
+        out_bytes = n_grid * k * esz
+        per_out = (out_bytes // world + 255) // 256 * 256
+        seg_in, hin, ok_in = shared_pinned(in_bytes, "in")
+        seg_out, hout, ok_out = shared_pinned(per_out * world, "out")
+        flag = torch.tensor([1.0 if (ok_in and ok_out) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        split_io = bool(flag.item() > 0.5)
+        if rank == 0:                                   # the host copy of the flat input buffer, byte for byte
+            off = 0
+            for (shape, dt_), src in zip([((n_obs, n_coord), np.float64), ((k, n_obs), ndt), ((n_obs,), ndt), ((1, k, n_grid), ndt)],
+                                         (data["obs_rows"][:, 1:], data["normed_perts"], data["normed_obs"],
+                                          data["state"].reshape(1, k, n_grid))):
+                a = np.ascontiguousarray(src, dtype=dt_)
+                hin[off:off + a.nbytes].numpy()[:] = a.reshape(-1).view(np.uint8)
+                off = (off + a.nbytes + InputBuffer.ALIGN - 1) // InputBuffer.ALIGN * InputBuffer.ALIGN
+        ctx.barrier()
+        xa_bytes = xa_dev.view(-1).view(torch.uint8)
+        per_in = in_bytes // world
+
         def e2e_step():
-            if rank == 0:
-                x_dev.copy_(x_host, non_blocking=True); y_dev.copy_(y_host, non_blocking=True)
-                d_dev.copy_(d_host, non_blocking=True); oc_dev.copy_(oc_host.t(), non_blocking=True)
-            step()
-            if rank == 0:
-                out_host.copy_(xa_dev, non_blocking=True)
-        out_host = torch.empty((1, k, n_grid), dtype=tdt).pin_memory() if rank == 0 else None
+            if split_io:
+                inbuf.slice_of(rank).copy_(hin[rank * per_in:(rank + 1) * per_in], non_blocking=True)
+                inbuf.allgather(rank)
+                step(transport=False)
+                o0, o1 = min(rank * per_out, out_bytes), min((rank + 1) * per_out, out_bytes)
+                if o1 > o0:
+                    hout[o0:o1].copy_(xa_bytes[o0:o1], non_blocking=True)
+            else:
+                if rank == 0:
+                    x_dev.copy_(x_host, non_blocking=True); y_dev.copy_(y_host, non_blocking=True)
+                    d_dev.copy_(d_host, non_blocking=True); oc_dev.copy_(oc_host.t(), non_blocking=True)
+                step()
+                if rank == 0:
+                    hout[:out_bytes].copy_(xa_bytes, non_blocking=True)
         e2e_step(); ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
         ctx.barrier()
         dt = ctx.max_over_ranks([(time.perf_counter() - t0) / e2e_steps])[0]
+        e2e_diff = None
         if rank == 0:
-            h2d = x_host.numel() * esz + y_host.numel() * esz + d_host.numel() * esz + oc_host.numel() * 8
-            e2e = {"value": n_grid / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n_grid * k * esz),
-                   "ms_per_step": dt * 1e3, "steps": e2e_steps,
-                   "api": "pinned host -> rank 0 -> NCCL broadcast -> analyse -> all-gather -> host"}
+            got = hout[:out_bytes].numpy().view(ndt)
+            e2e_diff = float(np.abs(got - xa_dev.cpu().numpy().reshape(-1)).max())
+        ctx.barrier()
+        for t_, seg in ((hin, seg_in), (hout, seg_out)):
+            try:
+                torch.cuda.cudart().cudaHostUnregister(t_.data_ptr())
+            except Exception:
+                pass
+        del hin, hout
+        if rank == 0:
+            h2d = in_bytes
+            e2e = {"value": n_grid / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_bytes),
+                   "ms_per_step": dt * 1e3, "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_diff,
+                   "api": ("host memory of the node (shared, page-locked) -> every rank uploads 1/N over its own PCIe link -> NVLink "
+                           "all-gather -> analyse -> all-gather -> every rank downloads 1/N of the analysis") if split_io else
+                          "pinned host -> rank 0 -> NCCL broadcast -> analyse -> all-gather -> host"}
+        for seg in (seg_in, seg_out):
+            try:
+                if rank == 0:
+                    seg.unlink()                        # the name goes away now, the mapping when the last view is dropped
+            except Exception:
+                pass
+            try:
+                seg.close()
+            except Exception:
+                pass
 
     # ---- parity sample against the oracle, outside every timed region (rank 0; the analysis is complete on every rank) ----
     parity = None
