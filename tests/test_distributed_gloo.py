@@ -240,3 +240,57 @@ def test_sharded_etkf_ranges_cover_and_align():
             assert rs[0][0] == 0 and rs[-1][1] == n
             assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
             assert all(a % 16 == 0 for a, _ in rs if a < n)
+
+
+def _worker_inputs(rank, world, port, ret):
+    """InputBuffer: views of one flat buffer travel with one collective (broadcast from the owner, or all-gather of the
+    slices every rank filled); then the work split by counts and its feedback re-cut."""
+    from pytassim_b200.parallel import InputBuffer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    specs = [((7, 2), torch.float64), ((3, 7), torch.float32), ((7,), torch.float32), ((1, 3, 11), torch.float64)]
+    ref = [torch.arange(int(np.prod(s)), dtype=torch.float64).reshape(s).to(dt) + 10 * i for i, (s, dt) in enumerate(specs)]
+    buf = InputBuffer(specs, "cpu", world, rank=rank)
+    if rank == 0:
+        for v, r in zip(buf.views, ref):
+            v.copy_(r)
+    else:
+        buf.flat.zero_()
+    buf.broadcast(0)
+    ok_b = all(torch.equal(v, r) for v, r in zip(buf.views, ref))
+    # all-gather transport: every rank owns (here: keeps) only its slice of the bytes
+    whole = buf.flat.clone()
+    buf.flat.zero_()
+    buf.slice_of(rank).copy_(whole[rank * (buf.nbytes // world):(rank + 1) * (buf.nbytes // world)])
+    buf.allgather(rank)
+    ok_a = torch.equal(buf.flat, whole) and all(v.data_ptr() >= buf.flat.data_ptr() for v in buf.views)
+    # work split: counts put all the work into the first third of the grid
+    data = syn.lorenz96_1d(96, 4, 2, seed=3)
+    eng = OracleEngine(data, 4.0, 1.1, 96.0)
+    eng.device = "cpu"
+    counts = np.zeros(96); counts[eng.order[:32]] = 100.0; counts[eng.order[32:]] = 1.0
+    r0 = list(ShardedAnalysis(eng, weights=counts).ranges)
+    # uniform counts: an even split; then rank 1 reports twice the time of rank 0: its range must shrink
+    sh = ShardedAnalysis(eng, weights=np.ones(96))
+    even = list(sh.ranges)
+    r1 = list(sh.rebalance(10.0 if rank == 0 else 20.0))
+    ret[rank] = (ok_b, ok_a, r0, r1, even)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_input_buffer_and_rebalance_two_ranks_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    manager = mp.Manager()
+    ret = manager.dict()
+    mp.spawn(_worker_inputs, args=(2, port, ret), nprocs=2, join=True)
+    for rank in (0, 1):
+        ok_b, ok_a, r0, r1, even = ret[rank]
+        assert ok_b and ok_a
+        assert r0 == ret[0][2] and r1 == ret[0][3]                      # every rank uses the same boundaries
+        assert r0[0][0] == 0 and r0[-1][1] == 12 and r0[0][1] == r0[1][0]
+        # 12 blocks of 8 points, the first 4 carry 800 each, the others 8 each: the cut sits inside the heavy part
+        assert r0[0][1] <= 4
+        assert even == [(0, 6), (6, 12)]
+        assert r1 == [(0, 8), (8, 12)]                                  # rank 1 was twice as slow: it hands two blocks to rank 0
