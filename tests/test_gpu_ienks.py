@@ -104,6 +104,40 @@ def test_localized_ienks_ring_against_oracle(k, tau, eps):
                                TOL9)
 
 
+def test_zero_gram_with_local_observations_is_handed_through():
+    """The one accepted semantic difference: the IEnKS pre-pass recognises "no local observation"
+    (core/ienks.py:143, the localized wrapper skips the module) by an all-zero Gram slot.  A grid point whose local observations
+    EXIST but whose localized perturbations and innovations are all exactly zero therefore keeps its incoming weights, whereas
+    the reference runs its update on the zero Gram.  Pinned here: (a) the device hands the weights through bit for bit,
+    (b) with the prior identity weights (first iteration of every IEnKS run) that IS the reference's result, the identity being
+    the fixed point of the update on a zero Gram, (c) with other incoming weights the reference's update differs - the
+    difference this test documents."""
+    n, k, tau = 64, 12, 0.7
+    data = syn.lorenz96_1d(n, k, 1, seed=9)
+    perts = np.zeros_like(data["normed_perts"])
+    innov = np.zeros_like(data["normed_obs"])
+    eng = LETKFEngine(k, 1, m.PeriodicDistance1D(float(n)), 4.0)
+    eng.set_grid(data["grid_rows"][:, 1:])
+    eng.bin_obs(data["obs_rows"][:, 1:], perts, innov)
+    counts, _ = eng.neighbour_counts()
+    assert int(counts.min()) > 0                                   # every grid point does have local observations
+    x = torch.as_tensor(data["state"].reshape(1, k, n)).cuda()
+    dist = orc.make_dist_periodic1d(float(n))
+    # (a) + (b): identity in, identity out on both sides
+    _, w_id = eng.ienks_step(x, np.eye(k), tau=tau)
+    assert np.array_equal(w_id.cpu().numpy(), np.broadcast_to(np.eye(k), (n, k, k)))
+    ref_id = orc.lienks_weights_point(data["grid_rows"][5], np.eye(k), perts, innov[None], data["obs_rows"], dist, (4.,), tau, None)
+    np.testing.assert_allclose(ref_id, np.eye(k), rtol=0, atol=1e-13)
+    # (a) + (c): a non-trivial incoming matrix is handed through by the device, moved by the reference
+    w_in = np.eye(k) + 0.05 * np.random.RandomState(4).normal(size=(k, k))
+    xa, w_out = eng.ienks_step(x, w_in, tau=tau)
+    assert np.array_equal(w_out.cpu().numpy(), np.broadcast_to(w_in, (n, k, k)))
+    np.testing.assert_allclose(xa.cpu().numpy().reshape(1, 1, k, n), orc.apply_weights(data["state"], np.broadcast_to(w_in, (n, k, k))),
+                               rtol=1e-12, atol=1e-12)
+    ref = orc.lienks_weights_point(data["grid_rows"][5], w_in, perts, innov[None], data["obs_rows"], dist, (4.,), tau, None)
+    assert np.abs(ref - w_in).max() > 1e-3                         # the reference's update on the zero Gram is not a no-op
+
+
 def test_ienks_argument_checks():
     eng = LETKFEngine(10, 1, m.AbsDistance1D(), 1.0)
     with pytest.raises(ValueError):
