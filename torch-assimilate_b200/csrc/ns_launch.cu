@@ -50,7 +50,9 @@ size_t ns_scratch_bytes(int kts) {
 #define B200DA_NS_CASE(KT) case KT: return launch_ns<KT>(P, st);
 #ifndef B200DA_NS_LARGE
 int dispatch_ns_large(int kts, const NsParams& P, cudaStream_t st);      // ns_launch_b.cu: 11 <= kts <= 16
+int dispatch_ns_few(int kts, const NsParams& P, cudaStream_t st);        // ns_launch_c.cu: fewer matrices than SMs
 int dispatch_ns(int kts, const NsParams& P, cudaStream_t st) {
+    if (P.n_slots <= 148 && kts >= 5 && kts <= 7) return dispatch_ns_few(kts, P, st);
     switch (kts) {
         B200DA_NS_CASE(1) B200DA_NS_CASE(2) B200DA_NS_CASE(3) B200DA_NS_CASE(4) B200DA_NS_CASE(5) B200DA_NS_CASE(6)
         B200DA_NS_CASE(7) B200DA_NS_CASE(8) B200DA_NS_CASE(9) B200DA_NS_CASE(10)
@@ -66,6 +68,26 @@ int dispatch_ns_large(int kts, const NsParams& P, cudaStream_t st) {
     }
 }
 #else
+// Fewer matrices than SMs (the reference's own benchmark shape: 40 grid points): the launch is one matrix deep, so its time is
+// the latency of ONE solve; four warps per matrix, one matrix per CTA, halve the tile rows every warp walks through per product.
+template <int KT>
+static int launch_ns_few(const NsParams& P, cudaStream_t st) {
+    constexpr int WPM = 4, GROUPS = 1;
+    constexpr size_t smem = NsCfg<KT, WPM>::GROUP_BYTES * GROUPS;
+    auto kern = k_letkf_solve_ns<KT, WPM, GROUPS>;
+    B200DA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(int)std::min<int64_t>(P.n_slots, 148), GROUPS * WPM * 32, smem, st>>>(P);
+    B200DA_LAUNCH_CHECK();
+    return B200DA_OK;
+}
+int dispatch_ns_few(int kts, const NsParams& P, cudaStream_t st) {
+    switch (kts) {
+        case 5: return launch_ns_few<5>(P, st);
+        case 6: return launch_ns_few<6>(P, st);
+        case 7: return launch_ns_few<7>(P, st);
+        default: return B200DA_ERR_UNSUPPORTED;
+    }
+}
 int dispatch_ns_large2(int kts, const NsParams& P, cudaStream_t st) {
     switch (kts) {
         B200DA_NS_CASE(14) B200DA_NS_CASE(15) B200DA_NS_CASE(16)
