@@ -50,7 +50,7 @@ size_t ns_scratch_bytes(int kts) {
 #define B200DA_NS_CASE(KT) case KT: return launch_ns<KT>(P, st);
 #ifndef B200DA_NS_LARGE
 int dispatch_ns_large(int kts, const NsParams& P, cudaStream_t st);      // ns_launch_b.cu: 11 <= kts <= 16
-int dispatch_ns_few(int kts, const NsParams& P, cudaStream_t st);        // ns_launch_c.cu: fewer matrices than SMs
+int dispatch_ns_few(int kts, const NsParams& P, cudaStream_t st);        // ns_launch_d.cu: fewer matrices than SMs
 int dispatch_ns(int kts, const NsParams& P, cudaStream_t st) {
     if (P.n_slots <= 148 && kts >= 5 && kts <= 7) return dispatch_ns_few(kts, P, st);
     switch (kts) {
@@ -65,6 +65,13 @@ int dispatch_ns_large(int kts, const NsParams& P, cudaStream_t st) {
     switch (kts) {
         B200DA_NS_CASE(11) B200DA_NS_CASE(12) B200DA_NS_CASE(13)
         default: return dispatch_ns_large2(kts, P, st);
+    }
+}
+#elif B200DA_NS_LARGE == 2
+int dispatch_ns_large2(int kts, const NsParams& P, cudaStream_t st) {
+    switch (kts) {
+        B200DA_NS_CASE(14) B200DA_NS_CASE(15) B200DA_NS_CASE(16)
+        default: return B200DA_ERR_UNSUPPORTED;
     }
 }
 #else
@@ -85,12 +92,6 @@ int dispatch_ns_few(int kts, const NsParams& P, cudaStream_t st) {
         case 5: return launch_ns_few<5>(P, st);
         case 6: return launch_ns_few<6>(P, st);
         case 7: return launch_ns_few<7>(P, st);
-        default: return B200DA_ERR_UNSUPPORTED;
-    }
-}
-int dispatch_ns_large2(int kts, const NsParams& P, cudaStream_t st) {
-    switch (kts) {
-        B200DA_NS_CASE(14) B200DA_NS_CASE(15) B200DA_NS_CASE(16)
         default: return B200DA_ERR_UNSUPPORTED;
     }
 }
