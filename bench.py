@@ -1037,7 +1037,7 @@ def main():
                 ent = run_etkf(ctx, wname, dtype, 5, 3, 1, cpu_info=cpu.get(wname), min_seconds=2.0)
             else:
                 big = ws["kind"] == "sphere"
-                ent = run_letkf(ctx, wname, dtype, 3 if big else 5, 1 if big else 3, 1, data=datasets.get(wname), fraction=fraction,
+                ent = run_letkf(ctx, wname, dtype, 3 if big else 5, 3, 1, data=datasets.get(wname), fraction=fraction,
                                 parity_points=6 if big else 8, cpu_info=cpu.get(wname), min_seconds=2.0)
         except Exception as exc:                                # one failing entry must not take the headline with it
             ent = {"error": repr(exc)}
