@@ -7,6 +7,12 @@
 namespace b200da {
 
 // ---- tensor-core solve (ns_solve_kernel.cuh): warps per matrix and matrices per CTA by ensemble size ----------------
+#ifndef B200DA_NS_WPM1_KT
+#define B200DA_NS_WPM1_KT 5      // largest tile count solved by one warp per matrix
+#endif
+#ifndef B200DA_NS_MAXW1
+#define B200DA_NS_MAXW1 8        // warps per CTA of the one-warp-per-matrix variants
+#endif
 template <int KT> struct NsPick {
 #ifdef B200DA_NS_WPM1
     static constexpr int WPM = KT <= 7 ? 1 : (KT <= 10 ? 2 : 4);
@@ -15,8 +21,8 @@ template <int KT> struct NsPick {
     // two warps per matrix from k > 40 on: with one warp per matrix only 5 (k = 50) warps fit next to their matrices in shared
     // memory and the DMMA pipe idles half of the time (ncu: 53 %); splitting the tiles of a matrix over two warps doubles the
     // warps per scheduler at the same shared-memory footprint (cfg3 solve 225 -> 192 ms; k = 40: 6.0 -> 6.3 ms, so not there)
-    static constexpr int WPM = KT <= 5 ? 1 : (KT <= 10 ? 2 : 4);
-    static constexpr int MAXW = WPM == 1 ? 8 : 16;
+    static constexpr int WPM = KT <= B200DA_NS_WPM1_KT ? 1 : (KT <= 10 ? 2 : 4);
+    static constexpr int MAXW = WPM == 1 ? B200DA_NS_MAXW1 : 16;
 #endif
     static constexpr size_t GB = NsCfg<KT, WPM>::GROUP_BYTES;
     static constexpr int FIT = (int)((kMaxSmem - 1024) / GB);

@@ -230,6 +230,50 @@ __device__ __forceinline__ void store_tiles(int sub, double* __restrict__ S, con
     }
 }
 
+// f(mt, nt, e) for every element slot e in [0, 64) of the lower-triangle tiles of warp SUB of the group (tile index % WPM == SUB):
+// 32 lanes x 2 passes per tile, (mt, nt) uniform over the warp and compile-time constants where the loops unroll (KT <= 6), so an
+// element pass over a tile-packed matrix is a handful of instructions with constant offsets instead of an index reconstruction
+// per element (the flat loops with their (i, j) stepping were 20 % of the samples of the k = 40 solve).
+template <int KT, int WPM, int SUB, typename F>
+__device__ __forceinline__ void for_tiles(int lane, F&& f) {
+    constexpr int kU = KT <= 6 ? KT : 1;
+    int idx = 0;
+#pragma unroll kU
+    for (int mt = 0; mt < KT; ++mt) {
+#pragma unroll kU
+        for (int nt = 0; nt <= mt; ++nt) {
+            if (idx % WPM == SUB) { f(mt, nt, lane); f(mt, nt, lane + 32); }
+            ++idx;
+        }
+    }
+}
+
+// sum_j row[j * stride] * v[j], j < k, in four independent chains (a single chain of k dependent DFMAs is latency bound with the
+// two warps per scheduler this kernel runs at)
+__device__ __forceinline__ double dot4(const double* __restrict__ row, int stride, const double* __restrict__ v, int k) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = 0;
+    for (; j + 3 < k; j += 4) {
+        a0 = fma(row[j * stride], v[j], a0);
+        a1 = fma(row[(j + 1) * stride], v[j + 1], a1);
+        a2 = fma(row[(j + 2) * stride], v[j + 2], a2);
+        a3 = fma(row[(j + 3) * stride], v[j + 3], a3);
+    }
+    for (; j < k; ++j) a0 = fma(row[j * stride], v[j], a0);
+    return (a0 + a1) + (a2 + a3);
+}
+
+// the same value in every lane of every warp that calls it with the same arguments: sum_i f(i), i < k, lanes stride over i,
+// xor-butterfly (commutative at every level, so all lanes end with identical bits)
+template <typename F>
+__device__ __forceinline__ double warp_sum_k(int lane, int k, F&& f) {
+    double a = 0.0;
+    for (int i = lane; i < k; i += 32) a += f(i);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    return a;
+}
+
 struct NsParams {
     const double* cmat;        // [n_slots][slot_stride]: tile-packed augmented Gram (rows 0..k-1 = C, row k = b)
     const Pos4* gpos;          // block-sorted grid positions (id = original index)
@@ -303,10 +347,23 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
     ns_sync<WPM>(bar_id);
     // ---- s = min(||A||_F, ||A||_inf) -------------------------------------------------------------------------------
     double rs_max = 0.0, sq = 0.0;
-    for (int i = gtid; i < k; i += GT) {
-        double rs = 0.0;
-        for (int j = 0; j < k; ++j) { const double a = sym_get(Y, i, j); rs += fabs(a); sq = fma(a, a, sq); }
-        rs_max = fmax(rs_max, rs);
+    for (int i = gtid; i < k; i += GT) {            // row i over all KT tile columns (the padding is zero): tile (mt, nt) read directly
+        const int mt = i >> 3, r = i & 7;           // for nt <= mt, tile (nt, mt) transposed beyond the diagonal
+        const int xr = (r & 2) << 1, r4 = r ^ 4;
+        double rs0 = 0.0, rs1 = 0.0, sq1 = 0.0;
+        for (int nt = 0; nt < KT; ++nt) {
+            const bool dir = nt <= mt;
+            const double* tp = Y + (dir ? tile_off(mt, nt) + r * 8 : tile_off(nt, mt));
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                const double a0 = tp[dir ? (c ^ xr) : c * 8 + ((c & 2) ? r4 : r)];
+                const double a1 = tp[dir ? ((c + 1) ^ xr) : (c + 1) * 8 + ((c & 2) ? r4 : r)];
+                rs0 += fabs(a0); sq = fma(a0, a0, sq);
+                rs1 += fabs(a1); sq1 = fma(a1, a1, sq1);
+            }
+        }
+        sq += sq1;
+        rs_max = fmax(rs_max, rs0 + rs1);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -329,46 +386,48 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         double lo = fmin(lo_abs * inv_sc, 1.0);
         double g = 3.0 / (1.0 + sqrt(lo) + lo);
         double sg = sqrt(g);
-        // e = tile * 64 + tile_elem(r, c); the tile coordinates (mt, nt) are stepped along with e (GT <= 128: at most two tiles
-        // per step) instead of being recovered from the tile index with a square root
-        int tile = gtid >> 6, mt = tile, nt = 0;
-        if (tile > 0) { mt = 1; nt = tile - 1; if (tile > 2) { mt = 2; nt = tile - 3; } }     // tiles 0..3: (0,0) (1,0) (1,1) (2,0)
-        for (int e = gtid; e < MAT; e += GT) {
-            for (; tile < (e >> 6); ++tile) { if (++nt > mt) { ++mt; nt = 0; } }
-            const int r = (e >> 3) & 7, c = (e & 7) ^ ((r & 2) << 1);
+        for_tiles<KT, WPM, SUB>(lane, [&](int mt, int nt, int e) {
+            const int o = tile_off(mt, nt) + e;
+            const int r = e >> 3, c = (e & 7) ^ ((r & 2) << 1);
             const bool on_diag = (mt == nt) && (r == c);
-            double y = (Y[e] + (on_diag ? shift : 0.0)) * inv_sc;
+            double y = (Y[o] + (on_diag ? shift : 0.0)) * inv_sc;
             if (on_diag && mt * 8 + r >= k) y = 1.0;                 // padding: decoupled unit eigenvalues
             const double t = fma(-0.5 * g, y, on_diag ? 1.5 : 0.0);
-            Y[e] = y; T[e] = t; Z[e] = sg * t;
-        }
+            Y[o] = y; T[o] = t; Z[o] = sg * t;
+        });
         ns_sync<WPM>(bar_id);
         int iters = 1;
-        {
-            sym_gemm_sub<KT, WPM, SUB>(Y, T, fo, acc);
-            ns_sync<WPM>(bar_id);
-            store_tiles_sub<KT, WPM, SUB>(Y, acc, sg, 0.0, lane);
-            ns_sync<WPM>(bar_id);
+        // the scaling of the NEXT iteration depends on the tracked bound only: it is computed ahead of the products of the current
+        // one, so that its divisions and square roots (dependent FP64 chains) interleave with the DMMA stream
+        auto next_scaling = [&]() {
             const double m = g * lo;
             lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
+            g = 3.0 / (1.0 + sqrt(lo) + lo);
+            sg = sqrt(g);
+        };
+        {
+            const double sgc = sg;
+            next_scaling();
+            sym_gemm_sub<KT, WPM, SUB>(Y, T, fo, acc);
+            ns_sync<WPM>(bar_id);
+            store_tiles_sub<KT, WPM, SUB>(Y, acc, sgc, 0.0, lane);
+            ns_sync<WPM>(bar_id);
         }
         for (; iters < 64; ++iters) {
             const bool last = (1.0 - lo) < P.conv;
-            g = 3.0 / (1.0 + sqrt(lo) + lo);
-            sg = sqrt(g);
+            const double gc = g, sgc = sg;
+            next_scaling();
             sym_gemm_sub<KT, WPM, SUB>(Z, Y, fo, acc);                    // M = Z Y
-            store_tiles_sub<KT, WPM, SUB>(T, acc, -0.5 * g, 1.5, lane);   // T = (3 I - g M) / 2
+            store_tiles_sub<KT, WPM, SUB>(T, acc, -0.5 * gc, 1.5, lane);  // T = (3 I - g M) / 2
             ns_sync<WPM>(bar_id);
             sym_gemm_sub<KT, WPM, SUB>(T, Z, fo, acc);                    // Z' = sqrt(g) T Z
             ns_sync<WPM>(bar_id);
-            store_tiles_sub<KT, WPM, SUB>(Z, acc, sg, 0.0, lane);
+            store_tiles_sub<KT, WPM, SUB>(Z, acc, sgc, 0.0, lane);
             if (last) break;
             sym_gemm_sub<KT, WPM, SUB>(Y, T, fo, acc);                    // Y' = sqrt(g) Y T
             ns_sync<WPM>(bar_id);
-            store_tiles_sub<KT, WPM, SUB>(Y, acc, sg, 0.0, lane);
+            store_tiles_sub<KT, WPM, SUB>(Y, acc, sgc, 0.0, lane);
             ns_sync<WPM>(bar_id);
-            const double m = g * lo;
-            lo = fmin(1.0, 0.25 * m * (3.0 - m) * (3.0 - m));
         }
         ns_sync<WPM>(bar_id);
         return iters + 1;
@@ -380,10 +439,13 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         // ---- one level: D = A^(-1/2) = Z / sqrt(s) ---------------------------------------------------------------------
         iters = inv_sqrt(0.0, s, alpha);
         const double zs = sqrt(1.0 / s);
-        for (int e = gtid, i = gtid / k, j = gtid - (gtid / k) * k; e < k * k; e += GT) {
-            D[i * LDW + j] = sym_get(Z, i, j) * zs;
-            for (j += GT; j >= k; j -= k) ++i;
-        }
+        for_tiles<KT, WPM, SUB>(lane, [&](int mt, int nt, int e) {       // tile-packed -> dense, both halves (padding included)
+            const int r = e >> 3, c = (e & 7) ^ ((r & 2) << 1);
+            const double v = Z[tile_off(mt, nt) + e] * zs;
+            const int i = mt * 8 + r, j = nt * 8 + c;
+            D[i * LDW + j] = v;
+            if (mt != nt) D[j * LDW + i] = v;
+        });
     } else {
         // ---- stiff matrix (s / a above P.stiff): two levels.  Every product of the iteration is stored as a symmetric matrix
         // (lower-triangle tiles); the rounding-level commutators this discards are amplified from one iteration to the next,
@@ -401,6 +463,7 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         double* gB = gA + MAT;
         double* gF = gB + MAT;
         for (int e = gtid; e < MAT; e += GT) gA[e] = Y[e];
+        ns_sync<WPM>(bar_id);            // the iteration's first pass rewrites Y tile-wise (another element-to-thread mapping)
         const double a1 = s / fmax(30.0, 0.5 * sqrt(s / alpha));
         const double shift = a1 - alpha;
         const double s1 = (s + shift) * (1.0 + 1e-12);
@@ -433,17 +496,9 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
     }
     if (P.stats && gtid == 0) { atomicAdd(P.stats + 2, (unsigned long long)iters); atomicAdd(P.stats + 3, 1ull); }
     ns_sync<WPM>(bar_id);
-    for (int i = gtid; i < k; i += GT) {                          // u = D b
-        double a = 0.0;
-        for (int j = 0; j < k; ++j) a = fma(D[i * LDW + j], bvec[j], a);
-        uvec[i] = a;
-    }
+    for (int i = gtid; i < k; i += GT) uvec[i] = dot4(D + i * LDW, 1, bvec, k);   // u = D b
     ns_sync<WPM>(bar_id);
-    for (int i = gtid; i < k; i += GT) {                          // w_mean = D u = A^-1 b        core/etkf.py:72-73
-        double a = 0.0;
-        for (int j = 0; j < k; ++j) a = fma(D[i * LDW + j], uvec[j], a);
-        wbar[i] = a;
-    }
+    for (int i = gtid; i < k; i += GT) wbar[i] = dot4(D + i * LDW, 1, uvec, k);   // w_mean = D u = A^-1 b        core/etkf.py:72-73
     ns_sync<WPM>(bar_id);
     // ---- iterative refinement of w_mean against the Gram in global memory.  D carries an unstructured error e |D|; through
     // w_mean = D D b with |b| ~ lambda_max it becomes e * (lambda_max / a) in w_mean.  One residual step with the exact A
@@ -456,41 +511,42 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
             xbuf[i] = a;
         }
         ns_sync<WPM>(bar_id);
-        for (int i = gtid; i < k; i += GT) {
-            double a = 0.0;
-            for (int j = 0; j < k; ++j) a = fma(D[i * LDW + j], xbuf[j], a);
-            uvec[i] = a;
-        }
+        for (int i = gtid; i < k; i += GT) uvec[i] = dot4(D + i * LDW, 1, xbuf, k);
         ns_sync<WPM>(bar_id);
-        for (int i = gtid; i < k; i += GT) {
-            double a = 0.0;
-            for (int j = 0; j < k; ++j) a = fma(D[i * LDW + j], uvec[j], a);
-            wbar[i] += a;
-        }
+        for (int i = gtid; i < k; i += GT) wbar[i] += dot4(D + i * LDW, 1, uvec, k);
         ns_sync<WPM>(bar_id);
     }
+    // ---- W = w_mean 1^T + sqrt(k-1) D (core/etkf.py:75-76,102) is only formed where it is exported; the update applies its two
+    // terms separately:  x_a[s, j, g] = mean + sum_i xp_i W[i][j] = mean + xp . w_mean + sqrt(k-1) (D xp)[j],  xp = x - mean
+    // (interface/base.py:257-278)
     const double sk = sqrt((double)(k - 1));
     const int64_t gi = P.gpos[P.slot_base + slot].id;
     const int f32 = P.io_f32;
-    for (int e = gtid, i = gtid / k, j = gtid - (gtid / k) * k; e < k * k; e += GT) {   // W = w_mean 1^T + sqrt(k-1) D   core/etkf.py:75-76,102
-        const double w = fma(sk, D[i * LDW + j], wbar[i]);
-        D[i * LDW + j] = w;
-        if (P.w_out) st_io(P.w_out, gi * (int64_t)k * k + e, w, f32);
-        for (j += GT; j >= k; j -= k) ++i;
+    if (P.w_out) {
+        for (int i = 0; i < k; ++i) {
+            const double wi = wbar[i];
+            const int64_t row = (gi * (int64_t)k + i) * k;
+            for (int j = gtid; j < k; j += GT) st_io(P.w_out, row + j, fma(sk, D[i * LDW + j], wi), f32);
+        }
     }
-    ns_sync<WPM>(bar_id);
-    // ---- x_a[s, j, g] = mean + sum_i (x[s, i, g] - mean) W[i][j]                                interface/base.py:257-278
     for (int sl = 0; sl < P.n_slices; ++sl) {
         const int64_t base = (int64_t)sl * k * P.n_grid + gi;
         for (int i = gtid; i < k; i += GT) xbuf[i] = ld_io(P.x, base + (int64_t)i * P.n_grid, f32);
         ns_sync<WPM>(bar_id);
-        double mean = 0.0;
-        for (int i = 0; i < k; ++i) mean += xbuf[i];              // same order in every thread
-        mean /= (double)k;
+        const double mean = warp_sum_k(lane, k, [&](int i) { return xbuf[i]; }) / (double)k;      // identical bits in every thread
+        const double c0 = warp_sum_k(lane, k, [&](int i) { return (xbuf[i] - mean) * wbar[i]; });
         for (int j = gtid; j < k; j += GT) {
-            double a = 0.0;
-            for (int i = 0; i < k; ++i) a = fma(xbuf[i] - mean, D[i * LDW + j], a);
-            st_io(P.xa, base + (int64_t)j * P.n_grid, mean + a, f32);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double* col = D + j;
+            int i = 0;
+            for (; i + 3 < k; i += 4) {
+                a0 = fma(xbuf[i] - mean, col[i * LDW], a0);
+                a1 = fma(xbuf[i + 1] - mean, col[(i + 1) * LDW], a1);
+                a2 = fma(xbuf[i + 2] - mean, col[(i + 2) * LDW], a2);
+                a3 = fma(xbuf[i + 3] - mean, col[(i + 3) * LDW], a3);
+            }
+            for (; i < k; ++i) a0 = fma(xbuf[i] - mean, col[i * LDW], a0);
+            st_io(P.xa, base + (int64_t)j * P.n_grid, mean + fma(sk, (a0 + a1) + (a2 + a3), c0), f32);
         }
         ns_sync<WPM>(bar_id);
     }
