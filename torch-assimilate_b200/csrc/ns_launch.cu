@@ -25,7 +25,7 @@ template <int KT> struct NsPick {
     static constexpr int MAXW = WPM == 1 ? B200DA_NS_MAXW1 : 16;
 #endif
     static constexpr size_t GB = NsCfg<KT, WPM>::GROUP_BYTES;
-    static constexpr int FIT = (int)((kMaxSmem - 1024) / GB);
+    static constexpr int FIT = (int)((kMaxSmem - 256) / GB);      // static shared memory: one slot word per group
     static constexpr int GROUPS = FIT * WPM >= MAXW ? MAXW / WPM : (FIT < 1 ? 1 : FIT);
 };
 

@@ -56,7 +56,7 @@ struct NsCfg {
     static constexpr int KP = KT * 8;
     static constexpr int MAT = NT * 64;                        // doubles per matrix
     static constexpr int LDW = KP + 1;                         // dense W overlay (odd: conflict-free rows and columns)
-    static constexpr int VEC = 4 * KP + 8;                     // b, u, w_mean, xbuf (+ reduction scratch)
+    static constexpr int VEC = 5 * KP + 8;                     // b (two buffers: the next matrix is prefetched), u, w_mean, xbuf (+ reduction scratch)
     static constexpr size_t GROUP_BYTES = sizeof(double) * (3 * (size_t)MAT + VEC);
     static_assert(2 * MAT >= KP * LDW, "dense overlay must fit in two tile-packed matrices");
 };
@@ -186,7 +186,8 @@ __device__ __forceinline__ void store_full(int sub, double* F, const double (&ac
 }
 
 // S <- scale * acc + diag * I over the warp's tiles; diagonal tiles are written symmetrically from their lower half
-template <int KT, int WPM, int SUB>
+// PLAIN: scale = 1, diag = 0 (no FP64 instruction: the DMULs of the scaled store share the datapath with the other warps' DMMAs)
+template <int KT, int WPM, int SUB, bool PLAIN = false>
 __device__ __forceinline__ void store_tiles_sub(double* __restrict__ S, const double (&acc)[NsCfg<KT, WPM>::OWN][2],
                                             double scale, double diag, int lane) {
     const int r = lane >> 2, c = (lane & 3) * 2;
@@ -197,11 +198,11 @@ __device__ __forceinline__ void store_tiles_sub(double* __restrict__ S, const do
         for (int nt = 0; nt <= mt; ++nt) {
             if (tile_owned<KT, WPM, SUB>(idx)) {
                 double* tp = S + tile_off(mt, nt);
-                const double v0 = acc[n][0] * scale, v1 = acc[n][1] * scale;
+                const double v0 = PLAIN ? acc[n][0] : acc[n][0] * scale, v1 = PLAIN ? acc[n][1] : acc[n][1] * scale;
                 if (mt != nt) {
                     *reinterpret_cast<double2*>(tp + tile_elem(r, c)) = make_double2(v0, v1);
                 } else {                       // four predicated stores, no divergent branches
-                    const double d0 = c == r ? v0 + diag : v0, d1 = c + 1 == r ? v1 + diag : v1;
+                    const double d0 = (!PLAIN && c == r) ? v0 + diag : v0, d1 = (!PLAIN && c + 1 == r) ? v1 + diag : v1;
                     if (c <= r) tp[tile_elem(r, c)] = d0;
                     if (c < r) tp[tile_elem(c, r)] = v0;
                     if (c + 1 <= r) tp[tile_elem(r, c + 1)] = d1;
@@ -298,6 +299,14 @@ struct NsParams {
 // doubles of global scratch per group: fixed-up A and B (tile-packed symmetric) + one full tile grid
 __host__ __device__ constexpr size_t ns_scratch_doubles(int kt) { return 2 * (size_t)tri_tiles(kt) * 64 + (size_t)kt * kt * 64; }
 
+__device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int WPM>
 __device__ __forceinline__ void ns_sync(int bar_id) {
     if constexpr (WPM == 1) __syncwarp();
@@ -307,28 +316,36 @@ __device__ __forceinline__ void ns_sync(int bar_id) {
 // SUB (the warp's index inside its group) is a template parameter: with a run-time index every product call is a branch over
 // WPM instantiations that all write the accumulator array, which the compiler then keeps in local memory (measured: ~700
 // LDL/STL.128 in the two-warp kernel).
-// One matrix: everything between "augmented Gram in global memory" and "analysis columns written".
+// Asynchronous load of one augmented Gram: flat copy of the lower-triangle tiles into `Yd`, b (row k) into `bd[0..k)`; the caller
+// waits (cp_async_wait_all + group barrier) before it reads them.
+template <int KT, int WPM>
+__device__ __forceinline__ void ns_issue_load(const NsParams& P, int64_t slot, double* Yd, double* bd, int gtid) {
+    constexpr int GT = WPM * 32, MAT = NsCfg<KT, WPM>::MAT;
+    const double* gC = P.cmat + (size_t)slot * (size_t)P.slot_stride;
+    const int k = P.k;
+    for (int e = gtid * 2; e < MAT; e += GT * 2) cp_async16(Yd + e, gC + e);
+    for (int c = gtid; c < k; c += GT) cp_async8(bd + c, gC + sym_off(k, c));
+}
+
+// One matrix: everything between "augmented Gram in shared memory (Y, bvec)" and "analysis columns written".  Buffers: the
+// iteration runs in Z, Y, T; the dense result D overlays the two adjacent buffers that are not Z; once D is complete Z is dead, and
+// the NEXT matrix of this group is fetched from the slot counter and copied into it (and its b into `bnext`) behind the rest of
+// this one (matrix-vector products, refinement, update).  Returns that next slot.
 template <int KT, int WPM, int SUB>
-__device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict__ Z, double* __restrict__ Y,
-                             double* __restrict__ T, double* __restrict__ vec, double* scratch, int gtid, int sub, int lane,
-                             int bar_id) {
+__device__ long long ns_solve_one(const NsParams& P, int64_t slot, double* Z, double* Y, double* T, double* D,
+                                  double* bvec, double* bnext, double* vec, double* scratch, long long* slot_sh,
+                                  int gtid, int sub, int lane, int bar_id) {
     using Cfg = NsCfg<KT, WPM>;
     constexpr int GT = WPM * 32, KP = Cfg::KP, MAT = Cfg::MAT, LDW = Cfg::LDW;
     const int k = P.k;
-    double* bvec = vec;                 // [KP]
-    double* uvec = vec + KP;            // [KP]
-    double* wbar = vec + 2 * KP;        // [KP]
-    double* xbuf = vec + 3 * KP;        // [KP]
-    double* red = vec + 4 * KP;         // [8] cross-warp reduction scratch
+    double* uvec = vec + 2 * KP;        // [KP]   (vec + 0, vec + KP: the two b buffers)
+    double* wbar = vec + 3 * KP;        // [KP]
+    double* xbuf = vec + 4 * KP;        // [KP]
+    double* red = vec + 5 * KP;         // [8] cross-warp reduction scratch
     const double* gC = P.cmat + (size_t)slot * (size_t)P.slot_stride;
     const double alpha = (double)(k - 1) / P.rho;
     const FragOff fo = make_frag_off(lane);
 
-    // ---- load: flat copy of the lower-triangle tiles, b from row k ---------------------------------------------------
-    for (int e = gtid * 2; e < MAT; e += GT * 2)
-        *reinterpret_cast<double2*>(Y + e) = *reinterpret_cast<const double2*>(gC + e);
-    for (int c = gtid; c < KP; c += GT) bvec[c] = c < k ? gC[sym_off(k, c)] : 0.0;
-    ns_sync<WPM>(bar_id);
     // ---- fix-up: zero the padding (and the b row if it shares the last tile row), mirror diagonal tiles, add a I -------
     if ((k & 7) != 0) {
         constexpr int MT = KT - 1;
@@ -382,7 +399,8 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
     // ---- Z <- ((Y + shift I) / sc)^(-1/2) for a symmetric Y whose shifted spectrum lies in [lo_abs, sc]; Y, T destroyed -------
     auto inv_sqrt = [&](const double shift, const double sc, const double lo_abs) -> int {
         const double inv_sc = 1.0 / sc;
-        // iteration 0 (Z0 = I): T = (3 I - g Y0) / 2, Z1 = sqrt(g) T, Y1 = sqrt(g) Y0 T
+        // iteration 0 (Z0 = I): T = (3 I - g Y0) / 2, Z1 = sqrt(g) T, Y1 = sqrt(g) Y0 T = Y0 Z1.  sqrt(g) is folded into the stored
+        // T of every iteration (T' = sqrt(g) T), so that the products Z' = T' Z and Y' = Y T' are stored as they come
         double lo = fmin(lo_abs * inv_sc, 1.0);
         double g = 3.0 / (1.0 + sqrt(lo) + lo);
         double sg = sqrt(g);
@@ -393,7 +411,7 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
             double y = (Y[o] + (on_diag ? shift : 0.0)) * inv_sc;
             if (on_diag && mt * 8 + r >= k) y = 1.0;                 // padding: decoupled unit eigenvalues
             const double t = fma(-0.5 * g, y, on_diag ? 1.5 : 0.0);
-            Y[o] = y; T[o] = t; Z[o] = sg * t;
+            Y[o] = y; Z[o] = sg * t;
         });
         ns_sync<WPM>(bar_id);
         int iters = 1;
@@ -406,11 +424,10 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
             sg = sqrt(g);
         };
         {
-            const double sgc = sg;
             next_scaling();
-            sym_gemm_sub<KT, WPM, SUB>(Y, T, fo, acc);
+            sym_gemm_sub<KT, WPM, SUB>(Y, Z, fo, acc);
             ns_sync<WPM>(bar_id);
-            store_tiles_sub<KT, WPM, SUB>(Y, acc, sgc, 0.0, lane);
+            store_tiles_sub<KT, WPM, SUB, true>(Y, acc, 1.0, 0.0, lane);
             ns_sync<WPM>(bar_id);
         }
         for (; iters < 64; ++iters) {
@@ -418,30 +435,34 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
             const double gc = g, sgc = sg;
             next_scaling();
             sym_gemm_sub<KT, WPM, SUB>(Z, Y, fo, acc);                    // M = Z Y
-            store_tiles_sub<KT, WPM, SUB>(T, acc, -0.5 * gc, 1.5, lane);  // T = (3 I - g M) / 2
+            store_tiles_sub<KT, WPM, SUB>(T, acc, -0.5 * gc * sgc, 1.5 * sgc, lane);   // T' = sqrt(g) (3 I - g M) / 2
             ns_sync<WPM>(bar_id);
-            sym_gemm_sub<KT, WPM, SUB>(T, Z, fo, acc);                    // Z' = sqrt(g) T Z
+            sym_gemm_sub<KT, WPM, SUB>(T, Z, fo, acc);                    // Z' = T' Z
             ns_sync<WPM>(bar_id);
-            store_tiles_sub<KT, WPM, SUB>(Z, acc, sgc, 0.0, lane);
+            store_tiles_sub<KT, WPM, SUB, true>(Z, acc, 1.0, 0.0, lane);
             if (last) break;
-            sym_gemm_sub<KT, WPM, SUB>(Y, T, fo, acc);                    // Y' = sqrt(g) Y T
+            sym_gemm_sub<KT, WPM, SUB>(Y, T, fo, acc);                    // Y' = Y T'
             ns_sync<WPM>(bar_id);
-            store_tiles_sub<KT, WPM, SUB>(Y, acc, sgc, 0.0, lane);
+            store_tiles_sub<KT, WPM, SUB, true>(Y, acc, 1.0, 0.0, lane);
             ns_sync<WPM>(bar_id);
         }
         ns_sync<WPM>(bar_id);
         return iters + 1;
     };
-    double* D = Y;                      // dense A^(-1/2), over the Y | T buffers
+    // D = dense A^(-1/2) / dscale, over the two buffers that are not Z
+    double dscale = 1.0;
     int iters;
+    unsigned int next_u = 0;
+    if constexpr (WPM == 1) { if (lane == 0) next_u = atomicAdd(P.counter, 1u); }     // the next slot: its latency hides behind the D pass
+    else { if (gtid == 0) *slot_sh = (long long)atomicAdd(P.counter, 1u); }           // (visible after the barrier below)
     const bool stiff_path = !(scratch == nullptr || s <= P.stiff * alpha);
     if (!stiff_path) {
         // ---- one level: D = A^(-1/2) = Z / sqrt(s) ---------------------------------------------------------------------
         iters = inv_sqrt(0.0, s, alpha);
-        const double zs = sqrt(1.0 / s);
+        dscale = sqrt(1.0 / s);
         for_tiles<KT, WPM, SUB>(lane, [&](int mt, int nt, int e) {       // tile-packed -> dense, both halves (padding included)
             const int r = e >> 3, c = (e & 7) ^ ((r & 2) << 1);
-            const double v = Z[tile_off(mt, nt) + e] * zs;
+            const double v = Z[tile_off(mt, nt) + e];
             const int i = mt * 8 + r, j = nt * 8 + c;
             D[i * LDW + j] = v;
             if (mt != nt) D[j * LDW + i] = v;
@@ -496,9 +517,15 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
     }
     if (P.stats && gtid == 0) { atomicAdd(P.stats + 2, (unsigned long long)iters); atomicAdd(P.stats + 3, 1ull); }
     ns_sync<WPM>(bar_id);
-    for (int i = gtid; i < k; i += GT) uvec[i] = dot4(D + i * LDW, 1, bvec, k);   // u = D b
+    // ---- Z is dead: the next matrix of this group starts to arrive in it ------------------------------------------------
+    long long next;
+    if constexpr (WPM == 1) next = (long long)__shfl_sync(0xffffffffu, next_u, 0);
+    else next = *slot_sh;
+    if (next < P.n_slots) ns_issue_load<KT, WPM>(P, next, Z, bnext, gtid);
+    const double ds2 = dscale * dscale;
+    for (int i = gtid; i < k; i += GT) uvec[i] = dot4(D + i * LDW, 1, bvec, k);         // u = D b
     ns_sync<WPM>(bar_id);
-    for (int i = gtid; i < k; i += GT) wbar[i] = dot4(D + i * LDW, 1, uvec, k);   // w_mean = D u = A^-1 b        core/etkf.py:72-73
+    for (int i = gtid; i < k; i += GT) wbar[i] = ds2 * dot4(D + i * LDW, 1, uvec, k);   // w_mean = D u = A^-1 b     core/etkf.py:72-73
     ns_sync<WPM>(bar_id);
     // ---- iterative refinement of w_mean against the Gram in global memory.  D carries an unstructured error e |D|; through
     // w_mean = D D b with |b| ~ lambda_max it becomes e * (lambda_max / a) in w_mean.  One residual step with the exact A
@@ -513,13 +540,13 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         ns_sync<WPM>(bar_id);
         for (int i = gtid; i < k; i += GT) uvec[i] = dot4(D + i * LDW, 1, xbuf, k);
         ns_sync<WPM>(bar_id);
-        for (int i = gtid; i < k; i += GT) wbar[i] += dot4(D + i * LDW, 1, uvec, k);
+        for (int i = gtid; i < k; i += GT) wbar[i] = fma(ds2, dot4(D + i * LDW, 1, uvec, k), wbar[i]);
         ns_sync<WPM>(bar_id);
     }
     // ---- W = w_mean 1^T + sqrt(k-1) D (core/etkf.py:75-76,102) is only formed where it is exported; the update applies its two
     // terms separately:  x_a[s, j, g] = mean + sum_i xp_i W[i][j] = mean + xp . w_mean + sqrt(k-1) (D xp)[j],  xp = x - mean
     // (interface/base.py:257-278)
-    const double sk = sqrt((double)(k - 1));
+    const double sk = sqrt((double)(k - 1)) * dscale;
     const int64_t gi = P.gpos[P.slot_base + slot].id;
     const int f32 = P.io_f32;
     if (P.w_out) {
@@ -534,22 +561,15 @@ __device__ void ns_solve_one(const NsParams& P, int64_t slot, double* __restrict
         for (int i = gtid; i < k; i += GT) xbuf[i] = ld_io(P.x, base + (int64_t)i * P.n_grid, f32);
         ns_sync<WPM>(bar_id);
         const double mean = warp_sum_k(lane, k, [&](int i) { return xbuf[i]; }) / (double)k;      // identical bits in every thread
-        const double c0 = warp_sum_k(lane, k, [&](int i) { return (xbuf[i] - mean) * wbar[i]; });
-        for (int j = gtid; j < k; j += GT) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            const double* col = D + j;
-            int i = 0;
-            for (; i + 3 < k; i += 4) {
-                a0 = fma(xbuf[i] - mean, col[i * LDW], a0);
-                a1 = fma(xbuf[i + 1] - mean, col[(i + 1) * LDW], a1);
-                a2 = fma(xbuf[i + 2] - mean, col[(i + 2) * LDW], a2);
-                a3 = fma(xbuf[i + 3] - mean, col[(i + 3) * LDW], a3);
-            }
-            for (; i < k; ++i) a0 = fma(xbuf[i] - mean, col[i * LDW], a0);
-            st_io(P.xa, base + (int64_t)j * P.n_grid, mean + fma(sk, (a0 + a1) + (a2 + a3), c0), f32);
-        }
+        ns_sync<WPM>(bar_id);
+        for (int i = gtid; i < k; i += GT) xbuf[i] -= mean;
+        ns_sync<WPM>(bar_id);
+        const double c0 = warp_sum_k(lane, k, [&](int i) { return xbuf[i] * wbar[i]; });
+        for (int j = gtid; j < k; j += GT)
+            st_io(P.xa, base + (int64_t)j * P.n_grid, mean + fma(sk, dot4(D + j, LDW, xbuf, k), c0), f32);
         ns_sync<WPM>(bar_id);
     }
+    return next;
 }
 
 template <int KT, int WPM, int GROUPS>
@@ -560,38 +580,52 @@ __global__ void __launch_bounds__(GROUPS * WPM * 32, 1) k_letkf_solve_ns(const N
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int group = warp / WPM, sub = warp % WPM, gtid = tid - group * WPM * 32;
     double* base = reinterpret_cast<double*>(smem_raw + (size_t)group * Cfg::GROUP_BYTES);
-    double* Z = base;
-    double* Y = base + Cfg::MAT;
-    double* T = base + 2 * Cfg::MAT;
+    double* b0 = base;                                   // three matrix buffers; the roles (Z, Y, T) alternate, see below
+    double* b1 = base + Cfg::MAT;
+    double* b2 = base + 2 * Cfg::MAT;
     double* vec = base + 3 * Cfg::MAT;
+    double* bA = vec;
+    double* bB = vec + Cfg::KP;
     const int bar_id = 1 + group;
     double* scratch = P.scratch ? P.scratch + ((size_t)blockIdx.x * GROUPS + group) * ns_scratch_doubles(KT) : nullptr;
     const long long t0 = clock64();
-    while (true) {
-        long long slot;
-        if constexpr (WPM == 1) {
-            unsigned int v = 0;
-            if (lane == 0) v = atomicAdd(P.counter, 1u);
-            slot = (long long)__shfl_sync(0xffffffffu, v, 0);
-        } else {
-            if (gtid == 0) next_slot[group] = (long long)atomicAdd(P.counter, 1u);
-            ns_sync<WPM>(bar_id);
-            slot = next_slot[group];
-            ns_sync<WPM>(bar_id);
-        }
-        if (slot >= P.n_slots) break;
-        if constexpr (WPM == 1) ns_solve_one<KT, 1, 0>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id);
+    for (int c = P.k + gtid; c < Cfg::KP; c += WPM * 32) { bA[c] = 0.0; bB[c] = 0.0; }      // the copies fill [0, k) only
+    long long slot;
+    if constexpr (WPM == 1) {
+        unsigned int v = 0;
+        if (lane == 0) v = atomicAdd(P.counter, 1u);
+        slot = (long long)__shfl_sync(0xffffffffu, v, 0);
+    } else {
+        if (gtid == 0) next_slot[group] = (long long)atomicAdd(P.counter, 1u);
+        ns_sync<WPM>(bar_id);
+        slot = next_slot[group];
+        ns_sync<WPM>(bar_id);
+    }
+    if (slot < P.n_slots) ns_issue_load<KT, WPM>(P, slot, b2, bA, gtid);
+    // The matrix of a slot arrives in an END buffer (b2, then b0, b2, ...): Y = that buffer, Z = the other end, T = b1; the dense
+    // result overlays Y and T, and the next matrix is copied into Z as soon as that result is complete.
+    int odd = 0;
+    while (slot < P.n_slots) {
+        double* Y = odd ? b0 : b2;
+        double* Z = odd ? b2 : b0;
+        double* D = odd ? b0 : b1;
+        double* bcur = odd ? bB : bA;
+        double* bnext = odd ? bA : bB;
+        cp_async_wait_all();
+        ns_sync<WPM>(bar_id);
+        if constexpr (WPM == 1) slot = ns_solve_one<KT, 1, 0>(P, slot, Z, Y, b1, D, bcur, bnext, vec, scratch, next_slot + group, gtid, sub, lane, bar_id);
         else if constexpr (WPM == 2) {
-            if (sub == 0) ns_solve_one<KT, 2, 0>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id);
-            else ns_solve_one<KT, 2, 1>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id);
+            if (sub == 0) slot = ns_solve_one<KT, 2, 0>(P, slot, Z, Y, b1, D, bcur, bnext, vec, scratch, next_slot + group, gtid, sub, lane, bar_id);
+            else slot = ns_solve_one<KT, 2, 1>(P, slot, Z, Y, b1, D, bcur, bnext, vec, scratch, next_slot + group, gtid, sub, lane, bar_id);
         } else {
             switch (sub) {
-                case 0: ns_solve_one<KT, 4, 0>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id); break;
-                case 1: ns_solve_one<KT, 4, 1>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id); break;
-                case 2: ns_solve_one<KT, 4, 2>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id); break;
-                default: ns_solve_one<KT, 4, 3>(P, slot, Z, Y, T, vec, scratch, gtid, sub, lane, bar_id); break;
+                case 0: slot = ns_solve_one<KT, 4, 0>(P, slot, Z, Y, b1, D, bcur, bnext, vec, scratch, next_slot + group, gtid, sub, lane, bar_id); break;
+                case 1: slot = ns_solve_one<KT, 4, 1>(P, slot, Z, Y, b1, D, bcur, bnext, vec, scratch, next_slot + group, gtid, sub, lane, bar_id); break;
+                case 2: slot = ns_solve_one<KT, 4, 2>(P, slot, Z, Y, b1, D, bcur, bnext, vec, scratch, next_slot + group, gtid, sub, lane, bar_id); break;
+                default: slot = ns_solve_one<KT, 4, 3>(P, slot, Z, Y, b1, D, bcur, bnext, vec, scratch, next_slot + group, gtid, sub, lane, bar_id); break;
             }
         }
+        odd ^= 1;
     }
     if (P.stats && tid == 0) atomicAdd(P.stats + 1, (unsigned long long)(clock64() - t0));
 }
