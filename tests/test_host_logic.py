@@ -623,6 +623,65 @@ def test_inplace_gauss_jordan_as_in_ienks_pre():
     np.testing.assert_allclose(invert(perm), np.linalg.inv(perm), atol=1e-15)
 
 
+def test_newton_schulz_solve_as_in_the_solve_kernel():
+    """numpy emulation of csrc/ns_solve_kernel.cuh against the reference's eigendecomposition route (core/etkf.py:57-77,102;
+    interface/base.py:257-278): scaled coupled Newton-Schulz iteration with the tracked spectral bound, every product kept as its
+    lower triangle (symmetric storage), sqrt(g) folded into the stored T, the dense result left unscaled, and the update applied
+    as  mean + xp . w_mean + sqrt(k - 1) zs (Z xp)  without forming W."""
+    def sym(m_):
+        return np.tril(m_) + np.tril(m_, -1).T
+
+    def inv_sqrt(a_mat, alpha, conv=2e-8):
+        k = len(a_mat)
+        s = min(np.linalg.norm(a_mat), np.abs(a_mat).sum(axis=1).max()) * (1.0 + 1e-12)
+        lo = min(alpha / s, 1.0)
+        g = 3.0 / (1.0 + np.sqrt(lo) + lo)
+        sg = np.sqrt(g)
+
+        def next_scaling(g, lo):
+            m_ = g * lo
+            lo = min(1.0, 0.25 * m_ * (3.0 - m_) ** 2)
+            g = 3.0 / (1.0 + np.sqrt(lo) + lo)
+            return g, np.sqrt(g), lo
+        y = a_mat / s
+        z = sg * (1.5 * np.eye(k) - 0.5 * g * y)                  # iteration 0: Z1 = sqrt(g) T, Y1 = Y0 Z1
+        g, sg, lo = next_scaling(g, lo)
+        y = sym(y @ z)
+        iters = 1
+        while iters < 64:
+            last = (1.0 - lo) < conv
+            gc, sgc = g, sg
+            g, sg, lo = next_scaling(g, lo)
+            t = sym(-0.5 * gc * sgc * (z @ y)) + 1.5 * sgc * np.eye(k)
+            z = sym(t @ z)
+            iters += 1
+            if last:
+                break
+            y = sym(y @ t)
+        return z, np.sqrt(1.0 / s), iters
+
+    rng = np.random.RandomState(11)
+    for k, p, scale, rho in ((40, 60, 1.0, 1.1), (50, 500, 0.3, 1.05), (16, 8, 2.0, 1.0), (24, 300, 1.5, 1.2)):
+        perts = rng.normal(size=(k, p)) * scale
+        perts -= perts.mean(axis=0)
+        obs = rng.normal(size=(1, p)) * scale
+        alpha = (k - 1) / rho
+        z, zs, iters = inv_sqrt(perts @ perts.T + alpha * np.eye(k), alpha)
+        assert iters <= 10
+        b = perts @ obs[0]
+        w_mean = zs * zs * (z @ (z @ b))
+        w_ref = orc.etkf_weights(perts, obs, rho)
+        np.testing.assert_allclose(w_mean[:, None] + np.sqrt(k - 1) * zs * z, w_ref, rtol=0, atol=1e-11 * np.abs(w_ref).max())
+        x = rng.normal(size=(1, 1, k, 3)) + 280.0
+        ref = orc.apply_weights(x, w_ref)
+        for gp in range(3):
+            col = x[0, 0, :, gp]
+            mean = col.sum() / k
+            xp = col - mean
+            xa = mean + (xp @ w_mean + np.sqrt(k - 1) * zs * (z @ xp))
+            np.testing.assert_allclose(xa, ref[0, 0, :, gp], rtol=1e-12, atol=0)
+
+
 class _OracleIenksEngine(object):
     """CPU stand-in for the engine behind ``VarAssimilation.update_state`` (test infrastructure: the oracle does the numerics)
     so that the control flow of the outer loop (interface/variational.py:105-135) is exercised without a GPU."""
