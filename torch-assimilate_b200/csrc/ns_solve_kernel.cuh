@@ -8,10 +8,13 @@
 //
 // (Higham, Functions of Matrices, eq. 6.35, with the scaling g chosen from a tracked spectral interval), which is
 // nothing but k x k x k matrix products: they run on the FP64 tensor pipe (DMMA m8n8k4) instead of the
-// shared-memory-bandwidth-bound rotations of a Jacobi sweep.  Then
+// shared-memory-bandwidth-bound rotations of a Jacobi sweep.  sqrt(g) is folded into the stored T, so the two products
+// Z' = T' Z, Y' = Y T' are stored as they come out of the accumulators.  Then
 //
 //     w_mean = Z (Z b) / s,  W_p = sqrt((k-1) / s) Z,  W = w_mean 1^T + W_p     (core/etkf.py:72-77,102)
-//     x_a = mean + (x - mean) W                                                   (interface/base.py:257-278)
+//     x_a = mean + (x - mean) W = mean + xp . w_mean + sqrt((k-1) / s) Z xp      (interface/base.py:257-278)
+//
+// W itself is only formed where it is exported (w_out).
 //
 // Spectrum.  C is a Gram matrix, so eig(A) lies in [a, s] with s = min(||A||_F, ||A||_inf); the reference's
 // clamp(min=0) (core/utils.py:58) only removes rounding noise of the same size as this kernel's own rounding.
@@ -24,8 +27,10 @@
 // tiles are stored (tile (mt, nt), nt <= mt, at ((mt (mt+1))/2 + nt) * 64 doubles; element (r, c) of a tile at
 // r * 8 + (c ^ ((r & 2) << 1)): the XOR makes both the direct and the transposed DMMA fragment reads
 // bank-conflict free).  The Gram kernel writes its accumulators to global memory in exactly this layout, so
-// loading a matrix is a flat copy.  One group of WPM warps owns one matrix (WPM = 1 up to k = 56: no CTA-wide
-// barrier anywhere in the iteration); a CTA holds several groups, each fetching grid slots from an atomic counter.
+// loading a matrix is a flat copy.  One group of WPM warps owns one matrix (WPM = 1 up to k = 40: no CTA-wide
+// barrier anywhere in the iteration; ns_launch.cu: NsPick); a CTA holds several groups, each fetching grid slots from an
+// atomic counter.  A group has three matrix buffers; the roles (Z, Y, T) alternate from one matrix to the next, because the
+// next matrix is copied (cp.async) into the buffer that is dead once the dense result of the current one is complete.
 #pragma once
 #include "plan.cuh"
 
