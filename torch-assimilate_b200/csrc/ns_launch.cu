@@ -66,7 +66,7 @@ int dispatch_ns(int kts, const NsParams& P, cudaStream_t st) {
     }
 }
 #elif B200DA_NS_LARGE == 1
-int dispatch_ns_large2(int kts, const NsParams& P, cudaStream_t st);     // ns_launch_c.cu: 14 <= kts <= 16
+int dispatch_ns_large2(int kts, const NsParams& P, cudaStream_t st);     // ns_launch_c.cu: kts 14, 15; ns_launch_e.cu: kts 16
 int dispatch_ns_large(int kts, const NsParams& P, cudaStream_t st) {
     switch (kts) {
         B200DA_NS_CASE(11) B200DA_NS_CASE(12) B200DA_NS_CASE(13)
@@ -74,9 +74,17 @@ int dispatch_ns_large(int kts, const NsParams& P, cudaStream_t st) {
     }
 }
 #elif B200DA_NS_LARGE == 2
+int dispatch_ns_large3(int kts, const NsParams& P, cudaStream_t st);     // ns_launch_e.cu: kts 16
 int dispatch_ns_large2(int kts, const NsParams& P, cudaStream_t st) {
     switch (kts) {
-        B200DA_NS_CASE(14) B200DA_NS_CASE(15) B200DA_NS_CASE(16)
+        B200DA_NS_CASE(14) B200DA_NS_CASE(15)
+        default: return dispatch_ns_large3(kts, P, st);
+    }
+}
+#elif B200DA_NS_LARGE == 4
+int dispatch_ns_large3(int kts, const NsParams& P, cudaStream_t st) {
+    switch (kts) {
+        B200DA_NS_CASE(16)
         default: return B200DA_ERR_UNSUPPORTED;
     }
 }
